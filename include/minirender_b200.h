@@ -1,0 +1,209 @@
+/*
+ * minirender_b200.h — C ABI of the B200 rasterization path.
+ *
+ * The reference (aslze/minirender) has no FFI: its only seam is the C++ class
+ * minirender::Renderer (reference include/minirender/Renderer.h:17-64). Our drop-in
+ * Renderer (include/minirender/Renderer.h in this repo) keeps that class API and calls the
+ * functions below from inside render()/getImage()/getDepth(); nothing else in the product
+ * touches CUDA. Everything here is plain C: pointers, sizes, ints, floats. No torch, no ASL.
+ *
+ * What each entry point replaces in the reference:
+ *   mr_set_size        Renderer::setSize            src/Renderer.cpp:100-106
+ *   mr_upload_scene    the arrays paintMesh reads   src/Renderer.cpp:341-380, Scene.h:73-87
+ *   mr_render          clear + loops A..E           src/Renderer.cpp:113-119, 163-309, 344-380
+ *   mr_read_image      Renderer::getImage           src/Renderer.cpp:383-386
+ *   mr_read_depth      Renderer::getDepth           include/minirender/Renderer.h:60
+ *   mr_read_normals    Renderer::getNormalsImage    include/minirender/Renderer.h:63
+ *   mr_read_range      Renderer::getRangeImage      src/Renderer.cpp:388-415
+ *   mr_read_rgb8       savePPM's quantiser          src/io.cpp:358-361
+ *
+ * Conventions: every function returns 0 on success or a negative MR_E_* code; the message
+ * for the last failure on a context is mr_last_error(ctx). No exceptions cross this ABI.
+ * A context owns all of its device memory, is bound to one GPU and one CUDA stream, and is
+ * not thread-safe (one context per host thread, like one reference Renderer per thread).
+ * Host pointers in descriptors are borrowed for the duration of the call only.
+ * mr_render is asynchronous (stream ordered); the mr_read_* calls synchronise.
+ * There is no CPU fallback: without a usable CUDA device mr_create fails.
+ */
+#ifndef MINIRENDER_B200_H
+#define MINIRENDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MR_API __attribute__((visibility("default")))
+#else
+#define MR_API
+#endif
+
+#define MR_ABI_VERSION 1
+
+enum
+{
+	MR_OK = 0,
+	MR_E_INVALID = -1,   /* bad argument / descriptor */
+	MR_E_CUDA = -2,      /* CUDA runtime error (see mr_last_error) */
+	MR_E_NO_DEVICE = -3, /* no CUDA device / driver: the product does not fall back to the CPU */
+	MR_E_NO_SCENE = -4,  /* mr_render before mr_upload_scene */
+	MR_E_OVERFLOW = -5,  /* internal queue overflow that could not be recovered by regrowing */
+	MR_E_NOMEM = -6
+};
+
+typedef struct mr_ctx mr_ctx;
+
+/* One TriMesh's geometry (reference Scene.h:73-87). Index arrays hold 3 ints per triangle
+ * and index into this mesh's own attribute arrays. idx_nrm is required (the reference reads
+ * normalsI unconditionally, Renderer.cpp:367-369). The mesh is textured-capable only when
+ * both n_texcoords > 0 and idx_uv != NULL (Renderer.cpp:371). */
+typedef struct mr_mesh_desc
+{
+	const float* positions; /* 3*n_positions floats, xyz packed (asl::Vec3 layout) */
+	const float* normals;   /* 3*n_normals floats */
+	const float* texcoords; /* 2*n_texcoords floats, or NULL */
+	const int32_t* idx_pos; /* 3*n_triangles */
+	const int32_t* idx_nrm; /* 3*n_triangles */
+	const int32_t* idx_uv;  /* 3*n_triangles, or NULL */
+	int32_t n_positions;
+	int32_t n_normals;
+	int32_t n_texcoords;
+	int32_t n_triangles;
+} mr_mesh_desc;
+
+/* Float RGB texture, row-major rows x cols x 3 (asl::Array2<asl::Vec3>, Scene.h:42). */
+typedef struct mr_texture_desc
+{
+	const float* texels;
+	int32_t rows;
+	int32_t cols;
+} mr_texture_desc;
+
+typedef struct mr_scene_desc
+{
+	const mr_mesh_desc* meshes;
+	const mr_texture_desc* textures;
+	int32_t n_meshes;
+	int32_t n_textures;
+} mr_scene_desc;
+
+/* Material snapshot (reference Scene.h:38-45; opacity is never read by the renderer). */
+typedef struct mr_material
+{
+	float diffuse[3];
+	float specular[3];
+	float emissive[3];
+	float shininess;
+	int32_t texture; /* index into mr_scene_desc.textures, or -1 */
+	int32_t _pad;
+} mr_material;
+
+/* One entry of the flattened scene (reference Scene.h:47-53), in submission order. The two
+ * matrices are computed on the host with the reference's own expressions
+ * (Renderer.cpp:337-338): modelview = view * world, normalmat = modelview.inverse().t();
+ * only their top three rows are used (affine asl::Matrix4 * Vec3). Row-major 3x4. */
+typedef struct mr_renderable
+{
+	float modelview[12];
+	float normalmat[12];
+	int32_t mesh;     /* index into mr_scene_desc.meshes */
+	int32_t material; /* index into mr_frame.materials */
+} mr_renderable;
+
+/* Per-frame state: everything Renderer::render() derives before its renderable loop
+ * (Renderer.cpp:313-326) plus the renderer's switches (Renderer.h:48-55). */
+typedef struct mr_frame
+{
+	float projection[16];  /* row-major 4x4 */
+	const mr_renderable* renderables;
+	const mr_material* materials;
+	int32_t n_renderables;
+	int32_t n_materials;
+	float light[3];        /* _lightdir: view-space position (point) or normalised direction */
+	int32_t light_is_point;
+	float ambient;         /* Scene::ambientLight */
+	float znear;           /* Renderer.cpp:325-326 */
+	int32_t lighting;
+	int32_t texturing;
+	int32_t save_normals;
+	float background[3];
+	int32_t row_begin;     /* render only image rows [row_begin,row_end); 0,0 = whole image.  */
+	int32_t row_end;       /* Used for strip sharding across GPUs; other rows are untouched.   */
+	int32_t keep;          /* 0: clear first (render()); 1: depth-test against and keep the
+	                          current buffers (immediate-mode paintMesh after clear()) */
+} mr_frame;
+
+/* Counters of the last completed mr_render on this context (valid after a sync/read). */
+typedef struct mr_stats
+{
+	int64_t triangles_in;      /* triangles submitted */
+	int64_t records;           /* set-up triangles that survived near test, reject and cull */
+	int64_t clipped_in;        /* input triangles that crossed the near plane */
+	int64_t bin_entries;       /* (tile, triangle) pairs */
+	int64_t wide_records;      /* triangles routed through the chain-checkpoint path */
+	int32_t tiles_x, tiles_y;
+	int32_t regrows;           /* times a queue had to be regrown and the frame re-run */
+	int32_t kernels_launched;  /* kernel launches issued for the frame */
+	float   ms_kernel[8];      /* per-stage device time of the last mr_profile_frame */
+} mr_stats;
+
+MR_API int mr_abi_version(void);
+MR_API int mr_device_count(void);
+
+MR_API mr_ctx* mr_create(int device, int* status);
+MR_API void mr_destroy(mr_ctx* ctx);
+MR_API const char* mr_last_error(const mr_ctx* ctx);
+
+/* Use an externally owned CUDA stream (cudaStream_t / CUstream as void*); NULL = ctx-owned. */
+MR_API int mr_set_stream(mr_ctx* ctx, void* cuda_stream);
+MR_API int mr_set_size(mr_ctx* ctx, int width, int height);
+MR_API int mr_upload_scene(mr_ctx* ctx, const mr_scene_desc* scene);
+
+MR_API int mr_render(mr_ctx* ctx, const mr_frame* frame);
+/* n frames over the same scene, pipelined over the context's frame slots. After each frame
+ * completes its float image/depth stay in slot (i % slots); `sink` (may be NULL) is called in
+ * order with device pointers once frame i is complete. */
+typedef void (*mr_frame_sink)(void* user, int index, const float* d_image, const float* d_depth);
+MR_API int mr_render_batch(mr_ctx* ctx, int n, const mr_frame* frames, mr_frame_sink sink, void* user);
+
+MR_API int mr_synchronize(mr_ctx* ctx);
+
+/* Blocking device->host reads of the last frame (full image, row-major, row 0 = top). */
+MR_API int mr_read_image(mr_ctx* ctx, float* host_rgb /* h*w*3 */);
+MR_API int mr_read_depth(mr_ctx* ctx, float* host_depth /* h*w */);
+MR_API int mr_read_normals(mr_ctx* ctx, float* host_nrm /* h*w*3 */);
+MR_API int mr_read_range(mr_ctx* ctx, const float* projection16, float znear, float* host_xyz /* h*w*3 */);
+MR_API int mr_read_rgb8(mr_ctx* ctx, uint8_t* host_rgb8 /* h*w*3 */);
+/* Same reads into caller-provided *pinned or pageable* memory without the final sync. */
+MR_API int mr_read_image_async(mr_ctx* ctx, float* host_rgb);
+MR_API int mr_read_rows_async(mr_ctx* ctx, float* host_rgb, float* host_depth, int row_begin, int row_end);
+
+/* Device pointers of the current output buffers (for interop: NCCL gather, checksums). */
+MR_API int mr_device_buffers(mr_ctx* ctx, void** d_image, void** d_depth, void** d_normals);
+/* Overwrite rows [row_begin,row_end) of the output buffers from device memory (strip gather). */
+MR_API int mr_write_rows(mr_ctx* ctx, const void* d_image_rows, const void* d_depth_rows, int row_begin, int row_end);
+/* Let tile stores of rows [row_begin,row_end) land directly in a peer GPU's framebuffer
+ * (pointers obtained from that peer's mr_device_buffers through CUDA IPC / symmetric memory). */
+MR_API int mr_set_remote_target(mr_ctx* ctx, void* d_peer_image, void* d_peer_depth);
+
+/* Page-lock caller memory so the mr_read_* copies run at full PCIe rate (optional). */
+MR_API int mr_host_register(void* host, size_t bytes);
+MR_API int mr_host_unregister(void* host);
+
+/* Verification aid: with flags & 1, mr_render also records for every pixel the submission id of
+ * the triangle that owns it (2 * triangle instance index + clip sub-triangle, -1 = background),
+ * which is what equal-depth ties are resolved on. Read it back with mr_read_winner_ids. */
+MR_API int mr_set_debug(mr_ctx* ctx, int flags);
+MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
+
+MR_API int mr_get_stats(mr_ctx* ctx, mr_stats* out);
+/* Re-run the last frame with CUDA events between the stages; fills mr_stats.ms_kernel. */
+MR_API int mr_profile_frame(mr_ctx* ctx, const mr_frame* frame, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

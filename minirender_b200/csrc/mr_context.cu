@@ -1,0 +1,966 @@
+// C ABI of the B200 rasterization path (include/minirender_b200.h): context, device memory,
+// scene upload, per-frame tables and kernel launches. Host code only; kernels are in
+// mr_kernels.cu. There is deliberately no CPU path here: every entry point that produces pixels
+// needs a CUDA device and fails with MR_E_NO_DEVICE / MR_E_CUDA otherwise.
+#include "../../include/minirender_b200.h"
+#include "mr_types.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf
+{
+	void* p;
+	size_t cap;
+	DevBuf() : p(0), cap(0) {}
+	cudaError_t ensure(size_t bytes, bool exact = false)
+	{
+		if (bytes <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFree(p);
+		p = 0;
+		cap = 0;
+		const size_t want = exact ? bytes : bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = 0;
+		cap = 0;
+	}
+	template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf
+{
+	void* p;
+	size_t cap;
+	PinBuf() : p(0), cap(0) {}
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFreeHost(p);
+		p = 0;
+		cap = 0;
+		const size_t want = bytes + bytes / 2 + 4096;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p)
+			cudaFreeHost(p);
+		p = 0;
+		cap = 0;
+	}
+};
+
+}
+
+struct mr_ctx
+{
+	int device;
+	cudaStream_t stream;
+	bool ownStream;
+	std::string error;
+
+	int w, h, tilesX, tilesY;
+
+	// scene-static device arrays
+	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes;
+	std::vector<MeshDev> hostMeshes;
+	std::vector<int> texOffset, texRows, texCols;
+	bool haveScene;
+	unsigned sceneSerial;
+
+	// per-frame tables
+	DevBuf rstat, rdyn, mats, vtxBlockR, triBlockR;
+	std::vector<int> structureKey; // mesh id per renderable of the tables currently on the device
+	unsigned structureSerial;
+	int nVertInst, nTriInst;
+	PinBuf stage;
+	cudaEvent_t stageFree;
+	bool stageBusy;
+
+	// scratch
+	DevBuf pv, recs, tileCount, tileOffset, pairs, bins, ctr;
+	size_t pairCap;
+
+	// outputs
+	DevBuf image, depth, normals, winner, scratchOut;
+	void *remoteImage, *remoteDepth;
+	int debugFlags;
+
+	// last frame (kept for overflow re-runs and profiling)
+	mr_frame lastFrame;
+	std::vector<mr_renderable> lastRenderables;
+	std::vector<mr_material> lastMaterials;
+	bool haveFrame;
+	bool frameChecked;
+	Counters* hostCtr; // pinned
+	cudaEvent_t frameDone;
+	mr_stats stats;
+
+	mr_ctx() : device(0), stream(0), ownStream(false), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
+	           structureSerial(~0u), nVertInst(0), nTriInst(0), stageFree(0), stageBusy(false), pairCap(0), remoteImage(0),
+	           remoteDepth(0), debugFlags(0), haveFrame(false), frameChecked(true), hostCtr(0), frameDone(0)
+	{
+		memset(&lastFrame, 0, sizeof(lastFrame));
+		memset(&stats, 0, sizeof(stats));
+	}
+};
+
+namespace {
+
+int setError(mr_ctx* c, int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (c)
+		c->error = buf;
+	return code;
+}
+
+#define MR_CUDA(c, call)                                                                                       \
+	do                                                                                                         \
+	{                                                                                                          \
+		cudaError_t e_ = (call);                                                                               \
+		if (e_ != cudaSuccess)                                                                                 \
+			return setError(c, e_ == cudaErrorMemoryAllocation ? MR_E_NOMEM : MR_E_CUDA, "%s: %s", #call,      \
+			                cudaGetErrorString(e_));                                                           \
+	} while (0)
+
+struct Bind
+{
+	int prev;
+	bool changed;
+	explicit Bind(int dev) : prev(-1), changed(false)
+	{
+		if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+		{
+			cudaSetDevice(dev);
+			changed = true;
+		}
+	}
+	~Bind()
+	{
+		if (changed)
+			cudaSetDevice(prev);
+	}
+};
+
+int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev);
+
+// Waits for the last frame and, if its pair queue overflowed, regrows it and re-runs the frame.
+int finishFrame(mr_ctx* c)
+{
+	if (!c->haveFrame || c->frameChecked)
+	{
+		MR_CUDA(c, cudaStreamSynchronize(c->stream));
+		return MR_OK;
+	}
+	for (int attempt = 0; attempt < 4; attempt++)
+	{
+		MR_CUDA(c, cudaEventSynchronize(c->frameDone));
+		const Counters k = *c->hostCtr;
+		c->stats.triangles_in = (int64_t)k.trianglesIn;
+		c->stats.records = (int64_t)k.records;
+		c->stats.clipped_in = (int64_t)k.clippedIn;
+		c->stats.bin_entries = (int64_t)k.pairTotal;
+		c->stats.wide_records = (int64_t)k.wideRecords;
+		c->stats.tiles_x = c->tilesX;
+		c->stats.tiles_y = c->tilesY;
+		if (!k.overflow)
+		{
+			c->frameChecked = true;
+			MR_CUDA(c, cudaStreamSynchronize(c->stream));
+			return MR_OK;
+		}
+		// not enough room for the (tile, triangle) pairs: grow and render the frame again
+		c->pairCap = (size_t)k.pairTotal + (size_t)k.pairTotal / 4 + 1024;
+		c->stats.regrows++;
+		mr_frame f = c->lastFrame;
+		f.renderables = c->lastRenderables.empty() ? 0 : &c->lastRenderables[0];
+		f.materials = c->lastMaterials.empty() ? 0 : &c->lastMaterials[0];
+		int rc = launchFrame(c, &f, 0);
+		if (rc)
+			return rc;
+	}
+	return setError(c, MR_E_OVERFLOW, "pair queue kept overflowing");
+}
+
+int ensureOutputs(mr_ctx* c, bool normals, bool winner)
+{
+	const size_t npix = (size_t)c->w * c->h;
+	const bool freshImage = c->image.cap < npix * 12;
+	MR_CUDA(c, c->image.ensure(npix * 12, true));
+	MR_CUDA(c, c->depth.ensure(npix * 4, true));
+	if (freshImage)
+	{
+		MR_CUDA(c, cudaMemsetAsync(c->image.p, 0, npix * 12, c->stream));
+		MR_CUDA(c, cudaMemsetAsync(c->depth.p, 0, npix * 4, c->stream));
+	}
+	if (normals && c->normals.cap < npix * 12)
+	{
+		MR_CUDA(c, c->normals.ensure(npix * 12, true));
+		MR_CUDA(c, cudaMemsetAsync(c->normals.p, 0, npix * 12, c->stream));
+	}
+	if (winner && c->winner.cap < npix * 4)
+	{
+		MR_CUDA(c, c->winner.ensure(npix * 4, true));
+		MR_CUDA(c, cudaMemsetAsync(c->winner.p, 0xff, npix * 4, c->stream));
+	}
+	return MR_OK;
+}
+
+int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
+{
+	const int nR = f->n_renderables;
+	// ---- validate + instance bases ----
+	std::vector<RStat> rs((size_t)nR);
+	long long vb = 0, tb = 0;
+	bool sameStructure = (c->structureSerial == c->sceneSerial) && ((int)c->structureKey.size() == nR);
+	for (int i = 0; i < nR; i++)
+	{
+		const mr_renderable& r = f->renderables[i];
+		if (r.mesh < 0 || r.mesh >= (int)c->hostMeshes.size())
+			return setError(c, MR_E_INVALID, "renderable %d: mesh index %d out of range", i, r.mesh);
+		if (r.material < 0 || r.material >= f->n_materials)
+			return setError(c, MR_E_INVALID, "renderable %d: material index %d out of range", i, r.material);
+		rs[i].mesh = r.mesh;
+		rs[i].vertBase = (int)vb;
+		rs[i].triBase = (int)tb;
+		rs[i].pad = 0;
+		vb += c->hostMeshes[r.mesh].nPos;
+		tb += c->hostMeshes[r.mesh].nTri;
+		if (sameStructure && c->structureKey[i] != r.mesh)
+			sameStructure = false;
+	}
+	if (vb > 0x3fffffffLL || tb > 0x3fffffffLL)
+		return setError(c, MR_E_INVALID, "frame too large: %lld vertex instances, %lld triangle instances", vb, tb);
+	c->nVertInst = (int)vb;
+	c->nTriInst = (int)tb;
+	const int nVB = (c->nVertInst + 255) / 256, nTB = (c->nTriInst + 255) / 256;
+
+	// ---- device buffers ----
+	const int nTiles = c->tilesX * c->tilesY;
+	MR_CUDA(c, c->rstat.ensure(sizeof(RStat) * (size_t)std::max(nR, 1)));
+	MR_CUDA(c, c->rdyn.ensure(sizeof(RDyn) * (size_t)std::max(nR, 1)));
+	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
+	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)std::max(nVB, 1)));
+	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)std::max(nTB, 1)));
+	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
+	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
+	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
+	MR_CUDA(c, c->tileOffset.ensure(sizeof(int) * (size_t)(nTiles + 1)));
+	MR_CUDA(c, c->ctr.ensure(sizeof(Counters)));
+	if (c->pairCap < (size_t)c->nTriInst * 2 + 65536)
+		c->pairCap = (size_t)c->nTriInst * 2 + 65536;
+	if (c->pairCap > 0x7fffffffULL)
+		return setError(c, MR_E_OVERFLOW, "more than 2^31 (tile, triangle) pairs");
+	MR_CUDA(c, c->pairs.ensure(sizeof(int4) * c->pairCap));
+	MR_CUDA(c, c->bins.ensure(sizeof(int) * c->pairCap));
+	c->pairCap = std::min(c->pairs.cap / sizeof(int4), c->bins.cap / sizeof(int));
+	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
+	if (rc)
+		return rc;
+
+	// ---- stage per-frame tables in pinned memory, one async copy each ----
+	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
+	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)nVB;
+	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)nTB;
+	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
+	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
+	const size_t total = szStat + szVB + szTB + szDyn + szMat + 64;
+	if (c->stageBusy)
+	{
+		MR_CUDA(c, cudaEventSynchronize(c->stageFree));
+		c->stageBusy = false;
+	}
+	MR_CUDA(c, c->stage.ensure(total));
+	char* sp = (char*)c->stage.p;
+	size_t off = 0;
+	if (!sameStructure)
+	{
+		memcpy(sp + off, rs.data(), szStat);
+		if (szStat) MR_CUDA(c, cudaMemcpyAsync(c->rstat.p, sp + off, szStat, cudaMemcpyHostToDevice, c->stream));
+		off += szStat;
+		int* vbr = (int*)(sp + off);
+		for (int b = 0, r = 0; b < nVB; b++)
+		{
+			const int first = b * 256;
+			while (r + 1 < nR && first >= rs[r + 1].vertBase)
+				r++;
+			vbr[b] = r;
+		}
+		if (szVB) MR_CUDA(c, cudaMemcpyAsync(c->vtxBlockR.p, sp + off, szVB, cudaMemcpyHostToDevice, c->stream));
+		off += szVB;
+		int* tbr = (int*)(sp + off);
+		for (int b = 0, r = 0; b < nTB; b++)
+		{
+			const int first = b * 256;
+			while (r + 1 < nR && first >= rs[r + 1].triBase)
+				r++;
+			tbr[b] = r;
+		}
+		if (szTB) MR_CUDA(c, cudaMemcpyAsync(c->triBlockR.p, sp + off, szTB, cudaMemcpyHostToDevice, c->stream));
+		off += szTB;
+		c->structureKey.resize((size_t)nR);
+		for (int i = 0; i < nR; i++)
+			c->structureKey[i] = rs[i].mesh;
+		c->structureSerial = c->sceneSerial;
+	}
+	off = (off + 15) & ~(size_t)15;
+	RDyn* rd = (RDyn*)(sp + off);
+	for (int i = 0; i < nR; i++)
+	{
+		memcpy(rd[i].mv, f->renderables[i].modelview, sizeof(float) * 12);
+		memcpy(rd[i].nm, f->renderables[i].normalmat, sizeof(float) * 12);
+		rd[i].material = f->renderables[i].material;
+		rd[i].pad[0] = rd[i].pad[1] = rd[i].pad[2] = 0;
+	}
+	if (szDyn) MR_CUDA(c, cudaMemcpyAsync(c->rdyn.p, rd, szDyn, cudaMemcpyHostToDevice, c->stream));
+	off += szDyn;
+	off = (off + 15) & ~(size_t)15;
+	MatDev* md = (MatDev*)(sp + off);
+	for (int i = 0; i < f->n_materials; i++)
+	{
+		const mr_material& m = f->materials[i];
+		memcpy(md[i].diffuse, m.diffuse, 12);
+		memcpy(md[i].specular, m.specular, 12);
+		memcpy(md[i].emissive, m.emissive, 12);
+		md[i].shininess = m.shininess;
+		md[i].texOffset = -1;
+		md[i].texRows = md[i].texCols = 0;
+		if (m.texture >= 0)
+		{
+			if (m.texture >= (int)c->texOffset.size())
+				return setError(c, MR_E_INVALID, "material %d: texture index %d out of range", i, m.texture);
+			md[i].texOffset = c->texOffset[m.texture];
+			md[i].texRows = c->texRows[m.texture];
+			md[i].texCols = c->texCols[m.texture];
+		}
+		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
+	}
+	if (szMat) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
+	MR_CUDA(c, cudaEventRecord(c->stageFree, c->stream));
+	c->stageBusy = true;
+
+	// ---- frame parameters ----
+	FrameParams fp;
+	memset(&fp, 0, sizeof(fp));
+	memcpy(fp.P, f->projection, sizeof(fp.P));
+	memcpy(fp.light, f->light, 12);
+	fp.ambient = f->ambient;
+	memcpy(fp.bg, f->background, 12);
+	fp.znear = f->znear;
+	fp.wf = (float)c->w;
+	fp.hf = (float)c->h;
+	fp.w = c->w;
+	fp.h = c->h;
+	fp.tilesX = c->tilesX;
+	fp.tilesY = c->tilesY;
+	int rb = 0, re = c->h;
+	if (f->row_end > f->row_begin)
+	{
+		rb = std::max(0, f->row_begin);
+		re = std::min(c->h, f->row_end);
+	}
+	fp.rowBegin = rb;
+	fp.rowEnd = re;
+	fp.tileRow0 = rb >> MR_TILE_SHIFT;
+	fp.tileRows = (re > rb) ? ((re + MR_TILE - 1) >> MR_TILE_SHIFT) - fp.tileRow0 : 0;
+	fp.persp = f->projection[15] == 0.0f;
+	fp.lightIsPoint = f->light_is_point;
+	fp.lighting = f->lighting;
+	fp.texturing = f->texturing;
+	fp.saveNormals = f->save_normals;
+	fp.keep = f->keep;
+	fp.nRenderables = nR;
+	fp.nVertInst = c->nVertInst;
+	fp.nTriInst = c->nTriInst;
+	fp.pairCap = (int)std::min<size_t>(c->pairCap, 0x7fffffff);
+	fp.pos4 = c->pos4.as<float4>();
+	fp.nrm4 = c->nrm4.as<float4>();
+	fp.uv2 = c->uv2.as<float2>();
+	fp.idxPos = c->idxPos.as<int>();
+	fp.idxNrm = c->idxNrm.as<int>();
+	fp.idxUv = c->idxUv.as<int>();
+	fp.texels = c->texels.as<float4>();
+	fp.meshes = c->meshes.as<MeshDev>();
+	fp.rstat = c->rstat.as<RStat>();
+	fp.rdyn = c->rdyn.as<RDyn>();
+	fp.mats = c->mats.as<MatDev>();
+	fp.vtxBlockR = c->vtxBlockR.as<int>();
+	fp.triBlockR = c->triBlockR.as<int>();
+	fp.pv = c->pv.as<float4>();
+	fp.recs = c->recs.as<Rec>();
+	fp.tileCount = c->tileCount.as<int>();
+	fp.tileOffset = c->tileOffset.as<int>();
+	fp.pairs = c->pairs.as<int4>();
+	fp.bins = c->bins.as<int>();
+	fp.ctr = c->ctr.as<Counters>();
+	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
+	fp.depth = (c->remoteDepth && !f->keep) ? (float*)c->remoteDepth : c->depth.as<float>();
+	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
+	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
+
+	mrk_launch_frame(fp, c->stream, ev);
+	MR_CUDA(c, cudaGetLastError());
+	MR_CUDA(c, cudaMemcpyAsync(c->hostCtr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+	MR_CUDA(c, cudaEventRecord(c->frameDone, c->stream));
+	c->stats.kernels_launched = 3 + (c->nTriInst > 0 ? 2 : 0);
+	c->frameChecked = false;
+	return MR_OK;
+}
+
+int rememberFrame(mr_ctx* c, const mr_frame* f)
+{
+	c->lastFrame = *f;
+	c->lastRenderables.assign(f->renderables, f->renderables + f->n_renderables);
+	c->lastMaterials.assign(f->materials, f->materials + f->n_materials);
+	c->lastFrame.renderables = 0;
+	c->lastFrame.materials = 0;
+	c->haveFrame = true;
+	return MR_OK;
+}
+
+int readBack(mr_ctx* c, void* host, const void* dev, size_t bytes)
+{
+	MR_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	return MR_OK;
+}
+
+}
+
+extern "C" {
+
+int mr_abi_version(void) { return MR_ABI_VERSION; }
+
+int mr_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+mr_ctx* mr_create(int device, int* status)
+{
+	int st = MR_OK;
+	mr_ctx* c = 0;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0)
+	{
+		cudaGetLastError();
+		st = MR_E_NO_DEVICE;
+	}
+	else if (device < 0 || device >= n)
+		st = MR_E_INVALID;
+	else
+	{
+		c = new mr_ctx();
+		c->device = device;
+		Bind bind(device);
+		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+		c->ownStream = ok;
+		ok = ok && cudaEventCreateWithFlags(&c->stageFree, cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaMallocHost((void**)&c->hostCtr, sizeof(Counters)) == cudaSuccess;
+		if (ok)
+		{
+			memset(c->hostCtr, 0, sizeof(Counters));
+			const int fma = mrk_selftest_no_fma(c->stream);
+			if (fma != 0)
+			{
+				fprintf(stderr, "minirender_b200: FMA contraction self-test failed (%d); build with --fmad=false\n", fma);
+				ok = false;
+			}
+		}
+		if (!ok)
+		{
+			cudaGetLastError();
+			mr_destroy(c);
+			c = 0;
+			st = MR_E_CUDA;
+		}
+	}
+	if (status)
+		*status = st;
+	return c;
+}
+
+void mr_destroy(mr_ctx* c)
+{
+	if (!c)
+		return;
+	Bind bind(c->device);
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
+		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount, &c->tileOffset,
+		               &c->pairs, &c->bins, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut };
+	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
+		bufs[i]->release();
+	c->stage.release();
+	if (c->hostCtr)
+		cudaFreeHost(c->hostCtr);
+	if (c->stageFree)
+		cudaEventDestroy(c->stageFree);
+	if (c->frameDone)
+		cudaEventDestroy(c->frameDone);
+	if (c->ownStream && c->stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char* mr_last_error(const mr_ctx* c) { return c ? c->error.c_str() : "no context (no CUDA device?)"; }
+
+int mr_set_stream(mr_ctx* c, void* s)
+{
+	if (!c)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->ownStream)
+	{
+		cudaStreamDestroy(c->stream);
+		c->ownStream = false;
+	}
+	if (s)
+		c->stream = (cudaStream_t)s;
+	else
+	{
+		MR_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		c->ownStream = true;
+	}
+	return MR_OK;
+}
+
+int mr_set_debug(mr_ctx* c, int flags)
+{
+	if (!c)
+		return MR_E_INVALID;
+	c->debugFlags = flags;
+	return MR_OK;
+}
+
+int mr_set_size(mr_ctx* c, int w, int h)
+{
+	if (!c)
+		return MR_E_INVALID;
+	if (w <= 0 || h <= 0 || w > 32768 || h > 32768)
+		return setError(c, MR_E_INVALID, "image size %dx%d out of range (1..32768)", w, h);
+	Bind bind(c->device);
+	if (w == c->w && h == c->h)
+		return MR_OK;
+	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->w = w;
+	c->h = h;
+	c->tilesX = (w + MR_TILE - 1) / MR_TILE;
+	c->tilesY = (h + MR_TILE - 1) / MR_TILE;
+	c->image.release();
+	c->depth.release();
+	c->normals.release();
+	c->winner.release();
+	c->haveFrame = false;
+	c->frameChecked = true;
+	return ensureOutputs(c, false, false);
+}
+
+int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
+{
+	if (!c || !s || s->n_meshes < 0 || s->n_textures < 0)
+		return setError(c, MR_E_INVALID, "bad scene descriptor");
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	// ---- validate and lay out ----
+	std::vector<MeshDev> md((size_t)s->n_meshes);
+	long long nPos = 0, nNrm = 0, nUv = 0, nTri = 0, nUvTri = 0;
+	for (int i = 0; i < s->n_meshes; i++)
+	{
+		const mr_mesh_desc& m = s->meshes[i];
+		if (m.n_positions < 0 || m.n_normals < 0 || m.n_texcoords < 0 || m.n_triangles < 0)
+			return setError(c, MR_E_INVALID, "mesh %d: negative count", i);
+		if (m.n_triangles > 0 && (!m.idx_pos || !m.idx_nrm || !m.positions || !m.normals))
+			return setError(c, MR_E_INVALID, "mesh %d: missing positions/normals/index arrays", i);
+		const bool hasUV = m.n_texcoords > 0 && m.idx_uv != 0 && m.texcoords != 0;
+		for (long long k = 0; k < 3LL * m.n_triangles; k++)
+		{
+			if ((unsigned)m.idx_pos[k] >= (unsigned)m.n_positions)
+				return setError(c, MR_E_INVALID, "mesh %d: position index %d out of range at corner %lld", i, m.idx_pos[k], k);
+			if ((unsigned)m.idx_nrm[k] >= (unsigned)m.n_normals)
+				return setError(c, MR_E_INVALID, "mesh %d: normal index %d out of range at corner %lld", i, m.idx_nrm[k], k);
+			if (hasUV && (unsigned)m.idx_uv[k] >= (unsigned)m.n_texcoords)
+				return setError(c, MR_E_INVALID, "mesh %d: texcoord index %d out of range at corner %lld", i, m.idx_uv[k], k);
+		}
+		md[i].posBase = (int)nPos;
+		md[i].nrmBase = (int)nNrm;
+		md[i].uvBase = (int)nUv;
+		md[i].triBase = (int)nTri;
+		md[i].uvTriBase = hasUV ? (int)nUvTri : -1;
+		md[i].nPos = m.n_positions;
+		md[i].nTri = m.n_triangles;
+		md[i].hasUV = hasUV;
+		nPos += m.n_positions;
+		nNrm += m.n_normals;
+		nTri += m.n_triangles;
+		if (hasUV)
+		{
+			nUv += m.n_texcoords;
+			nUvTri += m.n_triangles;
+		}
+	}
+	if (nPos > 0x3fffffffLL || nNrm > 0x3fffffffLL || nTri > 0x2aaaaaaaLL)
+		return setError(c, MR_E_INVALID, "scene too large for 32-bit indexing");
+	long long nTexel = 0;
+	std::vector<int> to((size_t)s->n_textures), tr((size_t)s->n_textures), tc((size_t)s->n_textures);
+	for (int i = 0; i < s->n_textures; i++)
+	{
+		const mr_texture_desc& t = s->textures[i];
+		if (t.rows <= 0 || t.cols <= 0 || !t.texels)
+			return setError(c, MR_E_INVALID, "texture %d: empty", i);
+		to[i] = (int)nTexel;
+		tr[i] = t.rows;
+		tc[i] = t.cols;
+		nTexel += (long long)t.rows * t.cols;
+	}
+	if (nTexel > 0x3fffffffLL)
+		return setError(c, MR_E_INVALID, "textures too large");
+
+	MR_CUDA(c, c->pos4.ensure(sizeof(float4) * (size_t)std::max(nPos, 1LL)));
+	MR_CUDA(c, c->nrm4.ensure(sizeof(float4) * (size_t)std::max(nNrm, 1LL)));
+	MR_CUDA(c, c->uv2.ensure(sizeof(float2) * (size_t)std::max(nUv, 1LL)));
+	MR_CUDA(c, c->idxPos.ensure(sizeof(int) * 3 * (size_t)std::max(nTri, 1LL)));
+	MR_CUDA(c, c->idxNrm.ensure(sizeof(int) * 3 * (size_t)std::max(nTri, 1LL)));
+	MR_CUDA(c, c->idxUv.ensure(sizeof(int) * 3 * (size_t)std::max(nUvTri, 1LL)));
+	MR_CUDA(c, c->texels.ensure(sizeof(float4) * (size_t)std::max(nTexel, 1LL)));
+	MR_CUDA(c, c->meshes.ensure(sizeof(MeshDev) * (size_t)std::max(s->n_meshes, 1)));
+
+	// packed xyz / rgb arrays go through a device staging buffer and are widened to float4 there
+	size_t maxRaw = 0;
+	for (int i = 0; i < s->n_meshes; i++)
+		maxRaw = std::max(maxRaw, sizeof(float) * 3 * (size_t)std::max(s->meshes[i].n_positions, s->meshes[i].n_normals));
+	for (int i = 0; i < s->n_textures; i++)
+		maxRaw = std::max(maxRaw, sizeof(float) * 3 * (size_t)s->textures[i].rows * s->textures[i].cols);
+	MR_CUDA(c, c->scratchOut.ensure(std::max<size_t>(maxRaw, 16)));
+	float* raw = c->scratchOut.as<float>();
+	for (int i = 0; i < s->n_meshes; i++)
+	{
+		const mr_mesh_desc& m = s->meshes[i];
+		if (m.n_positions)
+		{
+			MR_CUDA(c, cudaMemcpyAsync(raw, m.positions, sizeof(float) * 3 * (size_t)m.n_positions, cudaMemcpyHostToDevice, c->stream));
+			mrk_launch_pack(c->pos4.as<float4>() + md[i].posBase, raw, m.n_positions, 3, 1.0f, c->stream);
+		}
+		if (m.n_normals)
+		{
+			MR_CUDA(c, cudaMemcpyAsync(raw, m.normals, sizeof(float) * 3 * (size_t)m.n_normals, cudaMemcpyHostToDevice, c->stream));
+			mrk_launch_pack(c->nrm4.as<float4>() + md[i].nrmBase, raw, m.n_normals, 3, 0.0f, c->stream);
+		}
+		if (md[i].hasUV)
+		{
+			MR_CUDA(c, cudaMemcpyAsync(c->uv2.as<float2>() + md[i].uvBase, m.texcoords, sizeof(float) * 2 * (size_t)m.n_texcoords,
+			                           cudaMemcpyHostToDevice, c->stream));
+			MR_CUDA(c, cudaMemcpyAsync(c->idxUv.as<int>() + 3 * (size_t)md[i].uvTriBase, m.idx_uv, sizeof(int) * 3 * (size_t)m.n_triangles,
+			                           cudaMemcpyHostToDevice, c->stream));
+		}
+		if (m.n_triangles)
+		{
+			MR_CUDA(c, cudaMemcpyAsync(c->idxPos.as<int>() + 3 * (size_t)md[i].triBase, m.idx_pos, sizeof(int) * 3 * (size_t)m.n_triangles,
+			                           cudaMemcpyHostToDevice, c->stream));
+			MR_CUDA(c, cudaMemcpyAsync(c->idxNrm.as<int>() + 3 * (size_t)md[i].triBase, m.idx_nrm, sizeof(int) * 3 * (size_t)m.n_triangles,
+			                           cudaMemcpyHostToDevice, c->stream));
+		}
+	}
+	for (int i = 0; i < s->n_textures; i++)
+	{
+		const mr_texture_desc& t = s->textures[i];
+		const size_t n = (size_t)t.rows * t.cols;
+		MR_CUDA(c, cudaMemcpyAsync(raw, t.texels, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+		mrk_launch_pack(c->texels.as<float4>() + to[i], raw, (int)n, 3, 0.0f, c->stream);
+	}
+	if (s->n_meshes)
+		MR_CUDA(c, cudaMemcpyAsync(c->meshes.p, md.data(), sizeof(MeshDev) * md.size(), cudaMemcpyHostToDevice, c->stream));
+	MR_CUDA(c, cudaGetLastError());
+	MR_CUDA(c, cudaStreamSynchronize(c->stream)); // host arrays are only borrowed for this call
+	c->hostMeshes.swap(md);
+	c->texOffset.swap(to);
+	c->texRows.swap(tr);
+	c->texCols.swap(tc);
+	c->haveScene = true;
+	c->sceneSerial++;
+	c->haveFrame = false;
+	c->frameChecked = true;
+	return MR_OK;
+}
+
+int mr_render(mr_ctx* c, const mr_frame* f)
+{
+	if (!c || !f)
+		return MR_E_INVALID;
+	if (!c->haveScene)
+		return setError(c, MR_E_NO_SCENE, "mr_render before mr_upload_scene");
+	if (c->w <= 0)
+		return setError(c, MR_E_INVALID, "mr_render before mr_set_size");
+	if (f->n_renderables < 0 || f->n_materials < 0 || (f->n_renderables > 0 && (!f->renderables || !f->materials)))
+		return setError(c, MR_E_INVALID, "bad frame descriptor");
+	Bind bind(c->device);
+	// the previous frame must have been verified (overflow re-run) before its tables are replaced
+	if (c->haveFrame && !c->frameChecked)
+	{
+		int rc = finishFrame(c);
+		if (rc)
+			return rc;
+	}
+	rememberFrame(c, f);
+	return launchFrame(c, f, 0);
+}
+
+int mr_render_batch(mr_ctx* c, int n, const mr_frame* frames, mr_frame_sink sink, void* user)
+{
+	if (!c || n < 0 || (n > 0 && !frames))
+		return MR_E_INVALID;
+	for (int i = 0; i < n; i++)
+	{
+		int rc = mr_render(c, &frames[i]);
+		if (rc)
+			return rc;
+		if (sink)
+		{
+			rc = finishFrame(c);
+			if (rc)
+				return rc;
+			sink(user, i, c->image.as<float>(), c->depth.as<float>());
+		}
+	}
+	return MR_OK;
+}
+
+int mr_synchronize(mr_ctx* c)
+{
+	if (!c)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	return finishFrame(c);
+}
+
+int mr_read_image(mr_ctx* c, float* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	return readBack(c, host, c->image.p, (size_t)c->w * c->h * 12);
+}
+
+int mr_read_depth(mr_ctx* c, float* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	return readBack(c, host, c->depth.p, (size_t)c->w * c->h * 4);
+}
+
+int mr_read_normals(mr_ctx* c, float* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	rc = ensureOutputs(c, true, false);
+	if (rc)
+		return rc;
+	return readBack(c, host, c->normals.p, (size_t)c->w * c->h * 12);
+}
+
+int mr_read_winner_ids(mr_ctx* c, int32_t* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	if (!(c->debugFlags & 1) || !c->winner.p)
+		return setError(c, MR_E_INVALID, "winner ids not enabled (mr_set_debug(ctx, 1) before mr_render)");
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	return readBack(c, host, c->winner.p, (size_t)c->w * c->h * 4);
+}
+
+int mr_read_range(mr_ctx* c, const float* P, float znear, float* host)
+{
+	(void)znear;
+	if (!c || !host || !P)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	const size_t bytes = (size_t)c->w * c->h * 12;
+	MR_CUDA(c, c->scratchOut.ensure(bytes));
+	mrk_launch_range(c->depth.as<float>(), c->scratchOut.as<float>(), c->w, c->h, P, c->stream);
+	MR_CUDA(c, cudaGetLastError());
+	return readBack(c, host, c->scratchOut.p, bytes);
+}
+
+int mr_read_rgb8(mr_ctx* c, uint8_t* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	const size_t n = (size_t)c->w * c->h * 3;
+	MR_CUDA(c, c->scratchOut.ensure(n));
+	mrk_launch_rgb8(c->image.as<float>(), c->scratchOut.as<uint8_t>(), n, c->stream);
+	MR_CUDA(c, cudaGetLastError());
+	return readBack(c, host, c->scratchOut.p, n);
+}
+
+int mr_read_image_async(mr_ctx* c, float* host)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaMemcpyAsync(host, c->image.p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->stream));
+	return MR_OK;
+}
+
+int mr_read_rows_async(mr_ctx* c, float* host_rgb, float* host_depth, int rb, int re)
+{
+	if (!c || rb < 0 || re > c->h || re < rb)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	const size_t w = (size_t)c->w;
+	if (host_rgb)
+		MR_CUDA(c, cudaMemcpyAsync(host_rgb + 3 * w * rb, c->image.as<float>() + 3 * w * rb, 12 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
+	if (host_depth)
+		MR_CUDA(c, cudaMemcpyAsync(host_depth + w * rb, c->depth.as<float>() + w * rb, 4 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
+	return MR_OK;
+}
+
+int mr_host_register(void* host, size_t bytes)
+{
+	return cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess ? MR_OK : (cudaGetLastError(), MR_E_CUDA);
+}
+
+int mr_host_unregister(void* host)
+{
+	return cudaHostUnregister(host) == cudaSuccess ? MR_OK : (cudaGetLastError(), MR_E_CUDA);
+}
+
+int mr_device_buffers(mr_ctx* c, void** image, void** depth, void** normals)
+{
+	if (!c)
+		return MR_E_INVALID;
+	if (image) *image = c->image.p;
+	if (depth) *depth = c->depth.p;
+	if (normals) *normals = c->normals.p;
+	return MR_OK;
+}
+
+int mr_write_rows(mr_ctx* c, const void* img, const void* dep, int rb, int re)
+{
+	if (!c || rb < 0 || re > c->h || re < rb)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	const size_t w = (size_t)c->w;
+	if (img)
+		MR_CUDA(c, cudaMemcpyAsync(c->image.as<float>() + 3 * w * rb, img, 12 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
+	if (dep)
+		MR_CUDA(c, cudaMemcpyAsync(c->depth.as<float>() + w * rb, dep, 4 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
+	return MR_OK;
+}
+
+int mr_set_remote_target(mr_ctx* c, void* img, void* dep)
+{
+	if (!c)
+		return MR_E_INVALID;
+	c->remoteImage = img;
+	c->remoteDepth = dep;
+	return MR_OK;
+}
+
+int mr_get_stats(mr_ctx* c, mr_stats* out)
+{
+	if (!c || !out)
+		return MR_E_INVALID;
+	*out = c->stats;
+	return MR_OK;
+}
+
+int mr_profile_frame(mr_ctx* c, const mr_frame* f, int repeats)
+{
+	if (!c || !f || repeats <= 0)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = mr_render(c, f); // warm, also settles queue sizes
+	if (rc)
+		return rc;
+	rc = finishFrame(c);
+	if (rc)
+		return rc;
+	cudaEvent_t ev[6];
+	for (int i = 0; i < 6; i++)
+		MR_CUDA(c, cudaEventCreate(&ev[i]));
+	float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	for (int it = 0; it < repeats; it++)
+	{
+		rc = launchFrame(c, f, ev);
+		if (rc)
+			break;
+		MR_CUDA(c, cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < 5; i++)
+		{
+			float ms = 0;
+			cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+			acc[i] += ms;
+		}
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ev[0], ev[5]);
+		acc[5] += ms;
+	}
+	for (int i = 0; i < 6; i++)
+		cudaEventDestroy(ev[i]);
+	for (int i = 0; i < 8; i++)
+		c->stats.ms_kernel[i] = acc[i] / repeats;
+	if (rc)
+		return rc;
+	return finishFrame(c);
+}
+
+}

@@ -1,0 +1,139 @@
+// Device-side data model of the B200 rasterization pipeline (shared by kernels and host code).
+//
+// Scene-static arrays (uploaded by mr_upload_scene, resident in HBM):
+//   pos4[]   float4 per mesh vertex   (x,y,z,1)      -- one LDG.128 per vertex, 16 B aligned
+//   nrm4[]   float4 per mesh normal   (x,y,z,0)
+//   uv2[]    float2 per texcoord
+//   idxPos[] idxNrm[] idxUv[]  int per triangle corner (3 per triangle)
+//   texels[] float4 per texel (r,g,b,0), all textures concatenated
+//   MeshDev[] per mesh: base offsets into the arrays above
+// Per-frame arrays:
+//   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
+//   MatDev[]       materials
+//   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
+//   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
+//                  triangle instance index in submission order: the index IS the submission id
+//                  that resolves equal-depth ties
+//   tileCount[] tileOffset[] pairs[] bins[]   16x16-tile binning
+#ifndef MR_TYPES_H
+#define MR_TYPES_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MR_TILE 16
+#define MR_TILE_SHIFT 4
+#define MR_TILE_PIXELS 256
+
+struct MeshDev
+{
+	int posBase, nrmBase, uvBase; // into pos4 / nrm4 / uv2
+	int triBase;                  // first triangle in idxPos/idxNrm (units: triangles)
+	int uvTriBase;                // first triangle in idxUv, or -1 when the mesh has no uv stream
+	int nPos, nTri, hasUV;
+};
+
+struct RStat // per renderable, changes only when the flattened structure changes
+{
+	int mesh;
+	int vertBase; // first vertex instance (into pv)
+	int triBase;  // first triangle instance (submission order)
+	int pad;
+};
+
+struct __align__(16) RDyn // per renderable, per frame
+{
+	float mv[12]; // modelview, row-major 3x4
+	float nm[12]; // normal matrix, row-major 3x4
+	int material;
+	int pad[3];
+};
+
+struct __align__(16) MatDev
+{
+	float diffuse[3];
+	float shininess;
+	float specular[3];
+	int texOffset; // into texels, -1 = no texture
+	float emissive[3];
+	int texRows;
+	int texCols;
+	int pad[3];
+};
+
+// 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
+struct __align__(16) Rec
+{
+	float p0x, p0y, p2x, p2y; // edge origins (e1 is measured from p2, e2 from p0)
+	float n1x, n1y, n2x, n2y; // scaled edge normals
+	float d0, d1, d2;         // iz[] (perspective) or zz[] (ortho)
+	int renderable;
+	uint32_t xspan;           // x0 | x1 << 16 : first / last pixel column of the clamped bbox
+	uint32_t yspan;           // y0 | y1 << 16
+	int flags;                // bit 0: produced by the near-plane clipper
+	int tri;                  // triangle index inside the mesh
+};
+
+struct Counters
+{
+	unsigned long long trianglesIn;
+	unsigned long long records;
+	unsigned long long clippedIn;
+	unsigned long long pairTotal;   // (tile, triangle) pairs produced (may exceed capacity)
+	unsigned long long wideRecords;
+	unsigned int overflow;          // pairs did not fit: the frame must be re-run with more room
+	unsigned int pad;
+};
+
+struct FrameParams
+{
+	float P[16];
+	float light[3];
+	float ambient;
+	float bg[3];
+	float znear;
+	float wf, hf;
+	int w, h;
+	int tilesX, tilesY;
+	int tileRow0, tileRows; // tile rows covered by this frame (strip rendering)
+	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
+	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
+	int nRenderables, nVertInst, nTriInst;
+	int pairCap;
+
+	const float4* pos4;
+	const float4* nrm4;
+	const float2* uv2;
+	const int* idxPos;
+	const int* idxNrm;
+	const int* idxUv;
+	const float4* texels;
+	const MeshDev* meshes;
+	const RStat* rstat;
+	const RDyn* rdyn;
+	const MatDev* mats;
+	const int* vtxBlockR; // renderable that owns the first vertex instance of each 256-block
+	const int* triBlockR; // same for triangle instances
+
+	float4* pv;
+	Rec* recs;
+	int* tileCount;
+	int* tileOffset;
+	int4* pairs;
+	int* bins;
+	Counters* ctr;
+
+	float* image;   // h*w*3
+	float* depth;   // h*w
+	float* normals; // h*w*3 or NULL
+	int* winner;    // h*w submission ids (debug) or NULL
+};
+
+// kernel launchers (mr_kernels.cu)
+void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */);
+int mrk_selftest_no_fma(cudaStream_t stream);
+void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
+void mrk_launch_rgb8(const float* image, uint8_t* out, size_t nFloats, cudaStream_t stream);
+void mrk_launch_pack(float4* dst4, const float* src, int n, int comps, float w, cudaStream_t stream);
+
+#endif

@@ -1,0 +1,588 @@
+// Drop-in minirender::Renderer on top of the CUDA pipeline.
+//
+// Host part of the reference's Renderer::render (reference src/Renderer.cpp:311-338): flatten
+// the scene, derive the light vector, ambient term, projection kind and near plane, and form
+// modelview / normal matrices per renderable with the same asl:: expressions. Everything after
+// that (reference loops A..E, src/Renderer.cpp:344-380 and :163-309) runs on the GPU behind the
+// C ABI of <minirender_b200.h>. No pixel is ever produced on the host.
+#include <minirender/Renderer.h>
+#include <minirender_b200.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace asl;
+
+namespace minirender {
+
+// ---- projection builders (reference src/Renderer.cpp:40-83); `tan` is evaluated in double like
+// the reference's unqualified call, then narrowed ----
+
+Matrix4 projectionOrtho(float l, float r, float b, float t, float n, float f)
+{
+	const float w = r - l, h = t - b, d = f - n;
+	return Matrix4(2 / w, 0, 0, -(r + l) / w,
+	               0, 2 / h, 0, -(t + b) / h,
+	               0, 0, -2 / d, -(f + n) / d,
+	               0, 0, 0, 1);
+}
+
+Matrix4 projectionPerspective(float l, float r, float b, float t, float n, float f)
+{
+	const float w = r - l, h = t - b, d = f - n;
+	return Matrix4(2 * n / w, 0, (r + l) / w, 0,
+	               0, 2 * n / h, (t + b) / h, 0,
+	               0, 0, -(f + n) / d, -2 * f * n / d,
+	               0, 0, -1, 0);
+}
+
+Matrix4 projectionCV(const Matrix4& K, float w, float h, float n, float f)
+{
+	const float d = f - n;
+	return Matrix4(K(0, 0) * 2 / w, K(0, 1) * 2 / w, -2 * K(0, 2) / w + 1, 0,
+	               K(1, 0) * 2 / h, K(1, 1) * 2 / h, 2 * K(1, 2) / h - 1, 0,
+	               0, 0, -(f + n) / d, -2 * f * n / d,
+	               0, 0, -1, 0);
+}
+
+static inline float halfTan(float fov)
+{
+	return (float)::tan((double)(fov / 2));
+}
+
+Matrix4 projectionFrustum(float fov, float aspect, float n, float f)
+{
+	const float t = halfTan(fov);
+	return projectionPerspective(-n * t * aspect, n * t * aspect, -n * t, n * t, n, f);
+}
+
+Matrix4 projectionFrustumH(float fov, float aspect, float n, float f)
+{
+	const float t = halfTan(fov);
+	return projectionPerspective(-n * t, n * t, -n * t / aspect, n * t / aspect, n, f);
+}
+
+Matrix4 projectionOrtho(float fov, float aspect, float n, float f)
+{
+	return projectionOrtho(-fov * aspect / 2, fov * aspect / 2, -fov / 2, fov / 2, n, f);
+}
+
+// ---- implementation state ----
+
+namespace {
+
+struct MeshSig
+{
+	const void* p[6];
+	int n[6];
+	bool operator==(const MeshSig& o) const { return memcmp(this, &o, sizeof(MeshSig)) == 0; }
+};
+
+struct TexSig
+{
+	const void* p;
+	int rows, cols;
+	bool operator==(const TexSig& o) const { return p == o.p && rows == o.rows && cols == o.cols; }
+};
+
+void copy3x4(float* dst, const Matrix4& m)
+{
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 4; j++)
+			dst[4 * i + j] = m(i, j);
+}
+
+}
+
+struct Renderer::Impl
+{
+	mr_ctx* ctx;
+	int device;
+	int ctxW, ctxH;
+
+	// flattened scene + descriptors of the current frame
+	Array<Renderable> renderables;
+	std::vector<mr_mesh_desc> meshes;
+	std::vector<mr_texture_desc> textures;
+	std::vector<mr_renderable> rlist;
+	std::vector<mr_material> materials;
+	mr_scene_desc sceneDesc;
+	mr_frame frame;
+
+	// what is currently mirrored in HBM
+	std::vector<MeshSig> upMeshes;
+	std::vector<TexSig> upTextures;
+	unsigned upStamp;
+	bool uploaded;
+
+	// frame constants snapshotted by render() (reference members _lightdir/_znear/_ambient)
+	Vec3 lightdir;
+	float znear, ambient;
+	bool haveSnapshot;
+
+	// lazily filled host mirrors of the device images
+	Array2<Vec3> image, normals, points;
+	Array2<float> depth;
+	bool imageValid, depthValid, normalsValid;
+
+	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), upStamp(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false),
+	         imageValid(false), depthValid(false), normalsValid(false)
+	{
+		memset(&sceneDesc, 0, sizeof(sceneDesc));
+		memset(&frame, 0, sizeof(frame));
+		const char* env = getenv("MINIRENDER_B200_DEVICE");
+		if (env)
+			device = atoi(env);
+	}
+};
+
+static void fail(mr_ctx* ctx, const char* what, int code)
+{
+	std::string msg = std::string("minirender_b200: ") + what + " failed (" + std::to_string(code) + ")";
+	if (ctx && mr_last_error(ctx)[0])
+		msg += std::string(": ") + mr_last_error(ctx);
+	throw std::runtime_error(msg);
+}
+
+Renderer::Renderer() : _impl(new Impl), _w(800), _h(600)
+{
+	// defaults of the reference constructor (src/Renderer.cpp:85-98); the members the reference
+	// leaves uninitialised (_saveNormals, _view) get defined values here
+	_projection = projectionOrtho(-40, 40, -30, 30, 50, 120);
+	_view = Matrix4::identity();
+	_light = Vec3(-0.15f, 0.6f, 1).normalized();
+	_defmaterial = new Material();
+	_material = _defmaterial;
+	_scene = NULL;
+	_lighting = true;
+	_texturing = true;
+	_saveNormals = false;
+	_lightIsPoint = false;
+	_bgcolor = Vec3(0, 0, 0);
+	_rowBegin = _rowEnd = 0;
+	_geometryStamp = 0;
+}
+
+Renderer::~Renderer()
+{
+	if (_impl->ctx)
+		mr_destroy(_impl->ctx);
+	delete _impl;
+}
+
+void Renderer::setDevice(int device)
+{
+	if (_impl->ctx && device != _impl->device)
+	{
+		mr_destroy(_impl->ctx);
+		_impl->ctx = 0;
+		_impl->uploaded = false;
+	}
+	_impl->device = device;
+}
+
+void Renderer::ensureContext()
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+	{
+		int status = 0;
+		s.ctx = mr_create(s.device, &status);
+		if (!s.ctx)
+			fail(0, "mr_create (this library has no CPU rasterizer; a CUDA device is required)", status);
+		s.ctxW = s.ctxH = 0;
+		s.uploaded = false;
+	}
+	if (s.ctxW != _w || s.ctxH != _h)
+	{
+		int rc = mr_set_size(s.ctx, _w, _h);
+		if (rc)
+			fail(s.ctx, "mr_set_size", rc);
+		s.ctxW = _w;
+		s.ctxH = _h;
+	}
+}
+
+mr_ctx* Renderer::context()
+{
+	ensureContext();
+	return _impl->ctx;
+}
+
+void Renderer::synchronize()
+{
+	if (_impl->ctx)
+		mr_synchronize(_impl->ctx);
+}
+
+void Renderer::setSize(int w, int h)
+{
+	_w = w;
+	_h = h;
+	_impl->imageValid = _impl->depthValid = _impl->normalsValid = false;
+	if (_impl->ctx) // the reference's setSize ends with clear()
+		clear();
+}
+
+void Renderer::setScene(Shared<Scene> scene)
+{
+	_scene = scene;
+}
+
+// Builds descriptors for `list` (already flattened). Geometry descriptors borrow the meshes'
+// own arrays (asl::Vec3 / Vec2 are packed floats).
+static void describe(Renderer::Impl& s, const Array<Renderable>& list, const Matrix4& view, Material* defmat)
+{
+	std::map<const TriMesh*, int> meshIndex;
+	std::map<const Material*, int> matIndex;
+	std::map<const void*, int> texIndex;
+	s.meshes.clear();
+	s.textures.clear();
+	s.materials.clear();
+	s.rlist.clear();
+	s.rlist.reserve(list.length());
+
+	for (int i = 0; i < list.length(); i++)
+	{
+		TriMesh* mesh = list[i].mesh;
+		std::map<const TriMesh*, int>::iterator mi = meshIndex.find(mesh);
+		int meshId;
+		if (mi == meshIndex.end())
+		{
+			if (mesh->normalsI.length() < mesh->indices.length())
+				throw std::runtime_error("minirender_b200: TriMesh::normalsI shorter than TriMesh::indices");
+			mr_mesh_desc d;
+			memset(&d, 0, sizeof(d));
+			d.positions = (const float*)mesh->vertices.ptr();
+			d.n_positions = mesh->vertices.length();
+			d.normals = (const float*)mesh->normals.ptr();
+			d.n_normals = mesh->normals.length();
+			d.idx_pos = mesh->indices.ptr();
+			d.idx_nrm = mesh->normalsI.ptr();
+			d.n_triangles = mesh->indices.length() / 3;
+			// textured-capable only with both arrays present (reference Renderer.cpp:371)
+			if (mesh->texcoords.length() > 0 && mesh->texcoordsI.length() >= mesh->indices.length() && mesh->texcoordsI.length() > 0)
+			{
+				d.texcoords = (const float*)mesh->texcoords.ptr();
+				d.n_texcoords = mesh->texcoords.length();
+				d.idx_uv = mesh->texcoordsI.ptr();
+			}
+			meshId = (int)s.meshes.size();
+			s.meshes.push_back(d);
+			meshIndex[mesh] = meshId;
+		}
+		else
+			meshId = mi->second;
+
+		Material* mat = mesh->material ? (Material*)mesh->material : defmat;
+		std::map<const Material*, int>::iterator ti = matIndex.find(mat);
+		int matId;
+		if (ti == matIndex.end())
+		{
+			mr_material m;
+			memset(&m, 0, sizeof(m));
+			m.diffuse[0] = mat->diffuse.x; m.diffuse[1] = mat->diffuse.y; m.diffuse[2] = mat->diffuse.z;
+			m.specular[0] = mat->specular.x; m.specular[1] = mat->specular.y; m.specular[2] = mat->specular.z;
+			m.emissive[0] = mat->emissive.x; m.emissive[1] = mat->emissive.y; m.emissive[2] = mat->emissive.z;
+			m.shininess = mat->shininess;
+			m.texture = -1;
+			if (mat->texture.rows() > 0 && mat->texture.cols() > 0)
+			{
+				const void* key = mat->texture.data().ptr();
+				std::map<const void*, int>::iterator xi = texIndex.find(key);
+				if (xi == texIndex.end())
+				{
+					mr_texture_desc t;
+					t.texels = (const float*)mat->texture.data().ptr();
+					t.rows = mat->texture.rows();
+					t.cols = mat->texture.cols();
+					m.texture = (int)s.textures.size();
+					texIndex[key] = m.texture;
+					s.textures.push_back(t);
+				}
+				else
+					m.texture = xi->second;
+			}
+			matId = (int)s.materials.size();
+			s.materials.push_back(m);
+			matIndex[mat] = matId;
+		}
+		else
+			matId = ti->second;
+
+		mr_renderable r;
+		const Matrix4 modelview = view * list[i].transform;        // reference Renderer.cpp:337
+		const Matrix4 normalmat = modelview.inverse().t();         // reference Renderer.cpp:338
+		copy3x4(r.modelview, modelview);
+		copy3x4(r.normalmat, normalmat);
+		r.mesh = meshId;
+		r.material = matId;
+		s.rlist.push_back(r);
+	}
+	s.sceneDesc.meshes = s.meshes.empty() ? 0 : &s.meshes[0];
+	s.sceneDesc.n_meshes = (int)s.meshes.size();
+	s.sceneDesc.textures = s.textures.empty() ? 0 : &s.textures[0];
+	s.sceneDesc.n_textures = (int)s.textures.size();
+	s.frame.renderables = s.rlist.empty() ? 0 : &s.rlist[0];
+	s.frame.n_renderables = (int)s.rlist.size();
+	s.frame.materials = s.materials.empty() ? 0 : &s.materials[0];
+	s.frame.n_materials = (int)s.materials.size();
+}
+
+static void fillFrameConstants(mr_frame& f, const Matrix4& P, const Vec3& lightdir, bool point, float ambient, float znear,
+                               bool lighting, bool texturing, bool saveNormals, const Vec3& bg, int rowBegin, int rowEnd, int keep)
+{
+	for (int i = 0; i < 4; i++)
+		for (int j = 0; j < 4; j++)
+			f.projection[4 * i + j] = P(i, j);
+	f.light[0] = lightdir.x; f.light[1] = lightdir.y; f.light[2] = lightdir.z;
+	f.light_is_point = point;
+	f.ambient = ambient;
+	f.znear = znear;
+	f.lighting = lighting;
+	f.texturing = texturing;
+	f.save_normals = saveNormals;
+	f.background[0] = bg.x; f.background[1] = bg.y; f.background[2] = bg.z;
+	f.row_begin = rowBegin;
+	f.row_end = rowEnd;
+	f.keep = keep;
+}
+
+void Renderer::prepare()
+{
+	Impl& s = *_impl;
+	if (!_scene)
+		throw std::runtime_error("minirender_b200: Renderer::render() without a scene");
+	s.renderables.clear();
+	_scene->collectShapes(s.renderables, Matrix4::identity());
+
+	// reference Renderer.cpp:317-326
+	s.lightdir = _lightIsPoint ? _view * _light : _light.normalized();
+	s.ambient = _scene->ambientLight;
+	const bool persp = _projection(3, 3) == 0;
+	float zn = persp ? _projection(2, 3) / (_projection(2, 2) - 1) : (_projection(2, 3) + 1) / _projection(2, 2);
+	s.znear = -zn;
+	s.haveSnapshot = true;
+
+	describe(s, s.renderables, _view, _defmaterial);
+	fillFrameConstants(s.frame, _projection, s.lightdir, _lightIsPoint, s.ambient, s.znear, _lighting, _texturing, _saveNormals,
+	                   _bgcolor, _rowBegin, _rowEnd, 0);
+}
+
+const mr_scene_desc* Renderer::sceneDesc() const { return &_impl->sceneDesc; }
+const mr_frame* Renderer::frameDesc() const { return &_impl->frame; }
+
+// Uploads the geometry if what is mirrored in HBM does not match the descriptors.
+static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
+{
+	std::vector<MeshSig> ms(s.meshes.size());
+	for (size_t i = 0; i < s.meshes.size(); i++)
+	{
+		const mr_mesh_desc& d = s.meshes[i];
+		const void* p[6] = { d.positions, d.normals, d.texcoords, d.idx_pos, d.idx_nrm, d.idx_uv };
+		const int n[6] = { d.n_positions, d.n_normals, d.n_texcoords, d.n_triangles, d.n_triangles, d.idx_uv ? d.n_triangles : 0 };
+		memset(&ms[i], 0, sizeof(MeshSig));
+		memcpy(ms[i].p, p, sizeof(p));
+		memcpy(ms[i].n, n, sizeof(n));
+	}
+	std::vector<TexSig> ts(s.textures.size());
+	for (size_t i = 0; i < s.textures.size(); i++)
+	{
+		ts[i].p = s.textures[i].texels;
+		ts[i].rows = s.textures[i].rows;
+		ts[i].cols = s.textures[i].cols;
+	}
+	if (!force && s.uploaded && stamp == s.upStamp && ms == s.upMeshes && ts == s.upTextures)
+		return;
+	int rc = mr_upload_scene(s.ctx, &s.sceneDesc);
+	if (rc)
+		fail(s.ctx, "mr_upload_scene", rc);
+	s.upMeshes.swap(ms);
+	s.upTextures.swap(ts);
+	s.upStamp = stamp;
+	s.uploaded = true;
+}
+
+void Renderer::render()
+{
+	prepare();
+	ensureContext();
+	Impl& s = *_impl;
+	syncGeometry(s, _geometryStamp, false);
+	int rc = mr_render(s.ctx, &s.frame);
+	if (rc)
+		fail(s.ctx, "mr_render", rc);
+	s.imageValid = s.depthValid = s.normalsValid = false;
+}
+
+void Renderer::clear()
+{
+	// reference Renderer.cpp:113-119: fill with background / 1e11f. On the device this is a
+	// frame with no renderables (every tile is written once with the clear values).
+	ensureContext();
+	Impl& s = *_impl;
+	mr_frame f;
+	memset(&f, 0, sizeof(f));
+	fillFrameConstants(f, _projection, Vec3(0, 0, 1), false, 0.1f, 0.f, _lighting, _texturing, _saveNormals, _bgcolor, 0, 0, 0);
+	if (!s.uploaded)
+	{
+		mr_scene_desc empty;
+		memset(&empty, 0, sizeof(empty));
+		int rc = mr_upload_scene(s.ctx, &empty);
+		if (rc)
+			fail(s.ctx, "mr_upload_scene", rc);
+		s.upMeshes.clear();
+		s.upTextures.clear();
+		s.uploaded = true;
+		s.upStamp = _geometryStamp;
+	}
+	int rc = mr_render(s.ctx, &f);
+	if (rc)
+		fail(s.ctx, "mr_render(clear)", rc);
+	s.imageValid = s.depthValid = s.normalsValid = false;
+}
+
+// Immediate mode (reference Renderer.h:58-59): paints into the current buffers without
+// clearing, using the frame constants of the last render() like the reference's members do.
+void Renderer::paintMesh(TriMesh* mesh, const Matrix4& transform)
+{
+	ensureContext();
+	Impl& s = *_impl;
+	if (!s.haveSnapshot)
+	{
+		s.lightdir = _lightIsPoint ? _view * _light : _light.normalized();
+		s.ambient = _scene ? _scene->ambientLight : 0.1f;
+		const bool persp = _projection(3, 3) == 0;
+		float zn = persp ? _projection(2, 3) / (_projection(2, 2) - 1) : (_projection(2, 3) + 1) / _projection(2, 2);
+		s.znear = -zn;
+	}
+	Array<Renderable> one;
+	one << Renderable(mesh, transform);
+	describe(s, one, _view, _defmaterial);
+	_material = mesh->material ? mesh->material : _defmaterial; // reference Renderer.cpp:336
+	fillFrameConstants(s.frame, _projection, s.lightdir, _lightIsPoint, s.ambient, s.znear, _lighting, _texturing, _saveNormals,
+	                   _bgcolor, _rowBegin, _rowEnd, 1);
+	syncGeometry(s, _geometryStamp, true);
+	int rc = mr_render(s.ctx, &s.frame);
+	if (rc)
+		fail(s.ctx, "mr_render(paintMesh)", rc);
+	mr_synchronize(s.ctx); // the borrowed mesh may go away after this call
+	s.uploaded = false;    // next render() re-mirrors the scene
+	s.imageValid = s.depthValid = s.normalsValid = false;
+}
+
+void Renderer::paintTriangle(const Vertex& a, const Vertex& b, const Vertex& c, bool world)
+{
+	// Vertices are already in view space (reference Renderer.cpp:163-177). With world == false
+	// the reference skips the near-plane test; that variant only exists for its own clipper, so
+	// here it is accepted only for triangles that are entirely in front of the near plane.
+	(void)world;
+	TriMesh tri;
+	tri.vertices << a.position << b.position << c.position;
+	tri.normals << a.normal << b.normal << c.normal;
+	tri.texcoords << a.uv << b.uv << c.uv;
+	tri.indices << 0 << 1 << 2;
+	tri.normalsI = tri.indices;
+	tri.texcoordsI = tri.indices;
+	tri.material = _material;
+	const Matrix4 savedView = _view;
+	_view = Matrix4::identity();
+	try
+	{
+		paintMesh(&tri, Matrix4::identity());
+	}
+	catch (...)
+	{
+		_view = savedView;
+		throw;
+	}
+	_view = savedView;
+}
+
+Array2<Vec3> Renderer::getImage() const
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+		const_cast<Renderer*>(this)->clear();
+	if (!s.imageValid)
+	{
+		if (s.image.rows() != _h || s.image.cols() != _w)
+			s.image = Array2<Vec3>(_h, _w);
+		int rc = mr_read_image(s.ctx, (float*)s.image.data().ptr());
+		if (rc)
+			fail(s.ctx, "mr_read_image", rc);
+		s.imageValid = true;
+	}
+	return s.image;
+}
+
+Array2<float> Renderer::getDepth() const
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+		const_cast<Renderer*>(this)->clear();
+	if (!s.depthValid)
+	{
+		if (s.depth.rows() != _h || s.depth.cols() != _w)
+			s.depth = Array2<float>(_h, _w);
+		int rc = mr_read_depth(s.ctx, s.depth.data().ptr());
+		if (rc)
+			fail(s.ctx, "mr_read_depth", rc);
+		s.depthValid = true;
+	}
+	return s.depth;
+}
+
+Array2<Vec3> Renderer::getNormalsImage() const
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+		const_cast<Renderer*>(this)->clear();
+	if (!s.normalsValid)
+	{
+		if (s.normals.rows() != _h || s.normals.cols() != _w)
+			s.normals = Array2<Vec3>(_h, _w);
+		int rc = mr_read_normals(s.ctx, (float*)s.normals.data().ptr());
+		if (rc)
+			fail(s.ctx, "mr_read_normals", rc);
+		s.normalsValid = true;
+	}
+	return s.normals;
+}
+
+Array2<Vec3> Renderer::getRangeImage()
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+		clear();
+	if (s.points.rows() != _h || s.points.cols() != _w)
+		s.points = Array2<Vec3>(_h, _w);
+	float P[16];
+	for (int i = 0; i < 4; i++)
+		for (int j = 0; j < 4; j++)
+			P[4 * i + j] = _projection(i, j);
+	int rc = mr_read_range(s.ctx, P, s.znear, (float*)s.points.data().ptr());
+	if (rc)
+		fail(s.ctx, "mr_read_range", rc);
+	return s.points;
+}
+
+Array<byte> Renderer::getImageRGB8() const
+{
+	Impl& s = *_impl;
+	if (!s.ctx)
+		const_cast<Renderer*>(this)->clear();
+	Array<byte> out(_w * _h * 3);
+	int rc = mr_read_rgb8(s.ctx, out.ptr());
+	if (rc)
+		fail(s.ctx, "mr_read_rgb8", rc);
+	return out;
+}
+
+}
