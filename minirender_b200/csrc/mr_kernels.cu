@@ -5,7 +5,7 @@
 //
 //   k_vertex  reference loop A            src/Renderer.cpp:344-345 + htransform :13-20, :195-196
 //   k_setup   reference loop C + setup    src/Renderer.cpp:351-380, :163-224, clipTriangle :131-161
-//   k_scan / k_scatter                    16x16 tile binning (no reference counterpart)
+//   scanTiles / k_scatter                 16x16 tile binning (no reference counterpart)
 //   k_raster  reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
 #include <math.h>
@@ -13,7 +13,6 @@
 namespace {
 
 struct V3 { float x, y, z; };
-struct Vert { V3 pos; V3 nrm; float u, v; };
 
 __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ V3 add3(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -86,7 +85,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, int start, 
 // Kernel 1: vertex transform. One thread per vertex instance: one LDG.128 in, one STG.128 out,
 // both fully coalesced. Also zeroes the per-frame tile counters and statistics.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_vertex(const FrameParams fp)
+__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
@@ -95,7 +94,8 @@ __global__ void __launch_bounds__(256) k_vertex(const FrameParams fp)
 	if (vi == 0)
 	{
 		Counters* c = fp.ctr;
-		c->trianglesIn = 0; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->wideRecords = 0; c->overflow = 0;
+		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->wideRecords = 0;
+		c->overflow = 0; c->ctasDone = 0;
 	}
 	if (vi >= fp.nVertInst)
 		return;
@@ -110,8 +110,15 @@ __global__ void __launch_bounds__(256) k_vertex(const FrameParams fp)
 // ------------------------------------------------------------------------------------------
 // Triangle setup shared by the direct and the clipped path (Renderer.cpp:198-224).
 // a,b,c = projected corners (pixel x, pixel y, view z, depth term). Returns false if rejected.
+// Everything stays in registers (the caller passes scalars by reference and is inlined).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool setupTriangle(const FrameParams& fp, float4 a, float4 b, float4 c, Rec& rec)
+struct Setup
+{
+	float n1x, n1y, n2x, n2y;
+	int x0, x1, y0, y1;
+};
+
+__device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float4 a, const float4 b, const float4 c, Setup& s)
 {
 	const float w = fp.wf, h = fp.hf;
 	float minx = 1e30f, miny = 1e30f, maxx = -1e30f, maxy = -1e30f;
@@ -127,130 +134,227 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, float4 a, f
 	if (!(area > 0.0f))
 		return false;
 	const float i2a = -1.0f / area;
-	rec.n1x = -(a.y - c.y) * i2a;
-	rec.n1y = (a.x - c.x) * i2a;
-	rec.n2x = -(b.y - a.y) * i2a;
-	rec.n2y = (b.x - a.x) * i2a;
+	s.n1x = -(a.y - c.y) * i2a;
+	s.n1y = (a.x - c.x) * i2a;
+	s.n2x = -(b.y - a.y) * i2a;
+	s.n2y = (b.x - a.x) * i2a;
 	minx = tclamp(minx, 0.0f, w - 1.0f);
 	maxx = tclamp(maxx, 0.0f, w - 1.0f);
 	miny = tclamp(miny, 0.0f, h - 1.0f);
 	maxy = tclamp(maxy, 0.0f, h - 1.0f);
 	// Pixel loops: x = floor(minx)+0.5, +1 ... while x <= maxx+0.5 (float sum), same in y.
 	// All loop values are exact half-integers, so the last index is floor((max+0.5f) - 0.5f).
-	const int x0 = (int)floorf(minx), y0 = (int)floorf(miny);
+	s.x0 = (int)floorf(minx);
+	s.y0 = (int)floorf(miny);
 	const float xlim = maxx + 0.5f, ylim = maxy + 0.5f;
 	int x1 = (int)floorf(xlim - 0.5f), y1 = (int)floorf(ylim - 0.5f);
 	if ((float)x1 + 0.5f > xlim) x1--;
 	if ((float)(x1 + 1) + 0.5f <= xlim) x1++;
 	if ((float)y1 + 0.5f > ylim) y1--;
 	if ((float)(y1 + 1) + 0.5f <= ylim) y1++;
-	rec.p0x = a.x; rec.p0y = a.y; rec.p2x = c.x; rec.p2y = c.y;
-	rec.d0 = a.w; rec.d1 = b.w; rec.d2 = c.w;
-	rec.xspan = (uint32_t)x0 | ((uint32_t)x1 << 16);
-	rec.yspan = (uint32_t)y0 | ((uint32_t)y1 << 16);
+	s.x1 = x1;
+	s.y1 = y1;
 	return true;
 }
 
-// Gathers one corner of triangle `tri` of renderable r in view space (loops A/B/C of paintMesh).
-__device__ __forceinline__ Vert fetchCorner(const FrameParams& fp, const MeshDev& m, const RDyn& rd, int tri, int corner)
+__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s, int r, int flags, int tri)
 {
-	Vert v;
+	float4* d4 = reinterpret_cast<float4*>(dst);
+	d4[0] = make_float4(a.x, a.y, c.x, c.y);
+	d4[1] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
+	d4[2] = make_float4(a.w, b.w, c.w, __int_as_float(r));
+	d4[3] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
+	                    __int_as_float(flags), __int_as_float(tri));
+}
+
+// One corner of triangle `tri` of a renderable, in view space (loops A/B/C of paintMesh).
+struct Corner
+{
+	float px, py, pz, nx, ny, nz, u, v;
+};
+
+__device__ __forceinline__ Corner fetchCorner(const FrameParams& fp, const MeshDev& m, const RDyn* __restrict__ rd, int tri, int corner)
+{
+	Corner v;
 	const int ip = __ldg(&fp.idxPos[(m.triBase + tri) * 3 + corner]);
 	const int in = __ldg(&fp.idxNrm[(m.triBase + tri) * 3 + corner]);
 	const float4 p = __ldg(&fp.pos4[m.posBase + ip]);
 	const float4 n = __ldg(&fp.nrm4[m.nrmBase + in]);
-	v.pos = affine(rd.mv, p.x, p.y, p.z);
-	v.nrm = affine(rd.nm, n.x, n.y, n.z);
+	const V3 pos = affine(rd->mv, p.x, p.y, p.z);
+	const V3 nrm = affine(rd->nm, n.x, n.y, n.z);
+	v.px = pos.x; v.py = pos.y; v.pz = pos.z;
+	v.nx = nrm.x; v.ny = nrm.y; v.nz = nrm.z;
+	v.u = 0.0f; v.v = 0.0f;
 	if (m.hasUV)
 	{
 		const int iu = __ldg(&fp.idxUv[(m.uvTriBase + tri) * 3 + corner]);
 		const float2 t = __ldg(&fp.uv2[m.uvBase + iu]);
 		v.u = t.x; v.v = t.y;
 	}
-	else
-	{
-		v.u = 0.0f; v.v = 0.0f;
-	}
 	return v;
 }
 
 // reference clip(), Renderer.cpp:121-129
-__device__ __forceinline__ Vert clipEdge(float z, const Vert& a, const Vert& b)
+__device__ __forceinline__ Corner clipEdge(float z, const Corner& a, const Corner& b)
 {
-	const float k = (fabsf(b.pos.z - a.pos.z) < 1e-6f) ? 0.5f : (z - a.pos.z) / (b.pos.z - a.pos.z);
+	const float k = (fabsf(b.pz - a.pz) < 1e-6f) ? 0.5f : (z - a.pz) / (b.pz - a.pz);
 	const float k1 = 1.0f - k;
-	Vert v;
-	v.pos = add3(scale3(b.pos, k), scale3(a.pos, k1));
-	v.nrm = add3(scale3(b.nrm, k), scale3(a.nrm, k1));
+	Corner v;
+	v.px = b.px * k + a.px * k1; v.py = b.py * k + a.py * k1; v.pz = b.pz * k + a.pz * k1;
+	v.nx = b.nx * k + a.nx * k1; v.ny = b.ny * k + a.ny * k1; v.nz = b.nz * k + a.nz * k1;
 	v.u = b.u * k + a.u * k1;
 	v.v = b.v * k + a.v * k1;
 	return v;
 }
 
-// reference clipTriangle(), Renderer.cpp:131-161. v[] is rotated in place; returns the number of
-// output triangles (1 or 2) written to out[k][0..2]. Precondition: not all three beyond z.
-__device__ __noinline__ int clipTriangle(float z, Vert* v, Vert (*out)[3])
+// reference clipTriangle(), Renderer.cpp:131-161, for one requested output triangle `sub`.
+// v0..v2 are rotated until v0 has the largest z (at most two rotations), then cut.
+// Returns the number of output triangles (1 or 2); o0..o2 receive triangle `sub`.
+__device__ __forceinline__ int clipTriangle(float z, Corner v0, Corner v1, Corner v2, int sub, Corner& o0, Corner& o1, Corner& o2)
 {
-	for (int guard = 0; guard < 3 && (v[0].pos.z < v[1].pos.z || v[0].pos.z < v[2].pos.z); guard++)
+#pragma unroll
+	for (int guard = 0; guard < 2; guard++)
+		if (v0.pz < v1.pz || v0.pz < v2.pz)
+		{
+			const Corner t = v0; // swap(v0,v1); swap(v0,v2)  ==  (v0,v1,v2) <- (v2,v0,v1)
+			v0 = v2; v2 = v1; v1 = t;
+		}
+	if (v1.pz > z)
 	{
-		Vert t = v[0]; v[0] = v[1]; v[1] = t;
-		t = v[0]; v[0] = v[2]; v[2] = t;
-	}
-	if (v[1].pos.z > z)
-	{
-		out[0][0] = clipEdge(z, v[0], v[2]);
-		out[0][1] = clipEdge(z, v[1], v[2]);
-		out[0][2] = v[2];
+		o0 = clipEdge(z, v0, v2); o1 = clipEdge(z, v1, v2); o2 = v2;
 		return 1;
 	}
-	if (v[2].pos.z > z)
+	if (v2.pz > z)
 	{
-		out[0][0] = clipEdge(z, v[0], v[1]);
-		out[0][1] = v[1];
-		out[0][2] = clipEdge(z, v[1], v[2]);
+		o0 = clipEdge(z, v0, v1); o1 = v1; o2 = clipEdge(z, v1, v2);
 		return 1;
 	}
-	const Vert v01 = clipEdge(z, v[0], v[1]);
-	const Vert v02 = clipEdge(z, v[0], v[2]);
-	out[0][0] = v01; out[0][1] = v[1]; out[0][2] = v[2];
-	out[1][0] = v01; out[1][1] = v[2]; out[1][2] = v02;
+	const Corner v01 = clipEdge(z, v0, v1);
+	if (sub == 0)
+	{
+		o0 = v01; o1 = v1; o2 = v2;
+	}
+	else
+	{
+		o0 = v01; o1 = v2; o2 = clipEdge(z, v0, v2);
+	}
 	return 2;
 }
 
-// Near-plane path of k_setup: rebuilds the three corners in view space, clips, sets up.
-__device__ __noinline__ int setupClipped(const FrameParams& fp, int r, int tri, Rec* rec)
+// Emits the (tile, slot, record) pairs of one record with plain per-thread atomics (slow paths).
+__device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, const Setup& s)
+{
+	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
+	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
+	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, tyLo), ty1 = min(s.y1 >> MR_TILE_SHIFT, tyHi);
+	if (ty1 < ty0)
+		return;
+	const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+	const unsigned long long base = atomicAdd(&fp.ctr->pairTotal, (unsigned long long)n);
+	if (base + (unsigned long long)n > (unsigned long long)fp.pairCap)
+	{
+		fp.ctr->overflow = 1u;
+		return;
+	}
+	int4* dst = fp.pairs + base;
+	for (int ty = ty0; ty <= ty1; ty++)
+		for (int tx = tx0; tx <= tx1; tx++)
+		{
+			const int tile = ty * fp.tilesX + tx;
+			*dst++ = make_int4(tile, atomicAdd(&fp.tileCount[tile], 1), id, 0);
+		}
+}
+
+// Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up, stores
+// the records and emits their pairs. Self-contained so that its stack never touches the fast path.
+__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri)
 {
 	const RStat rs = fp.rstat[r];
 	const MeshDev m = fp.meshes[rs.mesh];
-	const RDyn& rd = fp.rdyn[r];
-	Vert v[3];
-	Vert out[2][3];
-	for (int c = 0; c < 3; c++)
-		v[c] = fetchCorner(fp, m, rd, tri, c);
-	const int n = clipTriangle(fp.znear, v, out);
-	int mask = 0;
-	for (int k = 0; k < n; k++)
+	const RDyn* rd = &fp.rdyn[r];
+	const Corner v0 = fetchCorner(fp, m, rd, tri, 0), v1 = fetchCorner(fp, m, rd, tri, 1), v2 = fetchCorner(fp, m, rd, tri, 2);
+	int nrec = 0;
+	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
+	for (int sub = 0; sub < 2; sub++)
 	{
-		const float4 a = project(fp, out[k][0].pos), b = project(fp, out[k][1].pos), c = project(fp, out[k][2].pos);
-		if (setupTriangle(fp, a, b, c, rec[k]))
-			mask |= 1 << k;
+		Corner o0, o1, o2;
+		const int n = clipTriangle(fp.znear, v0, v1, v2, sub, o0, o1, o2);
+		if (sub >= n)
+			break;
+		const float4 a = project(fp, mk3(o0.px, o0.py, o0.pz)), b = project(fp, mk3(o1.px, o1.py, o1.pz)), c = project(fp, mk3(o2.px, o2.py, o2.pz));
+		Setup s;
+		if (!setupTriangle(fp, a, b, c, s))
+			continue;
+		if (min(s.y1 >> MR_TILE_SHIFT, tyHi) < max(s.y0 >> MR_TILE_SHIFT, tyLo))
+			continue;
+		const int id = 2 * t + sub;
+		storeRec(&fp.recs[id], a, b, c, s, r, 1, tri);
+		emitPairsSerial(fp, id, s);
+		nrec++;
 	}
-	return mask;
+	return nrec;
 }
 
 // ------------------------------------------------------------------------------------------
 // Kernel 2: near test, clip, setup, and (tile, triangle) pair emission.
-// One thread per triangle instance t. Surviving triangles are written at recs[2t+sub]; their
-// (tile, slot, record) pairs are compacted into pairs[] with a warp prefix sum and one
-// atomicAdd per warp; `slot` is the triangle's rank inside its tile (from the tile counter).
+// One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
+// outputs at 2t and 2t+1): the index is the submission id. Its (tile, slot, record) pairs are
+// compacted into pairs[] with a warp prefix sum and one atomicAdd per warp; `slot`, the
+// triangle's rank inside its tile, comes from the tile counter with one atomic per distinct
+// tile per warp (__match_any_sync), because neighbouring triangles mostly share a tile.
+// The last CTA to finish turns the tile counters into offsets (exclusive scan).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_setup(const FrameParams fp)
+#define MR_AGG_ROUNDS 4
+
+__device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 34 ints */)
 {
+	// exclusive scan of tileCount[0..n) into tileOffset[], by one 256-thread CTA
+	const int n = fp.tilesX * fp.tilesY;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int per = (n + 255) / 256;
+	const int lo = min(tid * per, n), hi = min(lo + per, n);
+	int sum = 0;
+	for (int i = lo; i < hi; i++)
+		sum += __ldcg(&fp.tileCount[i]);
+	int incl = sum;
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const int u = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o)
+			incl += u;
+	}
+	if (lane == 31)
+		sh[wid] = incl;
+	__syncthreads();
+	if (wid == 0)
+	{
+		int v = (lane < 8) ? sh[lane] : 0, s = v;
+		for (int o = 1; o < 8; o <<= 1)
+		{
+			const int u = __shfl_up_sync(0xffffffffu, s, o);
+			if (lane >= o)
+				s += u;
+		}
+		if (lane < 8)
+			sh[lane] = s - v;
+	}
+	__syncthreads();
+	int run = sh[wid] + incl - sum;
+	for (int i = lo; i < hi; i++)
+	{
+		fp.tileOffset[i] = run;
+		run += __ldcg(&fp.tileCount[i]);
+	}
+}
+
+__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FrameParams fp)
+{
+	__shared__ int sh[40];
 	const int t = blockIdx.x * 256 + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	Rec rec[2];
-	int mask = 0;
-	int clipped = 0;
+	bool valid = false;
+	int nclip = 0, nrecSlow = 0;
+	int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
 	if (t < fp.nTriInst)
 	{
 		const int r = findRenderable(fp, fp.triBlockR[blockIdx.x], t, true);
@@ -267,49 +371,34 @@ __global__ void __launch_bounds__(256) k_setup(const FrameParams fp)
 		{
 			if (!(a.z > zn && b.z > zn && c.z > zn))
 			{
-				clipped = 1;
-				mask = setupClipped(fp, r, tri, rec);
+				nclip = 1;
+				nrecSlow = setupClipped(fp, t, r, tri);
 			}
 		}
-		else if (setupTriangle(fp, a, b, c, rec[0]))
-			mask = 1;
-		for (int k = 0; k < 2; k++)
-			if (mask & (1 << k))
-			{
-				rec[k].renderable = r;
-				rec[k].flags = clipped;
-				rec[k].tri = tri;
-			}
-	}
-
-	// tile ranges, restricted to the tile rows of this frame's strip
-	int tx0[2], tx1[2], ty0[2], ty1[2];
-	int npairs = 0;
-	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
-	for (int k = 0; k < 2; k++)
-	{
-		tx0[k] = 0; tx1[k] = -1; ty0[k] = 0; ty1[k] = -1;
-		if (mask & (1 << k))
+		else
 		{
-			tx0[k] = (int)(rec[k].xspan & 0xffffu) >> MR_TILE_SHIFT;
-			tx1[k] = (int)(rec[k].xspan >> 16) >> MR_TILE_SHIFT;
-			ty0[k] = max((int)(rec[k].yspan & 0xffffu) >> MR_TILE_SHIFT, tyLo);
-			ty1[k] = min((int)(rec[k].yspan >> 16) >> MR_TILE_SHIFT, tyHi);
-			if (ty1[k] >= ty0[k])
+			Setup s;
+			if (setupTriangle(fp, a, b, c, s))
 			{
-				npairs += (tx1[k] - tx0[k] + 1) * (ty1[k] - ty0[k] + 1);
-				Rec* dst = &fp.recs[2 * (size_t)t + k];
-				const float4* s4 = reinterpret_cast<const float4*>(&rec[k]);
-				float4* d4 = reinterpret_cast<float4*>(dst);
-				d4[0] = s4[0]; d4[1] = s4[1]; d4[2] = s4[2]; d4[3] = s4[3];
+				tx0 = s.x0 >> MR_TILE_SHIFT;
+				tx1 = s.x1 >> MR_TILE_SHIFT;
+				ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
+				ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
+				if (ty1 >= ty0)
+				{
+					valid = true;
+					storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, r, 0, tri);
+				}
 			}
-			else
-				mask &= ~(1 << k);
 		}
 	}
+	__syncwarp();
 
-	// warp-level compaction of the pair ranges
+	// ---- warp-level compaction of the pair ranges ----
+	const int nx = tx1 - tx0 + 1;
+	const int npairs = valid ? nx * (ty1 - ty0 + 1) : 0;
 	int incl = npairs;
+#pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
 		const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -317,87 +406,67 @@ __global__ void __launch_bounds__(256) k_setup(const FrameParams fp)
 			incl += v;
 	}
 	const int total = __shfl_sync(0xffffffffu, incl, 31);
-	const int nrecWarp = __reduce_add_sync(0xffffffffu, __popc(mask));
-	const int nclipWarp = __reduce_add_sync(0xffffffffu, clipped);
-	const int ninWarp = __reduce_add_sync(0xffffffffu, (t < fp.nTriInst) ? 1 : 0);
+	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
+	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
 	unsigned long long base = 0;
 	if (lane == 31)
 	{
 		if (total > 0)
+		{
 			base = atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
+			if (base + (unsigned long long)total > (unsigned long long)fp.pairCap)
+				fp.ctr->overflow = 1u;
+		}
 		if (nrecWarp) atomicAdd(&fp.ctr->records, (unsigned long long)nrecWarp);
 		if (nclipWarp) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nclipWarp);
-		if (ninWarp) atomicAdd(&fp.ctr->trianglesIn, (unsigned long long)ninWarp);
-		if (total > 0 && base + (unsigned long long)total > (unsigned long long)fp.pairCap)
-			fp.ctr->overflow = 1u;
 	}
 	base = __shfl_sync(0xffffffffu, base, 31);
-	if (total == 0 || base + (unsigned long long)total > (unsigned long long)fp.pairCap)
-		return;
-	int4* dst = fp.pairs + base + (incl - npairs);
-	for (int k = 0; k < 2; k++)
-		if (mask & (1 << k))
-		{
-			const int id = 2 * t + k;
-			for (int ty = ty0[k]; ty <= ty1[k]; ty++)
-				for (int tx = tx0[k]; tx <= tx1[k]; tx++)
-				{
-					const int tile = ty * fp.tilesX + tx;
-					const int slot = atomicAdd(&fp.tileCount[tile], 1);
-					*dst++ = make_int4(tile, slot, id, 0);
-				}
-		}
-}
-
-// ------------------------------------------------------------------------------------------
-// Kernel 3a: exclusive scan of the tile counters (one CTA). 3b: scatter pairs into bins.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan(const FrameParams fp)
-{
-	__shared__ int warpSums[32];
-	__shared__ int carry;
-	const int n = fp.tilesX * fp.tilesY;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	if (threadIdx.x == 0)
-		carry = 0;
-	__syncthreads();
-	for (int base = 0; base < n; base += 1024)
+	if (total > 0 && base + (unsigned long long)total <= (unsigned long long)fp.pairCap)
 	{
-		const int i = base + threadIdx.x;
-		const int v = (i < n) ? fp.tileCount[i] : 0;
-		int incl = v;
-		for (int o = 1; o < 32; o <<= 1)
+		int4* dst = fp.pairs + base + (incl - npairs);
+		const int id = 2 * t;
+		const int rounds = min(__reduce_max_sync(0xffffffffu, npairs), MR_AGG_ROUNDS);
+		for (int k = 0; k < rounds; k++)
 		{
-			const int u = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o)
-				incl += u;
+			const bool on = k < npairs;
+			const int tile = on ? (ty0 + k / nx) * fp.tilesX + tx0 + k % nx : -1 - lane;
+			const unsigned peers = __match_any_sync(0xffffffffu, tile);
+			const int leader = __ffs(peers) - 1;
+			int slot = 0;
+			if (on && lane == leader)
+				slot = atomicAdd(&fp.tileCount[tile], __popc(peers));
+			slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+			if (on)
+				dst[k] = make_int4(tile, slot, id, 0);
 		}
-		if (lane == 31)
-			warpSums[wid] = incl;
-		__syncthreads();
-		if (wid == 0)
+		for (int k = MR_AGG_ROUNDS; k < npairs; k++) // large triangles: the remaining tiles one by one
 		{
-			int s = warpSums[lane];
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const int u = __shfl_up_sync(0xffffffffu, s, o);
-				if (lane >= o)
-					s += u;
-			}
-			warpSums[lane] = s;
+			const int tile = (ty0 + k / nx) * fp.tilesX + tx0 + k % nx;
+			dst[k] = make_int4(tile, atomicAdd(&fp.tileCount[tile], 1), id, 0);
 		}
-		__syncthreads();
-		const int prefix = carry + (wid ? warpSums[wid - 1] : 0) + incl - v;
-		if (i < n)
-			fp.tileOffset[i] = prefix;
-		__syncthreads();
-		if (threadIdx.x == 1023)
-			carry = prefix + v;
-		__syncthreads();
+	}
+
+	// ---- last CTA done: tile counters -> tile offsets ----
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		sh[39] = (atomicAdd(&fp.ctr->ctasDone, 1u) == gridDim.x - 1) ? 1 : 0;
+	__syncthreads();
+	if (sh[39])
+	{
+		__threadfence();
+		scanTiles(fp, sh);
 	}
 }
 
-__global__ void __launch_bounds__(256) k_scatter(const FrameParams fp)
+// Frames without triangles still need zero offsets for the raster kernel.
+__global__ void __launch_bounds__(256) k_scan_only(const __grid_constant__ FrameParams fp)
+{
+	__shared__ int sh[40];
+	scanTiles(fp, sh);
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ FrameParams fp)
 {
 	const Counters* c = fp.ctr;
 	if (c->overflow)
@@ -412,52 +481,91 @@ __global__ void __launch_bounds__(256) k_scatter(const FrameParams fp)
 
 // ------------------------------------------------------------------------------------------
 // Kernel 4: tile rasterizer + shader. One CTA per 16x16 tile, 256 threads.
-// Phase 1 (thread per binned triangle): reference loops D/E with the float edge chain replayed
-//   from the triangle's own bbox start (e += n.x per column, Renderer.cpp:243), depth resolved
-//   by 64-bit atomicMin in shared memory on (orderable z) << 32 | (record index + 1). The low
-//   word makes equal-z fragments resolve to the earliest submitted triangle, which is what the
-//   reference's strict `<` test over in-order submission does.
+// Phase 1 (four threads per binned triangle, rows interleaved): reference loops D/E with the
+//   float edge chain replayed from the triangle's own bbox start (e += n.x per column,
+//   Renderer.cpp:243), depth resolved by 64-bit atomicMin in shared memory on
+//   (orderable z) << 32 | (record index + 1). The low word makes equal-z fragments resolve to
+//   the earliest submitted triangle, which is what the reference's strict `<` test over in-order
+//   submission does.
 // Phase 2 (thread per pixel): the winner's barycentrics are re-derived by the same chain, then
 //   depth, perspective correction, texture and Blinn-Phong exactly as Renderer.cpp:253-305;
 //   pixels without a winner get the clear values (Renderer.cpp:113-119) unless fp.keep.
 // ------------------------------------------------------------------------------------------
-struct TriShade
+struct ShadeIn
 {
-	V3 pos[3];
-	V3 nrm[3];
-	float u[3], v[3];
+	float k0, k1, k2;
+	Corner c0, c1, c2;
 };
 
-__device__ __noinline__ void loadTriShade(const FrameParams& fp, const Rec& rec, int sub, TriShade& ts)
+// Renderer.cpp:271-305 for one pixel; writes image (and the normals image).
+__device__ __forceinline__ void shadePixel(const FrameParams& fp, const MatDev& mat, const ShadeIn& in, size_t pix)
 {
-	const int r = rec.renderable;
-	const RStat rs = fp.rstat[r];
-	const MeshDev m = fp.meshes[rs.mesh];
-	const RDyn& rd = fp.rdyn[r];
-	Vert v[3];
-	for (int c = 0; c < 3; c++)
-		v[c] = fetchCorner(fp, m, rd, rec.tri, c);
-	if (rec.flags & 1)
+	const float k0 = in.k0, k1 = in.k1, k2 = in.k2;
+	V3 color = mk3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
+	V3 value = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
+	if (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0)
 	{
-		Vert out[2][3];
-		clipTriangle(fp.znear, v, out);
-		for (int c = 0; c < 3; c++)
-			v[c] = out[sub][c];
+		const float u = in.c0.u * k0 + in.c1.u * k1 + in.c2.u * k2;
+		const float v = in.c0.v * k0 + in.c1.v * k1 + in.c2.v * k2;
+		const float fv = v - floorf(v), fu = u - floorf(u);
+		int ti = (int)(fv * (float)mat.texRows), tj = (int)(fu * (float)mat.texCols);
+		// fract() == 1.0f (tiny negative input) indexes one past the end in the reference;
+		// clamp instead (documented divergence on UB input)
+		ti = min(max(ti, 0), mat.texRows - 1);
+		tj = min(max(tj, 0), mat.texCols - 1);
+		const float4 tex = __ldg(&fp.texels[mat.texOffset + ti * mat.texCols + tj]);
+		color = mk3(tex.x, tex.y, tex.z);
 	}
-	for (int c = 0; c < 3; c++)
+	if (fp.lighting)
 	{
-		ts.pos[c] = v[c].pos;
-		ts.nrm[c] = v[c].nrm;
-		ts.u[c] = v[c].u;
-		ts.v[c] = v[c].v;
+		const V3 position = mk3(in.c0.px * k0 + in.c1.px * k1 + in.c2.px * k2, in.c0.py * k0 + in.c1.py * k1 + in.c2.py * k2,
+		                        in.c0.pz * k0 + in.c1.pz * k1 + in.c2.pz * k2);
+		const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
+		const V3 lightdir = fp.lightIsPoint ? normalized3(sub3(light, position)) : light;
+		const V3 normal = mk3(in.c0.nx * k0 + in.c1.nx * k1 + in.c2.nx * k2, in.c0.ny * k0 + in.c1.ny * k1 + in.c2.ny * k2,
+		                      in.c0.nz * k0 + in.c1.nz * k1 + in.c2.nz * k2);
+		const float nl = dot3(normal, lightdir);
+		const float nlen = len3(normal);
+		const float d = ((0.0f > nl) ? 0.0f : nl) / nlen + fp.ambient;
+		value = add3(value, scale3(color, d));
+		if (mat.shininess != 0.0f)
+		{
+			const V3 viewdir = normalized3(position);
+			const V3 hv = sub3(lightdir, viewdir);
+			const float hn = dot3(hv, normal);
+			const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
+			// the reference's unqualified pow() is the double overload
+			const float specular = (float)pow((double)base, (double)mat.shininess);
+			value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
+		}
+		if (fp.saveNormals && fp.normals)
+		{
+			float* pn = fp.normals + 3 * pix;
+			pn[0] = normal.x; pn[1] = normal.y; pn[2] = normal.z;
+		}
 	}
+	float* img = fp.image + 3 * pix;
+	img[0] = value.x; img[1] = value.y; img[2] = value.z;
 }
 
-__global__ void __launch_bounds__(256) k_raster(const FrameParams fp)
+// Shading of a pixel won by a clipper-made triangle (rare): re-runs the clip to get the corners.
+__device__ __noinline__ void shadeClippedPixel(const FrameParams& fp, int r, int tri, int sub, float k0, float k1, float k2, size_t pix)
+{
+	const RStat rs = fp.rstat[r];
+	const MeshDev m = fp.meshes[rs.mesh];
+	const RDyn* rd = &fp.rdyn[r];
+	const Corner v0 = fetchCorner(fp, m, rd, tri, 0), v1 = fetchCorner(fp, m, rd, tri, 1), v2 = fetchCorner(fp, m, rd, tri, 2);
+	ShadeIn in;
+	in.k0 = k0; in.k1 = k1; in.k2 = k2;
+	clipTriangle(fp.znear, v0, v1, v2, sub, in.c0, in.c1, in.c2);
+	const MatDev mat = fp.mats[rd->material];
+	shadePixel(fp, mat, in, pix);
+}
+
+__global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
-	const Counters* ctr = fp.ctr;
-	if (ctr->overflow)
+	if (__ldcg(&fp.ctr->overflow))
 		return; // the host regrows the pair buffers and re-runs the frame
 	const int tx = blockIdx.x % fp.tilesX;
 	const int ty = fp.tileRow0 + blockIdx.x / fp.tilesX;
@@ -467,72 +575,15 @@ __global__ void __launch_bounds__(256) k_raster(const FrameParams fp)
 	const int py = ty * MR_TILE + (tid >> 4);
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
 	const size_t pix = (size_t)py * fp.w + px;
+	const int count = fp.tileCount[tile];
+	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
 
+	if (count == 0 && !fp.keep)
 	{
-		unsigned long long k0 = 0ull; // pixels outside the image / strip can never be won
+		// empty tile: clear values only
 		if (inImage)
 		{
-			const float d0 = fp.keep ? fp.depth[pix] : 1e11f;
-			k0 = (unsigned long long)zkey(d0) << 32;
-		}
-		keys[tid] = k0;
-	}
-	__syncthreads();
-
-	// ---- phase 1: coverage + depth ----
-	const int count = fp.tileCount[tile];
-	const int* bin = fp.bins + fp.tileOffset[tile];
-	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
-	for (int i = tid; i < count; i += 256)
-	{
-		const int id = bin[i];
-		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-		const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
-		const float p0x = q0.x, p0y = q0.y, p2x = q0.z, p2y = q0.w;
-		const float n1x = q1.x, n1y = q1.y, n2x = q1.z, n2y = q1.w;
-		const float d0 = q2.x, d1 = q2.y, d2 = q2.z;
-		const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
-		const int x0 = xspan & 0xffffu, x1 = min((int)(xspan >> 16), tileX0 + MR_TILE - 1);
-		const int y0 = max((int)(yspan & 0xffffu), tileY0), y1 = min((int)(yspan >> 16), tileY0 + MR_TILE - 1);
-		const float ptx = (float)x0 + 0.5f;
-		const unsigned long long low = (unsigned long long)(uint32_t)(id + 1);
-		for (int y = y0; y <= y1; y++)
-		{
-			const float fy = (float)y + 0.5f;
-			float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
-			float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
-			for (int x = x0; x <= x1; x++, e1 += n1x, e2 += n2x)
-			{
-				if (x < tileX0)
-					continue;
-				const float k0 = 1.0f - e1 - e2;
-				if (e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)
-					continue;
-				float z;
-				if (fp.persp)
-					z = 1.0f / (k0 * d0 + e1 * d1 + e2 * d2);
-				else
-					z = k0 * d0 + e1 * d1 + e2 * d2 + 0.0f * 1.0f;
-				if (!(z == z))
-					continue;
-				const unsigned long long key = ((unsigned long long)zkey(z) << 32) | low;
-				unsigned long long* slot = &keys[(y - tileY0) * MR_TILE + (x - tileX0)];
-				if (key < *(volatile unsigned long long*)slot)
-					atomicMin(slot, key);
-			}
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 2: resolve + shade ----
-	if (!inImage)
-		return;
-	const uint32_t win = (uint32_t)(keys[tid] & 0xffffffffull);
-	float* img = fp.image + 3 * pix;
-	if (win == 0u)
-	{
-		if (!fp.keep)
-		{
+			float* img = fp.image + 3 * pix;
 			img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
 			fp.depth[pix] = 1e11f;
 			if (fp.saveNormals && fp.normals)
@@ -545,82 +596,168 @@ __global__ void __launch_bounds__(256) k_raster(const FrameParams fp)
 		}
 		return;
 	}
-	const int id = (int)(win - 1u);
-	const Rec rec = fp.recs[id];
-	// replay the edge chain of this row up to this pixel
-	const int x0 = rec.xspan & 0xffffu;
-	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
-	float e1 = rec.n1x * (ptx - rec.p2x) + rec.n1y * (fy - rec.p2y);
-	float e2 = rec.n2x * (ptx - rec.p0x) + rec.n2y * (fy - rec.p0y);
-	for (int x = x0; x < px; x++)
 	{
-		e1 += rec.n1x;
-		e2 += rec.n2x;
+		unsigned long long k0 = 0ull; // pixels outside the image / strip can never be won
+		if (inImage)
+		{
+			const float d0 = fp.keep ? fp.depth[pix] : 1e11f;
+			k0 = (unsigned long long)zkey(d0) << 32;
+		}
+		keys[tid] = k0;
+	}
+	__syncthreads();
+
+	// ---- phase 1: coverage + depth, a quad of threads per triangle ----
+	const int* bin = fp.bins + fp.tileOffset[tile];
+	const int q = tid & 3;
+	for (int i = tid >> 2; i < count; i += 64)
+	{
+		const int id = __ldg(&bin[i]);
+		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
+		const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
+		const float p0x = q0.x, p0y = q0.y, p2x = q0.z, p2y = q0.w;
+		const float n1x = q1.x, n1y = q1.y, n2x = q1.z, n2y = q1.w;
+		const float d0 = q2.x, d1 = q2.y, d2 = q2.z;
+		const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
+		const int x0 = xspan & 0xffffu, x1 = min((int)(xspan >> 16), tileX0 + MR_TILE - 1);
+		const int y0 = max((int)(yspan & 0xffffu), tileY0), y1 = min((int)(yspan >> 16), tileY0 + MR_TILE - 1);
+		const int xs = max(x0, tileX0); // first column tested in this tile
+		const float ptx = (float)x0 + 0.5f;
+		const unsigned long long low = (unsigned long long)(uint32_t)(id + 1);
+		for (int y = y0 + q; y <= y1; y += 4)
+		{
+			const float fy = (float)y + 0.5f;
+			float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
+			float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
+			for (int x = x0; x < xs; x++) // chain prefix left of the tile
+			{
+				e1 += n1x;
+				e2 += n2x;
+			}
+			unsigned long long* row = &keys[(y - tileY0) * MR_TILE - tileX0];
+			for (int x = xs; x <= x1; x++, e1 += n1x, e2 += n2x)
+			{
+				const float k0 = 1.0f - e1 - e2;
+				if (e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)
+					continue;
+				float z;
+				if (fp.persp)
+					z = 1.0f / (k0 * d0 + e1 * d1 + e2 * d2);
+				else
+					z = k0 * d0 + e1 * d1 + e2 * d2 + 0.0f * 1.0f;
+				if (!(z == z))
+					continue;
+				const unsigned long long key = ((unsigned long long)zkey(z) << 32) | low;
+				if (key < *(volatile unsigned long long*)&row[x])
+					atomicMin(&row[x], key);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: resolve + shade ----
+	const uint32_t win = inImage ? (uint32_t)(keys[tid] & 0xffffffffull) : 0u;
+	// Replay of the winner's edge chain. Lanes of the same pixel row (a half warp) that share a
+	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
+	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
+	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+	int id = -1;
+	if (win != 0u)
+	{
+		id = (int)(win - 1u);
+		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
+		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+	}
+	const int x0 = (int)(__float_as_uint(q3.x) & 0xffffu);
+	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
+	float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
+	float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
+	int xcur = x0;
+	{
+		const int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
+		const unsigned long long groupKey = (prefix > 0) ? (((unsigned long long)(uint32_t)id << 1) | (unsigned long long)((tid >> 4) & 1))
+		                                                 : (0x8000000000000000ull | (unsigned long long)(tid & 31));
+		const unsigned peers = __match_any_sync(0xffffffffu, groupKey);
+		const int leader = __ffs(peers) - 1;
+		if ((tid & 31) == leader && prefix > 0)
+			for (int x = 0; x < prefix; x++)
+			{
+				e1 += q1.x;
+				e2 += q1.z;
+			}
+		const float s1 = __shfl_sync(0xffffffffu, e1, leader), s2 = __shfl_sync(0xffffffffu, e2, leader);
+		if (prefix > 0)
+		{
+			e1 = s1;
+			e2 = s2;
+			xcur = tileX0;
+		}
+	}
+	if (!inImage)
+		return;
+	if (win == 0u)
+	{
+		if (!fp.keep)
+		{
+			float* img = fp.image + 3 * pix;
+			img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
+			fp.depth[pix] = 1e11f;
+			if (fp.saveNormals && fp.normals)
+			{
+				float* pn = fp.normals + 3 * pix;
+				pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
+			}
+			if (fp.winner)
+				fp.winner[pix] = -1;
+		}
+		return;
+	}
+	for (int x = xcur; x < px; x++)
+	{
+		e1 += q1.x;
+		e2 += q1.z;
 	}
 	float k0 = 1.0f - e1 - e2, k1 = e1, k2 = e2;
 	float z;
 	if (fp.persp)
 	{
-		z = 1.0f / (k0 * rec.d0 + k1 * rec.d1 + k2 * rec.d2);
-		k0 *= rec.d0 * z;
-		k1 *= rec.d1 * z;
-		k2 *= rec.d2 * z;
+		z = 1.0f / (k0 * q2.x + k1 * q2.y + k2 * q2.z);
+		k0 *= q2.x * z;
+		k1 *= q2.y * z;
+		k2 *= q2.z * z;
 	}
 	else
-		z = k0 * rec.d0 + k1 * rec.d1 + k2 * rec.d2 + 0.0f * 1.0f;
+		z = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 	fp.depth[pix] = z;
 	if (fp.winner)
 		fp.winner[pix] = id;
 
-	const MatDev mat = fp.mats[fp.rdyn[rec.renderable].material];
-	V3 color = mk3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
-	const bool hastexture = fp.texturing && mat.texOffset >= 0 && mat.texRows > 0;
-	V3 value = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
-	if (hastexture || fp.lighting)
+	const int r = __float_as_int(q2.w), flags = __float_as_int(q3.z), tri = __float_as_int(q3.w);
+	if (flags & 1)
 	{
-		TriShade ts;
-		loadTriShade(fp, rec, id & 1, ts);
-		if (hastexture)
-		{
-			const float u = ts.u[0] * k0 + ts.u[1] * k1 + ts.u[2] * k2;
-			const float v = ts.v[0] * k0 + ts.v[1] * k1 + ts.v[2] * k2;
-			const float fv = v - floorf(v), fu = u - floorf(u);
-			int ti = (int)(fv * (float)mat.texRows), tj = (int)(fu * (float)mat.texCols);
-			// fract() == 1.0f (tiny negative input) indexes one past the end in the reference;
-			// clamp instead (documented divergence on UB input)
-			ti = min(max(ti, 0), mat.texRows - 1);
-			tj = min(max(tj, 0), mat.texCols - 1);
-			const float4 tex = __ldg(&fp.texels[mat.texOffset + ti * mat.texCols + tj]);
-			color = mk3(tex.x, tex.y, tex.z);
-		}
-		if (fp.lighting)
-		{
-			const V3 position = add3(add3(scale3(ts.pos[0], k0), scale3(ts.pos[1], k1)), scale3(ts.pos[2], k2));
-			const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
-			const V3 lightdir = fp.lightIsPoint ? normalized3(sub3(light, position)) : light;
-			const V3 normal = add3(add3(scale3(ts.nrm[0], k0), scale3(ts.nrm[1], k1)), scale3(ts.nrm[2], k2));
-			const float nl = dot3(normal, lightdir);
-			const float nlen = len3(normal);
-			const float d = ((0.0f > nl) ? 0.0f : nl) / nlen + fp.ambient;
-			value = add3(value, scale3(color, d));
-			if (mat.shininess != 0.0f)
-			{
-				const V3 viewdir = normalized3(position);
-				const V3 hv = sub3(lightdir, viewdir);
-				const float hn = dot3(hv, normal);
-				const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
-				// the reference's unqualified pow() is the double overload
-				const float specular = (float)pow((double)base, (double)mat.shininess);
-				value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
-			}
-			if (fp.saveNormals && fp.normals)
-			{
-				float* pn = fp.normals + 3 * pix;
-				pn[0] = normal.x; pn[1] = normal.y; pn[2] = normal.z;
-			}
-		}
+		shadeClippedPixel(fp, r, tri, id & 1, k0, k1, k2, pix);
+		return;
 	}
-	img[0] = value.x; img[1] = value.y; img[2] = value.z;
+	const RDyn* rd = &fp.rdyn[r];
+	const MatDev mat = fp.mats[rd->material];
+	const bool needGeom = fp.lighting || (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0);
+	ShadeIn in;
+	in.k0 = k0; in.k1 = k1; in.k2 = k2;
+	if (needGeom)
+	{
+		const RStat rs = fp.rstat[r];
+		const MeshDev m = fp.meshes[rs.mesh];
+		in.c0 = fetchCorner(fp, m, rd, tri, 0);
+		in.c1 = fetchCorner(fp, m, rd, tri, 1);
+		in.c2 = fetchCorner(fp, m, rd, tri, 2);
+	}
+	else
+	{
+		Corner z0;
+		z0.px = z0.py = z0.pz = z0.nx = z0.ny = z0.nz = z0.u = z0.v = 0.0f;
+		in.c0 = z0; in.c1 = z0; in.c2 = z0;
+	}
+	shadePixel(fp, mat, in, pix);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -692,8 +829,9 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	if (ev) cudaEventRecord(ev[1], stream);
 	if (fp.nTriInst > 0)
 		k_setup<<<(fp.nTriInst + 255) / 256, 256, 0, stream>>>(fp);
+	else
+		k_scan_only<<<1, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[2], stream);
-	k_scan<<<1, 1024, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[3], stream);
 	if (fp.nTriInst > 0)
 		k_scatter<<<148 * 8, 256, 0, stream>>>(fp);

@@ -82,7 +82,7 @@ struct Counters
 	unsigned long long pairTotal;   // (tile, triangle) pairs produced (may exceed capacity)
 	unsigned long long wideRecords;
 	unsigned int overflow;          // pairs did not fit: the frame must be re-run with more room
-	unsigned int pad;
+	unsigned int ctasDone;          // k_setup CTAs finished (the last one scans the tile counters)
 };
 
 struct FrameParams
