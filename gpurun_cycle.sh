@@ -1,2 +1,3 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools_perf_probe.py 2>&1 | grep -v "^$"
+python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --steps 20 --warmup 3 2>&1 | tail -3

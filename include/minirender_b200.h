@@ -147,7 +147,9 @@ typedef struct mr_stats
 	int32_t tiles_x, tiles_y;
 	int32_t regrows;           /* times a queue had to be regrown and the frame re-run */
 	int32_t kernels_launched;  /* kernel launches issued for the frame */
-	float   ms_kernel[8];      /* per-stage device time of the last mr_profile_frame */
+	float   ms_kernel[8];      /* per-stage device time of the last mr_profile_frame:
+	                              0 vertex, 1 setup+scan, 2 (unused), 3 scatter, 4 raster, 5 whole frame */
+	int64_t h2d_bytes;         /* host->device bytes the last mr_render copied (per-frame tables) */
 } mr_stats;
 
 MR_API int mr_abi_version(void);
@@ -200,7 +202,11 @@ MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 
 MR_API int mr_get_stats(mr_ctx* ctx, mr_stats* out);
-/* Re-run the last frame with CUDA events between the stages; fills mr_stats.ms_kernel. */
+/* Evict the L2 cache by writing a 256 MiB scratch buffer on the context's stream (benchmark
+ * hygiene: cold-cache timing between steps). */
+MR_API int mr_flush_l2(mr_ctx* ctx);
+/* Render `frame` `repeats` times with CUDA events between the stages; fills mr_stats.ms_kernel
+ * with the averages. With mr_set_debug flag 2 the L2 is flushed before every repeat. */
 MR_API int mr_profile_frame(mr_ctx* ctx, const mr_frame* frame, int repeats);
 
 #ifdef __cplusplus

@@ -76,6 +76,8 @@ _PRODUCT_ONLY = {
     "mrx_renderer_context": (C.c_void_p, [C.c_void_p]),
     "mrx_renderer_get_rgb8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mrx_renderer_synchronize": (C.c_int, [C.c_void_p]),
+    "mrx_renderer_image_ptr": (C.POINTER(C.c_float), [C.c_void_p]),
+    "mrx_renderer_depth_ptr": (C.POINTER(C.c_float), [C.c_void_p]),
     "mrx_save_ppm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "mrx_load_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
@@ -331,6 +333,19 @@ class Renderer:
         if not p:
             raise RuntimeError("mrx_renderer_context failed: %s" % self.be.lib.mrx_last_error().decode())
         return p
+
+    def image_view(self):
+        """getImage() as a zero-copy numpy view of the Renderer's host mirror (valid until the next call)."""
+        p = self.be.lib.mrx_renderer_image_ptr(self.h_)
+        if not p:
+            raise RuntimeError("getImage failed: %s" % self.be.lib.mrx_last_error().decode())
+        return np.ctypeslib.as_array(p, (self.h, self.w, 3))
+
+    def depth_view(self):
+        p = self.be.lib.mrx_renderer_depth_ptr(self.h_)
+        if not p:
+            raise RuntimeError("getDepth failed: %s" % self.be.lib.mrx_last_error().decode())
+        return np.ctypeslib.as_array(p, (self.h, self.w))
 
     def get_rgb8(self):
         out = np.empty((self.h, self.w, 3), np.uint8)

@@ -58,7 +58,7 @@ class Stats(C.Structure):
     _fields_ = [("triangles_in", C.c_int64), ("records", C.c_int64), ("clipped_in", C.c_int64),
                 ("bin_entries", C.c_int64), ("wide_records", C.c_int64),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("regrows", C.c_int32),
-                ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8)]
+                ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8), ("h2d_bytes", C.c_int64)]
 
 
 FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
@@ -91,6 +91,7 @@ PROTOTYPES = {
     "mr_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "mr_read_winner_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "mr_flush_l2": (C.c_int, [C.c_void_p]),
     "mr_profile_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
 }
 

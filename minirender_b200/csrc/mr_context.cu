@@ -94,16 +94,27 @@ struct mr_ctx
 	std::vector<int> structureKey; // mesh id per renderable of the tables currently on the device
 	unsigned structureSerial;
 	int nVertInst, nTriInst;
-	PinBuf stage;
-	cudaEvent_t stageFree;
-	bool stageBusy;
+	// per-frame host staging + counters, a ring so that mr_render never waits for the GPU
+	struct Slot
+	{
+		PinBuf stage;
+		Counters* hostCtr; // pinned
+		cudaEvent_t done;
+		bool pending;
+		Slot() : hostCtr(0), done(0), pending(false) {}
+	};
+	enum { kSlots = 4 };
+	Slot slots[kSlots];
+	int slotNext;   // slot the next frame uses
+	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, tileCount, tileOffset, pairs, bins, ctr;
+	DevBuf pv, recs, tileCount, tileOffset, pairs, warpPairCount, ovfPairs, bins, ctr;
 	size_t pairCap;
+	size_t h2dBytesLastFrame;
 
 	// outputs
-	DevBuf image, depth, normals, winner, scratchOut;
+	DevBuf image, depth, normals, winner, scratchOut, flushBuf;
 	void *remoteImage, *remoteDepth;
 	int debugFlags;
 
@@ -112,14 +123,11 @@ struct mr_ctx
 	std::vector<mr_renderable> lastRenderables;
 	std::vector<mr_material> lastMaterials;
 	bool haveFrame;
-	bool frameChecked;
-	Counters* hostCtr; // pinned
-	cudaEvent_t frameDone;
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), nVertInst(0), nTriInst(0), stageFree(0), stageBusy(false), pairCap(0), remoteImage(0),
-	           remoteDepth(0), debugFlags(0), haveFrame(false), frameChecked(true), hostCtr(0), frameDone(0)
+	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), pairCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           remoteDepth(0), debugFlags(0), haveFrame(false)
 	{
 		memset(&lastFrame, 0, sizeof(lastFrame));
 		memset(&stats, 0, sizeof(stats));
@@ -170,34 +178,57 @@ struct Bind
 
 int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev);
 
-// Waits for the last frame and, if its pair queue overflowed, regrows it and re-runs the frame.
+void absorbCounters(mr_ctx* c, const Counters& k)
+{
+	c->stats.triangles_in = (int64_t)k.trianglesIn;
+	c->stats.records = (int64_t)k.records;
+	c->stats.clipped_in = (int64_t)k.clippedIn;
+	c->stats.bin_entries = (int64_t)k.pairTotal;
+	c->stats.wide_records = (int64_t)k.wideRecords;
+	c->stats.tiles_x = c->tilesX;
+	c->stats.tiles_y = c->tilesY;
+}
+
+// Retires one slot: waits for its frame, reads its counters. Returns 1 if that frame overflowed
+// its pair queues (then pairCap has been raised), 0 if fine, <0 on error.
+int retireSlot(mr_ctx* c, int i)
+{
+	mr_ctx::Slot& s = c->slots[i];
+	if (!s.pending)
+		return 0;
+	MR_CUDA(c, cudaEventSynchronize(s.done));
+	s.pending = false;
+	const Counters k = *s.hostCtr;
+	absorbCounters(c, k);
+	if (!k.overflow)
+		return 0;
+	const size_t need = std::max((size_t)k.pairTotal, (size_t)k.ovfTotal);
+	c->pairCap = std::max(c->pairCap, need + need / 4 + 1024);
+	c->stats.regrows++;
+	return 1;
+}
+
+// Waits for everything in flight. If the most recent frame overflowed its pair queues it is
+// rendered again with more room (earlier frames have been overwritten by then anyway).
 int finishFrame(mr_ctx* c)
 {
-	if (!c->haveFrame || c->frameChecked)
+	for (int attempt = 0; attempt < 5; attempt++)
 	{
-		MR_CUDA(c, cudaStreamSynchronize(c->stream));
-		return MR_OK;
-	}
-	for (int attempt = 0; attempt < 4; attempt++)
-	{
-		MR_CUDA(c, cudaEventSynchronize(c->frameDone));
-		const Counters k = *c->hostCtr;
-		c->stats.triangles_in = (int64_t)k.trianglesIn;
-		c->stats.records = (int64_t)k.records;
-		c->stats.clipped_in = (int64_t)k.clippedIn;
-		c->stats.bin_entries = (int64_t)k.pairTotal;
-		c->stats.wide_records = (int64_t)k.wideRecords;
-		c->stats.tiles_x = c->tilesX;
-		c->stats.tiles_y = c->tilesY;
-		if (!k.overflow)
+		int newestOverflowed = 0;
+		for (int n = 0; n < mr_ctx::kSlots; n++)
 		{
-			c->frameChecked = true;
+			const int i = (c->slotNext + n) % mr_ctx::kSlots; // oldest first
+			const int rc = retireSlot(c, i);
+			if (rc < 0)
+				return rc;
+			if (i == c->slotNewest)
+				newestOverflowed = rc;
+		}
+		if (!newestOverflowed || !c->haveFrame)
+		{
 			MR_CUDA(c, cudaStreamSynchronize(c->stream));
 			return MR_OK;
 		}
-		// not enough room for the (tile, triangle) pairs: grow and render the frame again
-		c->pairCap = (size_t)k.pairTotal + (size_t)k.pairTotal / 4 + 1024;
-		c->stats.regrows++;
 		mr_frame f = c->lastFrame;
 		f.renderables = c->lastRenderables.empty() ? 0 : &c->lastRenderables[0];
 		f.materials = c->lastMaterials.empty() ? 0 : &c->lastMaterials[0];
@@ -277,9 +308,14 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		c->pairCap = (size_t)c->nTriInst * 2 + 65536;
 	if (c->pairCap > 0x7fffffffULL)
 		return setError(c, MR_E_OVERFLOW, "more than 2^31 (tile, triangle) pairs");
-	MR_CUDA(c, c->pairs.ensure(sizeof(int4) * c->pairCap));
+	{
+		const size_t nWarps = ((size_t)c->nTriInst + 31) / 32;
+		MR_CUDA(c, c->pairs.ensure(sizeof(int4) * 32 * MR_SEG_PER_LANE * std::max<size_t>(nWarps, 1)));
+		MR_CUDA(c, c->warpPairCount.ensure(sizeof(int) * (std::max<size_t>(nWarps, 1) + 8)));
+	}
+	MR_CUDA(c, c->ovfPairs.ensure(sizeof(int4) * c->pairCap));
 	MR_CUDA(c, c->bins.ensure(sizeof(int) * c->pairCap));
-	c->pairCap = std::min(c->pairs.cap / sizeof(int4), c->bins.cap / sizeof(int));
+	c->pairCap = std::min(c->ovfPairs.cap / sizeof(int4), c->bins.cap / sizeof(int));
 	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
 	if (rc)
 		return rc;
@@ -291,13 +327,15 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
 	const size_t total = szStat + szVB + szTB + szDyn + szMat + 64;
-	if (c->stageBusy)
+	const int slotIndex = c->slotNext;
 	{
-		MR_CUDA(c, cudaEventSynchronize(c->stageFree));
-		c->stageBusy = false;
+		const int rc0 = retireSlot(c, slotIndex); // normally long finished
+		if (rc0 < 0)
+			return rc0;
 	}
-	MR_CUDA(c, c->stage.ensure(total));
-	char* sp = (char*)c->stage.p;
+	mr_ctx::Slot& slot = c->slots[slotIndex];
+	MR_CUDA(c, slot.stage.ensure(total));
+	char* sp = (char*)slot.stage.p;
 	size_t off = 0;
 	if (!sameStructure)
 	{
@@ -362,8 +400,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
 	if (szMat) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	MR_CUDA(c, cudaEventRecord(c->stageFree, c->stream));
-	c->stageBusy = true;
+	c->h2dBytesLastFrame = szStat + szVB + szTB + szDyn + szMat + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -417,6 +454,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.tileCount = c->tileCount.as<int>();
 	fp.tileOffset = c->tileOffset.as<int>();
 	fp.pairs = c->pairs.as<int4>();
+	fp.warpPairCount = c->warpPairCount.as<int>();
+	fp.ovfPairs = c->ovfPairs.as<int4>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>();
 	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
@@ -426,10 +465,12 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 
 	mrk_launch_frame(fp, c->stream, ev);
 	MR_CUDA(c, cudaGetLastError());
-	MR_CUDA(c, cudaMemcpyAsync(c->hostCtr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-	MR_CUDA(c, cudaEventRecord(c->frameDone, c->stream));
-	c->stats.kernels_launched = 3 + (c->nTriInst > 0 ? 2 : 0);
-	c->frameChecked = false;
+	MR_CUDA(c, cudaMemcpyAsync(slot.hostCtr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+	MR_CUDA(c, cudaEventRecord(slot.done, c->stream));
+	slot.pending = true;
+	c->slotNewest = slotIndex;
+	c->slotNext = (slotIndex + 1) % mr_ctx::kSlots;
+	c->stats.kernels_launched = (c->nTriInst > 0) ? 4 : 3;
 	return MR_OK;
 }
 
@@ -488,12 +529,15 @@ mr_ctx* mr_create(int device, int* status)
 		Bind bind(device);
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
-		ok = ok && cudaEventCreateWithFlags(&c->stageFree, cudaEventDisableTiming) == cudaSuccess;
-		ok = ok && cudaEventCreateWithFlags(&c->frameDone, cudaEventDisableTiming) == cudaSuccess;
-		ok = ok && cudaMallocHost((void**)&c->hostCtr, sizeof(Counters)) == cudaSuccess;
+		for (int i = 0; i < mr_ctx::kSlots && ok; i++)
+		{
+			ok = ok && cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
+			ok = ok && cudaMallocHost((void**)&c->slots[i].hostCtr, sizeof(Counters)) == cudaSuccess;
+			if (ok)
+				memset(c->slots[i].hostCtr, 0, sizeof(Counters));
+		}
 		if (ok)
 		{
-			memset(c->hostCtr, 0, sizeof(Counters));
 			const int fma = mrk_selftest_no_fma(c->stream);
 			if (fma != 0)
 			{
@@ -523,16 +567,17 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount, &c->tileOffset,
-		               &c->pairs, &c->bins, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut };
+		               &c->pairs, &c->warpPairCount, &c->ovfPairs, &c->bins, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
-	c->stage.release();
-	if (c->hostCtr)
-		cudaFreeHost(c->hostCtr);
-	if (c->stageFree)
-		cudaEventDestroy(c->stageFree);
-	if (c->frameDone)
-		cudaEventDestroy(c->frameDone);
+	for (int i = 0; i < mr_ctx::kSlots; i++)
+	{
+		c->slots[i].stage.release();
+		if (c->slots[i].hostCtr)
+			cudaFreeHost(c->slots[i].hostCtr);
+		if (c->slots[i].done)
+			cudaEventDestroy(c->slots[i].done);
+	}
 	if (c->ownStream && c->stream)
 		cudaStreamDestroy(c->stream);
 	delete c;
@@ -578,7 +623,11 @@ int mr_set_size(mr_ctx* c, int w, int h)
 	Bind bind(c->device);
 	if (w == c->w && h == c->h)
 		return MR_OK;
-	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	{
+		int rc = finishFrame(c);
+		if (rc)
+			return rc;
+	}
 	c->w = w;
 	c->h = h;
 	c->tilesX = (w + MR_TILE - 1) / MR_TILE;
@@ -588,7 +637,6 @@ int mr_set_size(mr_ctx* c, int w, int h)
 	c->normals.release();
 	c->winner.release();
 	c->haveFrame = false;
-	c->frameChecked = true;
 	return ensureOutputs(c, false, false);
 }
 
@@ -717,7 +765,6 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 	c->haveScene = true;
 	c->sceneSerial++;
 	c->haveFrame = false;
-	c->frameChecked = true;
 	return MR_OK;
 }
 
@@ -732,13 +779,6 @@ int mr_render(mr_ctx* c, const mr_frame* f)
 	if (f->n_renderables < 0 || f->n_materials < 0 || (f->n_renderables > 0 && (!f->renderables || !f->materials)))
 		return setError(c, MR_E_INVALID, "bad frame descriptor");
 	Bind bind(c->device);
-	// the previous frame must have been verified (overflow re-run) before its tables are replaced
-	if (c->haveFrame && !c->frameChecked)
-	{
-		int rc = finishFrame(c);
-		if (rc)
-			return rc;
-	}
 	rememberFrame(c, f);
 	return launchFrame(c, f, 0);
 }
@@ -919,7 +959,20 @@ int mr_get_stats(mr_ctx* c, mr_stats* out)
 {
 	if (!c || !out)
 		return MR_E_INVALID;
+	c->stats.h2d_bytes = (int64_t)c->h2dBytesLastFrame;
 	*out = c->stats;
+	return MR_OK;
+}
+
+int mr_flush_l2(mr_ctx* c)
+{
+	if (!c)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	const size_t bytes = (size_t)256 << 20; // twice the 126 MB L2
+	MR_CUDA(c, c->flushBuf.ensure(bytes, true));
+	static int v = 0;
+	MR_CUDA(c, cudaMemsetAsync(c->flushBuf.p, (++v) & 0xff, bytes, c->stream));
 	return MR_OK;
 }
 
@@ -940,6 +993,8 @@ int mr_profile_frame(mr_ctx* c, const mr_frame* f, int repeats)
 	float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	for (int it = 0; it < repeats; it++)
 	{
+		if (c->debugFlags & 2)
+			mr_flush_l2(c);
 		rc = launchFrame(c, f, ev);
 		if (rc)
 			break;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	{
 		Counters* c = fp.ctr;
 		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->wideRecords = 0;
-		c->overflow = 0; c->ctasDone = 0;
+		c->overflow = 0; c->ctasDone = 0; c->ovfTotal = 0;
 	}
 	if (vi >= fp.nVertInst)
 		return;
@@ -241,7 +241,8 @@ __device__ __forceinline__ int clipTriangle(float z, Corner v0, Corner v1, Corne
 	return 2;
 }
 
-// Emits the (tile, slot, record) pairs of one record with plain per-thread atomics (slow paths).
+// Emits the (tile, slot, record) pairs of one record with plain per-thread atomics into the
+// overflow pair list (slow paths: clipper output, triangles spanning more than MR_SEG_PER_LANE tiles).
 __device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, const Setup& s)
 {
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
@@ -250,13 +251,13 @@ __device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, c
 	if (ty1 < ty0)
 		return;
 	const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-	const unsigned long long base = atomicAdd(&fp.ctr->pairTotal, (unsigned long long)n);
+	const unsigned long long base = atomicAdd(&fp.ctr->ovfTotal, (unsigned long long)n);
 	if (base + (unsigned long long)n > (unsigned long long)fp.pairCap)
 	{
 		fp.ctr->overflow = 1u;
 		return;
 	}
-	int4* dst = fp.pairs + base;
+	int4* dst = fp.ovfPairs + base;
 	for (int ty = ty0; ty <= ty1; ty++)
 		for (int tx = tx0; tx <= tx1; tx++)
 		{
@@ -298,14 +299,13 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 // ------------------------------------------------------------------------------------------
 // Kernel 2: near test, clip, setup, and (tile, triangle) pair emission.
 // One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
-// outputs at 2t and 2t+1): the index is the submission id. Its (tile, slot, record) pairs are
-// compacted into pairs[] with a warp prefix sum and one atomicAdd per warp; `slot`, the
-// triangle's rank inside its tile, comes from the tile counter with one atomic per distinct
-// tile per warp (__match_any_sync), because neighbouring triangles mostly share a tile.
-// The last CTA to finish turns the tile counters into offsets (exclusive scan).
+// outputs at 2t and 2t+1): the index is the submission id. Its (tile, slot, record) pairs go to
+// the warp's private segment of pairs[] (MR_SEG_PER_LANE entries per lane, compacted with a warp
+// prefix sum, no global allocation); `slot`, the triangle's rank inside its tile, comes from the
+// tile counter with one atomic per distinct tile per warp (__match_any_sync), because
+// neighbouring triangles mostly share a tile. Triangles covering more tiles use the overflow
+// list. The last CTA to finish turns the tile counters into offsets (exclusive scan).
 // ------------------------------------------------------------------------------------------
-#define MR_AGG_ROUNDS 4
-
 __device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 34 ints */)
 {
 	// exclusive scan of tileCount[0..n) into tileOffset[], by one 256-thread CTA
@@ -328,15 +328,22 @@ __device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 3
 	__syncthreads();
 	if (wid == 0)
 	{
-		int v = (lane < 8) ? sh[lane] : 0, s = v;
+		int v = (lane < 8) ? sh[lane] : 0, t = v;
 		for (int o = 1; o < 8; o <<= 1)
 		{
-			const int u = __shfl_up_sync(0xffffffffu, s, o);
+			const int u = __shfl_up_sync(0xffffffffu, t, o);
 			if (lane >= o)
-				s += u;
+				t += u;
 		}
 		if (lane < 8)
-			sh[lane] = s - v;
+			sh[lane] = t - v;
+		if (lane == 7)
+		{
+			// total number of (tile, triangle) pairs of the frame; must fit the bin array
+			fp.ctr->pairTotal = (unsigned long long)t;
+			if (t > fp.pairCap)
+				fp.ctr->overflow = 1u;
+		}
 	}
 	__syncthreads();
 	int run = sh[wid] + incl - sum;
@@ -349,12 +356,14 @@ __device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 3
 
 __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int sh[40];
+	__shared__ int sh[48];
 	const int t = blockIdx.x * 256 + threadIdx.x;
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	bool valid = false;
 	int nclip = 0, nrecSlow = 0;
 	int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+	Setup s;
+	s.x0 = s.x1 = s.y0 = s.y1 = 0;
 	if (t < fp.nTriInst)
 	{
 		const int r = findRenderable(fp, fp.triBlockR[blockIdx.x], t, true);
@@ -375,28 +384,26 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 				nrecSlow = setupClipped(fp, t, r, tri);
 			}
 		}
-		else
+		else if (setupTriangle(fp, a, b, c, s))
 		{
-			Setup s;
-			if (setupTriangle(fp, a, b, c, s))
+			tx0 = s.x0 >> MR_TILE_SHIFT;
+			tx1 = s.x1 >> MR_TILE_SHIFT;
+			ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
+			ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
+			if (ty1 >= ty0)
 			{
-				tx0 = s.x0 >> MR_TILE_SHIFT;
-				tx1 = s.x1 >> MR_TILE_SHIFT;
-				ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
-				ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
-				if (ty1 >= ty0)
-				{
-					valid = true;
-					storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, r, 0, tri);
-				}
+				valid = true;
+				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, r, 0, tri);
 			}
 		}
 	}
 	__syncwarp();
 
-	// ---- warp-level compaction of the pair ranges ----
+	// ---- pairs: warp-private segment for triangles covering <= MR_SEG_PER_LANE tiles ----
 	const int nx = tx1 - tx0 + 1;
-	const int npairs = valid ? nx * (ty1 - ty0 + 1) : 0;
+	const int ntiles = valid ? nx * (ty1 - ty0 + 1) : 0;
+	const bool big = ntiles > MR_SEG_PER_LANE;
+	const int npairs = big ? 0 : ntiles;
 	int incl = npairs;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
@@ -405,27 +412,13 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 		if (lane >= o)
 			incl += v;
 	}
-	const int total = __shfl_sync(0xffffffffu, incl, 31);
-	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
-	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
-	unsigned long long base = 0;
+	const int gw = blockIdx.x * 8 + wid; // global warp index == t / 32
 	if (lane == 31)
+		fp.warpPairCount[gw] = incl;
 	{
-		if (total > 0)
-		{
-			base = atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
-			if (base + (unsigned long long)total > (unsigned long long)fp.pairCap)
-				fp.ctr->overflow = 1u;
-		}
-		if (nrecWarp) atomicAdd(&fp.ctr->records, (unsigned long long)nrecWarp);
-		if (nclipWarp) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nclipWarp);
-	}
-	base = __shfl_sync(0xffffffffu, base, 31);
-	if (total > 0 && base + (unsigned long long)total <= (unsigned long long)fp.pairCap)
-	{
-		int4* dst = fp.pairs + base + (incl - npairs);
+		int4* dst = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE) + (incl - npairs);
 		const int id = 2 * t;
-		const int rounds = min(__reduce_max_sync(0xffffffffu, npairs), MR_AGG_ROUNDS);
+		const int rounds = __reduce_max_sync(0xffffffffu, npairs);
 		for (int k = 0; k < rounds; k++)
 		{
 			const bool on = k < npairs;
@@ -439,20 +432,35 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 			if (on)
 				dst[k] = make_int4(tile, slot, id, 0);
 		}
-		for (int k = MR_AGG_ROUNDS; k < npairs; k++) // large triangles: the remaining tiles one by one
-		{
-			const int tile = (ty0 + k / nx) * fp.tilesX + tx0 + k % nx;
-			dst[k] = make_int4(tile, atomicAdd(&fp.tileCount[tile], 1), id, 0);
-		}
 	}
+	if (big)
+		emitPairsSerial(fp, 2 * t, s);
 
+	// ---- statistics: one atomic per CTA ----
+	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
+	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
+	if (lane == 0)
+	{
+		sh[32 + wid] = nrecWarp;
+		sh[40 + wid] = nclipWarp;
+	}
 	// ---- last CTA done: tile counters -> tile offsets ----
-	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0)
-		sh[39] = (atomicAdd(&fp.ctr->ctasDone, 1u) == gridDim.x - 1) ? 1 : 0;
+	{
+		int nr = 0, nc = 0;
+		for (int i = 0; i < 8; i++)
+		{
+			nr += sh[32 + i];
+			nc += sh[40 + i];
+		}
+		if (nr) atomicAdd(&fp.ctr->records, (unsigned long long)nr);
+		if (nc) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nc);
+		__threadfence();
+		sh[31] = (atomicAdd(&fp.ctr->ctasDone, 1u) == gridDim.x - 1) ? 1 : 0;
+	}
 	__syncthreads();
-	if (sh[39])
+	if (sh[31])
 	{
 		__threadfence();
 		scanTiles(fp, sh);
@@ -466,15 +474,29 @@ __global__ void __launch_bounds__(256) k_scan_only(const __grid_constant__ Frame
 	scanTiles(fp, sh);
 }
 
+// Kernel 3: scatter the pairs into the per-tile bins (a warp per k_setup warp segment, then the
+// overflow list).
 __global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ FrameParams fp)
 {
-	const Counters* c = fp.ctr;
-	if (c->overflow)
+	if (__ldcg(&fp.ctr->overflow))
 		return;
-	const unsigned long long total = c->pairTotal;
-	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * 256)
+	const int lane = threadIdx.x & 31;
+	const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+	const int nWarps = (fp.nTriInst + 31) >> 5;
+	if (gw < nWarps)
 	{
-		const int4 p = fp.pairs[i];
+		const int n = fp.warpPairCount[gw];
+		const int4* src = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE);
+		for (int k = lane; k < n; k += 32)
+		{
+			const int4 p = src[k];
+			fp.bins[fp.tileOffset[p.x] + p.y] = p.z;
+		}
+	}
+	const unsigned long long ovf = fp.ctr->ovfTotal;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < ovf; i += (unsigned long long)gridDim.x * 256)
+	{
+		const int4 p = fp.ovfPairs[i];
 		fp.bins[fp.tileOffset[p.x] + p.y] = p.z;
 	}
 }
@@ -562,15 +584,56 @@ __device__ __noinline__ void shadeClippedPixel(const FrameParams& fp, int r, int
 	shadePixel(fp, mat, in, pix);
 }
 
+// Per-warp fragment queue of phase 1. Coverage is sparse (a small triangle covers one or two of
+// the ~12 pixel centres of its bbox), so the expensive per-fragment work (exact division, key,
+// atomic) is not done inside the divergent scan loop: covered pixels are appended to a queue in
+// shared memory and consumed 32 at a time by the whole warp.
+#define MR_FQ_CAP 64   // entries per warp (power of two)
+#define MR_FQ_SLOTS 16 // triangle slots per warp: 8 quads per iteration, two iterations in flight
+
+struct WarpQueue
+{
+	float e1[MR_FQ_CAP];
+	float e2[MR_FQ_CAP];
+	uint32_t info[MR_FQ_CAP]; // pixel index in tile | triangle slot << 8
+	float4 tri[MR_FQ_SLOTS];  // d0, d1, d2, record id + 1
+};
+
+__device__ __forceinline__ void consumeFragments(const FrameParams& fp, WarpQueue& wq, unsigned long long* keys, int head, int n, int lane)
+{
+	if (lane < n)
+	{
+		const int i = (head + lane) & (MR_FQ_CAP - 1);
+		const float e1 = wq.e1[i], e2 = wq.e2[i];
+		const uint32_t info = wq.info[i];
+		const float4 t = wq.tri[info >> 8];
+		const float k0 = 1.0f - e1 - e2;
+		float z;
+		if (fp.persp)
+			z = 1.0f / (k0 * t.x + e1 * t.y + e2 * t.z); // Renderer.cpp:255
+		else
+			z = k0 * t.x + e1 * t.y + e2 * t.z + 0.0f * 1.0f; // Renderer.cpp:261
+		if (z == z) // a NaN depth never passes `z < pixdepth`
+		{
+			const unsigned long long key = ((unsigned long long)zkey(z) << 32) | (unsigned long long)__float_as_uint(t.w);
+			unsigned long long* slot = &keys[info & 0xffu];
+			if (key < *(volatile unsigned long long*)slot)
+				atomicMin(slot, key);
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
+	__shared__ WarpQueue queues[8];
 	if (__ldcg(&fp.ctr->overflow))
 		return; // the host regrows the pair buffers and re-runs the frame
-	const int tx = blockIdx.x % fp.tilesX;
-	const int ty = fp.tileRow0 + blockIdx.x / fp.tilesX;
+	const int tx = blockIdx.x;
+	const int ty = fp.tileRow0 + blockIdx.y;
 	const int tile = ty * fp.tilesX + tx;
 	const int tid = threadIdx.x;
+	const int lane = tid & 31;
 	const int px = tx * MR_TILE + (tid & 15);
 	const int py = ty * MR_TILE + (tid >> 4);
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
@@ -607,50 +670,97 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	}
 	__syncthreads();
 
-	// ---- phase 1: coverage + depth, a quad of threads per triangle ----
-	const int* bin = fp.bins + fp.tileOffset[tile];
-	const int q = tid & 3;
-	for (int i = tid >> 2; i < count; i += 64)
+	// ---- phase 1: coverage + depth. A quad of lanes per triangle, rows interleaved; all loop
+	// bounds are made warp-uniform so that ballots and the queue stay convergent. ----
 	{
-		const int id = __ldg(&bin[i]);
-		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-		const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
-		const float p0x = q0.x, p0y = q0.y, p2x = q0.z, p2y = q0.w;
-		const float n1x = q1.x, n1y = q1.y, n2x = q1.z, n2y = q1.w;
-		const float d0 = q2.x, d1 = q2.y, d2 = q2.z;
-		const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
-		const int x0 = xspan & 0xffffu, x1 = min((int)(xspan >> 16), tileX0 + MR_TILE - 1);
-		const int y0 = max((int)(yspan & 0xffffu), tileY0), y1 = min((int)(yspan >> 16), tileY0 + MR_TILE - 1);
-		const int xs = max(x0, tileX0); // first column tested in this tile
-		const float ptx = (float)x0 + 0.5f;
-		const unsigned long long low = (unsigned long long)(uint32_t)(id + 1);
-		for (int y = y0 + q; y <= y1; y += 4)
+		WarpQueue& wq = queues[tid >> 5];
+		const int* bin = fp.bins + fp.tileOffset[tile];
+		const int q = lane & 3;
+		const int quad = lane >> 2;
+		int qhead = 0, qcount = 0; // warp-uniform
+		int parity = 0;
+		for (int base = (tid >> 5) * 8; base < count; base += 64, parity ^= 1)
 		{
-			const float fy = (float)y + 0.5f;
-			float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
-			float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
-			for (int x = x0; x < xs; x++) // chain prefix left of the tile
+			const int i = base + quad;
+			const bool have = i < count;
+			float p0x = 0, p0y = 0, p2x = 0, p2y = 0, n1x = 0, n1y = 0, n2x = 0, n2y = 0;
+			int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+			const int slot = parity * 8 + quad;
+			if (have)
 			{
-				e1 += n1x;
-				e2 += n2x;
+				const int id = __ldg(&bin[i]);
+				const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
+				const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
+				p0x = q0.x; p0y = q0.y; p2x = q0.z; p2y = q0.w;
+				n1x = q1.x; n1y = q1.y; n2x = q1.z; n2y = q1.w;
+				const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
+				x0 = xspan & 0xffffu;
+				x1 = min((int)(xspan >> 16), tileX0 + MR_TILE - 1);
+				y0 = max((int)(yspan & 0xffffu), tileY0);
+				y1 = min((int)(yspan >> 16), tileY0 + MR_TILE - 1);
+				if (q == 0)
+					wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 			}
-			unsigned long long* row = &keys[(y - tileY0) * MR_TILE - tileX0];
-			for (int x = xs; x <= x1; x++, e1 += n1x, e2 += n2x)
+			const int xs = max(x0, tileX0);       // first column tested in this tile
+			const int ncols = have ? max(x1 - xs + 1, 0) : 0;
+			const int myRows = have ? max((y1 - y0 - q + 4) >> 2, 0) : 0; // rows y0+q, y0+q+4, ...
+			const float ptx = (float)x0 + 0.5f;
+			const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
+			const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
+			__syncwarp();
+			for (int rr = 0; rr < maxRows; rr++)
 			{
-				const float k0 = 1.0f - e1 - e2;
-				if (e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)
-					continue;
-				float z;
-				if (fp.persp)
-					z = 1.0f / (k0 * d0 + e1 * d1 + e2 * d2);
-				else
-					z = k0 * d0 + e1 * d1 + e2 * d2 + 0.0f * 1.0f;
-				if (!(z == z))
-					continue;
-				const unsigned long long key = ((unsigned long long)zkey(z) << 32) | low;
-				if (key < *(volatile unsigned long long*)&row[x])
-					atomicMin(&row[x], key);
+				const bool rowOn = rr < myRows;
+				const int y = y0 + q + 4 * rr;
+				const float fy = (float)y + 0.5f;
+				float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
+				float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
+				if (rowOn)
+					for (int x = x0; x < xs; x++) // chain prefix left of the tile
+					{
+						e1 += n1x;
+						e2 += n2x;
+					}
+				const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)slot << 8);
+				for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
+				{
+					const float k0 = 1.0f - e1 - e2;
+					const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
+					const unsigned m = __ballot_sync(0xffffffffu, inside);
+					if (m == 0u)
+						continue;
+					if (inside)
+					{
+						const int w = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & (MR_FQ_CAP - 1);
+						wq.e1[w] = e1;
+						wq.e2[w] = e2;
+						wq.info[w] = rowInfo + (uint32_t)cc;
+					}
+					qcount += __popc(m);
+					if (qcount >= 32)
+					{
+						__syncwarp();
+						consumeFragments(fp, wq, keys, qhead, 32, lane);
+						qhead = (qhead + 32) & (MR_FQ_CAP - 1);
+						qcount -= 32;
+					}
+				}
 			}
+			// Triangle slots of this parity are overwritten two iterations from now; fragments
+			// still queued then must not refer to them, so drain before reusing a parity.
+			if (parity == 1 && qcount > 0)
+			{
+				__syncwarp();
+				consumeFragments(fp, wq, keys, qhead, qcount, lane);
+				qhead = (qhead + qcount) & (MR_FQ_CAP - 1);
+				qcount = 0;
+			}
+			__syncwarp();
+		}
+		if (qcount > 0)
+		{
+			__syncwarp();
+			consumeFragments(fp, wq, keys, qhead, qcount, lane);
 		}
 	}
 	__syncthreads();
@@ -834,10 +944,10 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);
 	if (fp.nTriInst > 0)
-		k_scatter<<<148 * 8, 256, 0, stream>>>(fp);
+		k_scatter<<<(fp.nTriInst + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[4], stream);
 	if (fp.tileRows > 0)
-		k_raster<<<fp.tilesX * fp.tileRows, 256, 0, stream>>>(fp);
+		k_raster<<<dim3(fp.tilesX, fp.tileRows), 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[5], stream);
 }
 

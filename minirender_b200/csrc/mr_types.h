@@ -24,6 +24,7 @@
 #define MR_TILE 16
 #define MR_TILE_SHIFT 4
 #define MR_TILE_PIXELS 256
+#define MR_SEG_PER_LANE 4 // pair slots per k_setup lane in its warp's private segment
 
 struct MeshDev
 {
@@ -81,6 +82,7 @@ struct Counters
 	unsigned long long clippedIn;
 	unsigned long long pairTotal;   // (tile, triangle) pairs produced (may exceed capacity)
 	unsigned long long wideRecords;
+	unsigned long long ovfTotal;    // entries in the overflow pair list
 	unsigned int overflow;          // pairs did not fit: the frame must be re-run with more room
 	unsigned int ctasDone;          // k_setup CTAs finished (the last one scans the tile counters)
 };
@@ -119,7 +121,9 @@ struct FrameParams
 	Rec* recs;
 	int* tileCount;
 	int* tileOffset;
-	int4* pairs;
+	int4* pairs;         // warp segments: 32*MR_SEG_PER_LANE entries per k_setup warp
+	int* warpPairCount;  // used entries per segment
+	int4* ovfPairs;      // overflow list (pairCap entries)
 	int* bins;
 	Counters* ctr;
 

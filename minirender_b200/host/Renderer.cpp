@@ -130,9 +130,11 @@ struct Renderer::Impl
 	Array2<Vec3> image, normals, points;
 	Array2<float> depth;
 	bool imageValid, depthValid, normalsValid;
+	void* pinnedImage; // page-locked (mr_host_register) so that D2H runs at full PCIe rate
+	void* pinnedDepth;
 
 	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), upStamp(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false),
-	         imageValid(false), depthValid(false), normalsValid(false)
+	         imageValid(false), depthValid(false), normalsValid(false), pinnedImage(0), pinnedDepth(0)
 	{
 		memset(&sceneDesc, 0, sizeof(sceneDesc));
 		memset(&frame, 0, sizeof(frame));
@@ -169,8 +171,17 @@ Renderer::Renderer() : _impl(new Impl), _w(800), _h(600)
 	_geometryStamp = 0;
 }
 
+static void unpin(void*& p)
+{
+	if (p)
+		mr_host_unregister(p);
+	p = 0;
+}
+
 Renderer::~Renderer()
 {
+	unpin(_impl->pinnedImage);
+	unpin(_impl->pinnedDepth);
 	if (_impl->ctx)
 		mr_destroy(_impl->ctx);
 	delete _impl;
@@ -513,7 +524,12 @@ Array2<Vec3> Renderer::getImage() const
 	if (!s.imageValid)
 	{
 		if (s.image.rows() != _h || s.image.cols() != _w)
+		{
+			unpin(s.pinnedImage);
 			s.image = Array2<Vec3>(_h, _w);
+			if (mr_host_register(s.image.data().ptr(), sizeof(Vec3) * (size_t)_w * _h) == 0)
+				s.pinnedImage = s.image.data().ptr();
+		}
 		int rc = mr_read_image(s.ctx, (float*)s.image.data().ptr());
 		if (rc)
 			fail(s.ctx, "mr_read_image", rc);
@@ -530,7 +546,12 @@ Array2<float> Renderer::getDepth() const
 	if (!s.depthValid)
 	{
 		if (s.depth.rows() != _h || s.depth.cols() != _w)
+		{
+			unpin(s.pinnedDepth);
 			s.depth = Array2<float>(_h, _w);
+			if (mr_host_register(s.depth.data().ptr(), sizeof(float) * (size_t)_w * _h) == 0)
+				s.pinnedDepth = s.depth.data().ptr();
+		}
 		int rc = mr_read_depth(s.ctx, s.depth.data().ptr());
 		if (rc)
 			fail(s.ctx, "mr_read_depth", rc);

@@ -495,6 +495,22 @@ int mrx_renderer_get_rgb8(void* r, uint8_t* out)
 	MRX_CATCH(-1)
 }
 
+const float* mrx_renderer_image_ptr(void* r)
+{
+	MRX_TRY
+	Array2<Vec3> img = ((Renderer*)r)->getImage();
+	return (const float*)&img(0, 0);
+	MRX_CATCH(0)
+}
+
+const float* mrx_renderer_depth_ptr(void* r)
+{
+	MRX_TRY
+	Array2<float> d = ((Renderer*)r)->getDepth();
+	return &d(0, 0);
+	MRX_CATCH(0)
+}
+
 int mrx_renderer_synchronize(void* r)
 {
 	MRX_TRY

@@ -93,6 +93,9 @@ MRX_API const void* mrx_renderer_scene_desc(void* r);    /* const mr_scene_desc*
 MRX_API const void* mrx_renderer_frame_desc(void* r);    /* const mr_frame* */
 MRX_API void* mrx_renderer_context(void* r);             /* mr_ctx* (creates it) */
 MRX_API int mrx_renderer_get_rgb8(void* r, uint8_t* out);
+/* getImage()/getDepth() without the extra copy: pointer to the Renderer's own host mirror (valid until the next call) */
+MRX_API const float* mrx_renderer_image_ptr(void* r);
+MRX_API const float* mrx_renderer_depth_ptr(void* r);
 MRX_API int mrx_renderer_synchronize(void* r);
 MRX_API int mrx_save_ppm(const float* image, int w, int h, const char* filename);
 MRX_API int mrx_load_ppm(const char* filename, float* out, int* rows, int* cols); /* out may be NULL to query the size */

@@ -1,5 +1,5 @@
 import sys, time
-sys.path.insert(0, 'oracle'); sys.path.insert(0, 'tests')
+import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R, R+'/oracle', R+'/tests']
 import numpy as np
 import minirender_b200 as m
 from minirender_b200 import scenes, cabi
