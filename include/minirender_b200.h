@@ -190,6 +190,11 @@ MR_API int mr_write_rows(mr_ctx* ctx, const void* d_image_rows, const void* d_de
 /* Let tile stores of rows [row_begin,row_end) land directly in a peer GPU's framebuffer
  * (pointers obtained from that peer's mr_device_buffers through CUDA IPC / symmetric memory). */
 MR_API int mr_set_remote_target(mr_ctx* ctx, void* d_peer_image, void* d_peer_depth);
+/* CUDA IPC plumbing for that: export this context's image+depth buffers as two 64-byte
+ * cudaIpcMemHandle_t (128 bytes), open a peer's handles on this context's device, close them. */
+MR_API int mr_ipc_export(mr_ctx* ctx, void* handles128);
+MR_API int mr_ipc_open(mr_ctx* ctx, const void* handles128, void** d_image, void** d_depth);
+MR_API int mr_ipc_close(mr_ctx* ctx, void* d_image, void* d_depth);
 
 /* Page-lock caller memory so the mr_read_* copies run at full PCIe rate (optional). */
 MR_API int mr_host_register(void* host, size_t bytes);

@@ -86,6 +86,9 @@ PROTOTYPES = {
     "mr_device_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mr_write_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mr_set_remote_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mr_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mr_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mr_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mr_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mr_host_unregister": (C.c_int, [C.c_void_p]),
     "mr_set_debug": (C.c_int, [C.c_void_p, C.c_int]),

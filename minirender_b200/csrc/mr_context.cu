@@ -955,6 +955,42 @@ int mr_set_remote_target(mr_ctx* c, void* img, void* dep)
 	return MR_OK;
 }
 
+/* ---- CUDA IPC: lets another rank's tile rasterizer store straight into this framebuffer ---- */
+int mr_ipc_export(mr_ctx* c, void* handles128)
+{
+	if (!c || !handles128 || !c->image.p || !c->depth.p)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	cudaIpcMemHandle_t h[2];
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[0], c->image.p));
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[1], c->depth.p));
+	memcpy(handles128, h, sizeof(h));
+	return MR_OK;
+}
+
+int mr_ipc_open(mr_ctx* c, const void* handles128, void** image, void** depth)
+{
+	if (!c || !handles128 || !image || !depth)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	cudaIpcMemHandle_t h[2];
+	memcpy(h, handles128, sizeof(h));
+	MR_CUDA(c, cudaIpcOpenMemHandle(image, h[0], cudaIpcMemLazyEnablePeerAccess));
+	MR_CUDA(c, cudaIpcOpenMemHandle(depth, h[1], cudaIpcMemLazyEnablePeerAccess));
+	return MR_OK;
+}
+
+int mr_ipc_close(mr_ctx* c, void* image, void* depth)
+{
+	if (!c)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (image) MR_CUDA(c, cudaIpcCloseMemHandle(image));
+	if (depth) MR_CUDA(c, cudaIpcCloseMemHandle(depth));
+	return MR_OK;
+}
+
 int mr_get_stats(mr_ctx* c, mr_stats* out)
 {
 	if (!c || !out)

@@ -1,0 +1,98 @@
+"""How the render path shards across the GPUs of one box. Pure host logic plus
+torch.distributed plumbing; no pixel is computed here.
+
+  view batch (BASELINE.json configs[4])  every rank holds a replica of the scene and renders its own
+      views; nothing is exchanged on the data path.
+  strips (configs[2])  one frame, rank r renders image rows strip_rows(h, r, N); rows of the edge
+      chain are independent and winners are order-independent given submission ids, so the union
+      of the strips is byte-identical to the single-GPU frame. Finished strips reach rank 0 either
+      by NCCL send/recv (gather_strips) or, fused with the tile store, directly through peer memory
+      over NVLink (open_peer_target + Renderer row range: the rasterizer's stores land in rank 0's
+      framebuffer, no separate gather step).
+"""
+import ctypes as C
+
+import numpy as np
+
+TILE = 16
+
+
+def views_for_rank(n_views, rank, world):
+    """Interleaved assignment: rank r renders views r, r+N, r+2N, ..."""
+    return list(range(rank, n_views, world))
+
+
+def strip_rows(height, rank, world, tile=TILE):
+    """Contiguous horizontal strips of whole tile rows, as even as possible. Returns (begin, end);
+    begin == end for ranks left without rows (more ranks than tile rows)."""
+    tile_rows = (height + tile - 1) // tile
+    base, extra = divmod(tile_rows, world)
+    first = rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    return min(first * tile, height), min((first + count) * tile, height)
+
+
+def all_strips(height, world, tile=TILE):
+    return [strip_rows(height, r, world, tile) for r in range(world)]
+
+
+class DeviceArray:
+    """Wraps a raw device pointer for torch (``torch.as_tensor(DeviceArray(...), device='cuda')``)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+def device_tensors(ctx_lib, ctx, h, w, device):
+    """The context's float image (h,w,3) and depth (h,w) buffers as torch tensors (zero copy)."""
+    import torch
+    a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert ctx_lib.mr_device_buffers(ctx, C.byref(a), C.byref(b), C.byref(c)) == 0
+    img = torch.as_tensor(DeviceArray(a.value, (h, w, 3)), device=device)
+    dep = torch.as_tensor(DeviceArray(b.value, (h, w)), device=device)
+    return img, dep
+
+
+def gather_strips(image, depth, height, rank, world, dist, dst=0):
+    """Moves every rank's finished rows into rank `dst`'s framebuffer with point-to-point
+    send/recv (NCCL on GPUs, gloo on CPU tensors). `image` (h,w,3) and `depth` (h,w) are each rank's
+    full-size buffers; only the rank's own rows are valid on input. Works on torch tensors."""
+    strips = all_strips(height, world)
+    ops = []
+    if rank == dst:
+        for r, (rb, re) in enumerate(strips):
+            if r == dst or re <= rb:
+                continue
+            ops.append(dist.P2POp(dist.irecv, image[rb:re], r))
+            ops.append(dist.P2POp(dist.irecv, depth[rb:re], r))
+    else:
+        rb, re = strips[rank]
+        if re > rb:
+            ops.append(dist.P2POp(dist.isend, image[rb:re], dst))
+            ops.append(dist.P2POp(dist.isend, depth[rb:re], dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def open_peer_target(ctx_lib, ctx, rank, world, dist, dst=0):
+    """Makes this rank's tile stores land in rank `dst`'s framebuffer (peer memory over NVLink).
+    Returns a closer callable. Needs one process per GPU on one node."""
+    handles = (C.c_ubyte * 128)()
+    if rank == dst:
+        assert ctx_lib.mr_ipc_export(ctx, handles) == 0
+    payload = [bytes(handles) if rank == dst else None]
+    dist.broadcast_object_list(payload, src=dst)
+    if rank == dst:
+        return lambda: None
+    buf = (C.c_ubyte * 128).from_buffer_copy(payload[0])
+    pi, pd = C.c_void_p(), C.c_void_p()
+    rc = ctx_lib.mr_ipc_open(ctx, buf, C.byref(pi), C.byref(pd))
+    if rc != 0:
+        raise RuntimeError("mr_ipc_open failed: %s" % ctx_lib.mr_last_error(ctx).decode())
+    assert ctx_lib.mr_set_remote_target(ctx, pi, pd) == 0
+
+    def close():
+        ctx_lib.mr_set_remote_target(ctx, None, None)
+        ctx_lib.mr_ipc_close(ctx, pi, pd)
+    return close

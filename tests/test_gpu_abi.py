@@ -1,0 +1,158 @@
+"""GPU: the C ABI called directly (no C++ facade) on the golden fixtures, plus the ABI's other
+entry points: strips, range image, 8-bit image, immediate mode, error paths, queue regrowth."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import minirender_b200 as m
+from minirender_b200 import cabi, scenes, sharding
+import golden_io
+import pyoracle
+from parity import assert_parity, bits, compare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cabi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_golden_through_c_abi(ctx, name):
+    scene, frame, want = golden_io.load(name)
+    ctx.set_size(want["width"], want["height"])
+    ctx.upload_scene(scene.ptr)
+    ctx.render(frame.ptr)
+    rep = compare(ctx.read_image(), ctx.read_depth(), want["image"], want["depth"])
+    print(name, rep)
+    assert_parity(rep, name)
+    if "normals" in want:
+        assert np.abs(ctx.read_normals() - want["normals"]).max() <= 1e-5
+
+
+def test_strips_union_is_byte_identical(be):
+    setup = scenes.SMALL_SCENES["cloud_small"](be)
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    full_i, full_d = r.get_image(), r.get_depth()
+    for world in (2, 3, 5):
+        r2 = setup.apply(m.Renderer(be))
+        r2.set_background((0.5, 0.25, 0.125))  # rows outside a strip must stay untouched
+        r2.clear()
+        r2.set_background(setup.background)
+        for rank in range(world):
+            rb, re = sharding.strip_rows(setup.height, rank, world)
+            r2.set_row_range(rb, re)
+            r2.render()
+        assert (bits(r2.get_depth()) == bits(full_d)).all(), world
+        assert (bits(r2.get_image()) == bits(full_i)).all(), world
+    # an unaligned row range clips inside tiles
+    r3 = setup.apply(m.Renderer(be))
+    r3.clear()
+    r3.set_row_range(37, 101)
+    r3.render()
+    d = r3.get_depth()
+    assert (bits(d[37:101]) == bits(full_d[37:101])).all()
+    assert (d[:37] == np.float32(1e11)).all() and (d[101:] == np.float32(1e11)).all()
+
+
+def test_range_rgb8_and_normals(be):
+    setup = scenes.primitives_scene(be, point_light=False, save_normals=True)
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    depth, image = r.get_depth(), r.get_image()
+    assert (bits(r.get_range()) == bits(pyoracle.range_image(setup.projection, depth))).all()
+    assert (r.get_rgb8() == pyoracle.quantize_rgb8(image)).all()
+    r.prepare()
+    want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), setup.width, setup.height, normals=True)
+    n = r.get_normals()
+    assert (bits(n[depth >= 1e10]) == bits(want["normals"][depth >= 1e10])).all()  # cleared to (0,0,1)
+    assert np.abs(n - want["normals"]).max() <= 1e-5
+
+
+def test_lighting_off_and_texturing_off(be):
+    for kw in (dict(lighting=False), dict(texturing=False)):
+        setup = scenes.textured_scene(be)
+        for k, v in kw.items():
+            setattr(setup, k, v)
+        r = setup.apply(m.Renderer(be))
+        r.render()
+        r.prepare()
+        want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), setup.width, setup.height)
+        assert_parity(compare(r.get_image(), r.get_depth(), want["image"], want["depth"]), str(kw))
+
+
+def test_immediate_mode_paint_mesh_keeps_buffers(be, ref):
+    """clear(); paintMesh(a); paintMesh(b) accumulates with the depth test (reference Renderer.h:58)."""
+    out = []
+    for b in (be, ref):
+        setup = scenes.primitives_scene(b, point_light=False)
+        r = setup.apply(m.Renderer(b))
+        r.render()  # snapshots light / near plane like the reference's members
+        r.clear()
+        sc = m.Scene(b)
+        n1 = sc.add_sphere(40.0, 12, 20)
+        n2 = sc.add_cube(50.0)
+        r.paint_mesh(sc, n1, b.translate(-20, 0, 0))
+        r.paint_mesh(sc, n2, b.mul(b.translate(25, 0, 10), b.rotate_vec(0.3, 0.4, 0.1)))
+        out.append((r.get_image(), r.get_depth()))
+    assert_parity(compare(out[0][0], out[0][1], out[1][0], out[1][1]), "immediate mode")
+    assert (out[0][1] < 1e10).sum() > 1000
+
+
+def test_empty_scene_and_clear(be):
+    r = m.Renderer(be, 100, 60)
+    r.set_background((0.25, 0.5, 0.75))
+    r.clear()
+    assert (r.get_depth() == np.float32(1e11)).all()
+    assert (r.get_image() == np.array([0.25, 0.5, 0.75], np.float32)).all()
+    sc = m.Scene(be)
+    r.set_scene(sc)
+    r.render()
+    assert (r.get_depth() == np.float32(1e11)).all()
+
+
+def test_invalid_descriptors_are_rejected(ctx):
+    pos = np.zeros((3, 3), np.float32)
+    bad = cabi.SceneArrays([dict(positions=pos, normals=pos, idx_pos=np.array([[0, 1, 3]], np.int32))])
+    ctx.set_size(64, 64)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ctx.upload_scene(bad.ptr)
+    ok = cabi.SceneArrays([dict(positions=pos, normals=pos, idx_pos=np.array([[0, 1, 2]], np.int32))])
+    ctx.upload_scene(ok.ptr)
+    eye = np.eye(4, dtype=np.float32)
+    mat = [dict(diffuse=(1, 1, 1), specular=(0, 0, 0), emissive=(0, 0, 0), shininess=0.0)]
+    fr = cabi.FrameArrays(eye, [dict(modelview=eye, normalmat=eye, mesh=5, material=0)], mat, (0, 0, 1))
+    with pytest.raises(RuntimeError, match="mesh index"):
+        ctx.render(fr.ptr)
+    lib = cabi.load()
+    assert lib.mr_set_size(ctx.ctx, 0, 10) == cabi.MR_E_INVALID
+    assert lib.mr_render(ctx.ctx, None) == cabi.MR_E_INVALID
+
+
+def test_pair_queue_regrows(be):
+    """Many screen-filling triangles overflow the initial pair capacity; the frame is re-run."""
+    setup = scenes.big_triangles_scene(be, width=1920, height=1080, count=400, spread=4000.0, seed=9)
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    depth, image = r.get_depth(), r.get_image()
+    st = cabi.Stats()
+    cabi.load().mr_get_stats(r.context_ptr(), C.byref(st))
+    assert st.regrows >= 1 and st.bin_entries > 2 * st.triangles_in + 65536
+    r.prepare()
+    want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), setup.width, setup.height)
+    assert_parity(compare(image, depth, want["image"], want["depth"]), "regrow")
+
+
+def test_render_is_asynchronous_and_repeatable(be):
+    setup = scenes.SMALL_SCENES["bench_small"](be)
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    first = r.get_depth().copy()
+    for _ in range(12):  # more frames than slots in flight, no read in between
+        r.render()
+    assert (bits(r.get_depth()) == bits(first)).all()

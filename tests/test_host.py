@@ -1,0 +1,139 @@
+"""CPU: host-side product code (drop-in C++ API, C-ABI library surface) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import minirender_b200 as m
+from minirender_b200 import api, cabi, scenes, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "minirender_b200.h")).read()
+    return sorted(set(re.findall(r"MR_API\s+[\w\s\*]+?\b(mr_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(cabi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in include/minirender_b200.h but not exported: %s" % missing
+    # and the ctypes mirror covers the same set
+    assert sorted(cabi.PROTOTYPES) == names
+
+
+def test_abi_version_and_no_cpu_fallback():
+    lib = cabi.load()
+    assert lib.mr_abi_version() == 1
+    if lib.mr_device_count() == 0:
+        st = C.c_int(0)
+        assert not lib.mr_create(0, C.byref(st))
+        assert st.value == cabi.MR_E_NO_DEVICE
+        # the drop-in Renderer refuses to render instead of falling back to a CPU path
+        be = m.Backend()
+        setup = scenes.SMALL_SCENES["primitives"](be)
+        r = setup.apply(m.Renderer(be))
+        with pytest.raises(RuntimeError, match="no CPU rasterizer|mr_create"):
+            r.render()
+
+
+def test_ctypes_struct_sizes_match_header(tmp_path):
+    """sizeof of every descriptor as the C compiler sees include/minirender_b200.h."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "minirender_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(mr_mesh_desc),sizeof(mr_texture_desc),sizeof(mr_scene_desc),sizeof(mr_material),sizeof(mr_renderable),'
+                   'sizeof(mr_frame),sizeof(mr_stats));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    mirror = [cabi.MeshDesc, cabi.TextureDesc, cabi.SceneDesc, cabi.Material, cabi.Renderable, cabi.Frame, cabi.Stats]
+    assert sizes == [C.sizeof(t) for t in mirror]
+
+
+@pytest.mark.parametrize("kind,args", [(api.PRIM_CUBE, (7.5,)), (api.PRIM_SPHERE, (3.0, 0.0, 9, 14)),
+                                       (api.PRIM_SPHERE, (100.0, 0.0, 2, 3)), (api.PRIM_CYLINDER, (2.0, 5.0, 11, 3, 1)),
+                                       (api.PRIM_CYLINDER, (2.0, 5.0, 5, 1, 0))])
+def test_primitives_identical_to_reference(be, ref, kind, args):
+    out = []
+    for b in (be, ref):
+        sc = api.Scene(b)
+        a = list(args) + [0.0, 0, 0, 1][len(args) - 1:] if len(args) < 5 else list(args)
+        node = sc.add_primitive(kind, a[0], a[1] if len(a) > 1 else 0.0, int(a[2]) if len(a) > 2 else 0,
+                                int(a[3]) if len(a) > 3 else 0, bool(a[4]) if len(a) > 4 else True)
+        out.append(sc.mesh_arrays(node))
+    for k in out[0]:
+        assert out[0][k].shape == out[1][k].shape, k
+        assert (out[0][k].view(np.uint8) == out[1][k].view(np.uint8)).all(), k
+
+
+def test_projection_builders_and_matrices_identical_to_reference(be, ref):
+    for kind, args in [(api.PROJ_ORTHO6, (-40, 40, -30, 30, 50, 120)), (api.PROJ_PERSPECTIVE6, (-1, 2, -1.5, 1, 0.5, 90)),
+                       (api.PROJ_FRUSTUM, (0.61, 1.7777, 10, 7000)), (api.PROJ_FRUSTUM_H, (0.9, 1.3, 1, 100)),
+                       (api.PROJ_ORTHO4, (35.0, 1.5, 1, 200))]:
+        assert (be.projection(kind, *args).view(np.uint32) == ref.projection(kind, *args).view(np.uint32)).all()
+    K = np.array([[800, 0, 320, 0], [0, 810, 240, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    assert (be.projection_cv(K, 640, 480, 0.1, 50).view(np.uint32) == ref.projection_cv(K, 640, 480, 0.1, 50).view(np.uint32)).all()
+    a = be.mul(be.translate(1, 2, 3), be.rotate_vec(0.3, -0.2, 0.9), be.scale(1.5, 0.5, 2))
+    b = ref.mul(ref.translate(1, 2, 3), ref.rotate_vec(0.3, -0.2, 0.9), ref.scale(1.5, 0.5, 2))
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    assert (be.inverse(a).view(np.uint32) == ref.inverse(b).view(np.uint32)).all()
+
+
+def test_scene_bbox_and_triangle_count_match_reference(be, ref):
+    for fn in (scenes.SMALL_SCENES["cloud_small"], scenes.SMALL_SCENES["ties"]):
+        sa, sb = fn(be), fn(ref)
+        assert sa.scene.triangles() == sb.scene.triangles()
+        for x, y in zip(sa.scene.bbox(), sb.scene.bbox()):
+            assert (x.view(np.uint32) == y.view(np.uint32)).all()
+
+
+def test_prepare_flattens_in_submission_order(be):
+    setup = scenes.ties_scene(be)
+    r = setup.apply(m.Renderer(be))
+    r.prepare()
+    f = cabi.frame_to_dict(r.frame_desc_ptr())
+    meshes, _ = cabi.scene_to_lists(r.scene_desc_ptr())
+    # 3 spheres + 2 cubes + (instanced sphere, instanced cube) under a group = 7 renderables, 5 distinct meshes
+    assert len(f["renderables"]) == 7 and len(meshes) == 5
+    assert [x["mesh"] for x in f["renderables"]] == [0, 1, 2, 3, 4, 0, 3]
+    assert f["znear"] == pytest.approx(-10.0, rel=1e-5) and f["ambient"] == pytest.approx(0.2)
+
+
+def test_ppm_roundtrip(be, tmp_path):
+    rng = np.random.default_rng(0)
+    img = rng.uniform(-0.2, 1.2, (13, 17, 3)).astype(np.float32)
+    path = str(tmp_path / "a.ppm").encode()
+    assert be.lib.mrx_save_ppm(img.ctypes.data, 17, 13, path) == 0
+    raw = open(path, "rb").read()
+    assert raw.startswith(b"P6\n17 13\n255\n") and len(raw) == len(b"P6\n17 13\n255\n") + 13 * 17 * 3
+    rows, cols = C.c_int(), C.c_int()
+    back = np.empty((13, 17, 3), np.float32)
+    assert be.lib.mrx_load_ppm(path, back.ctypes.data, C.byref(rows), C.byref(cols)) == 0
+    assert (rows.value, cols.value) == (13, 17)
+    q = be.quantize_rgb8(img)  # truncation of clamp(v*255, 0, 255)
+    assert (q == np.frombuffer(raw[-13 * 17 * 3:], np.uint8).reshape(13, 17, 3)).all()
+    inv = np.float32(1) / np.float32(255)  # asl Vec3 / float multiplies by the reciprocal
+    assert (back.view(np.uint32) == (q.astype(np.float32) * inv).view(np.uint32)).all()
+    # comments in the header are skipped
+    with open(path, "wb") as f:
+        f.write(b"P6\n# a comment\n2 1\n255\n" + bytes([0, 128, 255, 1, 2, 3]))
+    assert be.lib.mrx_load_ppm(path, None, C.byref(rows), C.byref(cols)) == 0 and (rows.value, cols.value) == (1, 2)
+
+
+def test_strip_partition_covers_image_once():
+    for h in (1080, 2160, 17, 16, 1, 100):
+        for world in (1, 2, 3, 4, 8):
+            strips = sharding.all_strips(h, world)
+            assert strips[0][0] == 0 and max(e for _, e in strips) == h
+            rows = np.zeros(h, int)
+            for b, e in strips:
+                assert e == b or (b % 16 == 0 and (e % 16 == 0 or e == h))
+                rows[b:e] += 1
+            assert (rows == 1).all()
+    assert sharding.views_for_rank(10, 1, 4) == [1, 5, 9]
