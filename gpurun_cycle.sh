@@ -1,3 +1,8 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py --steps 20 --warmup 3 2>&1 | tail -3
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('fps', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'stages', {k: round(v*1000,1) for k,v in d['stage_ms'].items()}, 'stats', d['stats'], 'clk', d['clocks'])
+    else: print(l.rstrip())
+"

@@ -140,10 +140,10 @@ typedef struct mr_frame
 typedef struct mr_stats
 {
 	int64_t triangles_in;      /* triangles submitted */
-	int64_t records;           /* set-up triangles that survived near test, reject and cull */
+	int64_t records;           /* set-up triangles that survived near test, reject, cull and the zero-coverage test */
 	int64_t clipped_in;        /* input triangles that crossed the near plane */
 	int64_t bin_entries;       /* (tile, triangle) pairs */
-	int64_t wide_records;      /* triangles routed through the chain-checkpoint path */
+	int64_t zero_coverage;     /* set-up triangles dropped because they cover no pixel centre */
 	int32_t tiles_x, tiles_y;
 	int32_t regrows;           /* times a queue had to be regrown and the frame re-run */
 	int32_t kernels_launched;  /* kernel launches issued for the frame */

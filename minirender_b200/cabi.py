@@ -56,7 +56,7 @@ class Frame(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("triangles_in", C.c_int64), ("records", C.c_int64), ("clipped_in", C.c_int64),
-                ("bin_entries", C.c_int64), ("wide_records", C.c_int64),
+                ("bin_entries", C.c_int64), ("zero_coverage", C.c_int64),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("regrows", C.c_int32),
                 ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8), ("h2d_bytes", C.c_int64)]
 

@@ -109,7 +109,7 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, tileCount, tileOffset, pairs, warpPairCount, ovfPairs, bins, ctr;
+	DevBuf pv, recs, srecs, tileCount, tileOffset, tileCursor, pairs, warpPairCount, ovfPairs, bins, ctr;
 	size_t pairCap;
 	size_t h2dBytesLastFrame;
 
@@ -184,7 +184,7 @@ void absorbCounters(mr_ctx* c, const Counters& k)
 	c->stats.records = (int64_t)k.records;
 	c->stats.clipped_in = (int64_t)k.clippedIn;
 	c->stats.bin_entries = (int64_t)k.pairTotal;
-	c->stats.wide_records = (int64_t)k.wideRecords;
+	c->stats.zero_coverage = (int64_t)k.zeroCov;
 	c->stats.tiles_x = c->tilesX;
 	c->stats.tiles_y = c->tilesY;
 }
@@ -280,7 +280,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		rs[i].mesh = r.mesh;
 		rs[i].vertBase = (int)vb;
 		rs[i].triBase = (int)tb;
-		rs[i].pad = 0;
+		rs[i].idxBase = c->hostMeshes[r.mesh].triBase;
 		vb += c->hostMeshes[r.mesh].nPos;
 		tb += c->hostMeshes[r.mesh].nTri;
 		if (sameStructure && c->structureKey[i] != r.mesh)
@@ -297,10 +297,12 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->rstat.ensure(sizeof(RStat) * (size_t)std::max(nR, 1)));
 	MR_CUDA(c, c->rdyn.ensure(sizeof(RDyn) * (size_t)std::max(nR, 1)));
 	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
-	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)std::max(nVB, 1)));
-	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)std::max(nTB, 1)));
+	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
+	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
+	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
+	MR_CUDA(c, c->tileCursor.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->tileOffset.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->ctr.ensure(sizeof(Counters)));
@@ -310,20 +312,20 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		return setError(c, MR_E_OVERFLOW, "more than 2^31 (tile, triangle) pairs");
 	{
 		const size_t nWarps = ((size_t)c->nTriInst + 31) / 32;
-		MR_CUDA(c, c->pairs.ensure(sizeof(int4) * 32 * MR_SEG_PER_LANE * std::max<size_t>(nWarps, 1)));
+		MR_CUDA(c, c->pairs.ensure(sizeof(int2) * 32 * MR_SEG_PER_LANE * std::max<size_t>(nWarps, 1)));
 		MR_CUDA(c, c->warpPairCount.ensure(sizeof(int) * (std::max<size_t>(nWarps, 1) + 8)));
 	}
-	MR_CUDA(c, c->ovfPairs.ensure(sizeof(int4) * c->pairCap));
+	MR_CUDA(c, c->ovfPairs.ensure(sizeof(int2) * c->pairCap));
 	MR_CUDA(c, c->bins.ensure(sizeof(int) * c->pairCap));
-	c->pairCap = std::min(c->ovfPairs.cap / sizeof(int4), c->bins.cap / sizeof(int));
+	c->pairCap = std::min(c->ovfPairs.cap / sizeof(int2), c->bins.cap / sizeof(int));
 	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
 	if (rc)
 		return rc;
 
 	// ---- stage per-frame tables in pinned memory, one async copy each ----
 	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
-	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)nVB;
-	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)nTB;
+	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)(nVB + 1);
+	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)(nTB + 1);
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
 	const size_t total = szStat + szVB + szTB + szDyn + szMat + 64;
@@ -350,6 +352,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 				r++;
 			vbr[b] = r;
 		}
+		vbr[nVB] = std::max(nR - 1, 0); // sentinel: upper bound of the last block's renderable range
 		if (szVB) MR_CUDA(c, cudaMemcpyAsync(c->vtxBlockR.p, sp + off, szVB, cudaMemcpyHostToDevice, c->stream));
 		off += szVB;
 		int* tbr = (int*)(sp + off);
@@ -360,6 +363,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 				r++;
 			tbr[b] = r;
 		}
+		tbr[nTB] = std::max(nR - 1, 0);
 		if (szTB) MR_CUDA(c, cudaMemcpyAsync(c->triBlockR.p, sp + off, szTB, cudaMemcpyHostToDevice, c->stream));
 		off += szTB;
 		c->structureKey.resize((size_t)nR);
@@ -453,9 +457,11 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.recs = c->recs.as<Rec>();
 	fp.tileCount = c->tileCount.as<int>();
 	fp.tileOffset = c->tileOffset.as<int>();
-	fp.pairs = c->pairs.as<int4>();
+	fp.pairs = c->pairs.as<int2>();
 	fp.warpPairCount = c->warpPairCount.as<int>();
-	fp.ovfPairs = c->ovfPairs.as<int4>();
+	fp.ovfPairs = c->ovfPairs.as<int2>();
+	fp.tileCursor = c->tileCursor.as<int>();
+	fp.srecs = c->srecs.as<ShadeRec>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>();
 	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
@@ -567,7 +573,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount, &c->tileOffset,
-		               &c->pairs, &c->warpPairCount, &c->ovfPairs, &c->bins, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->pairs, &c->warpPairCount, &c->ovfPairs, &c->bins, &c->srecs, &c->tileCursor, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)

@@ -3,10 +3,11 @@
 // for bit, so every multiply and add below rounds separately, in the reference's association.
 // IEEE division and square root are nvcc's defaults (-prec-div=true -prec-sqrt=true -ftz=false).
 //
-//   k_vertex  reference loop A            src/Renderer.cpp:344-345 + htransform :13-20, :195-196
-//   k_setup   reference loop C + setup    src/Renderer.cpp:351-380, :163-224, clipTriangle :131-161
-//   scanTiles / k_scatter                 16x16 tile binning (no reference counterpart)
-//   k_raster  reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
+//   k_vertex   reference loop A            src/Renderer.cpp:344-345 + htransform :13-20, :195-196
+//   k_setup    reference loop C + setup    src/Renderer.cpp:351-380, :163-224, clipTriangle :131-161,
+//              plus the exact coverage mask of small triangles (loops D/E :238-249 without depth)
+//   k_scatter  16x16 tile binning (no reference counterpart)
+//   k_raster   reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
 #include <math.h>
 
@@ -67,18 +68,41 @@ __device__ __forceinline__ uint32_t zkey(float z)
 	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__device__ __forceinline__ int findRenderable(const FrameParams& fp, int start, int inst, bool tri)
+// Renderable that owns instance `inst` (a vertex or triangle instance) of this 256-thread block.
+// blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
+// and searched there. Must be called by every thread of the block.
+__device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* __restrict__ blockR, int inst, bool tri, int* shBases)
 {
-	int r = start;
-	const int last = fp.nRenderables - 1;
-	while (r < last)
+	const int r0 = __ldg(&blockR[blockIdx.x]), r1 = __ldg(&blockR[blockIdx.x + 1]);
+	if (r0 >= r1)
+		return r0; // the whole block belongs to one renderable
+	const int n = r1 - r0 + 1;
+	if (n <= 256)
 	{
-		const RStat& nx = fp.rstat[r + 1];
-		if (inst < (tri ? nx.triBase : nx.vertBase))
-			break;
-		r++;
+		for (int i = threadIdx.x; i < n; i += 256)
+			shBases[i] = tri ? fp.rstat[r0 + i].triBase : fp.rstat[r0 + i].vertBase;
+		__syncthreads();
+		int lo = 0, hi = n - 1; // largest i with base[i] <= inst
+		while (lo < hi)
+		{
+			const int mid = (lo + hi + 1) >> 1;
+			if (shBases[mid] <= inst)
+				lo = mid;
+			else
+				hi = mid - 1;
+		}
+		return r0 + lo;
 	}
-	return r;
+	int lo = r0, hi = r1; // pathological: more than 256 renderables inside one block
+	while (lo < hi)
+	{
+		const int mid = (lo + hi + 1) >> 1;
+		if ((tri ? fp.rstat[mid].triBase : fp.rstat[mid].vertBase) <= inst)
+			lo = mid;
+		else
+			hi = mid - 1;
+	}
+	return lo;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -87,19 +111,25 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, int start, 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
+	__shared__ int shBases[256];
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
+	{
 		fp.tileCount[vi] = 0;
+		fp.tileCursor[vi] = 0;
+	}
 	if (vi == 0)
 	{
 		Counters* c = fp.ctr;
-		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->wideRecords = 0;
+		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->zeroCov = 0;
 		c->overflow = 0; c->ctasDone = 0; c->ovfTotal = 0;
 	}
+	if (blockIdx.x * 256 >= fp.nVertInst)
+		return; // blocks that only clear counters
+	const int r = findRenderable(fp, fp.vtxBlockR, vi, false, shBases);
 	if (vi >= fp.nVertInst)
 		return;
-	const int r = findRenderable(fp, fp.vtxBlockR[blockIdx.x], vi, false);
 	const RStat rs = fp.rstat[r];
 	const MeshDev& m = fp.meshes[rs.mesh];
 	const float4 p = __ldg(&fp.pos4[m.posBase + (vi - rs.vertBase)]);
@@ -110,12 +140,12 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 // ------------------------------------------------------------------------------------------
 // Triangle setup shared by the direct and the clipped path (Renderer.cpp:198-224).
 // a,b,c = projected corners (pixel x, pixel y, view z, depth term). Returns false if rejected.
-// Everything stays in registers (the caller passes scalars by reference and is inlined).
 // ------------------------------------------------------------------------------------------
 struct Setup
 {
 	float n1x, n1y, n2x, n2y;
 	int x0, x1, y0, y1;
+	uint32_t mask, flags;
 };
 
 __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float4 a, const float4 b, const float4 c, Setup& s)
@@ -154,41 +184,95 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float
 	if ((float)(y1 + 1) + 0.5f <= ylim) y1++;
 	s.x1 = x1;
 	s.y1 = y1;
+	s.mask = 0u;
+	s.flags = 0u;
 	return true;
 }
 
-__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s, int r, int flags, int tri)
+// Exact coverage of a triangle whose bbox holds at most 32 pixel centres: the reference's loops
+// D/E (Renderer.cpp:238-249) without the depth part. Bit (y-y0)*W + (x-x0). A triangle that covers
+// no pixel centre can never write anything and is dropped before binning.
+__device__ __forceinline__ uint32_t coverageMask(const float4 a, const float4 c, const Setup& s)
+{
+	const int W = s.x1 - s.x0 + 1;
+	const float ptx = (float)s.x0 + 0.5f;
+	uint32_t mask = 0u, bit = 1u;
+	for (int y = s.y0; y <= s.y1; y++)
+	{
+		const float fy = (float)y + 0.5f;
+		float e1 = s.n1x * (ptx - c.x) + s.n1y * (fy - c.y);
+		float e2 = s.n2x * (ptx - a.x) + s.n2y * (fy - a.y);
+		for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x, bit <<= 1)
+		{
+			const float k0 = 1.0f - e1 - e2;
+			if (!(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)) // Renderer.cpp:245 (NaN counts as inside, like there)
+				mask |= bit;
+		}
+	}
+	return mask;
+}
+
+// Bits of a record's coverage mask that fall inside tile (tileX0, tileY0).
+__device__ __forceinline__ uint32_t maskInTile(uint32_t mask, int x0, int x1, int y0, int y1, int tileX0, int tileY0)
+{
+	const int W = x1 - x0 + 1;
+	const int c0 = max(tileX0 - x0, 0), c1 = min(tileX0 + MR_TILE - 1, x1) - x0;
+	const int r0 = max(tileY0 - y0, 0), r1 = min(tileY0 + MR_TILE - 1, y1) - y0;
+	if (c1 < c0 || r1 < r0)
+		return 0u;
+	const uint32_t cols = ((c1 - c0 + 1 >= 32) ? 0xffffffffu : ((1u << (c1 - c0 + 1)) - 1u)) << c0;
+	uint32_t m = 0u;
+	for (int r = r0; r <= r1; r++)
+		m |= cols << (r * W);
+	return mask & m;
+}
+
+__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s)
 {
 	float4* d4 = reinterpret_cast<float4*>(dst);
 	d4[0] = make_float4(a.x, a.y, c.x, c.y);
 	d4[1] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
-	d4[2] = make_float4(a.w, b.w, c.w, __int_as_float(r));
+	d4[2] = make_float4(a.w, b.w, c.w, __uint_as_float(s.mask));
 	d4[3] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
-	                    __int_as_float(flags), __int_as_float(tri));
+	                    __uint_as_float(s.flags), 0.0f);
 }
 
-// One corner of triangle `tri` of a renderable, in view space (loops A/B/C of paintMesh).
+// Absolute attribute indices of triangle `tri` of renderable r (winner-only part of loop C).
+__device__ __forceinline__ void storeShadeRec(const FrameParams& fp, ShadeRec* dst, int r, const RStat& rs, int tri, int ia, int ib, int ic)
+{
+	const MeshDev m = fp.meshes[rs.mesh];
+	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
+	int iu0 = -1, iu1 = -1, iu2 = -1;
+	if (m.hasUV)
+	{
+		const int* iu = fp.idxUv + (size_t)(m.uvTriBase + tri) * 3;
+		iu0 = m.uvBase + __ldg(iu); iu1 = m.uvBase + __ldg(iu + 1); iu2 = m.uvBase + __ldg(iu + 2);
+	}
+	int4* d4 = reinterpret_cast<int4*>(dst);
+	d4[0] = make_int4(m.posBase + ia, m.posBase + ib, m.posBase + ic, m.nrmBase + __ldg(in));
+	d4[1] = make_int4(m.nrmBase + __ldg(in + 1), m.nrmBase + __ldg(in + 2), iu0, iu1);
+	d4[2] = make_int4(iu2, fp.rdyn[r].material, r, tri);
+}
+
+// One corner in view space (loops A/B of paintMesh, evaluated for the winner only).
 struct Corner
 {
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
-__device__ __forceinline__ Corner fetchCorner(const FrameParams& fp, const MeshDev& m, const RDyn* __restrict__ rd, int tri, int corner)
+__device__ __forceinline__ Corner fetchCorner(const FrameParams& fp, const RDyn* __restrict__ rd, int ip, int in, int iu)
 {
 	Corner v;
-	const int ip = __ldg(&fp.idxPos[(m.triBase + tri) * 3 + corner]);
-	const int in = __ldg(&fp.idxNrm[(m.triBase + tri) * 3 + corner]);
-	const float4 p = __ldg(&fp.pos4[m.posBase + ip]);
-	const float4 n = __ldg(&fp.nrm4[m.nrmBase + in]);
+	const float4 p = __ldg(&fp.pos4[ip]);
+	const float4 n = __ldg(&fp.nrm4[in]);
 	const V3 pos = affine(rd->mv, p.x, p.y, p.z);
 	const V3 nrm = affine(rd->nm, n.x, n.y, n.z);
 	v.px = pos.x; v.py = pos.y; v.pz = pos.z;
 	v.nx = nrm.x; v.ny = nrm.y; v.nz = nrm.z;
 	v.u = 0.0f; v.v = 0.0f;
-	if (m.hasUV)
+	if (iu >= 0)
 	{
-		const int iu = __ldg(&fp.idxUv[(m.uvTriBase + tri) * 3 + corner]);
-		const float2 t = __ldg(&fp.uv2[m.uvBase + iu]);
+		const float2 t = __ldg(&fp.uv2[iu]);
 		v.u = t.x; v.v = t.y;
 	}
 	return v;
@@ -241,8 +325,8 @@ __device__ __forceinline__ int clipTriangle(float z, Corner v0, Corner v1, Corne
 	return 2;
 }
 
-// Emits the (tile, slot, record) pairs of one record with plain per-thread atomics into the
-// overflow pair list (slow paths: clipper output, triangles spanning more than MR_SEG_PER_LANE tiles).
+// Emits the (tile, record) pairs of one record with plain per-thread atomics into the overflow
+// pair list (slow paths: clipper output, triangles spanning more than MR_SEG_PER_LANE tiles).
 __device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, const Setup& s)
 {
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
@@ -257,23 +341,33 @@ __device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, c
 		fp.ctr->overflow = 1u;
 		return;
 	}
-	int4* dst = fp.ovfPairs + base;
+	int2* dst = fp.ovfPairs + base;
 	for (int ty = ty0; ty <= ty1; ty++)
 		for (int tx = tx0; tx <= tx1; tx++)
 		{
 			const int tile = ty * fp.tilesX + tx;
-			*dst++ = make_int4(tile, atomicAdd(&fp.tileCount[tile], 1), id, 0);
+			atomicAdd(&fp.tileCount[tile], 1);
+			*dst++ = make_int2(tile, id);
 		}
 }
 
 // Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up, stores
 // the records and emits their pairs. Self-contained so that its stack never touches the fast path.
-__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri)
+__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
 {
 	const RStat rs = fp.rstat[r];
 	const MeshDev m = fp.meshes[rs.mesh];
 	const RDyn* rd = &fp.rdyn[r];
-	const Corner v0 = fetchCorner(fp, m, rd, tri, 0), v1 = fetchCorner(fp, m, rd, tri, 1), v2 = fetchCorner(fp, m, rd, tri, 2);
+	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
+	int iu0 = -1, iu1 = -1, iu2 = -1;
+	if (m.hasUV)
+	{
+		const int* iu = fp.idxUv + (size_t)(m.uvTriBase + tri) * 3;
+		iu0 = m.uvBase + __ldg(iu); iu1 = m.uvBase + __ldg(iu + 1); iu2 = m.uvBase + __ldg(iu + 2);
+	}
+	const Corner v0 = fetchCorner(fp, rd, m.posBase + ia, m.nrmBase + __ldg(in), iu0);
+	const Corner v1 = fetchCorner(fp, rd, m.posBase + ib, m.nrmBase + __ldg(in + 1), iu1);
+	const Corner v2 = fetchCorner(fp, rd, m.posBase + ic, m.nrmBase + __ldg(in + 2), iu2);
 	int nrec = 0;
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
 	for (int sub = 0; sub < 2; sub++)
@@ -288,27 +382,19 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 			continue;
 		if (min(s.y1 >> MR_TILE_SHIFT, tyHi) < max(s.y0 >> MR_TILE_SHIFT, tyLo))
 			continue;
+		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
-		storeRec(&fp.recs[id], a, b, c, s, r, 1, tri);
+		storeRec(&fp.recs[id], a, b, c, s);
+		storeShadeRec(fp, &fp.srecs[id], r, rs, tri, ia, ib, ic);
 		emitPairsSerial(fp, id, s);
 		nrec++;
 	}
 	return nrec;
 }
 
-// ------------------------------------------------------------------------------------------
-// Kernel 2: near test, clip, setup, and (tile, triangle) pair emission.
-// One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
-// outputs at 2t and 2t+1): the index is the submission id. Its (tile, slot, record) pairs go to
-// the warp's private segment of pairs[] (MR_SEG_PER_LANE entries per lane, compacted with a warp
-// prefix sum, no global allocation); `slot`, the triangle's rank inside its tile, comes from the
-// tile counter with one atomic per distinct tile per warp (__match_any_sync), because
-// neighbouring triangles mostly share a tile. Triangles covering more tiles use the overflow
-// list. The last CTA to finish turns the tile counters into offsets (exclusive scan).
-// ------------------------------------------------------------------------------------------
+// exclusive scan of tileCount[0..n) into tileOffset[], by one 256-thread CTA
 __device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 34 ints */)
 {
-	// exclusive scan of tileCount[0..n) into tileOffset[], by one 256-thread CTA
 	const int n = fp.tilesX * fp.tilesY;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int per = (n + 255) / 256;
@@ -354,23 +440,33 @@ __device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 3
 	}
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 2: near test, clip, setup, coverage mask, and (tile, triangle) pair emission.
+// One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
+// outputs at 2t and 2t+1): the index is the submission id. Its (tile, record) pairs go to the
+// warp's private segment of pairs[] (MR_SEG_PER_LANE entries per lane, compacted with a warp
+// prefix sum, no global allocation) and the tile counters are bumped with one fire-and-forget
+// atomic per distinct tile per warp (__match_any_sync: neighbouring triangles mostly share a
+// tile). Triangles covering more tiles use the overflow list. The last CTA to finish turns the
+// tile counters into offsets (exclusive scan).
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int sh[48];
+	__shared__ int sh[56];
+	__shared__ int shBases[256];
 	const int t = blockIdx.x * 256 + threadIdx.x;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int r = findRenderable(fp, fp.triBlockR, t, true, shBases);
 	bool valid = false;
-	int nclip = 0, nrecSlow = 0;
-	int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
 	s.x0 = s.x1 = s.y0 = s.y1 = 0;
+	s.mask = s.flags = 0u;
 	if (t < fp.nTriInst)
 	{
-		const int r = findRenderable(fp, fp.triBlockR[blockIdx.x], t, true);
 		const RStat rs = fp.rstat[r];
-		const MeshDev& m = fp.meshes[rs.mesh];
 		const int tri = t - rs.triBase;
-		const int* ix = fp.idxPos + (size_t)(m.triBase + tri) * 3;
+		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
 		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
 		const float4 a = fp.pv[rs.vertBase + ia];
 		const float4 b = fp.pv[rs.vertBase + ib];
@@ -381,29 +477,44 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 			if (!(a.z > zn && b.z > zn && c.z > zn))
 			{
 				nclip = 1;
-				nrecSlow = setupClipped(fp, t, r, tri);
+				nrecSlow = setupClipped(fp, t, r, tri, ia, ib, ic);
 			}
 		}
 		else if (setupTriangle(fp, a, b, c, s))
 		{
-			tx0 = s.x0 >> MR_TILE_SHIFT;
-			tx1 = s.x1 >> MR_TILE_SHIFT;
-			ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
-			ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
-			if (ty1 >= ty0)
+			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
+			if (valid && (s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= 32)
 			{
-				valid = true;
-				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, r, 0, tri);
+				s.flags = MR_REC_MASKED;
+				s.mask = coverageMask(a, c, s);
+				valid = s.mask != 0u;
+				nzero = valid ? 0 : 1;
+			}
+			if (valid)
+			{
+				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s);
+				storeShadeRec(fp, &fp.srecs[2 * (size_t)t], r, rs, tri, ia, ib, ic);
 			}
 		}
 	}
 	__syncwarp();
 
 	// ---- pairs: warp-private segment for triangles covering <= MR_SEG_PER_LANE tiles ----
+	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
+	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
 	const int nx = tx1 - tx0 + 1;
 	const int ntiles = valid ? nx * (ty1 - ty0 + 1) : 0;
 	const bool big = ntiles > MR_SEG_PER_LANE;
-	const int npairs = big ? 0 : ntiles;
+	// tiles of the bbox that actually contain covered pixels (masked triangles), as a bit set
+	uint32_t live = 0u;
+	if (valid && !big)
+		for (int k = 0; k < ntiles; k++)
+		{
+			const int tx = tx0 + k % nx, ty = ty0 + k / nx;
+			if (!(s.flags & MR_REC_MASKED) || maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) != 0u)
+				live |= 1u << k;
+		}
+	const int npairs = __popc(live);
 	int incl = npairs;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
@@ -416,21 +527,23 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 	if (lane == 31)
 		fp.warpPairCount[gw] = incl;
 	{
-		int4* dst = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE) + (incl - npairs);
+		int2* dst = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE) + (incl - npairs);
 		const int id = 2 * t;
 		const int rounds = __reduce_max_sync(0xffffffffu, npairs);
+		uint32_t rest = live;
 		for (int k = 0; k < rounds; k++)
 		{
-			const bool on = k < npairs;
-			const int tile = on ? (ty0 + k / nx) * fp.tilesX + tx0 + k % nx : -1 - lane;
+			const bool on = rest != 0u;
+			const int kk = on ? __ffs(rest) - 1 : 0;
+			rest &= rest - 1u;
+			const int tile = on ? (ty0 + kk / nx) * fp.tilesX + tx0 + kk % nx : -1 - lane;
 			const unsigned peers = __match_any_sync(0xffffffffu, tile);
-			const int leader = __ffs(peers) - 1;
-			int slot = 0;
-			if (on && lane == leader)
-				slot = atomicAdd(&fp.tileCount[tile], __popc(peers));
-			slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
 			if (on)
-				dst[k] = make_int4(tile, slot, id, 0);
+			{
+				if (lane == __ffs(peers) - 1)
+					atomicAdd(&fp.tileCount[tile], __popc(peers)); // result unused: a RED, no round trip
+				dst[k] = make_int2(tile, id);
+			}
 		}
 	}
 	if (big)
@@ -439,23 +552,27 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 	// ---- statistics: one atomic per CTA ----
 	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
 	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
+	const int nzeroWarp = __reduce_add_sync(0xffffffffu, nzero);
 	if (lane == 0)
 	{
 		sh[32 + wid] = nrecWarp;
 		sh[40 + wid] = nclipWarp;
+		sh[48 + wid] = nzeroWarp;
 	}
 	// ---- last CTA done: tile counters -> tile offsets ----
 	__syncthreads();
 	if (threadIdx.x == 0)
 	{
-		int nr = 0, nc = 0;
+		int nr = 0, nc = 0, nz = 0;
 		for (int i = 0; i < 8; i++)
 		{
 			nr += sh[32 + i];
 			nc += sh[40 + i];
+			nz += sh[48 + i];
 		}
 		if (nr) atomicAdd(&fp.ctr->records, (unsigned long long)nr);
 		if (nc) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nc);
+		if (nz) atomicAdd(&fp.ctr->zeroCov, (unsigned long long)nz);
 		__threadfence();
 		sh[31] = (atomicAdd(&fp.ctr->ctasDone, 1u) == gridDim.x - 1) ? 1 : 0;
 	}
@@ -474,8 +591,12 @@ __global__ void __launch_bounds__(256) k_scan_only(const __grid_constant__ Frame
 	scanTiles(fp, sh);
 }
 
-// Kernel 3: scatter the pairs into the per-tile bins (a warp per k_setup warp segment, then the
-// overflow list).
+// ------------------------------------------------------------------------------------------
+// Kernel 3: scatter the pairs into the per-tile bins. A warp per k_setup warp segment (then the
+// overflow list); the position inside a tile's bin comes from the tile's fill cursor, again one
+// atomic per distinct tile per warp. The order inside a bin does not matter: depth ties are
+// resolved on the record index (submission id), not on arrival order.
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ FrameParams fp)
 {
 	if (__ldcg(&fp.ctr->overflow))
@@ -486,110 +607,50 @@ __global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ FramePa
 	if (gw < nWarps)
 	{
 		const int n = fp.warpPairCount[gw];
-		const int4* src = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE);
-		for (int k = lane; k < n; k += 32)
+		const int2* src = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE);
+		for (int k0 = 0; k0 < n; k0 += 32)
 		{
-			const int4 p = src[k];
-			fp.bins[fp.tileOffset[p.x] + p.y] = p.z;
+			const int k = k0 + lane;
+			const bool on = k < n;
+			int2 p = make_int2(-1 - lane, 0);
+			if (on)
+				p = src[k];
+			const unsigned peers = __match_any_sync(0xffffffffu, p.x);
+			const int leader = __ffs(peers) - 1;
+			int slot = 0;
+			if (on && lane == leader)
+				slot = atomicAdd(&fp.tileCursor[p.x], __popc(peers));
+			slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+			if (on)
+				fp.bins[fp.tileOffset[p.x] + slot] = p.y;
 		}
 	}
 	const unsigned long long ovf = fp.ctr->ovfTotal;
 	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < ovf; i += (unsigned long long)gridDim.x * 256)
 	{
-		const int4 p = fp.ovfPairs[i];
-		fp.bins[fp.tileOffset[p.x] + p.y] = p.z;
+		const int2 p = fp.ovfPairs[i];
+		fp.bins[fp.tileOffset[p.x] + atomicAdd(&fp.tileCursor[p.x], 1)] = p.y;
 	}
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 4: tile rasterizer + shader. One CTA per 16x16 tile, 256 threads.
-// Phase 1 (four threads per binned triangle, rows interleaved): reference loops D/E with the
-//   float edge chain replayed from the triangle's own bbox start (e += n.x per column,
-//   Renderer.cpp:243), depth resolved by 64-bit atomicMin in shared memory on
-//   (orderable z) << 32 | (record index + 1). The low word makes equal-z fragments resolve to
-//   the earliest submitted triangle, which is what the reference's strict `<` test over in-order
-//   submission does.
+// Kernel 4: tile rasterizer + shader. One CTA per 16x16 tile, 256 threads; the tile's depth keys
+// live in shared memory.
+// Phase 1: coverage + depth. A lane per binned triangle loads its record. Small triangles carry
+//   their exact coverage mask from k_setup: their covered pixels inside the tile go straight to
+//   the warp's fragment queue. Larger triangles are scanned by a quad of lanes each (rows
+//   interleaved), reference loops D/E with the float edge chain replayed from the triangle's own
+//   bbox start (e += n.x per column, Renderer.cpp:243). The queue is consumed 32 fragments at a
+//   time by the whole warp: exact z, then a 64-bit atomicMin in shared memory on
+//   (orderable z) << 32 | (record index + 1). The low word makes equal-z fragments resolve to the
+//   earliest submitted triangle, which is what the reference's strict `<` over in-order submission
+//   does.
 // Phase 2 (thread per pixel): the winner's barycentrics are re-derived by the same chain, then
 //   depth, perspective correction, texture and Blinn-Phong exactly as Renderer.cpp:253-305;
 //   pixels without a winner get the clear values (Renderer.cpp:113-119) unless fp.keep.
 // ------------------------------------------------------------------------------------------
-struct ShadeIn
-{
-	float k0, k1, k2;
-	Corner c0, c1, c2;
-};
-
-// Renderer.cpp:271-305 for one pixel; writes image (and the normals image).
-__device__ __forceinline__ void shadePixel(const FrameParams& fp, const MatDev& mat, const ShadeIn& in, size_t pix)
-{
-	const float k0 = in.k0, k1 = in.k1, k2 = in.k2;
-	V3 color = mk3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
-	V3 value = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
-	if (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0)
-	{
-		const float u = in.c0.u * k0 + in.c1.u * k1 + in.c2.u * k2;
-		const float v = in.c0.v * k0 + in.c1.v * k1 + in.c2.v * k2;
-		const float fv = v - floorf(v), fu = u - floorf(u);
-		int ti = (int)(fv * (float)mat.texRows), tj = (int)(fu * (float)mat.texCols);
-		// fract() == 1.0f (tiny negative input) indexes one past the end in the reference;
-		// clamp instead (documented divergence on UB input, SURVEY §7.3.5)
-		ti = min(max(ti, 0), mat.texRows - 1);
-		tj = min(max(tj, 0), mat.texCols - 1);
-		const float4 tex = __ldg(&fp.texels[mat.texOffset + ti * mat.texCols + tj]);
-		color = mk3(tex.x, tex.y, tex.z);
-	}
-	if (fp.lighting)
-	{
-		const V3 position = mk3(in.c0.px * k0 + in.c1.px * k1 + in.c2.px * k2, in.c0.py * k0 + in.c1.py * k1 + in.c2.py * k2,
-		                        in.c0.pz * k0 + in.c1.pz * k1 + in.c2.pz * k2);
-		const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
-		const V3 lightdir = fp.lightIsPoint ? normalized3(sub3(light, position)) : light;
-		const V3 normal = mk3(in.c0.nx * k0 + in.c1.nx * k1 + in.c2.nx * k2, in.c0.ny * k0 + in.c1.ny * k1 + in.c2.ny * k2,
-		                      in.c0.nz * k0 + in.c1.nz * k1 + in.c2.nz * k2);
-		const float nl = dot3(normal, lightdir);
-		const float nlen = len3(normal);
-		const float d = ((0.0f > nl) ? 0.0f : nl) / nlen + fp.ambient;
-		value = add3(value, scale3(color, d));
-		if (mat.shininess != 0.0f)
-		{
-			const V3 viewdir = normalized3(position);
-			const V3 hv = sub3(lightdir, viewdir);
-			const float hn = dot3(hv, normal);
-			const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
-			// the reference's unqualified pow() is the double overload
-			const float specular = (float)pow((double)base, (double)mat.shininess);
-			value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
-		}
-		if (fp.saveNormals && fp.normals)
-		{
-			float* pn = fp.normals + 3 * pix;
-			pn[0] = normal.x; pn[1] = normal.y; pn[2] = normal.z;
-		}
-	}
-	float* img = fp.image + 3 * pix;
-	img[0] = value.x; img[1] = value.y; img[2] = value.z;
-}
-
-// Shading of a pixel won by a clipper-made triangle (rare): re-runs the clip to get the corners.
-__device__ __noinline__ void shadeClippedPixel(const FrameParams& fp, int r, int tri, int sub, float k0, float k1, float k2, size_t pix)
-{
-	const RStat rs = fp.rstat[r];
-	const MeshDev m = fp.meshes[rs.mesh];
-	const RDyn* rd = &fp.rdyn[r];
-	const Corner v0 = fetchCorner(fp, m, rd, tri, 0), v1 = fetchCorner(fp, m, rd, tri, 1), v2 = fetchCorner(fp, m, rd, tri, 2);
-	ShadeIn in;
-	in.k0 = k0; in.k1 = k1; in.k2 = k2;
-	clipTriangle(fp.znear, v0, v1, v2, sub, in.c0, in.c1, in.c2);
-	const MatDev mat = fp.mats[rd->material];
-	shadePixel(fp, mat, in, pix);
-}
-
-// Per-warp fragment queue of phase 1. Coverage is sparse (a small triangle covers one or two of
-// the ~12 pixel centres of its bbox), so the expensive per-fragment work (exact division, key,
-// atomic) is not done inside the divergent scan loop: covered pixels are appended to a queue in
-// shared memory and consumed 32 at a time by the whole warp.
-#define MR_FQ_CAP 64   // entries per warp (power of two)
-#define MR_FQ_SLOTS 16 // triangle slots per warp: 8 quads per iteration, two iterations in flight
+#define MR_FQ_CAP 64   // fragment queue entries per warp (power of two)
+#define MR_FQ_SLOTS 64 // triangle slots per warp: 32 lanes per iteration, two iterations in flight
 
 struct WarpQueue
 {
@@ -623,6 +684,108 @@ __device__ __forceinline__ void consumeFragments(const FrameParams& fp, WarpQueu
 	}
 }
 
+// Appends this lane's fragment (if `on`) to the warp queue; consumes a batch when 32 are queued.
+__device__ __forceinline__ void pushFragment(const FrameParams& fp, WarpQueue& wq, unsigned long long* keys, int& qhead, int& qcount,
+                                             int lane, bool on, float e1, float e2, uint32_t info)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, on);
+	if (m == 0u)
+		return;
+	if (on)
+	{
+		const int w = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & (MR_FQ_CAP - 1);
+		wq.e1[w] = e1;
+		wq.e2[w] = e2;
+		wq.info[w] = info;
+	}
+	qcount += __popc(m);
+	if (qcount >= 32)
+	{
+		__syncwarp();
+		consumeFragments(fp, wq, keys, qhead, 32, lane);
+		qhead = (qhead + 32) & (MR_FQ_CAP - 1);
+		qcount -= 32;
+	}
+}
+
+// Renderer.cpp:271-305 for one pixel; writes image (and the normals image).
+__device__ __forceinline__ void shadePixel(const FrameParams& fp, const MatDev& mat, float k0, float k1, float k2,
+                                           const Corner& c0, const Corner& c1, const Corner& c2, size_t pix)
+{
+	V3 color = mk3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
+	V3 value = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
+	if (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0)
+	{
+		const float u = c0.u * k0 + c1.u * k1 + c2.u * k2;
+		const float v = c0.v * k0 + c1.v * k1 + c2.v * k2;
+		const float fv = v - floorf(v), fu = u - floorf(u);
+		int ti = (int)(fv * (float)mat.texRows), tj = (int)(fu * (float)mat.texCols);
+		// fract() == 1.0f (tiny negative input) indexes one past the end in the reference;
+		// clamp instead (documented divergence on UB input, SURVEY §7.3.5)
+		ti = min(max(ti, 0), mat.texRows - 1);
+		tj = min(max(tj, 0), mat.texCols - 1);
+		const float4 tex = __ldg(&fp.texels[mat.texOffset + ti * mat.texCols + tj]);
+		color = mk3(tex.x, tex.y, tex.z);
+	}
+	if (fp.lighting)
+	{
+		const V3 position = mk3(c0.px * k0 + c1.px * k1 + c2.px * k2, c0.py * k0 + c1.py * k1 + c2.py * k2,
+		                        c0.pz * k0 + c1.pz * k1 + c2.pz * k2);
+		const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
+		const V3 lightdir = fp.lightIsPoint ? normalized3(sub3(light, position)) : light;
+		const V3 normal = mk3(c0.nx * k0 + c1.nx * k1 + c2.nx * k2, c0.ny * k0 + c1.ny * k1 + c2.ny * k2,
+		                      c0.nz * k0 + c1.nz * k1 + c2.nz * k2);
+		const float nl = dot3(normal, lightdir);
+		const float nlen = len3(normal);
+		const float d = ((0.0f > nl) ? 0.0f : nl) / nlen + fp.ambient;
+		value = add3(value, scale3(color, d));
+		if (mat.shininess != 0.0f)
+		{
+			const V3 viewdir = normalized3(position);
+			const V3 hv = sub3(lightdir, viewdir);
+			const float hn = dot3(hv, normal);
+			const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
+			// the reference's unqualified pow() is the double overload
+			const float specular = (float)pow((double)base, (double)mat.shininess);
+			value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
+		}
+		if (fp.saveNormals && fp.normals)
+		{
+			float* pn = fp.normals + 3 * pix;
+			pn[0] = normal.x; pn[1] = normal.y; pn[2] = normal.z;
+		}
+	}
+	float* img = fp.image + 3 * pix;
+	img[0] = value.x; img[1] = value.y; img[2] = value.z;
+}
+
+// Shading of a pixel won by a clipper-made triangle (rare): re-runs the clip to get the corners.
+__device__ __noinline__ void shadeClippedPixel(const FrameParams& fp, const ShadeRec* sr, int sub, float k0, float k1, float k2, size_t pix)
+{
+	const int4* s4 = reinterpret_cast<const int4*>(sr);
+	const int4 sa = __ldg(s4), sb = __ldg(s4 + 1), sc = __ldg(s4 + 2);
+	const RDyn* rd = &fp.rdyn[sc.z];
+	const Corner v0 = fetchCorner(fp, rd, sa.x, sa.w, sb.z), v1 = fetchCorner(fp, rd, sa.y, sb.x, sb.w), v2 = fetchCorner(fp, rd, sa.z, sb.y, sc.x);
+	Corner c0, c1, c2;
+	clipTriangle(fp.znear, v0, v1, v2, sub, c0, c1, c2);
+	const MatDev mat = fp.mats[sc.y];
+	shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
+}
+
+__device__ __forceinline__ void writeClear(const FrameParams& fp, size_t pix)
+{
+	float* img = fp.image + 3 * pix;
+	img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
+	fp.depth[pix] = 1e11f;
+	if (fp.saveNormals && fp.normals)
+	{
+		float* pn = fp.normals + 3 * pix;
+		pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
+	}
+	if (fp.winner)
+		fp.winner[pix] = -1;
+}
+
 __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
@@ -643,20 +806,8 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 
 	if (count == 0 && !fp.keep)
 	{
-		// empty tile: clear values only
 		if (inImage)
-		{
-			float* img = fp.image + 3 * pix;
-			img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
-			fp.depth[pix] = 1e11f;
-			if (fp.saveNormals && fp.normals)
-			{
-				float* pn = fp.normals + 3 * pix;
-				pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
-			}
-			if (fp.winner)
-				fp.winner[pix] = -1;
-		}
+			writeClear(fp, pix); // empty tile: clear values only
 		return;
 	}
 	{
@@ -670,81 +821,106 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	}
 	__syncthreads();
 
-	// ---- phase 1: coverage + depth. A quad of lanes per triangle, rows interleaved; all loop
-	// bounds are made warp-uniform so that ballots and the queue stay convergent. ----
+	// ---- phase 1: coverage + depth ----
 	{
 		WarpQueue& wq = queues[tid >> 5];
 		const int* bin = fp.bins + fp.tileOffset[tile];
-		const int q = lane & 3;
-		const int quad = lane >> 2;
 		int qhead = 0, qcount = 0; // warp-uniform
 		int parity = 0;
-		for (int base = (tid >> 5) * 8; base < count; base += 64, parity ^= 1)
+		for (int base = (tid >> 5) * 32; base < count; base += 256, parity ^= 1)
 		{
-			const int i = base + quad;
+			const int i = base + lane;
 			const bool have = i < count;
-			float p0x = 0, p0y = 0, p2x = 0, p2y = 0, n1x = 0, n1y = 0, n2x = 0, n2y = 0;
-			int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-			const int slot = parity * 8 + quad;
+			const int slot = parity * 32 + lane;
+			int id = 0;
+			float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
 			if (have)
 			{
-				const int id = __ldg(&bin[i]);
+				id = __ldg(&bin[i]);
 				const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-				const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
-				p0x = q0.x; p0y = q0.y; p2x = q0.z; p2y = q0.w;
-				n1x = q1.x; n1y = q1.y; n2x = q1.z; n2y = q1.w;
-				const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
-				x0 = xspan & 0xffffu;
-				x1 = min((int)(xspan >> 16), tileX0 + MR_TILE - 1);
-				y0 = max((int)(yspan & 0xffffu), tileY0);
-				y1 = min((int)(yspan >> 16), tileY0 + MR_TILE - 1);
-				if (q == 0)
-					wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
+				q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+				wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 			}
-			const int xs = max(x0, tileX0);       // first column tested in this tile
-			const int ncols = have ? max(x1 - xs + 1, 0) : 0;
-			const int myRows = have ? max((y1 - y0 - q + 4) >> 2, 0) : 0; // rows y0+q, y0+q+4, ...
-			const float ptx = (float)x0 + 0.5f;
-			const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
-			const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
+			const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y), flags = __float_as_uint(q3.z);
+			const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
+			const bool masked = have && (flags & MR_REC_MASKED);
 			__syncwarp();
-			for (int rr = 0; rr < maxRows; rr++)
+
+			// small triangles: exact coverage is known, push the covered pixels of this tile
 			{
-				const bool rowOn = rr < myRows;
-				const int y = y0 + q + 4 * rr;
-				const float fy = (float)y + 0.5f;
-				float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
-				float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
-				if (rowOn)
-					for (int x = x0; x < xs; x++) // chain prefix left of the tile
-					{
-						e1 += n1x;
-						e2 += n2x;
-					}
-				const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)slot << 8);
-				for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
+				uint32_t tm = masked ? maskInTile(__float_as_uint(q2.w), x0, x1, y0, y1, tileX0, tileY0) : 0u;
+				const int W = x1 - x0 + 1;
+				const float ptx = (float)x0 + 0.5f;
+				const int rounds = __reduce_max_sync(0xffffffffu, __popc(tm));
+				for (int k = 0; k < rounds; k++)
 				{
-					const float k0 = 1.0f - e1 - e2;
-					const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
-					const unsigned m = __ballot_sync(0xffffffffu, inside);
-					if (m == 0u)
-						continue;
-					if (inside)
+					const bool on = tm != 0u;
+					const int bit = on ? __ffs(tm) - 1 : 0;
+					tm &= tm - 1u;
+					int yy = 0, xx = bit;
+					while (xx >= W) // at most 31 subtractions, usually 0-3
 					{
-						const int w = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & (MR_FQ_CAP - 1);
-						wq.e1[w] = e1;
-						wq.e2[w] = e2;
-						wq.info[w] = rowInfo + (uint32_t)cc;
+						xx -= W;
+						yy++;
 					}
-					qcount += __popc(m);
-					if (qcount >= 32)
+					const float fy = (float)(y0 + yy) + 0.5f;
+					float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
+					float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
+					for (int j = 0; j < xx; j++)
 					{
-						__syncwarp();
-						consumeFragments(fp, wq, keys, qhead, 32, lane);
-						qhead = (qhead + 32) & (MR_FQ_CAP - 1);
-						qcount -= 32;
+						e1 += q1.x;
+						e2 += q1.z;
+					}
+					const uint32_t info = (uint32_t)((y0 + yy - tileY0) * MR_TILE + (x0 + xx - tileX0)) | ((uint32_t)slot << 8);
+					pushFragment(fp, wq, keys, qhead, qcount, lane, on, e1, e2, info);
+				}
+			}
+
+			// larger triangles of this batch: a quad of lanes scans each, rows interleaved
+			unsigned large = __ballot_sync(0xffffffffu, have && !masked);
+			while (large != 0u)
+			{
+				const int q = lane & 3, quad = lane >> 2;
+				const int src = __fns(large, 0, quad + 1); // lane that owns this quad's triangle, or -1
+				const bool on = src >= 0 && src < 32;
+				const int s = on ? src : 0;
+				const float p0x = __shfl_sync(0xffffffffu, q0.x, s), p0y = __shfl_sync(0xffffffffu, q0.y, s);
+				const float p2x = __shfl_sync(0xffffffffu, q0.z, s), p2y = __shfl_sync(0xffffffffu, q0.w, s);
+				const float n1x = __shfl_sync(0xffffffffu, q1.x, s), n1y = __shfl_sync(0xffffffffu, q1.y, s);
+				const float n2x = __shfl_sync(0xffffffffu, q1.z, s), n2y = __shfl_sync(0xffffffffu, q1.w, s);
+				const int bx0 = __shfl_sync(0xffffffffu, x0, s), bx1 = min(__shfl_sync(0xffffffffu, x1, s), tileX0 + MR_TILE - 1);
+				const int by0 = max(__shfl_sync(0xffffffffu, y0, s), tileY0), by1 = min(__shfl_sync(0xffffffffu, y1, s), tileY0 + MR_TILE - 1);
+				const int tslot = parity * 32 + s;
+				const int xs = max(bx0, tileX0);
+				const int ncols = on ? max(bx1 - xs + 1, 0) : 0;
+				const int myRows = on ? max((by1 - by0 - q + 4) >> 2, 0) : 0; // rows by0+q, by0+q+4, ...
+				const float ptx = (float)bx0 + 0.5f;
+				const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
+				const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
+				for (int rr = 0; rr < maxRows; rr++)
+				{
+					const bool rowOn = rr < myRows;
+					const int y = by0 + q + 4 * rr;
+					const float fy = (float)y + 0.5f;
+					float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
+					float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
+					if (rowOn)
+						for (int x = bx0; x < xs; x++) // chain prefix left of the tile
+						{
+							e1 += n1x;
+							e2 += n2x;
+						}
+					const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)tslot << 8);
+					for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
+					{
+						const float k0 = 1.0f - e1 - e2;
+						const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
+						pushFragment(fp, wq, keys, qhead, qcount, lane, inside, e1, e2, rowInfo + (uint32_t)cc);
 					}
 				}
+				// drop the (up to) eight triangles just done
+				for (int k = 0; k < 8 && large != 0u; k++)
+					large &= large - 1u;
 			}
 			// Triangle slots of this parity are overwritten two iterations from now; fragments
 			// still queued then must not refer to them, so drain before reusing a parity.
@@ -767,17 +943,20 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 
 	// ---- phase 2: resolve + shade ----
 	const uint32_t win = inImage ? (uint32_t)(keys[tid] & 0xffffffffull) : 0u;
-	// Replay of the winner's edge chain. Lanes of the same pixel row (a half warp) that share a
-	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
-	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
 	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+	int4 sa = make_int4(0, 0, 0, 0), sb = sa, sc = sa;
 	int id = -1;
 	if (win != 0u)
 	{
 		id = (int)(win - 1u);
 		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
+		const int4* s4 = reinterpret_cast<const int4*>(&fp.srecs[id]);
 		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+		sa = __ldg(s4); sb = __ldg(s4 + 1); sc = __ldg(s4 + 2);
 	}
+	// Replay of the winner's edge chain. Lanes of the same pixel row (a half warp) that share a
+	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
+	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
 	const int x0 = (int)(__float_as_uint(q3.x) & 0xffffu);
 	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
 	float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
@@ -785,22 +964,25 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	int xcur = x0;
 	{
 		const int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
-		const unsigned long long groupKey = (prefix > 0) ? (((unsigned long long)(uint32_t)id << 1) | (unsigned long long)((tid >> 4) & 1))
-		                                                 : (0x8000000000000000ull | (unsigned long long)(tid & 31));
-		const unsigned peers = __match_any_sync(0xffffffffu, groupKey);
-		const int leader = __ffs(peers) - 1;
-		if ((tid & 31) == leader && prefix > 0)
-			for (int x = 0; x < prefix; x++)
-			{
-				e1 += q1.x;
-				e2 += q1.z;
-			}
-		const float s1 = __shfl_sync(0xffffffffu, e1, leader), s2 = __shfl_sync(0xffffffffu, e2, leader);
-		if (prefix > 0)
+		if (__any_sync(0xffffffffu, prefix > 0))
 		{
-			e1 = s1;
-			e2 = s2;
-			xcur = tileX0;
+			const unsigned long long groupKey = (prefix > 0) ? (((unsigned long long)(uint32_t)id << 1) | (unsigned long long)((tid >> 4) & 1))
+			                                                 : (0x8000000000000000ull | (unsigned long long)lane);
+			const unsigned peers = __match_any_sync(0xffffffffu, groupKey);
+			const int leader = __ffs(peers) - 1;
+			if (lane == leader && prefix > 0)
+				for (int x = 0; x < prefix; x++)
+				{
+					e1 += q1.x;
+					e2 += q1.z;
+				}
+			const float s1 = __shfl_sync(0xffffffffu, e1, leader), s2 = __shfl_sync(0xffffffffu, e2, leader);
+			if (prefix > 0)
+			{
+				e1 = s1;
+				e2 = s2;
+				xcur = tileX0;
+			}
 		}
 	}
 	if (!inImage)
@@ -808,18 +990,7 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	if (win == 0u)
 	{
 		if (!fp.keep)
-		{
-			float* img = fp.image + 3 * pix;
-			img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
-			fp.depth[pix] = 1e11f;
-			if (fp.saveNormals && fp.normals)
-			{
-				float* pn = fp.normals + 3 * pix;
-				pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
-			}
-			if (fp.winner)
-				fp.winner[pix] = -1;
-		}
+			writeClear(fp, pix);
 		return;
 	}
 	for (int x = xcur; x < px; x++)
@@ -842,32 +1013,27 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	if (fp.winner)
 		fp.winner[pix] = id;
 
-	const int r = __float_as_int(q2.w), flags = __float_as_int(q3.z), tri = __float_as_int(q3.w);
-	if (flags & 1)
+	if (__float_as_uint(q3.z) & MR_REC_CLIPPED)
 	{
-		shadeClippedPixel(fp, r, tri, id & 1, k0, k1, k2, pix);
+		shadeClippedPixel(fp, &fp.srecs[id], id & 1, k0, k1, k2, pix);
 		return;
 	}
-	const RDyn* rd = &fp.rdyn[r];
-	const MatDev mat = fp.mats[rd->material];
-	const bool needGeom = fp.lighting || (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0);
-	ShadeIn in;
-	in.k0 = k0; in.k1 = k1; in.k2 = k2;
-	if (needGeom)
+	const RDyn* rd = &fp.rdyn[sc.z];
+	const MatDev mat = fp.mats[sc.y];
+	Corner c0, c1, c2;
+	if (fp.lighting || (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0))
 	{
-		const RStat rs = fp.rstat[r];
-		const MeshDev m = fp.meshes[rs.mesh];
-		in.c0 = fetchCorner(fp, m, rd, tri, 0);
-		in.c1 = fetchCorner(fp, m, rd, tri, 1);
-		in.c2 = fetchCorner(fp, m, rd, tri, 2);
+		c0 = fetchCorner(fp, rd, sa.x, sa.w, sb.z);
+		c1 = fetchCorner(fp, rd, sa.y, sb.x, sb.w);
+		c2 = fetchCorner(fp, rd, sa.z, sb.y, sc.x);
 	}
 	else
 	{
-		Corner z0;
-		z0.px = z0.py = z0.pz = z0.nx = z0.ny = z0.nz = z0.u = z0.v = 0.0f;
-		in.c0 = z0; in.c1 = z0; in.c2 = z0;
+		c0.px = c0.py = c0.pz = c0.nx = c0.ny = c0.nz = c0.u = c0.v = 0.0f;
+		c1 = c0;
+		c2 = c0;
 	}
-	shadePixel(fp, mat, in, pix);
+	shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ struct RStat // per renderable, changes only when the flattened structure change
 	int mesh;
 	int vertBase; // first vertex instance (into pv)
 	int triBase;  // first triangle instance (submission order)
-	int pad;
+	int idxBase;  // the mesh's first triangle in idxPos / idxNrm (== meshes[mesh].triBase)
 };
 
 struct __align__(16) RDyn // per renderable, per frame
@@ -63,16 +63,30 @@ struct __align__(16) MatDev
 };
 
 // 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
+#define MR_REC_CLIPPED 1u // produced by the near-plane clipper
+#define MR_REC_MASKED 2u  // bbox of at most 32 pixels: `mask` holds the exact coverage
 struct __align__(16) Rec
 {
 	float p0x, p0y, p2x, p2y; // edge origins (e1 is measured from p2, e2 from p0)
 	float n1x, n1y, n2x, n2y; // scaled edge normals
 	float d0, d1, d2;         // iz[] (perspective) or zz[] (ortho)
-	int renderable;
+	uint32_t mask;            // MR_REC_MASKED: bit (y-y0)*W + (x-x0) set iff the pixel passes the inside test
 	uint32_t xspan;           // x0 | x1 << 16 : first / last pixel column of the clamped bbox
 	uint32_t yspan;           // y0 | y1 << 16
-	int flags;                // bit 0: produced by the near-plane clipper
-	int tri;                  // triangle index inside the mesh
+	uint32_t flags;
+	uint32_t pad;
+};
+
+// 48-byte shading record of the same triangle: absolute attribute indices, so that the shading
+// pass reaches its inputs in one hop from the record (the winner-only work of paintMesh's loop C).
+struct __align__(16) ShadeRec
+{
+	int ip0, ip1, ip2; // into pos4
+	int in0, in1, in2; // into nrm4
+	int iu0, iu1, iu2; // into uv2, -1: the mesh has no texcoords
+	int material;      // into mats
+	int renderable;
+	int tri;           // triangle index inside the mesh (the clipper path re-derives its corners)
 };
 
 struct Counters
@@ -81,7 +95,7 @@ struct Counters
 	unsigned long long records;
 	unsigned long long clippedIn;
 	unsigned long long pairTotal;   // (tile, triangle) pairs produced (may exceed capacity)
-	unsigned long long wideRecords;
+	unsigned long long zeroCov;     // set-up triangles with an empty coverage mask (dropped)
 	unsigned long long ovfTotal;    // entries in the overflow pair list
 	unsigned int overflow;          // pairs did not fit: the frame must be re-run with more room
 	unsigned int ctasDone;          // k_setup CTAs finished (the last one scans the tile counters)
@@ -121,9 +135,11 @@ struct FrameParams
 	Rec* recs;
 	int* tileCount;
 	int* tileOffset;
-	int4* pairs;         // warp segments: 32*MR_SEG_PER_LANE entries per k_setup warp
+	int2* pairs;         // (tile, record) warp segments: 32*MR_SEG_PER_LANE entries per k_setup warp
 	int* warpPairCount;  // used entries per segment
-	int4* ovfPairs;      // overflow list (pairCap entries)
+	int2* ovfPairs;      // overflow list (pairCap entries)
+	int* tileCursor;     // per-tile fill cursor of the scatter pass
+	ShadeRec* srecs;
 	int* bins;
 	Counters* ctr;
 
