@@ -109,8 +109,10 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, srecs, tileCount, tileOffset, tileCursor, pairs, warpPairCount, ovfPairs, bins, ctr;
-	size_t pairCap;
+	DevBuf pv, recs, srecs, tileCount, ovfPairs, bins, ctr;
+	int binCap;    // entries per tile bin
+	int binCapWanted;
+	size_t ovfCap; // entries in the overflow list
 	size_t h2dBytesLastFrame;
 
 	// outputs
@@ -126,7 +128,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), pairCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), haveFrame(false)
 	{
 		memset(&lastFrame, 0, sizeof(lastFrame));
@@ -190,7 +192,7 @@ void absorbCounters(mr_ctx* c, const Counters& k)
 }
 
 // Retires one slot: waits for its frame, reads its counters. Returns 1 if that frame overflowed
-// its pair queues (then pairCap has been raised), 0 if fine, <0 on error.
+// its overflow list (then the capacities have been raised), 0 if fine, <0 on error.
 int retireSlot(mr_ctx* c, int i)
 {
 	mr_ctx::Slot& s = c->slots[i];
@@ -200,10 +202,18 @@ int retireSlot(mr_ctx* c, int i)
 	s.pending = false;
 	const Counters k = *s.hostCtr;
 	absorbCounters(c, k);
+	// Many spilled entries make the tile kernel scan a long overflow list: give the bins more room
+	// for the following frames (the current frame is still correct).
+	if (k.ovfTotal > 4096 && k.maxTile > (unsigned)c->binCap)
+	{
+		int want = c->binCap;
+		while (want < (int)std::min<unsigned>(k.maxTile, 1u << 20))
+			want <<= 1;
+		c->binCapWanted = std::max(c->binCapWanted, want);
+	}
 	if (!k.overflow)
 		return 0;
-	const size_t need = std::max((size_t)k.pairTotal, (size_t)k.ovfTotal);
-	c->pairCap = std::max(c->pairCap, need + need / 4 + 1024);
+	c->ovfCap = std::max(c->ovfCap, (size_t)k.ovfTotal + (size_t)k.ovfTotal / 4 + 1024);
 	c->stats.regrows++;
 	return 1;
 }
@@ -302,22 +312,26 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
-	MR_CUDA(c, c->tileCursor.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
-	MR_CUDA(c, c->tileOffset.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->ctr.ensure(sizeof(Counters)));
-	if (c->pairCap < (size_t)c->nTriInst * 2 + 65536)
-		c->pairCap = (size_t)c->nTriInst * 2 + 65536;
-	if (c->pairCap > 0x7fffffffULL)
-		return setError(c, MR_E_OVERFLOW, "more than 2^31 (tile, triangle) pairs");
 	{
-		const size_t nWarps = ((size_t)c->nTriInst + 31) / 32;
-		MR_CUDA(c, c->pairs.ensure(sizeof(int2) * 32 * MR_SEG_PER_LANE * std::max<size_t>(nWarps, 1)));
-		MR_CUDA(c, c->warpPairCount.ensure(sizeof(int) * (std::max<size_t>(nWarps, 1) + 8)));
+		// Bin capacity: a power of two, at least 256 and at least 8x the mean triangles per tile,
+		// within a 1 GiB budget for the bin array; doubled on demand when tiles spill a lot.
+		int want = 256;
+		const long long mean8 = 8LL * c->nTriInst / std::max(nTiles, 1);
+		while (want < mean8 && want < (1 << 20))
+			want <<= 1;
+		want = std::max(want, c->binCapWanted);
+		while (want > 256 && (long long)want * nTiles * 4 > (1LL << 30))
+			want >>= 1;
+		c->binCap = std::max(c->binCap, want);
+		if (c->ovfCap < 65536)
+			c->ovfCap = 65536;
+		if (c->ovfCap > 0x7fffffffULL)
+			return setError(c, MR_E_OVERFLOW, "more than 2^31 spilled (tile, triangle) pairs");
+		MR_CUDA(c, c->bins.ensure(sizeof(int) * (size_t)c->binCap * (size_t)nTiles));
+		MR_CUDA(c, c->ovfPairs.ensure(sizeof(int2) * c->ovfCap));
 	}
-	MR_CUDA(c, c->ovfPairs.ensure(sizeof(int2) * c->pairCap));
-	MR_CUDA(c, c->bins.ensure(sizeof(int) * c->pairCap));
-	c->pairCap = std::min(c->ovfPairs.cap / sizeof(int2), c->bins.cap / sizeof(int));
 	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
 	if (rc)
 		return rc;
@@ -439,7 +453,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.nRenderables = nR;
 	fp.nVertInst = c->nVertInst;
 	fp.nTriInst = c->nTriInst;
-	fp.pairCap = (int)std::min<size_t>(c->pairCap, 0x7fffffff);
+	fp.binCap = c->binCap;
+	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
 	fp.pos4 = c->pos4.as<float4>();
 	fp.nrm4 = c->nrm4.as<float4>();
 	fp.uv2 = c->uv2.as<float2>();
@@ -456,11 +471,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.pv = c->pv.as<float4>();
 	fp.recs = c->recs.as<Rec>();
 	fp.tileCount = c->tileCount.as<int>();
-	fp.tileOffset = c->tileOffset.as<int>();
-	fp.pairs = c->pairs.as<int2>();
-	fp.warpPairCount = c->warpPairCount.as<int>();
 	fp.ovfPairs = c->ovfPairs.as<int2>();
-	fp.tileCursor = c->tileCursor.as<int>();
 	fp.srecs = c->srecs.as<ShadeRec>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>();
@@ -476,7 +487,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	slot.pending = true;
 	c->slotNewest = slotIndex;
 	c->slotNext = (slotIndex + 1) % mr_ctx::kSlots;
-	c->stats.kernels_launched = (c->nTriInst > 0) ? 4 : 3;
+	c->stats.kernels_launched = (c->nTriInst > 0) ? 3 : 2;
 	return MR_OK;
 }
 
@@ -572,8 +583,8 @@ void mr_destroy(mr_ctx* c)
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
-		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount, &c->tileOffset,
-		               &c->pairs, &c->warpPairCount, &c->ovfPairs, &c->bins, &c->srecs, &c->tileCursor, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
+		               &c->ovfPairs, &c->bins, &c->srecs, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)
@@ -638,6 +649,8 @@ int mr_set_size(mr_ctx* c, int w, int h)
 	c->h = h;
 	c->tilesX = (w + MR_TILE - 1) / MR_TILE;
 	c->tilesY = (h + MR_TILE - 1) / MR_TILE;
+	c->binCap = 0;
+	c->bins.release();
 	c->image.release();
 	c->depth.release();
 	c->normals.release();

@@ -6,7 +6,6 @@
 //   k_vertex   reference loop A            src/Renderer.cpp:344-345 + htransform :13-20, :195-196
 //   k_setup    reference loop C + setup    src/Renderer.cpp:351-380, :163-224, clipTriangle :131-161,
 //              plus the exact coverage mask of small triangles (loops D/E :238-249 without depth)
-//   k_scatter  16x16 tile binning (no reference counterpart)
 //   k_raster   reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
 #include <math.h>
@@ -115,15 +114,12 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
-	{
 		fp.tileCount[vi] = 0;
-		fp.tileCursor[vi] = 0;
-	}
 	if (vi == 0)
 	{
 		Counters* c = fp.ctr;
 		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->zeroCov = 0;
-		c->overflow = 0; c->ctasDone = 0; c->ovfTotal = 0;
+		c->overflow = 0; c->ovfTotal = 0; c->maxTile = 0;
 	}
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return; // blocks that only clear counters
@@ -325,29 +321,36 @@ __device__ __forceinline__ int clipTriangle(float z, Corner v0, Corner v1, Corne
 	return 2;
 }
 
-// Emits the (tile, record) pairs of one record with plain per-thread atomics into the overflow
-// pair list (slow paths: clipper output, triangles spanning more than MR_SEG_PER_LANE tiles).
-__device__ __forceinline__ void emitPairsSerial(const FrameParams& fp, int id, const Setup& s)
+// Appends record `id` to tile `tile`'s bin at position `slot` (from the tile counter); entries
+// beyond the bin capacity go to the global overflow list that the tile kernel scans.
+__device__ __forceinline__ void binStore(const FrameParams& fp, int tile, int slot, int id)
+{
+	if (slot < fp.binCap)
+		fp.bins[(size_t)tile * fp.binCap + slot] = id;
+	else
+	{
+		const unsigned long long o = atomicAdd(&fp.ctr->ovfTotal, 1ull);
+		if (o < (unsigned long long)fp.ovfCap)
+			fp.ovfPairs[o] = make_int2(tile, id);
+		else
+			fp.ctr->overflow = 1u;
+	}
+}
+
+// Bins one record into every tile of its bbox with per-thread atomics (slow paths: clipper
+// output, triangles spanning more than MR_SEG_PER_LANE tiles).
+__device__ __forceinline__ void binSerial(const FrameParams& fp, int id, const Setup& s)
 {
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
 	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
 	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, tyLo), ty1 = min(s.y1 >> MR_TILE_SHIFT, tyHi);
-	if (ty1 < ty0)
-		return;
-	const int n = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-	const unsigned long long base = atomicAdd(&fp.ctr->ovfTotal, (unsigned long long)n);
-	if (base + (unsigned long long)n > (unsigned long long)fp.pairCap)
-	{
-		fp.ctr->overflow = 1u;
-		return;
-	}
-	int2* dst = fp.ovfPairs + base;
 	for (int ty = ty0; ty <= ty1; ty++)
 		for (int tx = tx0; tx <= tx1; tx++)
 		{
 			const int tile = ty * fp.tilesX + tx;
-			atomicAdd(&fp.tileCount[tile], 1);
-			*dst++ = make_int2(tile, id);
+			if ((s.flags & MR_REC_MASKED) && maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) == 0u)
+				continue;
+			binStore(fp, tile, atomicAdd(&fp.tileCount[tile], 1), id);
 		}
 }
 
@@ -386,69 +389,21 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 		const int id = 2 * t + sub;
 		storeRec(&fp.recs[id], a, b, c, s);
 		storeShadeRec(fp, &fp.srecs[id], r, rs, tri, ia, ib, ic);
-		emitPairsSerial(fp, id, s);
+		binSerial(fp, id, s);
 		nrec++;
 	}
 	return nrec;
 }
 
-// exclusive scan of tileCount[0..n) into tileOffset[], by one 256-thread CTA
-__device__ __forceinline__ void scanTiles(const FrameParams& fp, int* sh /* >= 34 ints */)
-{
-	const int n = fp.tilesX * fp.tilesY;
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const int per = (n + 255) / 256;
-	const int lo = min(tid * per, n), hi = min(lo + per, n);
-	int sum = 0;
-	for (int i = lo; i < hi; i++)
-		sum += __ldcg(&fp.tileCount[i]);
-	int incl = sum;
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		const int u = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o)
-			incl += u;
-	}
-	if (lane == 31)
-		sh[wid] = incl;
-	__syncthreads();
-	if (wid == 0)
-	{
-		int v = (lane < 8) ? sh[lane] : 0, t = v;
-		for (int o = 1; o < 8; o <<= 1)
-		{
-			const int u = __shfl_up_sync(0xffffffffu, t, o);
-			if (lane >= o)
-				t += u;
-		}
-		if (lane < 8)
-			sh[lane] = t - v;
-		if (lane == 7)
-		{
-			// total number of (tile, triangle) pairs of the frame; must fit the bin array
-			fp.ctr->pairTotal = (unsigned long long)t;
-			if (t > fp.pairCap)
-				fp.ctr->overflow = 1u;
-		}
-	}
-	__syncthreads();
-	int run = sh[wid] + incl - sum;
-	for (int i = lo; i < hi; i++)
-	{
-		fp.tileOffset[i] = run;
-		run += __ldcg(&fp.tileCount[i]);
-	}
-}
-
 // ------------------------------------------------------------------------------------------
-// Kernel 2: near test, clip, setup, coverage mask, and (tile, triangle) pair emission.
+// Kernel 2: near test, clip, setup, coverage mask, and binning.
 // One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
-// outputs at 2t and 2t+1): the index is the submission id. Its (tile, record) pairs go to the
-// warp's private segment of pairs[] (MR_SEG_PER_LANE entries per lane, compacted with a warp
-// prefix sum, no global allocation) and the tile counters are bumped with one fire-and-forget
-// atomic per distinct tile per warp (__match_any_sync: neighbouring triangles mostly share a
-// tile). Triangles covering more tiles use the overflow list. The last CTA to finish turns the
-// tile counters into offsets (exclusive scan).
+// outputs at 2t and 2t+1): the index is the submission id. It is appended to the bin of every
+// 16x16 tile that contains covered pixels: bins have a fixed capacity per tile (fp.binCap), the
+// position comes from the tile counter with one atomic per distinct tile per warp
+// (__match_any_sync: neighbouring triangles mostly share a tile), and the rare entries beyond the
+// capacity go to a global overflow list. The order inside a bin does not matter: depth ties are
+// resolved on the record index (submission id), not on arrival order.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FrameParams fp)
 {
@@ -499,7 +454,7 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 	}
 	__syncwarp();
 
-	// ---- pairs: warp-private segment for triangles covering <= MR_SEG_PER_LANE tiles ----
+	// ---- binning: up to MR_SEG_PER_LANE tiles per triangle, warp-aggregated ----
 	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
 	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
 	const int nx = tx1 - tx0 + 1;
@@ -514,40 +469,44 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 			if (!(s.flags & MR_REC_MASKED) || maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) != 0u)
 				live |= 1u << k;
 		}
-	const int npairs = __popc(live);
-	int incl = npairs;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
 	{
-		const int v = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o)
-			incl += v;
-	}
-	const int gw = blockIdx.x * 8 + wid; // global warp index == t / 32
-	if (lane == 31)
-		fp.warpPairCount[gw] = incl;
-	{
-		int2* dst = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE) + (incl - npairs);
 		const int id = 2 * t;
-		const int rounds = __reduce_max_sync(0xffffffffu, npairs);
+		const int rounds = __reduce_max_sync(0xffffffffu, __popc(live));
+		// issue the counter atomics of all rounds first, use their results afterwards
+		int tileOf[MR_SEG_PER_LANE], baseOf[MR_SEG_PER_LANE], rankOf[MR_SEG_PER_LANE], leadOf[MR_SEG_PER_LANE];
 		uint32_t rest = live;
-		for (int k = 0; k < rounds; k++)
+#pragma unroll
+		for (int k = 0; k < MR_SEG_PER_LANE; k++)
 		{
-			const bool on = rest != 0u;
-			const int kk = on ? __ffs(rest) - 1 : 0;
-			rest &= rest - 1u;
-			const int tile = on ? (ty0 + kk / nx) * fp.tilesX + tx0 + kk % nx : -1 - lane;
-			const unsigned peers = __match_any_sync(0xffffffffu, tile);
-			if (on)
+			tileOf[k] = -1; baseOf[k] = 0; rankOf[k] = 0; leadOf[k] = 0;
+			if (k < rounds)
 			{
-				if (lane == __ffs(peers) - 1)
-					atomicAdd(&fp.tileCount[tile], __popc(peers)); // result unused: a RED, no round trip
-				dst[k] = make_int2(tile, id);
+				const bool on = rest != 0u;
+				const int kk = on ? __ffs(rest) - 1 : 0;
+				rest &= rest - 1u;
+				const int tile = on ? (ty0 + kk / nx) * fp.tilesX + tx0 + kk % nx : -1 - lane;
+				const unsigned peers = __match_any_sync(0xffffffffu, tile);
+				leadOf[k] = __ffs(peers) - 1;
+				rankOf[k] = __popc(peers & ((1u << lane) - 1u));
+				if (on)
+				{
+					tileOf[k] = tile;
+					if (lane == leadOf[k])
+						baseOf[k] = atomicAdd(&fp.tileCount[tile], __popc(peers));
+				}
 			}
 		}
+#pragma unroll
+		for (int k = 0; k < MR_SEG_PER_LANE; k++)
+			if (k < rounds)
+			{
+				const int slot = __shfl_sync(0xffffffffu, baseOf[k], leadOf[k]) + rankOf[k];
+				if (tileOf[k] >= 0)
+					binStore(fp, tileOf[k], slot, id);
+			}
 	}
 	if (big)
-		emitPairsSerial(fp, 2 * t, s);
+		binSerial(fp, 2 * t, s);
 
 	// ---- statistics: one atomic per CTA ----
 	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
@@ -559,7 +518,6 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 		sh[40 + wid] = nclipWarp;
 		sh[48 + wid] = nzeroWarp;
 	}
-	// ---- last CTA done: tile counters -> tile offsets ----
 	__syncthreads();
 	if (threadIdx.x == 0)
 	{
@@ -573,63 +531,6 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 		if (nr) atomicAdd(&fp.ctr->records, (unsigned long long)nr);
 		if (nc) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nc);
 		if (nz) atomicAdd(&fp.ctr->zeroCov, (unsigned long long)nz);
-		__threadfence();
-		sh[31] = (atomicAdd(&fp.ctr->ctasDone, 1u) == gridDim.x - 1) ? 1 : 0;
-	}
-	__syncthreads();
-	if (sh[31])
-	{
-		__threadfence();
-		scanTiles(fp, sh);
-	}
-}
-
-// Frames without triangles still need zero offsets for the raster kernel.
-__global__ void __launch_bounds__(256) k_scan_only(const __grid_constant__ FrameParams fp)
-{
-	__shared__ int sh[40];
-	scanTiles(fp, sh);
-}
-
-// ------------------------------------------------------------------------------------------
-// Kernel 3: scatter the pairs into the per-tile bins. A warp per k_setup warp segment (then the
-// overflow list); the position inside a tile's bin comes from the tile's fill cursor, again one
-// atomic per distinct tile per warp. The order inside a bin does not matter: depth ties are
-// resolved on the record index (submission id), not on arrival order.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ FrameParams fp)
-{
-	if (__ldcg(&fp.ctr->overflow))
-		return;
-	const int lane = threadIdx.x & 31;
-	const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
-	const int nWarps = (fp.nTriInst + 31) >> 5;
-	if (gw < nWarps)
-	{
-		const int n = fp.warpPairCount[gw];
-		const int2* src = fp.pairs + (size_t)gw * (32 * MR_SEG_PER_LANE);
-		for (int k0 = 0; k0 < n; k0 += 32)
-		{
-			const int k = k0 + lane;
-			const bool on = k < n;
-			int2 p = make_int2(-1 - lane, 0);
-			if (on)
-				p = src[k];
-			const unsigned peers = __match_any_sync(0xffffffffu, p.x);
-			const int leader = __ffs(peers) - 1;
-			int slot = 0;
-			if (on && lane == leader)
-				slot = atomicAdd(&fp.tileCursor[p.x], __popc(peers));
-			slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
-			if (on)
-				fp.bins[fp.tileOffset[p.x] + slot] = p.y;
-		}
-	}
-	const unsigned long long ovf = fp.ctr->ovfTotal;
-	for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < ovf; i += (unsigned long long)gridDim.x * 256)
-	{
-		const int2 p = fp.ovfPairs[i];
-		fp.bins[fp.tileOffset[p.x] + atomicAdd(&fp.tileCursor[p.x], 1)] = p.y;
 	}
 }
 
@@ -786,12 +687,116 @@ __device__ __forceinline__ void writeClear(const FrameParams& fp, size_t pix)
 		fp.winner[pix] = -1;
 }
 
+// Phase 1 for one batch of up to 32 binned triangles (a lane each; `have` lanes hold record `id`).
+__device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq, unsigned long long* keys, int& qhead, int& qcount,
+                                            int& parity, int lane, bool have, int id, int tileX0, int tileY0)
+{
+	const int slot = parity * 32 + lane;
+	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+	if (have)
+	{
+		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
+		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
+	}
+	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y), flags = __float_as_uint(q3.z);
+	const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
+	const bool masked = have && (flags & MR_REC_MASKED);
+	__syncwarp();
+
+	// small triangles: exact coverage is known, push the covered pixels of this tile
+	{
+		uint32_t tm = masked ? maskInTile(__float_as_uint(q2.w), x0, x1, y0, y1, tileX0, tileY0) : 0u;
+		const int W = x1 - x0 + 1;
+		const float ptx = (float)x0 + 0.5f;
+		const int rounds = __reduce_max_sync(0xffffffffu, __popc(tm));
+		for (int k = 0; k < rounds; k++)
+		{
+			const bool on = tm != 0u;
+			const int bit = on ? __ffs(tm) - 1 : 0;
+			tm &= tm - 1u;
+			int yy = 0, xx = bit;
+			while (xx >= W) // at most 31 subtractions, usually 0-3
+			{
+				xx -= W;
+				yy++;
+			}
+			const float fy = (float)(y0 + yy) + 0.5f;
+			float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
+			float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
+			for (int j = 0; j < xx; j++)
+			{
+				e1 += q1.x;
+				e2 += q1.z;
+			}
+			const uint32_t info = (uint32_t)((y0 + yy - tileY0) * MR_TILE + (x0 + xx - tileX0)) | ((uint32_t)slot << 8);
+			pushFragment(fp, wq, keys, qhead, qcount, lane, on, e1, e2, info);
+		}
+	}
+
+	// larger triangles of this batch: a quad of lanes scans each, rows interleaved
+	unsigned large = __ballot_sync(0xffffffffu, have && !masked);
+	while (large != 0u)
+	{
+		const int q = lane & 3, quad = lane >> 2;
+		const int src = __fns(large, 0, quad + 1); // lane that owns this quad's triangle, or -1
+		const bool on = src >= 0 && src < 32;
+		const int s = on ? src : 0;
+		const float p0x = __shfl_sync(0xffffffffu, q0.x, s), p0y = __shfl_sync(0xffffffffu, q0.y, s);
+		const float p2x = __shfl_sync(0xffffffffu, q0.z, s), p2y = __shfl_sync(0xffffffffu, q0.w, s);
+		const float n1x = __shfl_sync(0xffffffffu, q1.x, s), n1y = __shfl_sync(0xffffffffu, q1.y, s);
+		const float n2x = __shfl_sync(0xffffffffu, q1.z, s), n2y = __shfl_sync(0xffffffffu, q1.w, s);
+		const int bx0 = __shfl_sync(0xffffffffu, x0, s), bx1 = min(__shfl_sync(0xffffffffu, x1, s), tileX0 + MR_TILE - 1);
+		const int by0 = max(__shfl_sync(0xffffffffu, y0, s), tileY0), by1 = min(__shfl_sync(0xffffffffu, y1, s), tileY0 + MR_TILE - 1);
+		const int tslot = parity * 32 + s;
+		const int xs = max(bx0, tileX0);
+		const int ncols = on ? max(bx1 - xs + 1, 0) : 0;
+		const int myRows = on ? max((by1 - by0 - q + 4) >> 2, 0) : 0; // rows by0+q, by0+q+4, ...
+		const float ptx = (float)bx0 + 0.5f;
+		const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
+		const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
+		for (int rr = 0; rr < maxRows; rr++)
+		{
+			const bool rowOn = rr < myRows;
+			const int y = by0 + q + 4 * rr;
+			const float fy = (float)y + 0.5f;
+			float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
+			float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
+			if (rowOn)
+				for (int x = bx0; x < xs; x++) // chain prefix left of the tile
+				{
+					e1 += n1x;
+					e2 += n2x;
+				}
+			const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)tslot << 8);
+			for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
+			{
+				const float k0 = 1.0f - e1 - e2;
+				const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
+				pushFragment(fp, wq, keys, qhead, qcount, lane, inside, e1, e2, rowInfo + (uint32_t)cc);
+			}
+		}
+		// drop the (up to) eight triangles just done
+		for (int k = 0; k < 8 && large != 0u; k++)
+			large &= large - 1u;
+	}
+	// Triangle slots of this parity are overwritten two batches from now; fragments still queued
+	// then must not refer to them, so drain before reusing a parity.
+	if (parity == 1 && qcount > 0)
+	{
+		__syncwarp();
+		consumeFragments(fp, wq, keys, qhead, qcount, lane);
+		qhead = (qhead + qcount) & (MR_FQ_CAP - 1);
+		qcount = 0;
+	}
+	parity ^= 1;
+	__syncwarp();
+}
+
 __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[8];
-	if (__ldcg(&fp.ctr->overflow))
-		return; // the host regrows the pair buffers and re-runs the frame
 	const int tx = blockIdx.x;
 	const int ty = fp.tileRow0 + blockIdx.y;
 	const int tile = ty * fp.tilesX + tx;
@@ -801,10 +806,16 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	const int py = ty * MR_TILE + (tid >> 4);
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
 	const size_t pix = (size_t)py * fp.w + px;
-	const int count = fp.tileCount[tile];
+	const int total = fp.tileCount[tile];                              // triangles binned to this tile
+	const unsigned long long ovfTotal = __ldcg(&fp.ctr->ovfTotal);     // (two independent loads)
+	const unsigned overflowed = __ldcg(&fp.ctr->overflow);
+	if (total > fp.binCap && threadIdx.x == 0)
+		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
+	if (overflowed)
+		return; // the overflow list itself overflowed: the host regrows it and re-runs the frame
 	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
 
-	if (count == 0 && !fp.keep)
+	if (total == 0 && !fp.keep)
 	{
 		if (inImage)
 			writeClear(fp, pix); // empty tile: clear values only
@@ -819,119 +830,38 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 		}
 		keys[tid] = k0;
 	}
+	if (tid == 0 && total > 0)
+		atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
 	__syncthreads();
 
 	// ---- phase 1: coverage + depth ----
 	{
 		WarpQueue& wq = queues[tid >> 5];
-		const int* bin = fp.bins + fp.tileOffset[tile];
+		const int count = min(total, fp.binCap);
+		const int* bin = fp.bins + (size_t)tile * fp.binCap;
 		int qhead = 0, qcount = 0; // warp-uniform
 		int parity = 0;
-		for (int base = (tid >> 5) * 32; base < count; base += 256, parity ^= 1)
+		for (int base = (tid >> 5) * 32; base < count; base += 256)
 		{
 			const int i = base + lane;
 			const bool have = i < count;
-			const int slot = parity * 32 + lane;
-			int id = 0;
-			float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-			if (have)
+			const int id = have ? __ldg(&bin[i]) : 0;
+			rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
+		}
+		if (total > fp.binCap)
+		{
+			// this tile spilled: its remaining triangles are somewhere in the global overflow list
+			const unsigned long long n = min(ovfTotal, (unsigned long long)fp.ovfCap);
+			for (unsigned long long base = (unsigned long long)(tid >> 5) * 32; base < n; base += 256)
 			{
-				id = __ldg(&bin[i]);
-				const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-				q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
-				wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
+				const unsigned long long i = base + lane;
+				int2 p = make_int2(-1, 0);
+				if (i < n)
+					p = __ldg(&fp.ovfPairs[i]);
+				const bool have = p.x == tile;
+				if (__any_sync(0xffffffffu, have))
+					rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, p.y, tileX0, tileY0);
 			}
-			const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y), flags = __float_as_uint(q3.z);
-			const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
-			const bool masked = have && (flags & MR_REC_MASKED);
-			__syncwarp();
-
-			// small triangles: exact coverage is known, push the covered pixels of this tile
-			{
-				uint32_t tm = masked ? maskInTile(__float_as_uint(q2.w), x0, x1, y0, y1, tileX0, tileY0) : 0u;
-				const int W = x1 - x0 + 1;
-				const float ptx = (float)x0 + 0.5f;
-				const int rounds = __reduce_max_sync(0xffffffffu, __popc(tm));
-				for (int k = 0; k < rounds; k++)
-				{
-					const bool on = tm != 0u;
-					const int bit = on ? __ffs(tm) - 1 : 0;
-					tm &= tm - 1u;
-					int yy = 0, xx = bit;
-					while (xx >= W) // at most 31 subtractions, usually 0-3
-					{
-						xx -= W;
-						yy++;
-					}
-					const float fy = (float)(y0 + yy) + 0.5f;
-					float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
-					float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
-					for (int j = 0; j < xx; j++)
-					{
-						e1 += q1.x;
-						e2 += q1.z;
-					}
-					const uint32_t info = (uint32_t)((y0 + yy - tileY0) * MR_TILE + (x0 + xx - tileX0)) | ((uint32_t)slot << 8);
-					pushFragment(fp, wq, keys, qhead, qcount, lane, on, e1, e2, info);
-				}
-			}
-
-			// larger triangles of this batch: a quad of lanes scans each, rows interleaved
-			unsigned large = __ballot_sync(0xffffffffu, have && !masked);
-			while (large != 0u)
-			{
-				const int q = lane & 3, quad = lane >> 2;
-				const int src = __fns(large, 0, quad + 1); // lane that owns this quad's triangle, or -1
-				const bool on = src >= 0 && src < 32;
-				const int s = on ? src : 0;
-				const float p0x = __shfl_sync(0xffffffffu, q0.x, s), p0y = __shfl_sync(0xffffffffu, q0.y, s);
-				const float p2x = __shfl_sync(0xffffffffu, q0.z, s), p2y = __shfl_sync(0xffffffffu, q0.w, s);
-				const float n1x = __shfl_sync(0xffffffffu, q1.x, s), n1y = __shfl_sync(0xffffffffu, q1.y, s);
-				const float n2x = __shfl_sync(0xffffffffu, q1.z, s), n2y = __shfl_sync(0xffffffffu, q1.w, s);
-				const int bx0 = __shfl_sync(0xffffffffu, x0, s), bx1 = min(__shfl_sync(0xffffffffu, x1, s), tileX0 + MR_TILE - 1);
-				const int by0 = max(__shfl_sync(0xffffffffu, y0, s), tileY0), by1 = min(__shfl_sync(0xffffffffu, y1, s), tileY0 + MR_TILE - 1);
-				const int tslot = parity * 32 + s;
-				const int xs = max(bx0, tileX0);
-				const int ncols = on ? max(bx1 - xs + 1, 0) : 0;
-				const int myRows = on ? max((by1 - by0 - q + 4) >> 2, 0) : 0; // rows by0+q, by0+q+4, ...
-				const float ptx = (float)bx0 + 0.5f;
-				const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
-				const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
-				for (int rr = 0; rr < maxRows; rr++)
-				{
-					const bool rowOn = rr < myRows;
-					const int y = by0 + q + 4 * rr;
-					const float fy = (float)y + 0.5f;
-					float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
-					float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
-					if (rowOn)
-						for (int x = bx0; x < xs; x++) // chain prefix left of the tile
-						{
-							e1 += n1x;
-							e2 += n2x;
-						}
-					const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)tslot << 8);
-					for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
-					{
-						const float k0 = 1.0f - e1 - e2;
-						const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
-						pushFragment(fp, wq, keys, qhead, qcount, lane, inside, e1, e2, rowInfo + (uint32_t)cc);
-					}
-				}
-				// drop the (up to) eight triangles just done
-				for (int k = 0; k < 8 && large != 0u; k++)
-					large &= large - 1u;
-			}
-			// Triangle slots of this parity are overwritten two iterations from now; fragments
-			// still queued then must not refer to them, so drain before reusing a parity.
-			if (parity == 1 && qcount > 0)
-			{
-				__syncwarp();
-				consumeFragments(fp, wq, keys, qhead, qcount, lane);
-				qhead = (qhead + qcount) & (MR_FQ_CAP - 1);
-				qcount = 0;
-			}
-			__syncwarp();
 		}
 		if (qcount > 0)
 		{
@@ -1105,12 +1035,8 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	if (ev) cudaEventRecord(ev[1], stream);
 	if (fp.nTriInst > 0)
 		k_setup<<<(fp.nTriInst + 255) / 256, 256, 0, stream>>>(fp);
-	else
-		k_scan_only<<<1, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);
-	if (fp.nTriInst > 0)
-		k_scatter<<<(fp.nTriInst + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[4], stream);
 	if (fp.tileRows > 0)
 		k_raster<<<dim3(fp.tilesX, fp.tileRows), 256, 0, stream>>>(fp);

@@ -14,7 +14,7 @@
 //   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
 //                  triangle instance index in submission order: the index IS the submission id
 //                  that resolves equal-depth ties
-//   tileCount[] tileOffset[] pairs[] bins[]   16x16-tile binning
+//   tileCount[] bins[] ovfPairs[]   16x16-tile binning: fixed-capacity bins + global overflow list
 #ifndef MR_TYPES_H
 #define MR_TYPES_H
 
@@ -24,7 +24,7 @@
 #define MR_TILE 16
 #define MR_TILE_SHIFT 4
 #define MR_TILE_PIXELS 256
-#define MR_SEG_PER_LANE 4 // pair slots per k_setup lane in its warp's private segment
+#define MR_SEG_PER_LANE 4 // tiles per triangle binned on the warp-aggregated fast path
 
 struct MeshDev
 {
@@ -94,11 +94,11 @@ struct Counters
 	unsigned long long trianglesIn;
 	unsigned long long records;
 	unsigned long long clippedIn;
-	unsigned long long pairTotal;   // (tile, triangle) pairs produced (may exceed capacity)
+	unsigned long long pairTotal;   // (tile, triangle) pairs of the frame (summed by the tile kernel)
 	unsigned long long zeroCov;     // set-up triangles with an empty coverage mask (dropped)
 	unsigned long long ovfTotal;    // entries in the overflow pair list
-	unsigned int overflow;          // pairs did not fit: the frame must be re-run with more room
-	unsigned int ctasDone;          // k_setup CTAs finished (the last one scans the tile counters)
+	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
+	unsigned int maxTile;           // largest per-tile count among tiles that spilled
 };
 
 struct FrameParams
@@ -115,7 +115,8 @@ struct FrameParams
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int nRenderables, nVertInst, nTriInst;
-	int pairCap;
+	int binCap; // entries per tile bin
+	int ovfCap; // entries in the overflow list
 
 	const float4* pos4;
 	const float4* nrm4;
@@ -133,14 +134,10 @@ struct FrameParams
 
 	float4* pv;
 	Rec* recs;
-	int* tileCount;
-	int* tileOffset;
-	int2* pairs;         // (tile, record) warp segments: 32*MR_SEG_PER_LANE entries per k_setup warp
-	int* warpPairCount;  // used entries per segment
-	int2* ovfPairs;      // overflow list (pairCap entries)
-	int* tileCursor;     // per-tile fill cursor of the scatter pass
+	int* tileCount;      // triangles binned per tile (may exceed binCap: the rest is in ovfPairs)
+	int* bins;           // tilesX*tilesY bins of binCap record indices
+	int2* ovfPairs;      // (tile, record) entries that did not fit their bin
 	ShadeRec* srecs;
-	int* bins;
 	Counters* ctr;
 
 	float* image;   // h*w*3
