@@ -609,6 +609,26 @@ __device__ __forceinline__ void pushFragment(const FrameParams& fp, WarpQueue& w
 	}
 }
 
+// pow(base, shininess) in double, as the reference evaluates it. Shininess is almost always a
+// small whole number: then the power is a few double multiplications (relative error below
+// 2^-49, invisible after the result is narrowed to float); anything else takes the library pow.
+__device__ __forceinline__ double powShininess(double base, float shininess)
+{
+	const int n = (int)shininess;
+	if ((float)n == shininess && n >= 1 && n <= 1024 && base >= 0.0 && base <= 2.0)
+	{
+		double r = 1.0, b = base;
+		for (int e = n; e != 0; e >>= 1)
+		{
+			if (e & 1)
+				r *= b;
+			b *= b;
+		}
+		return r;
+	}
+	return pow(base, (double)shininess);
+}
+
 // Renderer.cpp:271-305 for one pixel; writes image (and the normals image).
 __device__ __forceinline__ void shadePixel(const FrameParams& fp, const MatDev& mat, float k0, float k1, float k2,
                                            const Corner& c0, const Corner& c1, const Corner& c2, size_t pix)
@@ -647,7 +667,7 @@ __device__ __forceinline__ void shadePixel(const FrameParams& fp, const MatDev& 
 			const float hn = dot3(hv, normal);
 			const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
 			// the reference's unqualified pow() is the double overload
-			const float specular = (float)pow((double)base, (double)mat.shininess);
+			const float specular = (float)powShininess((double)base, mat.shininess);
 			value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
 		}
 		if (fp.saveNormals && fp.normals)
@@ -807,8 +827,10 @@ __global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FramePar
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
 	const size_t pix = (size_t)py * fp.w + px;
 	const int total = fp.tileCount[tile];                              // triangles binned to this tile
-	const unsigned long long ovfTotal = __ldcg(&fp.ctr->ovfTotal);     // (two independent loads)
-	const unsigned overflowed = __ldcg(&fp.ctr->overflow);
+	// (independent loads; the counters were written by the previous kernels, so the L1-cached
+	// read-only path is fine and keeps 8160 CTAs from hammering one L2 line)
+	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
+	const unsigned overflowed = __ldg(&fp.ctr->overflow);
 	if (total > fp.binCap && threadIdx.x == 0)
 		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
 	if (overflowed)

@@ -91,14 +91,20 @@ struct __align__(16) ShadeRec
 
 struct Counters
 {
+	// line 0: written by k_vertex / k_setup, only read by k_raster
 	unsigned long long trianglesIn;
 	unsigned long long records;
 	unsigned long long clippedIn;
-	unsigned long long pairTotal;   // (tile, triangle) pairs of the frame (summed by the tile kernel)
 	unsigned long long zeroCov;     // set-up triangles with an empty coverage mask (dropped)
-	unsigned long long ovfTotal;    // entries in the overflow pair list
+	unsigned long long ovfTotal;    // entries appended to the overflow list (may exceed its capacity)
 	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
+	unsigned int pad0;
+	unsigned long long pad1[10];
+	// line 1 (offset 128): written by k_raster
+	unsigned long long pairTotal;   // (tile, triangle) pairs of the frame (summed by the tile kernel)
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
+	unsigned int pad2;
+	unsigned long long pad3[14];
 };
 
 struct FrameParams

@@ -88,5 +88,20 @@ def main():
                                                              os.path.getsize(path) / 1024.0))
 
 
+def turntable_reference():
+    """Expected output of examples/turntable.cpp built against the reference's own headers and sources."""
+    import subprocess
+    import tempfile
+    ref, shim = "/root/reference", os.path.join(ROOT, "third_party", "asl_shim")
+    exe = os.path.join(tempfile.mkdtemp(), "turntable_ref")
+    srcs = [os.path.join(ref, "src", f) for f in ("Renderer.cpp", "Scene.cpp", "primitives.cpp")]
+    subprocess.check_call(["g++", "-std=c++11", "-O3", "-ffp-contract=off", "-I", os.path.join(ref, "include"), "-I", shim,
+                           os.path.join(ROOT, "examples", "turntable.cpp")] + srcs + ["-o", exe])
+    out = subprocess.check_output([exe, "4", "320", "200"], text=True)
+    open(os.path.join(HERE, "turntable_ref.txt"), "w").write(out)
+    print(out, end="")
+
+
 if __name__ == "__main__":
     main()
+    turntable_reference()

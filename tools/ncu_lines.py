@@ -21,3 +21,11 @@ ti = sum(f(r[ci]) for r in lines); ts = sum(f(r[cs]) for r in lines)
 print("total warp-instr %d  samples %d" % (ti, ts))
 for r in sorted(lines, key=lambda r: -f(r[ci]))[:n]:
     print("%5.1f%% instr %5.1f%% samp  L%-4s %s" % (100 * f(r[ci]) / ti, 100 * f(r[cs]) / max(ts, 1), r[0], r[1].strip()[:105]))
+
+if len(sys.argv) > 3:  # region totals: "name:lo-hi,name:lo-hi"
+    print("regions:")
+    for spec in sys.argv[3].split(","):
+        name, rng = spec.split(":")
+        lo, hi = [int(x) for x in rng.split("-")]
+        sel = [r for r in lines if lo <= int(r[0]) <= hi]
+        print("  %-14s %5.1f%% instr %5.1f%% samples" % (name, 100 * sum(f(r[ci]) for r in sel) / ti, 100 * sum(f(r[cs]) for r in sel) / max(ts, 1)))
