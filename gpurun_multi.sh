@@ -1,0 +1,3 @@
+nvidia-smi -L
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -15
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>&1 | tail -3 | cut -c1-900
