@@ -81,19 +81,21 @@ struct mr_ctx
 	std::string error;
 
 	int w, h, tilesX, tilesY;
+	int smCount;
 
 	// scene-static device arrays
 	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes;
 	std::vector<MeshDev> hostMeshes;
+	std::vector<int> hostNrmCount; // normals per mesh
 	std::vector<int> texOffset, texRows, texCols;
 	bool haveScene;
 	unsigned sceneSerial;
 
 	// per-frame tables
-	DevBuf rstat, rdyn, mats, vtxBlockR, triBlockR;
+	DevBuf rstat, rdyn, mats, vtxBlockR, triBlockR, nrmBlockR;
 	std::vector<int> structureKey; // mesh id per renderable of the tables currently on the device
 	unsigned structureSerial;
-	int nVertInst, nTriInst;
+	int nVertInst, nTriInst, nNrmInst;
 	// per-frame host staging + counters, a ring so that mr_render never waits for the GPU
 	struct Slot
 	{
@@ -109,7 +111,7 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, srecs, tileCount, ovfPairs, bins, ctr;
+	DevBuf pv, vpos4, vnrm4, recs, srecs, tileCount, ovfPairs, bins, ctr;
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -278,7 +280,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	const int nR = f->n_renderables;
 	// ---- validate + instance bases ----
 	std::vector<RStat> rs((size_t)nR);
-	long long vb = 0, tb = 0;
+	long long vb = 0, tb = 0, nb = 0;
 	bool sameStructure = (c->structureSerial == c->sceneSerial) && ((int)c->structureKey.size() == nR);
 	for (int i = 0; i < nR; i++)
 	{
@@ -287,20 +289,27 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 			return setError(c, MR_E_INVALID, "renderable %d: mesh index %d out of range", i, r.mesh);
 		if (r.material < 0 || r.material >= f->n_materials)
 			return setError(c, MR_E_INVALID, "renderable %d: material index %d out of range", i, r.material);
-		rs[i].mesh = r.mesh;
+		const MeshDev& hm = c->hostMeshes[r.mesh];
 		rs[i].vertBase = (int)vb;
 		rs[i].triBase = (int)tb;
-		rs[i].idxBase = c->hostMeshes[r.mesh].triBase;
-		vb += c->hostMeshes[r.mesh].nPos;
-		tb += c->hostMeshes[r.mesh].nTri;
+		rs[i].nrmBase = (int)nb;
+		rs[i].idxBase = hm.triBase;
+		rs[i].posBase = hm.posBase;
+		rs[i].nrmSrcBase = hm.nrmBase;
+		rs[i].uvBase = hm.uvBase;
+		rs[i].uvTriBase = hm.hasUV ? hm.uvTriBase : -1;
+		vb += hm.nPos;
+		tb += hm.nTri;
+		nb += c->hostNrmCount[r.mesh];
 		if (sameStructure && c->structureKey[i] != r.mesh)
 			sameStructure = false;
 	}
-	if (vb > 0x3fffffffLL || tb > 0x3fffffffLL)
+	if (vb > 0x3fffffffLL || tb > 0x3fffffffLL || nb > 0x3fffffffLL)
 		return setError(c, MR_E_INVALID, "frame too large: %lld vertex instances, %lld triangle instances", vb, tb);
 	c->nVertInst = (int)vb;
 	c->nTriInst = (int)tb;
-	const int nVB = (c->nVertInst + 255) / 256, nTB = (c->nTriInst + 255) / 256;
+	c->nNrmInst = (int)nb;
+	const int nVB = (c->nVertInst + 255) / 256, nTB = (c->nTriInst + 255) / 256, nNB = (c->nNrmInst + 255) / 256;
 
 	// ---- device buffers ----
 	const int nTiles = c->tilesX * c->tilesY;
@@ -309,6 +318,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
+	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
+	MR_CUDA(c, c->vpos4.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
+	MR_CUDA(c, c->vnrm4.ensure(sizeof(float4) * (size_t)std::max(c->nNrmInst, 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
@@ -340,9 +352,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
 	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)(nVB + 1);
 	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)(nTB + 1);
+	const size_t szNB = sameStructure ? 0 : sizeof(int) * (size_t)(nNB + 1);
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
-	const size_t total = szStat + szVB + szTB + szDyn + szMat + 64;
+	const size_t total = szStat + szVB + szTB + szNB + szDyn + szMat + 64;
 	const int slotIndex = c->slotNext;
 	{
 		const int rc0 = retireSlot(c, slotIndex); // normally long finished
@@ -380,9 +393,20 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		tbr[nTB] = std::max(nR - 1, 0);
 		if (szTB) MR_CUDA(c, cudaMemcpyAsync(c->triBlockR.p, sp + off, szTB, cudaMemcpyHostToDevice, c->stream));
 		off += szTB;
+		int* nbr = (int*)(sp + off);
+		for (int b = 0, r = 0; b < nNB; b++)
+		{
+			const int first = b * 256;
+			while (r + 1 < nR && first >= rs[r + 1].nrmBase)
+				r++;
+			nbr[b] = r;
+		}
+		nbr[nNB] = std::max(nR - 1, 0);
+		if (szNB) MR_CUDA(c, cudaMemcpyAsync(c->nrmBlockR.p, sp + off, szNB, cudaMemcpyHostToDevice, c->stream));
+		off += szNB;
 		c->structureKey.resize((size_t)nR);
 		for (int i = 0; i < nR; i++)
-			c->structureKey[i] = rs[i].mesh;
+			c->structureKey[i] = f->renderables[i].mesh;
 		c->structureSerial = c->sceneSerial;
 	}
 	off = (off + 15) & ~(size_t)15;
@@ -418,7 +442,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
 	if (szMat) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	c->h2dBytesLastFrame = szStat + szVB + szTB + szDyn + szMat + sizeof(FrameParams);
+	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + szDyn + szMat + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -453,7 +477,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.nRenderables = nR;
 	fp.nVertInst = c->nVertInst;
 	fp.nTriInst = c->nTriInst;
+	fp.nNrmInst = c->nNrmInst;
+	fp.debug = c->debugFlags;
 	fp.binCap = c->binCap;
+	fp.rasterCtas = c->smCount * 4; // 64 registers x 256 threads: four CTAs per SM
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
 	fp.pos4 = c->pos4.as<float4>();
 	fp.nrm4 = c->nrm4.as<float4>();
@@ -468,7 +495,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.mats = c->mats.as<MatDev>();
 	fp.vtxBlockR = c->vtxBlockR.as<int>();
 	fp.triBlockR = c->triBlockR.as<int>();
+	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
+	fp.vpos4 = c->vpos4.as<float4>();
+	fp.vnrm4 = c->vnrm4.as<float4>();
 	fp.recs = c->recs.as<Rec>();
 	fp.tileCount = c->tileCount.as<int>();
 	fp.ovfPairs = c->ovfPairs.as<int2>();
@@ -544,6 +574,8 @@ mr_ctx* mr_create(int device, int* status)
 		c = new mr_ctx();
 		c->device = device;
 		Bind bind(device);
+		c->smCount = 148;
+		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		for (int i = 0; i < mr_ctx::kSlots && ok; i++)
@@ -584,7 +616,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->srecs, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->ovfPairs, &c->bins, &c->srecs, &c->vpos4, &c->vnrm4, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)
@@ -778,6 +810,9 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 	MR_CUDA(c, cudaGetLastError());
 	MR_CUDA(c, cudaStreamSynchronize(c->stream)); // host arrays are only borrowed for this call
 	c->hostMeshes.swap(md);
+	c->hostNrmCount.resize((size_t)s->n_meshes);
+	for (int i = 0; i < s->n_meshes; i++)
+		c->hostNrmCount[i] = s->meshes[i].n_normals;
 	c->texOffset.swap(to);
 	c->texRows.swap(tr);
 	c->texCols.swap(tc);

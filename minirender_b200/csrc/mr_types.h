@@ -11,6 +11,7 @@
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
 //   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
+//   vpos4[] vnrm4[] float4 per vertex / normal instance: view-space position / normal (loops A, B)
 //   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
 //                  triangle instance index in submission order: the index IS the submission id
 //                  that resolves equal-depth ties
@@ -34,12 +35,16 @@ struct MeshDev
 	int nPos, nTri, hasUV;
 };
 
-struct RStat // per renderable, changes only when the flattened structure changes
+struct __align__(16) RStat // per renderable, changes only when the flattened structure changes
 {
-	int mesh;
-	int vertBase; // first vertex instance (into pv)
-	int triBase;  // first triangle instance (submission order)
-	int idxBase;  // the mesh's first triangle in idxPos / idxNrm (== meshes[mesh].triBase)
+	int vertBase;   // first vertex instance (into pv / vpos4)
+	int triBase;    // first triangle instance (submission order)
+	int nrmBase;    // first normal instance (into vnrm4)
+	int idxBase;    // the mesh's first triangle in idxPos / idxNrm
+	int posBase;    // the mesh's first vertex in pos4
+	int nrmSrcBase; // the mesh's first normal in nrm4
+	int uvBase;     // the mesh's first texcoord in uv2
+	int uvTriBase;  // the mesh's first triangle in idxUv, -1: no texcoords
 };
 
 struct __align__(16) RDyn // per renderable, per frame
@@ -103,7 +108,7 @@ struct Counters
 	// line 1 (offset 128): written by k_raster
 	unsigned long long pairTotal;   // (tile, triangle) pairs of the frame (summed by the tile kernel)
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
-	unsigned int pad2;
+	unsigned int nextTile;          // next tile index handed to a persistent k_raster CTA
 	unsigned long long pad3[14];
 };
 
@@ -120,7 +125,9 @@ struct FrameParams
 	int tileRow0, tileRows; // tile rows covered by this frame (strip rendering)
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
-	int nRenderables, nVertInst, nTriInst;
+	int nRenderables, nVertInst, nTriInst, nNrmInst;
+	int debug; // mr_set_debug flags (4: skip shading, 8: skip phase 1 — profiling experiments only)
+	int rasterCtas; // persistent k_raster CTAs (resident CTAs per SM x SM count)
 	int binCap; // entries per tile bin
 	int ovfCap; // entries in the overflow list
 
@@ -137,8 +144,11 @@ struct FrameParams
 	const MatDev* mats;
 	const int* vtxBlockR; // renderable that owns the first vertex instance of each 256-block
 	const int* triBlockR; // same for triangle instances
+	const int* nrmBlockR; // same for normal instances
 
-	float4* pv;
+	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
+	float4* vpos4;       // per vertex instance: view-space position (reference _vertices)
+	float4* vnrm4;       // per normal instance: view-space normal (reference _normals)
 	Rec* recs;
 	int* tileCount;      // triangles binned per tile (may exceed binCap: the rest is in ovfPairs)
 	int* bins;           // tilesX*tilesY bins of binCap record indices
