@@ -15,6 +15,11 @@ PKG = os.path.join(ROOT, "minirender_b200")
 LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(PKG, "_obj")
 LIB = os.path.join(LIB_DIR, "libminirender_b200.so")
+# experiment hooks: extra nvcc flags (e.g. -DMR_RASTER_MINB=5) and an alternative output name
+EXTRA = os.environ.get("MR_NVCC_EXTRA", "").split()
+if os.environ.get("MR_LIB_NAME"):
+    LIB = os.path.join(LIB_DIR, os.environ["MR_LIB_NAME"])
+    OBJ_DIR = OBJ_DIR + "_" + os.environ["MR_LIB_NAME"].replace(".", "_")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = os.environ.get("CXX") or "g++"
@@ -62,7 +67,7 @@ def build_product(force=False, verbose=False):
         s = os.path.join(PKG, src)
         o = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
         if force or _newer(o, [s] + headers):
-            _run([NVCC] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o], log)
+            _run([NVCC] + NVCC_FLAGS + EXTRA + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o], log)
         objs.append(o)
     for src in CXX_SOURCES:
         s = os.path.join(PKG, src)

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libminirender_b200.so")
+LIB_PATH = os.environ.get("MINIRENDER_B200_LIB") or os.path.join(_HERE, "lib", "libminirender_b200.so")
 
 MR_OK, MR_E_INVALID, MR_E_CUDA, MR_E_NO_DEVICE, MR_E_NO_SCENE, MR_E_OVERFLOW, MR_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 

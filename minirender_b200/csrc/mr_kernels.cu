@@ -353,25 +353,29 @@ __device__ __forceinline__ void binStore(const FrameParams& fp, int tile, int sl
 	}
 }
 
-// Bins one record into every tile of its bbox with per-thread atomics (slow paths: clipper
-// output, triangles spanning more than MR_SEG_PER_LANE tiles).
-__device__ __forceinline__ void binSerial(const FrameParams& fp, int id, const Setup& s)
+// Bins one record into every tile of its bbox, the whole warp working on it (32 tiles per step).
+// All arguments are warp-uniform. Used for triangles spanning more than MR_SEG_PER_LANE tiles and
+// for clipper output: a lone lane walking thousands of tiles is the critical path of scenes with
+// huge triangles.
+__device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, int id, int x0, int x1, int y0, int y1, uint32_t flags, uint32_t mask)
 {
-	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
-	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
-	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, tyLo), ty1 = min(s.y1 >> MR_TILE_SHIFT, tyHi);
-	for (int ty = ty0; ty <= ty1; ty++)
-		for (int tx = tx0; tx <= tx1; tx++)
-		{
-			const int tile = ty * fp.tilesX + tx;
-			if ((s.flags & MR_REC_MASKED) && maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) == 0u)
-				continue;
-			binStore(fp, tile, atomicAdd(&fp.tileCount[tile], 1), id);
-		}
+	const int tx0 = x0 >> MR_TILE_SHIFT, tx1 = x1 >> MR_TILE_SHIFT;
+	const int ty0 = max(y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
+	const int nx = tx1 - tx0 + 1, n = nx * (ty1 - ty0 + 1);
+	for (int k = lane; k < n; k += 32)
+	{
+		const int row = k / nx;
+		const int tx = tx0 + k - row * nx, ty = ty0 + row;
+		if ((flags & MR_REC_MASKED) && maskInTile(mask, x0, x1, y0, y1, tx * MR_TILE, ty * MR_TILE) == 0u)
+			continue;
+		const int tile = ty * fp.tilesX + tx;
+		binStore(fp, tile, atomicAdd(&fp.tileCount[tile], 1), id);
+	}
 }
 
-// Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up, stores
-// the records and emits their pairs. Self-contained so that its stack never touches the fast path.
+// Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up and stores
+// the records (the caller's warp bins them). Returns a bit per stored sub-triangle. Self-contained
+// so that its stack never touches the fast path.
 __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
 {
 	const RStat rs = fp.rstat[r];
@@ -403,8 +407,7 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 		const int id = 2 * t + sub;
 		storeRec(&fp.recs[id], a, b, c, s);
 		storeShadeRec(fp, &fp.srecs[id], r, rs, tri, ia, ib, ic);
-		binSerial(fp, id, s);
-		nrec++;
+		nrec |= 1 << sub;
 	}
 	return nrec;
 }
@@ -419,7 +422,10 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 // capacity go to a global overflow list. The order inside a bin does not matter: depth ties are
 // resolved on the record index (submission id), not on arrival order.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FrameParams fp)
+#ifndef MR_SETUP_MINB
+#define MR_SETUP_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int sh[56];
 	__shared__ int shBases[256];
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 		else if (setupTriangle(fp, a, b, c, s))
 		{
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
-			if (valid && (s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= 32)
+			if (valid && (s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= 32 && !(fp.debug & 64))
 			{
 				s.flags = MR_REC_MASKED;
 				s.mask = coverageMask(a, c, s);
@@ -461,8 +467,10 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 			}
 			if (valid)
 			{
-				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s);
-				storeShadeRec(fp, &fp.srecs[2 * (size_t)t], r, rs, tri, ia, ib, ic);
+				if (!(fp.debug & 128))
+					storeRec(&fp.recs[2 * (size_t)t], a, b, c, s);
+				if (!(fp.debug & 16))
+					storeShadeRec(fp, &fp.srecs[2 * (size_t)t], r, rs, tri, ia, ib, ic);
 			}
 		}
 	}
@@ -472,14 +480,15 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
 	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
 	const int nx = tx1 - tx0 + 1;
-	const int ntiles = valid ? nx * (ty1 - ty0 + 1) : 0;
+	const int ntiles = (valid && !(fp.debug & 32)) ? nx * (ty1 - ty0 + 1) : 0;
 	const bool big = ntiles > MR_SEG_PER_LANE;
 	// tiles of the bbox that actually contain covered pixels (masked triangles), as a bit set
 	uint32_t live = 0u;
 	if (valid && !big)
 		for (int k = 0; k < ntiles; k++)
 		{
-			const int tx = tx0 + k % nx, ty = ty0 + k / nx;
+			const int row = (k >= nx) + (k >= 2 * nx) + (k >= 3 * nx); // k / nx for k < 4
+			const int tx = tx0 + k - row * nx, ty = ty0 + row;
 			if (!(s.flags & MR_REC_MASKED) || maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) != 0u)
 				live |= 1u << k;
 		}
@@ -498,7 +507,8 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 				const bool on = rest != 0u;
 				const int kk = on ? __ffs(rest) - 1 : 0;
 				rest &= rest - 1u;
-				const int tile = on ? (ty0 + kk / nx) * fp.tilesX + tx0 + kk % nx : -1 - lane;
+				const int krow = (kk >= nx) + (kk >= 2 * nx) + (kk >= 3 * nx);
+				const int tile = on ? (ty0 + krow) * fp.tilesX + tx0 + kk - krow * nx : -1 - lane;
 				const unsigned peers = __match_any_sync(0xffffffffu, tile);
 				leadOf[k] = __ffs(peers) - 1;
 				rankOf[k] = __popc(peers & ((1u << lane) - 1u));
@@ -519,11 +529,34 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ FramePara
 					binStore(fp, tileOf[k], slot, id);
 			}
 	}
-	if (big)
-		binSerial(fp, 2 * t, s);
+	// Triangles spanning more tiles, and clipper output: the warp bins them together, one at a time.
+	unsigned bigLanes = __ballot_sync(0xffffffffu, big);
+	while (bigLanes != 0u)
+	{
+		const int src = __ffs(bigLanes) - 1;
+		bigLanes &= bigLanes - 1u;
+		binCooperative(fp, lane, 2 * (t - lane + src), __shfl_sync(0xffffffffu, s.x0, src), __shfl_sync(0xffffffffu, s.x1, src),
+		               __shfl_sync(0xffffffffu, s.y0, src), __shfl_sync(0xffffffffu, s.y1, src), __shfl_sync(0xffffffffu, s.flags, src),
+		               __shfl_sync(0xffffffffu, s.mask, src));
+	}
+	unsigned clipLanes = __ballot_sync(0xffffffffu, nrecSlow != 0);
+	while (clipLanes != 0u)
+	{
+		const int src = __ffs(clipLanes) - 1;
+		clipLanes &= clipLanes - 1u;
+		const int subs = __shfl_sync(0xffffffffu, nrecSlow, src);
+		for (int sub = 0; sub < 2; sub++)
+			if (subs & (1 << sub))
+			{
+				const int id = 2 * (t - lane + src) + sub;
+				const float4 q3 = reinterpret_cast<const float4*>(&fp.recs[id])[3]; // spans written by setupClipped
+				const uint32_t xs = __float_as_uint(q3.x), ys = __float_as_uint(q3.y);
+				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16, MR_REC_CLIPPED, 0u);
+			}
+	}
 
 	// ---- statistics: one atomic per CTA ----
-	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + nrecSlow);
+	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + __popc(nrecSlow));
 	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
 	const int nzeroWarp = __reduce_add_sync(0xffffffffu, nzero);
 	if (lane == 0)
@@ -1089,7 +1122,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 
 // One CTA per tile. (A persistent variant with a global tile counter measured 10 % slower: the
 // hardware CTA scheduler already balances 8160 small CTAs well.)
-__global__ void __launch_bounds__(256) k_raster(const __grid_constant__ FrameParams fp)
+#ifndef MR_RASTER_MINB
+#define MR_RASTER_MINB 4
+#endif
+__global__ void __launch_bounds__(256, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[8];
