@@ -165,6 +165,7 @@ struct FrameParams
 // kernel launchers (mr_kernels.cu)
 void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */);
 int mrk_selftest_no_fma(cudaStream_t stream);
+void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
 void mrk_launch_rgb8(const float* image, uint8_t* out, size_t nFloats, cudaStream_t stream);
 void mrk_launch_pack(float4* dst4, const float* src, int n, int comps, float w, cudaStream_t stream);

@@ -11,7 +11,7 @@ r = setup.apply(m.Renderer(be)); ctx = r.context_ptr()
 for i in range(30): r.render()
 r.synchronize(); r.prepare()
 for flags in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]:
-    lib.mr_set_debug(ctx, flags | 2)
+    lib.mr_set_debug(ctx, (flags & ~1024) | (0 if flags & 1024 else 2))
     assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 30) == 0
     st = cabi.Stats(); lib.mr_get_stats(ctx, C.byref(st)); ms = list(st.ms_kernel)
     print("%s flags %2d: vertex %.1f setup %.1f raster %.1f frame %.1f us | records %d pairs %d zero %d" % (
