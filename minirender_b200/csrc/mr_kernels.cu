@@ -114,7 +114,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int shBases[256];
+	__shared__ int shBases[256], shBasesN[256];
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
@@ -125,29 +125,35 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->zeroCov = 0;
 		c->overflow = 0; c->ovfTotal = 0; c->maxTile = 0; c->nextTile = 0;
 	}
+	// both lookups first, then both gathers, then the math: the vertex and the normal chain of a
+	// thread overlap instead of running back to back
+	int rv = 0, rn = 0;
 	if (blockIdx.x * 256 < fp.nVertInst)
-	{
-		const int r = findRenderable(fp, fp.vtxBlockR, vi, 0, shBases);
-		if (vi < fp.nVertInst)
-		{
-			const RStat rs = fp.rstat[r];
-			const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
-			const V3 view = affine(fp.rdyn[r].mv, p.x, p.y, p.z);
-			fp.pv[vi] = project(fp, view);
-			fp.vpos4[vi] = make_float4(view.x, view.y, view.z, 0.0f);
-		}
-	}
+		rv = findRenderable(fp, fp.vtxBlockR, vi, 0, shBases);
 	if (blockIdx.x * 256 < fp.nNrmInst)
+		rn = findRenderable(fp, fp.nrmBlockR, vi, 2, shBasesN);
+	const bool hv = vi < fp.nVertInst, hn = vi < fp.nNrmInst;
+	RStat rsv, rsn;
+	rsv.posBase = rsv.vertBase = rsn.nrmSrcBase = rsn.nrmBase = 0;
+	if (hv)
+		rsv = fp.rstat[rv];
+	if (hn)
+		rsn = fp.rstat[rn];
+	float4 p = make_float4(0, 0, 0, 0), n = p;
+	if (hv)
+		p = __ldg(&fp.pos4[rsv.posBase + (vi - rsv.vertBase)]);
+	if (hn)
+		n = __ldg(&fp.nrm4[rsn.nrmSrcBase + (vi - rsn.nrmBase)]);
+	if (hv)
 	{
-		__syncthreads(); // shBases is reused
-		const int r = findRenderable(fp, fp.nrmBlockR, vi, 2, shBases);
-		if (vi < fp.nNrmInst)
-		{
-			const RStat rs = fp.rstat[r];
-			const float4 n = __ldg(&fp.nrm4[rs.nrmSrcBase + (vi - rs.nrmBase)]);
-			const V3 vn = affine(fp.rdyn[r].nm, n.x, n.y, n.z);
-			fp.vnrm4[vi] = make_float4(vn.x, vn.y, vn.z, 0.0f);
-		}
+		const V3 view = affine(fp.rdyn[rv].mv, p.x, p.y, p.z);
+		fp.pv[vi] = project(fp, view);
+		fp.vpos4[vi] = make_float4(view.x, view.y, view.z, 0.0f);
+	}
+	if (hn)
+	{
+		const V3 vn = affine(fp.rdyn[rn].nm, n.x, n.y, n.z);
+		fp.vnrm4[vi] = make_float4(vn.x, vn.y, vn.z, 0.0f);
 	}
 }
 
@@ -901,102 +907,16 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	__syncwarp();
 }
 
-// One tile: phases 1 and 2. Called by all 256 threads of the CTA (contains barriers).
-__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
+// Per-pixel part of phase 2 for tile pixel `pi` (0..255). Warp-convergent: contains shuffles.
+// Returns the pixel's colour and depth (clear values when nothing won); side outputs (winner ids,
+// normals image) are written here.
+__device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsigned long long* keys, int pi, int tileX0, int tileY0, int lane,
+                                             V3& value, float& zout, bool& store)
 {
-	const int tile = ty * fp.tilesX + tx;
-	const int tid = threadIdx.x;
-	const int lane = tid & 31;
-	const int px = tx * MR_TILE + (tid & 15);
-	const int py = ty * MR_TILE + (tid >> 4);
+	const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
 	const size_t pix = (size_t)py * fp.w + px;
-	const int total = fp.tileCount[tile];                              // triangles binned to this tile
-	// (independent loads; the counters were written by the previous kernels, so the L1-cached
-	// read-only path is fine and keeps 8160 CTAs from hammering one L2 line)
-	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
-	const unsigned overflowed = __ldg(&fp.ctr->overflow);
-	if (total > fp.binCap && threadIdx.x == 0)
-		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
-	if (overflowed)
-		return; // the overflow list itself overflowed: the host regrows it and re-runs the frame
-	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
-	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
-	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
-	if (total == 0 && !fp.keep)
-	{
-		// empty tile: clear values only (Renderer.cpp:113-119)
-		if (vec)
-		{
-			storeTileRows(fp, tileX0, tileY0, tid, 0);
-			if (inImage && ((fp.saveNormals && fp.normals) || fp.winner))
-			{
-				if (fp.saveNormals && fp.normals)
-				{
-					float* pn = fp.normals + 3 * pix;
-					pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
-				}
-				if (fp.winner)
-					fp.winner[pix] = -1;
-			}
-		}
-		else if (inImage)
-			writeClear(fp, pix);
-		return;
-	}
-	{
-		unsigned long long k0 = 0ull; // pixels outside the image / strip can never be won
-		if (inImage)
-		{
-			const float d0 = fp.keep ? fp.depth[pix] : 1e11f;
-			k0 = (unsigned long long)zkey(d0) << 32;
-		}
-		keys[tid] = k0;
-	}
-	if (tid == 0 && total > 0)
-		atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
-	__syncthreads();
-
-	// ---- phase 1: coverage + depth ----
-	if (!(fp.debug & 8))
-	{
-		WarpQueue& wq = queues[tid >> 5];
-		const int count = min(total, fp.binCap);
-		const int* bin = fp.bins + (size_t)tile * fp.binCap;
-		int qhead = 0, qcount = 0; // warp-uniform
-		int parity = 0;
-		for (int base = (tid >> 5) * 32; base < count; base += 256)
-		{
-			const int i = base + lane;
-			const bool have = i < count;
-			const int id = have ? __ldg(&bin[i]) : 0;
-			rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
-		}
-		if (total > fp.binCap)
-		{
-			// this tile spilled: its remaining triangles are somewhere in the global overflow list
-			const unsigned long long n = min(ovfTotal, (unsigned long long)fp.ovfCap);
-			for (unsigned long long base = (unsigned long long)(tid >> 5) * 32; base < n; base += 256)
-			{
-				const unsigned long long i = base + lane;
-				int2 p = make_int2(-1, 0);
-				if (i < n)
-					p = __ldg(&fp.ovfPairs[i]);
-				const bool have = p.x == tile;
-				if (__any_sync(0xffffffffu, have))
-					rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, p.y, tileX0, tileY0);
-			}
-		}
-		if (qcount > 0)
-		{
-			__syncwarp();
-			consumeFragments(fp, wq, keys, qhead, qcount, lane);
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 2: resolve + shade ----
-	const uint32_t win = (inImage && !(fp.debug & 256)) ? (uint32_t)(keys[tid] & 0xffffffffull) : 0u;
+	const uint32_t win = (inImage && !(fp.debug & 256)) ? (uint32_t)(keys[pi] & 0xffffffffull) : 0u;
 	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
 	int4 sa = make_int4(0, 0, 0, 0), sb = sa, sc = sa;
 	int id = -1;
@@ -1020,7 +940,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		const int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
 		if (__any_sync(0xffffffffu, prefix > 0))
 		{
-			const unsigned long long groupKey = (prefix > 0) ? (((unsigned long long)(uint32_t)id << 1) | (unsigned long long)((tid >> 4) & 1))
+			const unsigned long long groupKey = (prefix > 0) ? (((unsigned long long)(uint32_t)id << 1) | (unsigned long long)((pi >> 4) & 1))
 			                                                 : (0x8000000000000000ull | (unsigned long long)lane);
 			const unsigned peers = __match_any_sync(0xffffffffu, groupKey);
 			const int leader = __ffs(peers) - 1;
@@ -1040,9 +960,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		}
 	}
 	// per-pixel result: the clear values unless a triangle won the pixel
-	V3 value = mk3(fp.bg[0], fp.bg[1], fp.bg[2]);
-	float zout = 1e11f;
+	value = mk3(fp.bg[0], fp.bg[1], fp.bg[2]);
+	zout = 1e11f;
 	const bool won = inImage && win != 0u;
+	store = inImage && (won || !fp.keep);
 	if (won)
 	{
 		for (int x = xcur; x < px; x++)
@@ -1098,38 +1019,159 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		if (fp.winner)
 			fp.winner[pix] = -1;
 	}
+}
+
+// One tile: phases 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice as
+// many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
+template <int NT>
+__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
+{
+	const int tile = ty * fp.tilesX + tx;
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int total = fp.tileCount[tile];                              // triangles binned to this tile
+	// (independent loads; the counters were written by the previous kernels, so the L1-cached
+	// read-only path is fine and keeps 8160 CTAs from hammering one L2 line)
+	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
+	const unsigned overflowed = __ldg(&fp.ctr->overflow);
+	if (total > fp.binCap && threadIdx.x == 0)
+		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
+	if (overflowed)
+		return; // the overflow list itself overflowed: the host regrows it and re-runs the frame
+	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
+	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
+	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
+	if (total == 0 && !fp.keep)
+	{
+		// empty tile: clear values only (Renderer.cpp:113-119)
+		for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
+		{
+			const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
+			const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
+			const size_t pix = (size_t)py * fp.w + px;
+			if (vec)
+			{
+				storeTileRows(fp, tileX0, tileY0, pi, 0);
+				if (inImage && fp.saveNormals && fp.normals)
+				{
+					float* pn = fp.normals + 3 * pix;
+					pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
+				}
+				if (inImage && fp.winner)
+					fp.winner[pix] = -1;
+			}
+			else if (inImage)
+				writeClear(fp, pix);
+		}
+		return;
+	}
+	for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
+	{
+		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
+		unsigned long long k0 = 0ull; // pixels outside the image / strip can never be won
+		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
+		{
+			const float d0 = fp.keep ? fp.depth[(size_t)py * fp.w + px] : 1e11f;
+			k0 = (unsigned long long)zkey(d0) << 32;
+		}
+		keys[pi] = k0;
+	}
+	if (tid == 0 && total > 0)
+		atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
+	__syncthreads();
+
+	// ---- phase 1: coverage + depth ----
+	if (!(fp.debug & 8))
+	{
+		WarpQueue& wq = queues[tid >> 5];
+		const int count = min(total, fp.binCap);
+		const int* bin = fp.bins + (size_t)tile * fp.binCap;
+		int qhead = 0, qcount = 0; // warp-uniform
+		int parity = 0;
+		for (int base = (tid >> 5) * 32; base < count; base += NT)
+		{
+			const int i = base + lane;
+			const bool have = i < count;
+			const int id = have ? __ldg(&bin[i]) : 0;
+			rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
+		}
+		if (total > fp.binCap)
+		{
+			// this tile spilled: its remaining triangles are somewhere in the global overflow list
+			const unsigned long long n = min(ovfTotal, (unsigned long long)fp.ovfCap);
+			for (unsigned long long base = (unsigned long long)(tid >> 5) * 32; base < n; base += NT)
+			{
+				const unsigned long long i = base + lane;
+				int2 p = make_int2(-1, 0);
+				if (i < n)
+					p = __ldg(&fp.ovfPairs[i]);
+				const bool have = p.x == tile;
+				if (__any_sync(0xffffffffu, have))
+					rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, p.y, tileX0, tileY0);
+			}
+		}
+		if (qcount > 0)
+		{
+			__syncwarp();
+			consumeFragments(fp, wq, keys, qhead, qcount, lane);
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: resolve + shade, 256 / NT pixels per thread ----
+	V3 value[MR_TILE_PIXELS / NT];
+	float zout[MR_TILE_PIXELS / NT];
+	bool store[MR_TILE_PIXELS / NT];
+#pragma unroll
+	for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+		resolvePixel(fp, keys, tid + pp * NT, tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
 
 	// ---- tile store ----
 	if (vec)
 	{
 		// stage the tile in shared memory (the fragment queues are idle now) and write full rows
 		TileOut* to = reinterpret_cast<TileOut*>(queues);
-		const int r = tid >> 4, c = tid & 15;
-		to->rgb[r][3 * c] = value.x;
-		to->rgb[r][3 * c + 1] = value.y;
-		to->rgb[r][3 * c + 2] = value.z;
-		to->z[r][c] = zout;
+#pragma unroll
+		for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+		{
+			const int pi = tid + pp * NT, r = pi >> 4, c = pi & 15;
+			to->rgb[r][3 * c] = value[pp].x;
+			to->rgb[r][3 * c + 1] = value[pp].y;
+			to->rgb[r][3 * c + 2] = value[pp].z;
+			to->z[r][c] = zout[pp];
+		}
 		__syncthreads();
-		storeTileRows(fp, tileX0, tileY0, tid, to);
+		for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
+			storeTileRows(fp, tileX0, tileY0, pi, to);
 	}
-	else if (inImage && (won || !fp.keep))
+	else
 	{
-		float* img = fp.image + 3 * pix;
-		img[0] = value.x; img[1] = value.y; img[2] = value.z;
-		fp.depth[pix] = zout;
+#pragma unroll
+		for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+			if (store[pp])
+			{
+				const int pi = tid + pp * NT;
+				const size_t pix = (size_t)(tileY0 + (pi >> 4)) * fp.w + tileX0 + (pi & 15);
+				float* img = fp.image + 3 * pix;
+				img[0] = value[pp].x; img[1] = value[pp].y; img[2] = value[pp].z;
+				fp.depth[pix] = zout[pp];
+			}
 	}
 }
 
 // One CTA per tile. (A persistent variant with a global tile counter measured 10 % slower: the
 // hardware CTA scheduler already balances 8160 small CTAs well.)
-#ifndef MR_RASTER_MINB
-#define MR_RASTER_MINB 4
+#ifndef MR_RASTER_THREADS
+#define MR_RASTER_THREADS 128
 #endif
-__global__ void __launch_bounds__(256, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
+#ifndef MR_RASTER_MINB
+#define MR_RASTER_MINB (1024 / MR_RASTER_THREADS)
+#endif
+__global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
-	__shared__ WarpQueue queues[8];
-	rasterTile(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
+	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
+	rasterTile<MR_RASTER_THREADS>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1222,7 +1264,7 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	if (ev) cudaEventRecord(ev[3], stream);
 	if (ev) cudaEventRecord(ev[4], stream);
 	if (fp.tileRows > 0)
-		k_raster<<<dim3(fp.tilesX, fp.tileRows), 256, 0, stream>>>(fp);
+		k_raster<<<dim3(fp.tilesX, fp.tileRows), MR_RASTER_THREADS, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[5], stream);
 }
 
