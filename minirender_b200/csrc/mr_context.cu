@@ -78,6 +78,7 @@ struct mr_ctx
 	int device;
 	cudaStream_t stream;
 	bool ownStream;
+	cudaStream_t aux; // counter read-back, off the render stream
 	std::string error;
 
 	int w, h, tilesX, tilesY;
@@ -101,9 +102,10 @@ struct mr_ctx
 	{
 		PinBuf stage;
 		Counters* hostCtr; // pinned
-		cudaEvent_t done;
+		cudaEvent_t kernelsDone; // on the render stream, after the frame's last kernel
+		cudaEvent_t done;        // on the aux stream, after the counters reached the host
 		bool pending;
-		Slot() : hostCtr(0), done(0), pending(false) {}
+		Slot() : hostCtr(0), kernelsDone(0), done(0), pending(false) {}
 	};
 	enum { kSlots = 4 };
 	Slot slots[kSlots];
@@ -129,7 +131,7 @@ struct mr_ctx
 	bool haveFrame;
 	mr_stats stats;
 
-	mr_ctx() : device(0), stream(0), ownStream(false), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
+	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
 	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), haveFrame(false)
 	{
@@ -325,7 +327,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
-	MR_CUDA(c, c->ctr.ensure(sizeof(Counters)));
+	MR_CUDA(c, c->ctr.ensure(sizeof(Counters) * mr_ctx::kSlots));
 	{
 		// Bin capacity: a power of two, at least 256 and at least 8x the mean triangles per tile,
 		// within a 1 GiB budget for the bin array; doubled on demand when tiles spill a lot.
@@ -418,7 +420,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		rd[i].material = f->renderables[i].material;
 		rd[i].pad[0] = rd[i].pad[1] = rd[i].pad[2] = 0;
 	}
-	if (szDyn) MR_CUDA(c, cudaMemcpyAsync(c->rdyn.p, rd, szDyn, cudaMemcpyHostToDevice, c->stream));
+	const bool inlineTables = nR <= MR_INLINE_TABLE && f->n_materials <= MR_INLINE_TABLE;
+	if (szDyn && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->rdyn.p, rd, szDyn, cudaMemcpyHostToDevice, c->stream));
 	off += szDyn;
 	off = (off + 15) & ~(size_t)15;
 	MatDev* md = (MatDev*)(sp + off);
@@ -441,8 +444,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		}
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
-	if (szMat) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + szDyn + szMat + sizeof(FrameParams);
+	if (szMat && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
+	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -479,6 +482,12 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.nTriInst = c->nTriInst;
 	fp.nNrmInst = c->nNrmInst;
 	fp.debug = c->debugFlags;
+	fp.inlineTables = inlineTables ? 1 : 0;
+	if (inlineTables)
+	{
+		memcpy(fp.rdynInline, rd, sizeof(RDyn) * (size_t)nR);
+		memcpy(fp.matsInline, md, sizeof(MatDev) * (size_t)f->n_materials);
+	}
 	fp.binCap = c->binCap;
 	fp.rasterCtas = c->smCount * 4; // 64 registers x 256 threads: four CTAs per SM
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
@@ -504,7 +513,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.ovfPairs = c->ovfPairs.as<int2>();
 	fp.srecs = c->srecs.as<ShadeRec>();
 	fp.bins = c->bins.as<int>();
-	fp.ctr = c->ctr.as<Counters>();
+	fp.ctr = c->ctr.as<Counters>() + slotIndex; // per-slot counters: the read-back overlaps the next frame
 	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
 	fp.depth = (c->remoteDepth && !f->keep) ? (float*)c->remoteDepth : c->depth.as<float>();
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
@@ -512,8 +521,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 
 	mrk_launch_frame(fp, c->stream, ev);
 	MR_CUDA(c, cudaGetLastError());
-	MR_CUDA(c, cudaMemcpyAsync(slot.hostCtr, c->ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-	MR_CUDA(c, cudaEventRecord(slot.done, c->stream));
+	MR_CUDA(c, cudaEventRecord(slot.kernelsDone, c->stream));
+	MR_CUDA(c, cudaStreamWaitEvent(c->aux, slot.kernelsDone, 0));
+	MR_CUDA(c, cudaMemcpyAsync(slot.hostCtr, fp.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->aux));
+	MR_CUDA(c, cudaEventRecord(slot.done, c->aux));
 	slot.pending = true;
 	c->slotNewest = slotIndex;
 	c->slotNext = (slotIndex + 1) % mr_ctx::kSlots;
@@ -578,9 +589,11 @@ mr_ctx* mr_create(int device, int* status)
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
+		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;
 		for (int i = 0; i < mr_ctx::kSlots && ok; i++)
 		{
 			ok = ok && cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
+			ok = ok && cudaEventCreateWithFlags(&c->slots[i].kernelsDone, cudaEventDisableTiming) == cudaSuccess;
 			ok = ok && cudaMallocHost((void**)&c->slots[i].hostCtr, sizeof(Counters)) == cudaSuccess;
 			if (ok)
 				memset(c->slots[i].hostCtr, 0, sizeof(Counters));
@@ -626,9 +639,16 @@ void mr_destroy(mr_ctx* c)
 			cudaFreeHost(c->slots[i].hostCtr);
 		if (c->slots[i].done)
 			cudaEventDestroy(c->slots[i].done);
+		if (c->slots[i].kernelsDone)
+			cudaEventDestroy(c->slots[i].kernelsDone);
 	}
 	if (c->ownStream && c->stream)
 		cudaStreamDestroy(c->stream);
+	if (c->aux)
+	{
+		cudaStreamSynchronize(c->aux);
+		cudaStreamDestroy(c->aux);
+	}
 	delete c;
 }
 

@@ -67,6 +67,10 @@ __device__ __forceinline__ uint32_t zkey(float z)
 	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Per-frame tables: in the kernel parameters for small scenes, in global memory otherwise.
+__device__ __forceinline__ const RDyn* frameRdyn(const FrameParams& fp) { return fp.inlineTables ? fp.rdynInline : fp.rdyn; }
+__device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return fp.inlineTables ? fp.matsInline : fp.mats; }
+
 // Renderable that owns instance `inst` (a vertex or triangle instance) of this 256-thread block.
 // blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
 // and searched there. Must be called by every thread of the block.
@@ -146,13 +150,13 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		n = __ldg(&fp.nrm4[rsn.nrmSrcBase + (vi - rsn.nrmBase)]);
 	if (hv)
 	{
-		const V3 view = affine(fp.rdyn[rv].mv, p.x, p.y, p.z);
+		const V3 view = affine(frameRdyn(fp)[rv].mv, p.x, p.y, p.z);
 		fp.pv[vi] = project(fp, view);
 		fp.vpos4[vi] = make_float4(view.x, view.y, view.z, 0.0f);
 	}
 	if (hn)
 	{
-		const V3 vn = affine(fp.rdyn[rn].nm, n.x, n.y, n.z);
+		const V3 vn = affine(frameRdyn(fp)[rn].nm, n.x, n.y, n.z);
 		fp.vnrm4[vi] = make_float4(vn.x, vn.y, vn.z, 0.0f);
 	}
 }
@@ -271,7 +275,7 @@ __device__ __forceinline__ void storeShadeRec(const FrameParams& fp, ShadeRec* d
 	int4* d4 = reinterpret_cast<int4*>(dst);
 	d4[0] = make_int4(rs.vertBase + ia, rs.vertBase + ib, rs.vertBase + ic, rs.nrmBase + __ldg(in));
 	d4[1] = make_int4(rs.nrmBase + __ldg(in + 1), rs.nrmBase + __ldg(in + 2), iu0, iu1);
-	d4[2] = make_int4(iu2, fp.rdyn[r].material, r, tri);
+	d4[2] = make_int4(iu2, frameRdyn(fp)[r].material, r, tri);
 }
 
 // One corner in view space (loops A/B of paintMesh, evaluated for the winner only).
@@ -740,7 +744,7 @@ __device__ __noinline__ float3 shadeClippedPixel(const FrameParams& fp, const Sh
 	const Corner v0 = fetchCorner(fp, sa.x, sa.w, sb.z), v1 = fetchCorner(fp, sa.y, sb.x, sb.w), v2 = fetchCorner(fp, sa.z, sb.y, sc.x);
 	Corner c0, c1, c2;
 	clipTriangle(fp.znear, v0, v1, v2, sub, c0, c1, c2);
-	const MatDev mat = fp.mats[sc.y];
+	const MatDev mat = frameMats(fp)[sc.y];
 	const V3 v = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
 	return make_float3(v.x, v.y, v.z);
 }
@@ -992,7 +996,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsign
 		}
 		else
 		{
-			const MatDev mat = fp.mats[sc.y];
+			const MatDev mat = frameMats(fp)[sc.y];
 			Corner c0, c1, c2;
 			if (fp.lighting || (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0))
 			{

@@ -112,6 +112,8 @@ struct Counters
 	unsigned long long pad3[14];
 };
 
+#define MR_INLINE_TABLE 12 // renderables / materials that travel inside the kernel parameters
+
 struct FrameParams
 {
 	float P[16];
@@ -155,6 +157,12 @@ struct FrameParams
 	int2* ovfPairs;      // (tile, record) entries that did not fit their bin
 	ShadeRec* srecs;
 	Counters* ctr;
+
+	// Small scenes: the per-frame tables ride in the kernel parameters (no H2D copy per frame).
+	// rdyn / mats point at these arrays then (set up on the device: see frameTables()).
+	int inlineTables;
+	RDyn rdynInline[MR_INLINE_TABLE];
+	MatDev matsInline[MR_INLINE_TABLE];
 
 	float* image;   // h*w*3
 	float* depth;   // h*w
