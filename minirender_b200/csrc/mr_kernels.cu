@@ -661,6 +661,7 @@ __device__ __forceinline__ void pushFragment(const FrameParams& fp, WarpQueue& w
 	{
 		__syncwarp();
 		consumeFragments(fp, wq, keys, qhead, 32, lane);
+		__syncwarp(); // the consumed entries may be overwritten by the next pushes
 		qhead = (qhead + 32) & (MR_FQ_CAP - 1);
 		qcount -= 32;
 	}
@@ -904,6 +905,7 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	{
 		__syncwarp();
 		consumeFragments(fp, wq, keys, qhead, qcount, lane);
+		__syncwarp();
 		qhead = (qhead + qcount) & (MR_FQ_CAP - 1);
 		qcount = 0;
 	}
