@@ -485,6 +485,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.inlineTables = inlineTables ? 1 : 0;
 	if (inlineTables)
 	{
+		memcpy(fp.rstatInline, rs.data(), sizeof(RStat) * (size_t)nR);
 		memcpy(fp.rdynInline, rd, sizeof(RDyn) * (size_t)nR);
 		memcpy(fp.matsInline, md, sizeof(MatDev) * (size_t)f->n_materials);
 	}

@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t zkey(float z)
 // Per-frame tables: in the kernel parameters for small scenes, in global memory otherwise.
 __device__ __forceinline__ const RDyn* frameRdyn(const FrameParams& fp) { return fp.inlineTables ? fp.rdynInline : fp.rdyn; }
 __device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return fp.inlineTables ? fp.matsInline : fp.mats; }
+__device__ __forceinline__ const RStat* frameRstat(const FrameParams& fp) { return fp.inlineTables ? fp.rstatInline : fp.rstat; }
 
 // Renderable that owns instance `inst` (a vertex or triangle instance) of this 256-thread block.
 // blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
@@ -78,6 +79,8 @@ __device__ __forceinline__ int instBase(const RStat& s, int kind) { return kind 
 
 __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* __restrict__ blockR, int inst, int kind, int* shBases)
 {
+	if (fp.nRenderables == 1)
+		return 0; // nothing to look up (and one dependent load less)
 	const int r0 = __ldg(&blockR[blockIdx.x]), r1 = __ldg(&blockR[blockIdx.x + 1]);
 	if (r0 >= r1)
 		return r0; // the whole block belongs to one renderable
@@ -85,7 +88,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 	if (n <= 256)
 	{
 		for (int i = threadIdx.x; i < n; i += 256)
-			shBases[i] = instBase(fp.rstat[r0 + i], kind);
+			shBases[i] = instBase(frameRstat(fp)[r0 + i], kind);
 		__syncthreads();
 		int lo = 0, hi = n - 1; // largest i with base[i] <= inst
 		while (lo < hi)
@@ -102,7 +105,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 	while (lo < hi)
 	{
 		const int mid = (lo + hi + 1) >> 1;
-		if (instBase(fp.rstat[mid], kind) <= inst)
+		if (instBase(frameRstat(fp)[mid], kind) <= inst)
 			lo = mid;
 		else
 			hi = mid - 1;
@@ -140,9 +143,9 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	RStat rsv, rsn;
 	rsv.posBase = rsv.vertBase = rsn.nrmSrcBase = rsn.nrmBase = 0;
 	if (hv)
-		rsv = fp.rstat[rv];
+		rsv = frameRstat(fp)[rv];
 	if (hn)
-		rsn = fp.rstat[rn];
+		rsn = frameRstat(fp)[rn];
 	float4 p = make_float4(0, 0, 0, 0), n = p;
 	if (hv)
 		p = __ldg(&fp.pos4[rsv.posBase + (vi - rsv.vertBase)]);
@@ -388,7 +391,7 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 // so that its stack never touches the fast path.
 __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
 {
-	const RStat rs = fp.rstat[r];
+	const RStat rs = frameRstat(fp)[r];
 	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
 	int iu0 = -1, iu1 = -1, iu2 = -1;
 	if (rs.uvTriBase >= 0)
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 	s.mask = s.flags = 0u;
 	if (t < fp.nTriInst)
 	{
-		const RStat rs = fp.rstat[r];
+		const RStat rs = frameRstat(fp)[r];
 		const int tri = t - rs.triBase;
 		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
 		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);

@@ -112,7 +112,7 @@ struct Counters
 	unsigned long long pad3[14];
 };
 
-#define MR_INLINE_TABLE 12 // renderables / materials that travel inside the kernel parameters
+#define MR_INLINE_TABLE 32 // renderables / materials that travel inside the kernel parameters
 
 struct FrameParams
 {
@@ -161,6 +161,7 @@ struct FrameParams
 	// Small scenes: the per-frame tables ride in the kernel parameters (no H2D copy per frame).
 	// rdyn / mats point at these arrays then (set up on the device: see frameTables()).
 	int inlineTables;
+	RStat rstatInline[MR_INLINE_TABLE];
 	RDyn rdynInline[MR_INLINE_TABLE];
 	MatDev matsInline[MR_INLINE_TABLE];
 
