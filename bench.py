@@ -328,6 +328,93 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# optional: BASELINE.json configs[2] — one 3840x2160 frame of a 10M-triangle textured mesh, screen
+# strips sharded across the ranks (strong scaling). Not the headline line; run with
+#   --workload strips4k [--gather peer|nccl]
+# ------------------------------------------------------------------------------------------------
+def run_strips(args, rank, local_rank, world):
+    import torch
+    import minirender_b200 as m
+    from minirender_b200 import cabi, scenes, sharding
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = cabi.load()
+    be = m.Backend()
+    W4, H4, LAT4 = 3840, 2160, 2237  # createSphere(r, 2237, 2237): 10,003,864 triangles
+    setup = scenes.sphere_scene(be, W4, H4, lat=LAT4, lon=LAT4, textured=True, d=330.0)
+    r = setup.apply(m.Renderer(be))
+    r.set_device(local_rank)
+    ctx = r.context_ptr()
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert lib.mr_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
+    rb, re = sharding.strip_rows(H4, rank, world)
+    r.clear()
+    r.synchronize()
+    close = None
+    if world > 1 and args.gather == "peer":
+        dist.barrier()
+        close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
+    r.set_row_range(rb, re)
+    img = dep = None
+    if world > 1 and args.gather == "nccl":
+        img, dep = sharding.device_tensors(lib, ctx, H4, W4, torch.device("cuda", local_rank))
+
+    def frame(i):
+        r.set_view(scenes.sphere_view(be, i, d=330.0))
+        r.render()
+        if world > 1:
+            if args.gather == "nccl":
+                r.synchronize()
+                sharding.gather_strips(img, dep, H4, rank, world, dist, dst=0)
+            else:
+                r.synchronize()
+                dist.barrier()  # every strip has landed in rank 0's framebuffer
+
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+    for i in range(Wm):
+        frame(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        frame(Wm + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([max(dev_ms, wall * 1000.0)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = cabi.Stats()
+    lib.mr_get_stats(ctx, C.byref(st))
+    if rank == 0:
+        ms = float(t[0]) / K
+        print(json.dumps({"metric": "frames_per_sec_4k_10Mtri_strips", "value": 1000.0 / ms, "unit": "frames/s", "n_gpus": world,
+                          "steps": K, "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "mtri_per_s": st.triangles_in / ms / 1e3, "mpix_per_s": W4 * H4 / ms / 1e3,
+                          "config": {"workload": "configs[2]: 3840x2160, createSphere(100,2237,2237) = 10.0M triangles, 256x256 float texture, "
+                                                 "strips of whole tile rows per rank (sort-first: every rank sets up all triangles)",
+                                     "gather": args.gather if world > 1 else "none", "l2": "working set (> 1 GB) exceeds the L2"},
+                          "stats": {"triangles_in": int(st.triangles_in), "records_rank0": int(st.records)}}), flush=True)
+    if close:
+        close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,12 +422,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sphere1m", choices=["sphere1m", "strips4k"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "strips4k":
+        run_strips(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 
