@@ -113,7 +113,7 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, vpos4, vnrm4, recs, srecs, tileCount, ovfPairs, bins, ctr;
+	DevBuf pv, recs, srecs, tileCount, ovfPairs, bins, ctr, gkeys;
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -246,6 +246,8 @@ int finishFrame(mr_ctx* c)
 		mr_frame f = c->lastFrame;
 		f.renderables = c->lastRenderables.empty() ? 0 : &c->lastRenderables[0];
 		f.materials = c->lastMaterials.empty() ? 0 : &c->lastMaterials[0];
+		// the aborted frame left fragments in the depth keys
+		MR_CUDA(c, cudaMemsetAsync(c->gkeys.p, 0xff, (size_t)c->w * c->h * 8, c->stream));
 		int rc = launchFrame(c, &f, 0);
 		if (rc)
 			return rc;
@@ -263,6 +265,12 @@ int ensureOutputs(mr_ctx* c, bool normals, bool winner)
 	{
 		MR_CUDA(c, cudaMemsetAsync(c->image.p, 0, npix * 12, c->stream));
 		MR_CUDA(c, cudaMemsetAsync(c->depth.p, 0, npix * 4, c->stream));
+	}
+	// per-pixel depth keys: all MR_KEY_EMPTY between frames (the tile kernel resets what it reads)
+	if (c->gkeys.cap < npix * 8)
+	{
+		MR_CUDA(c, c->gkeys.ensure(npix * 8, true));
+		MR_CUDA(c, cudaMemsetAsync(c->gkeys.p, 0xff, npix * 8, c->stream));
 	}
 	if (normals && c->normals.cap < npix * 12)
 	{
@@ -321,8 +329,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
-	MR_CUDA(c, c->vpos4.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
-	MR_CUDA(c, c->vnrm4.ensure(sizeof(float4) * (size_t)std::max(c->nNrmInst, 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
@@ -507,8 +513,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.triBlockR = c->triBlockR.as<int>();
 	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
-	fp.vpos4 = c->vpos4.as<float4>();
-	fp.vnrm4 = c->vnrm4.as<float4>();
+	fp.gkeys = c->gkeys.as<unsigned long long>();
 	fp.recs = c->recs.as<Rec>();
 	fp.tileCount = c->tileCount.as<int>();
 	fp.ovfPairs = c->ovfPairs.as<int2>();
@@ -630,7 +635,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->srecs, &c->vpos4, &c->vnrm4, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->ovfPairs, &c->bins, &c->srecs, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)
@@ -706,6 +711,7 @@ int mr_set_size(mr_ctx* c, int w, int h)
 	c->bins.release();
 	c->image.release();
 	c->depth.release();
+	c->gkeys.release();
 	c->normals.release();
 	c->winner.release();
 	c->haveFrame = false;

@@ -114,14 +114,14 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1: vertex + normal transform (reference loops A and B, Renderer.cpp:344-348).
-// Thread i handles vertex instance i (LDG.128 in; view-space position and projected vertex out as
-// two STG.128) and normal instance i (LDG.128 in, STG.128 out); all accesses fully coalesced.
-// Also zeroes the per-frame tile counters and statistics.
+// Kernel 1: vertex transform + projection (reference loop A, Renderer.cpp:344-345, and the
+// per-vertex part of paintTriangle, :186-196, :223-224). Thread i handles vertex instance i:
+// LDG.128 in, STG.128 out, fully coalesced. Also zeroes the per-frame tile counters and statistics.
+// Normals (loop B) are transformed only for the corners of triangles that survive setup (k_setup).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int shBases[256], shBasesN[256];
+	__shared__ int shBases[256];
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
@@ -132,36 +132,15 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->zeroCov = 0;
 		c->overflow = 0; c->ovfTotal = 0; c->maxTile = 0; c->nextTile = 0;
 	}
-	// both lookups first, then both gathers, then the math: the vertex and the normal chain of a
-	// thread overlap instead of running back to back
-	int rv = 0, rn = 0;
-	if (blockIdx.x * 256 < fp.nVertInst)
-		rv = findRenderable(fp, fp.vtxBlockR, vi, 0, shBases);
-	if (blockIdx.x * 256 < fp.nNrmInst)
-		rn = findRenderable(fp, fp.nrmBlockR, vi, 2, shBasesN);
-	const bool hv = vi < fp.nVertInst, hn = vi < fp.nNrmInst;
-	RStat rsv, rsn;
-	rsv.posBase = rsv.vertBase = rsn.nrmSrcBase = rsn.nrmBase = 0;
-	if (hv)
-		rsv = frameRstat(fp)[rv];
-	if (hn)
-		rsn = frameRstat(fp)[rn];
-	float4 p = make_float4(0, 0, 0, 0), n = p;
-	if (hv)
-		p = __ldg(&fp.pos4[rsv.posBase + (vi - rsv.vertBase)]);
-	if (hn)
-		n = __ldg(&fp.nrm4[rsn.nrmSrcBase + (vi - rsn.nrmBase)]);
-	if (hv)
-	{
-		const V3 view = affine(frameRdyn(fp)[rv].mv, p.x, p.y, p.z);
-		fp.pv[vi] = project(fp, view);
-		fp.vpos4[vi] = make_float4(view.x, view.y, view.z, 0.0f);
-	}
-	if (hn)
-	{
-		const V3 vn = affine(frameRdyn(fp)[rn].nm, n.x, n.y, n.z);
-		fp.vnrm4[vi] = make_float4(vn.x, vn.y, vn.z, 0.0f);
-	}
+	if (blockIdx.x * 256 >= fp.nVertInst)
+		return;
+	const int rv = findRenderable(fp, fp.vtxBlockR, vi, 0, shBases);
+	if (vi >= fp.nVertInst)
+		return;
+	const RStat& rs = frameRstat(fp)[rv];
+	const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
+	const V3 view = affine(frameRdyn(fp)[rv].mv, p.x, p.y, p.z);
+	fp.pv[vi] = project(fp, view);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -172,7 +151,7 @@ struct Setup
 {
 	float n1x, n1y, n2x, n2y;
 	int x0, x1, y0, y1;
-	uint32_t mask, flags;
+	uint32_t flags;
 };
 
 __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float4 a, const float4 b, const float4 c, Setup& s)
@@ -211,96 +190,108 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float
 	if ((float)(y1 + 1) + 0.5f <= ylim) y1++;
 	s.x1 = x1;
 	s.y1 = y1;
-	s.mask = 0u;
 	s.flags = 0u;
 	return true;
 }
 
-// Exact coverage of a triangle whose bbox holds at most 32 pixel centres: the reference's loops
-// D/E (Renderer.cpp:238-249) without the depth part. Bit (y-y0)*W + (x-x0). A triangle that covers
-// no pixel centre can never write anything and is dropped before binning.
-__device__ __forceinline__ uint32_t coverageMask(const float4 a, const float4 c, const Setup& s)
+// Depth of a covered pixel from its edge functions (Renderer.cpp:247-261); d = iz[] or zz[].
+__device__ __forceinline__ float pixelDepth(int persp, float e1, float e2, float d0, float d1, float d2)
 {
+	const float k0 = 1.0f - e1 - e2;
+	if (persp)
+		return 1.0f / (k0 * d0 + e1 * d1 + e2 * d2); // :255
+	return k0 * d0 + e1 * d1 + e2 * d2 + 0.0f * 1.0f; // :261
+}
+
+// Small triangle (bbox of at most MR_SMALL_AREA pixel centres): the reference's loops D/E
+// (Renderer.cpp:238-269) run right here by the setup thread; the depth test of every covered pixel
+// is one 64-bit atomicMin on the pixel's key in gkeys (fire-and-forget RED in L2). No binning, no
+// second pass over the triangle. Returns whether any fragment was emitted (if not, the triangle can
+// never own a pixel and needs no records).
+#ifndef MR_SMALL_AREA
+#define MR_SMALL_AREA 32
+#endif
+__device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 a, const float4 b, const float4 c, const Setup& s, int id)
+{
+	const int ya = max(s.y0, fp.rowBegin), yb = min(s.y1, fp.rowEnd - 1);
 	const int W = s.x1 - s.x0 + 1;
 	const float ptx = (float)s.x0 + 0.5f;
-	uint32_t mask = 0u, bit = 1u;
-	for (int y = s.y0; y <= s.y1; y++)
+	const unsigned long long idp1 = (unsigned long long)(uint32_t)(id + 1);
+	bool any = false;
+	for (int y = ya; y <= yb; y++)
 	{
 		const float fy = (float)y + 0.5f;
 		float e1 = s.n1x * (ptx - c.x) + s.n1y * (fy - c.y);
 		float e2 = s.n2x * (ptx - a.x) + s.n2y * (fy - a.y);
-		for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x, bit <<= 1)
+		unsigned long long* row = fp.gkeys + (size_t)y * fp.w + s.x0;
+		for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x)
 		{
 			const float k0 = 1.0f - e1 - e2;
-			if (!(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)) // Renderer.cpp:245 (NaN counts as inside, like there)
-				mask |= bit;
+			if (!(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)) // Renderer.cpp:245
+			{
+				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
+				if (z == z) // a NaN depth never passes `z < pixdepth`
+				{
+					atomicMin(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
+					any = true;
+				}
+			}
 		}
 	}
-	return mask;
+	return any;
 }
 
-// Bits of a record's coverage mask that fall inside tile (tileX0, tileY0).
-__device__ __forceinline__ uint32_t maskInTile(uint32_t mask, int x0, int x1, int y0, int y1, int tileX0, int tileY0)
-{
-	const int W = x1 - x0 + 1;
-	const int c0 = max(tileX0 - x0, 0), c1 = min(tileX0 + MR_TILE - 1, x1) - x0;
-	const int r0 = max(tileY0 - y0, 0), r1 = min(tileY0 + MR_TILE - 1, y1) - y0;
-	if (c1 < c0 || r1 < r0)
-		return 0u;
-	const uint32_t cols = ((c1 - c0 + 1 >= 32) ? 0xffffffffu : ((1u << (c1 - c0 + 1)) - 1u)) << c0;
-	uint32_t m = 0u;
-	for (int r = r0; r <= r1; r++)
-		m |= cols << (r * W);
-	return mask & m;
-}
-
-__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s)
+__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s, int material)
 {
 	float4* d4 = reinterpret_cast<float4*>(dst);
 	d4[0] = make_float4(a.x, a.y, c.x, c.y);
 	d4[1] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
-	d4[2] = make_float4(a.w, b.w, c.w, __uint_as_float(s.mask));
+	d4[2] = make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material));
 	d4[3] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
 	                    __uint_as_float(s.flags), 0.0f);
 }
 
-// Indices of triangle `tri`'s corners into the per-frame view-space arrays (vpos4 / vnrm4) and uv2
-// (winner-only part of loop C).
-__device__ __forceinline__ void storeShadeRec(const FrameParams& fp, ShadeRec* dst, int r, const RStat& rs, int tri, int ia, int ib, int ic)
-{
-	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
-	int iu0 = -1, iu1 = -1, iu2 = -1;
-	if (rs.uvTriBase >= 0)
-	{
-		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
-		iu0 = rs.uvBase + __ldg(iu); iu1 = rs.uvBase + __ldg(iu + 1); iu2 = rs.uvBase + __ldg(iu + 2);
-	}
-	int4* d4 = reinterpret_cast<int4*>(dst);
-	d4[0] = make_int4(rs.vertBase + ia, rs.vertBase + ib, rs.vertBase + ic, rs.nrmBase + __ldg(in));
-	d4[1] = make_int4(rs.nrmBase + __ldg(in + 1), rs.nrmBase + __ldg(in + 2), iu0, iu1);
-	d4[2] = make_int4(iu2, frameRdyn(fp)[r].material, r, tri);
-}
-
-// One corner in view space (loops A/B of paintMesh, evaluated for the winner only).
+// One corner in view space: what paintMesh's loops A/B/C hand to paintTriangle (Renderer.cpp:344-380).
 struct Corner
 {
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
-__device__ __forceinline__ Corner fetchCorner(const FrameParams& fp, int ip, int in, int iu)
+__device__ __forceinline__ void storeShadeRec(ShadeRec* dst, const Corner& c0, const Corner& c1, const Corner& c2)
 {
-	Corner v;
-	const float4 p = fp.vpos4[ip];
-	const float4 n = fp.vnrm4[in];
-	v.px = p.x; v.py = p.y; v.pz = p.z;
-	v.nx = n.x; v.ny = n.y; v.nz = n.z;
-	v.u = 0.0f; v.v = 0.0f;
-	if (iu >= 0)
+	float4* d = reinterpret_cast<float4*>(dst);
+	d[0] = make_float4(c0.px, c0.py, c0.pz, c0.u);
+	d[1] = make_float4(c1.px, c1.py, c1.pz, c0.v);
+	d[2] = make_float4(c2.px, c2.py, c2.pz, c1.u);
+	d[3] = make_float4(c0.nx, c0.ny, c0.nz, c1.v);
+	d[4] = make_float4(c1.nx, c1.ny, c1.nz, c2.u);
+	d[5] = make_float4(c2.nx, c2.ny, c2.nz, c2.v);
+}
+
+// The three view-space corners of triangle `tri` of renderable r: gathers the mesh's positions,
+// normals and texcoords through the three index arrays and transforms them with this frame's
+// modelview / normal matrix — the same expressions, in the same order, as k_vertex / loops A, B.
+// Evaluated only for triangles that survive setup.
+__device__ __forceinline__ void viewCorners(const FrameParams& fp, const RStat& rs, int r, int tri, int ia, int ib, int ic,
+                                            Corner& c0, Corner& c1, Corner& c2)
+{
+	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
+	const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
+	float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;
+	if (rs.uvTriBase >= 0)
 	{
-		const float2 t = __ldg(&fp.uv2[iu]);
-		v.u = t.x; v.v = t.y;
+		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
+		const int iu0 = __ldg(iu), iu1 = __ldg(iu + 1), iu2 = __ldg(iu + 2);
+		t0 = __ldg(&fp.uv2[rs.uvBase + iu0]); t1 = __ldg(&fp.uv2[rs.uvBase + iu1]); t2 = __ldg(&fp.uv2[rs.uvBase + iu2]);
 	}
-	return v;
+	const float4 p0 = __ldg(&fp.pos4[rs.posBase + ia]), p1 = __ldg(&fp.pos4[rs.posBase + ib]), p2 = __ldg(&fp.pos4[rs.posBase + ic]);
+	const float4 n0 = __ldg(&fp.nrm4[rs.nrmSrcBase + in0]), n1 = __ldg(&fp.nrm4[rs.nrmSrcBase + in1]), n2 = __ldg(&fp.nrm4[rs.nrmSrcBase + in2]);
+	const RDyn& rd = frameRdyn(fp)[r];
+	const V3 v0 = affine(rd.mv, p0.x, p0.y, p0.z), v1 = affine(rd.mv, p1.x, p1.y, p1.z), v2 = affine(rd.mv, p2.x, p2.y, p2.z);
+	const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
+	c0.px = v0.x; c0.py = v0.y; c0.pz = v0.z; c0.nx = m0.x; c0.ny = m0.y; c0.nz = m0.z; c0.u = t0.x; c0.v = t0.y;
+	c1.px = v1.x; c1.py = v1.y; c1.pz = v1.z; c1.nx = m1.x; c1.ny = m1.y; c1.nz = m1.z; c1.u = t1.x; c1.v = t1.y;
+	c2.px = v2.x; c2.py = v2.y; c2.pz = v2.z; c2.nx = m2.x; c2.ny = m2.y; c2.nz = m2.z; c2.u = t2.x; c2.v = t2.y;
 }
 
 // reference clip(), Renderer.cpp:121-129
@@ -370,7 +361,7 @@ __device__ __forceinline__ void binStore(const FrameParams& fp, int tile, int sl
 // All arguments are warp-uniform. Used for triangles spanning more than MR_SEG_PER_LANE tiles and
 // for clipper output: a lone lane walking thousands of tiles is the critical path of scenes with
 // huge triangles.
-__device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, int id, int x0, int x1, int y0, int y1, uint32_t flags, uint32_t mask)
+__device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, int id, int x0, int x1, int y0, int y1)
 {
 	const int tx0 = x0 >> MR_TILE_SHIFT, tx1 = x1 >> MR_TILE_SHIFT;
 	const int ty0 = max(y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
@@ -378,10 +369,7 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 	for (int k = lane; k < n; k += 32)
 	{
 		const int row = k / nx;
-		const int tx = tx0 + k - row * nx, ty = ty0 + row;
-		if ((flags & MR_REC_MASKED) && maskInTile(mask, x0, x1, y0, y1, tx * MR_TILE, ty * MR_TILE) == 0u)
-			continue;
-		const int tile = ty * fp.tilesX + tx;
+		const int tile = (ty0 + row) * fp.tilesX + tx0 + k - row * nx;
 		binStore(fp, tile, atomicAdd(&fp.tileCount[tile], 1), id);
 	}
 }
@@ -392,16 +380,9 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
 {
 	const RStat rs = frameRstat(fp)[r];
-	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
-	int iu0 = -1, iu1 = -1, iu2 = -1;
-	if (rs.uvTriBase >= 0)
-	{
-		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
-		iu0 = rs.uvBase + __ldg(iu); iu1 = rs.uvBase + __ldg(iu + 1); iu2 = rs.uvBase + __ldg(iu + 2);
-	}
-	const Corner v0 = fetchCorner(fp, rs.vertBase + ia, rs.nrmBase + __ldg(in), iu0);
-	const Corner v1 = fetchCorner(fp, rs.vertBase + ib, rs.nrmBase + __ldg(in + 1), iu1);
-	const Corner v2 = fetchCorner(fp, rs.vertBase + ic, rs.nrmBase + __ldg(in + 2), iu2);
+	Corner v0, v1, v2;
+	viewCorners(fp, rs, r, tri, ia, ib, ic, v0, v1, v2);
+	const int material = frameRdyn(fp)[r].material;
 	int nrec = 0;
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
 	for (int sub = 0; sub < 2; sub++)
@@ -418,22 +399,25 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 			continue;
 		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
-		storeRec(&fp.recs[id], a, b, c, s);
-		storeShadeRec(fp, &fp.srecs[id], r, rs, tri, ia, ib, ic);
+		storeRec(&fp.recs[id], a, b, c, s, material);
+		storeShadeRec(&fp.srecs[id], o0, o1, o2);
 		nrec |= 1 << sub;
 	}
 	return nrec;
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 2: near test, clip, setup, coverage mask, and binning.
-// One thread per triangle instance t. A surviving triangle is written at recs[2t] (clipper
-// outputs at 2t and 2t+1): the index is the submission id. It is appended to the bin of every
-// 16x16 tile that contains covered pixels: bins have a fixed capacity per tile (fp.binCap), the
-// position comes from the tile counter with one atomic per distinct tile per warp
-// (__match_any_sync: neighbouring triangles mostly share a tile), and the rare entries beyond the
-// capacity go to a global overflow list. The order inside a bin does not matter: depth ties are
-// resolved on the record index (submission id), not on arrival order.
+// Kernel 2: near test, clip, setup, and either direct rasterization (small triangles) or binning.
+// One thread per triangle instance t. A surviving triangle's records are written at index 2t
+// (clipper outputs at 2t and 2t+1): the index is the submission id.
+//  * bbox of at most MR_SMALL_AREA pixel centres: rasterSmall() depth-tests its covered pixels
+//    straight into gkeys; the triangle never enters a bin.
+//  * larger: appended to the bin of every 16x16 tile its bbox touches. Bins have a fixed capacity
+//    per tile (fp.binCap); the position comes from the tile counter with one atomic per distinct
+//    tile per warp (__match_any_sync: neighbouring triangles mostly share a tile), and the rare
+//    entries beyond the capacity go to a global overflow list.
+// The order in which fragments or bin entries arrive does not matter: depth ties are resolved on
+// the record index (submission id) carried in the low word of every depth key.
 // ------------------------------------------------------------------------------------------
 #ifndef MR_SETUP_MINB
 #define MR_SETUP_MINB 4
@@ -445,14 +429,14 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 	const int t = blockIdx.x * 256 + threadIdx.x;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const int r = findRenderable(fp, fp.triBlockR, t, 1, shBases);
-	bool valid = false;
+	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
 	s.x0 = s.x1 = s.y0 = s.y1 = 0;
-	s.mask = s.flags = 0u;
+	s.flags = 0u;
 	if (t < fp.nTriInst)
 	{
-		const RStat rs = frameRstat(fp)[r];
+		const RStat& rs = frameRstat(fp)[r];
 		const int tri = t - rs.triBase;
 		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
 		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
@@ -471,57 +455,49 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 		else if (setupTriangle(fp, a, b, c, s))
 		{
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
-			if (valid && (s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= 32 && !(fp.debug & 64))
+			if (valid)
 			{
-				s.flags = MR_REC_MASKED;
-				s.mask = coverageMask(a, c, s);
-				valid = s.mask != 0u;
-				nzero = valid ? 0 : 1;
+				if ((s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= MR_SMALL_AREA)
+				{
+					valid = rasterSmall(fp, a, b, c, s, 2 * t);
+					nzero = valid ? 0 : 1;
+				}
+				else
+					binned = true;
 			}
 			if (valid)
 			{
-				if (!(fp.debug & 128))
-					storeRec(&fp.recs[2 * (size_t)t], a, b, c, s);
-				if (!(fp.debug & 16))
-					storeShadeRec(fp, &fp.srecs[2 * (size_t)t], r, rs, tri, ia, ib, ic);
+				Corner c0, c1, c2;
+				viewCorners(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
+				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, frameRdyn(fp)[r].material);
+				storeShadeRec(&fp.srecs[2 * (size_t)t], c0, c1, c2);
 			}
 		}
 	}
 	__syncwarp();
 
-	// ---- binning: up to MR_SEG_PER_LANE tiles per triangle, warp-aggregated ----
-	const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
-	const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
-	const int nx = tx1 - tx0 + 1;
-	const int ntiles = (valid && !(fp.debug & 32)) ? nx * (ty1 - ty0 + 1) : 0;
-	const bool big = ntiles > MR_SEG_PER_LANE;
-	// tiles of the bbox that actually contain covered pixels (masked triangles), as a bit set
-	uint32_t live = 0u;
-	if (valid && !big)
-		for (int k = 0; k < ntiles; k++)
-		{
-			const int row = (k >= nx) + (k >= 2 * nx) + (k >= 3 * nx); // k / nx for k < 4
-			const int tx = tx0 + k - row * nx, ty = ty0 + row;
-			if (!(s.flags & MR_REC_MASKED) || maskInTile(s.mask, s.x0, s.x1, s.y0, s.y1, tx * MR_TILE, ty * MR_TILE) != 0u)
-				live |= 1u << k;
-		}
+	// ---- binning of the larger triangles: up to MR_SEG_PER_LANE tiles each, warp-aggregated ----
+	if (__any_sync(0xffffffffu, binned))
 	{
+		const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
+		const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
+		const int nx = tx1 - tx0 + 1;
+		const int ntiles = binned ? nx * (ty1 - ty0 + 1) : 0;
+		const bool big = ntiles > MR_SEG_PER_LANE;
+		const int mine = big ? 0 : ntiles;
 		const int id = 2 * t;
-		const int rounds = __reduce_max_sync(0xffffffffu, __popc(live));
+		const int rounds = __reduce_max_sync(0xffffffffu, mine);
 		// issue the counter atomics of all rounds first, use their results afterwards
 		int tileOf[MR_SEG_PER_LANE], baseOf[MR_SEG_PER_LANE], rankOf[MR_SEG_PER_LANE], leadOf[MR_SEG_PER_LANE];
-		uint32_t rest = live;
 #pragma unroll
 		for (int k = 0; k < MR_SEG_PER_LANE; k++)
 		{
 			tileOf[k] = -1; baseOf[k] = 0; rankOf[k] = 0; leadOf[k] = 0;
 			if (k < rounds)
 			{
-				const bool on = rest != 0u;
-				const int kk = on ? __ffs(rest) - 1 : 0;
-				rest &= rest - 1u;
-				const int krow = (kk >= nx) + (kk >= 2 * nx) + (kk >= 3 * nx);
-				const int tile = on ? (ty0 + krow) * fp.tilesX + tx0 + kk - krow * nx : -1 - lane;
+				const bool on = k < mine;
+				const int krow = (k >= nx) + (k >= 2 * nx) + (k >= 3 * nx); // k / nx for k < 4
+				const int tile = on ? (ty0 + krow) * fp.tilesX + tx0 + k - krow * nx : -1 - lane;
 				const unsigned peers = __match_any_sync(0xffffffffu, tile);
 				leadOf[k] = __ffs(peers) - 1;
 				rankOf[k] = __popc(peers & ((1u << lane) - 1u));
@@ -541,17 +517,17 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 				if (tileOf[k] >= 0)
 					binStore(fp, tileOf[k], slot, id);
 			}
+		// Triangles spanning more tiles: the warp bins them together, one at a time.
+		unsigned bigLanes = __ballot_sync(0xffffffffu, big);
+		while (bigLanes != 0u)
+		{
+			const int src = __ffs(bigLanes) - 1;
+			bigLanes &= bigLanes - 1u;
+			binCooperative(fp, lane, 2 * (t - lane + src), __shfl_sync(0xffffffffu, s.x0, src), __shfl_sync(0xffffffffu, s.x1, src),
+			               __shfl_sync(0xffffffffu, s.y0, src), __shfl_sync(0xffffffffu, s.y1, src));
+		}
 	}
-	// Triangles spanning more tiles, and clipper output: the warp bins them together, one at a time.
-	unsigned bigLanes = __ballot_sync(0xffffffffu, big);
-	while (bigLanes != 0u)
-	{
-		const int src = __ffs(bigLanes) - 1;
-		bigLanes &= bigLanes - 1u;
-		binCooperative(fp, lane, 2 * (t - lane + src), __shfl_sync(0xffffffffu, s.x0, src), __shfl_sync(0xffffffffu, s.x1, src),
-		               __shfl_sync(0xffffffffu, s.y0, src), __shfl_sync(0xffffffffu, s.y1, src), __shfl_sync(0xffffffffu, s.flags, src),
-		               __shfl_sync(0xffffffffu, s.mask, src));
-	}
+	// clipper output: binned by the whole warp as well
 	unsigned clipLanes = __ballot_sync(0xffffffffu, nrecSlow != 0);
 	while (clipLanes != 0u)
 	{
@@ -564,7 +540,7 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 				const int id = 2 * (t - lane + src) + sub;
 				const float4 q3 = reinterpret_cast<const float4*>(&fp.recs[id])[3]; // spans written by setupClipped
 				const uint32_t xs = __float_as_uint(q3.x), ys = __float_as_uint(q3.y);
-				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16, MR_REC_CLIPPED, 0u);
+				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16);
 			}
 	}
 
@@ -595,17 +571,17 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 4: tile rasterizer + shader. One CTA per 16x16 tile, 256 threads; the tile's depth keys
-// live in shared memory.
-// Phase 1: coverage + depth. A lane per binned triangle loads its record. Small triangles carry
-//   their exact coverage mask from k_setup: their covered pixels inside the tile go straight to
-//   the warp's fragment queue. Larger triangles are scanned by a quad of lanes each (rows
-//   interleaved), reference loops D/E with the float edge chain replayed from the triangle's own
-//   bbox start (e += n.x per column, Renderer.cpp:243). The queue is consumed 32 fragments at a
-//   time by the whole warp: exact z, then a 64-bit atomicMin in shared memory on
-//   (orderable z) << 32 | (record index + 1). The low word makes equal-z fragments resolve to the
-//   earliest submitted triangle, which is what the reference's strict `<` over in-order submission
-//   does.
+// Kernel 3: tile rasterizer + resolve + shader. One CTA per 16x16 tile.
+// Phase 0: the tile's depth keys are fetched from gkeys (the small triangles' fragments have
+//   already been depth-tested there by k_setup) and the entries are reset for the next frame.
+// Phase 1 (only for tiles with binned triangles): coverage + depth of the larger triangles, with
+//   the tile's keys in shared memory. A lane per binned triangle loads its record; each triangle is
+//   then scanned by a quad of lanes (rows interleaved), reference loops D/E with the float edge
+//   chain replayed from the triangle's own bbox start (e += n.x per column, Renderer.cpp:243).
+//   Fragments go through a per-warp queue and are consumed 32 at a time by the whole warp: exact z,
+//   then a 64-bit atomicMin in shared memory on (orderable z) << 32 | (record index + 1). The low
+//   word makes equal-z fragments resolve to the earliest submitted triangle, which is what the
+//   reference's strict `<` over in-order submission does.
 // Phase 2 (thread per pixel): the winner's barycentrics are re-derived by the same chain, then
 //   depth, perspective correction, texture and Blinn-Phong exactly as Renderer.cpp:253-305;
 //   pixels without a winner get the clear values (Renderer.cpp:113-119) unless fp.keep.
@@ -629,12 +605,7 @@ __device__ __forceinline__ void consumeFragments(const FrameParams& fp, WarpQueu
 		const float e1 = wq.e1[i], e2 = wq.e2[i];
 		const uint32_t info = wq.info[i];
 		const float4 t = wq.tri[info >> 8];
-		const float k0 = 1.0f - e1 - e2;
-		float z;
-		if (fp.persp)
-			z = 1.0f / (k0 * t.x + e1 * t.y + e2 * t.z); // Renderer.cpp:255
-		else
-			z = k0 * t.x + e1 * t.y + e2 * t.z + 0.0f * 1.0f; // Renderer.cpp:261
+		const float z = pixelDepth(fp.persp, e1, e2, t.x, t.y, t.z);
 		if (z == z) // a NaN depth never passes `z < pixdepth`
 		{
 			const unsigned long long key = ((unsigned long long)zkey(z) << 32) | (unsigned long long)__float_as_uint(t.w);
@@ -740,19 +711,6 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 	return value;
 }
 
-// Shading of a pixel won by a clipper-made triangle (rare): re-runs the clip to get the corners.
-__device__ __noinline__ float3 shadeClippedPixel(const FrameParams& fp, const ShadeRec* sr, int sub, float k0, float k1, float k2, size_t pix)
-{
-	const int4* s4 = reinterpret_cast<const int4*>(sr);
-	const int4 sa = __ldg(s4), sb = __ldg(s4 + 1), sc = __ldg(s4 + 2);
-	const Corner v0 = fetchCorner(fp, sa.x, sa.w, sb.z), v1 = fetchCorner(fp, sa.y, sb.x, sb.w), v2 = fetchCorner(fp, sa.z, sb.y, sc.x);
-	Corner c0, c1, c2;
-	clipTriangle(fp.znear, v0, v1, v2, sub, c0, c1, c2);
-	const MatDev mat = frameMats(fp)[sc.y];
-	const V3 v = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
-	return make_float3(v.x, v.y, v.z);
-}
-
 // Tile output staging: 16 rows x (48 rgb floats + 16 depth floats); written to HBM as float4 rows.
 struct TileOut
 {
@@ -792,20 +750,6 @@ __device__ __forceinline__ void storeTileRows(const FrameParams& fp, int tileX0,
 	}
 }
 
-__device__ __forceinline__ void writeClear(const FrameParams& fp, size_t pix)
-{
-	float* img = fp.image + 3 * pix;
-	img[0] = fp.bg[0]; img[1] = fp.bg[1]; img[2] = fp.bg[2];
-	fp.depth[pix] = 1e11f;
-	if (fp.saveNormals && fp.normals)
-	{
-		float* pn = fp.normals + 3 * pix;
-		pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
-	}
-	if (fp.winner)
-		fp.winner[pix] = -1;
-}
-
 // Phase 1 for one batch of up to 32 binned triangles (a lane each; `have` lanes hold record `id`).
 __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq, unsigned long long* keys, int& qhead, int& qcount,
                                             int& parity, int lane, bool have, int id, int tileX0, int tileY0)
@@ -817,47 +761,13 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
 		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
 		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
-		// most binned triangles win a pixel: pull their shading record towards this SM now, so that
-		// phase 2's first hop is an L1 hit instead of an L2 round trip
-		asm volatile("prefetch.global.L1 [%0];" ::"l"(&fp.srecs[id]));
 	}
-	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y), flags = __float_as_uint(q3.z);
+	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
 	const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
-	const bool masked = have && (flags & MR_REC_MASKED);
 	__syncwarp();
 
-	// small triangles: exact coverage is known, push the covered pixels of this tile
-	{
-		uint32_t tm = masked ? maskInTile(__float_as_uint(q2.w), x0, x1, y0, y1, tileX0, tileY0) : 0u;
-		const int W = x1 - x0 + 1;
-		const float ptx = (float)x0 + 0.5f;
-		const int rounds = __reduce_max_sync(0xffffffffu, __popc(tm));
-		for (int k = 0; k < rounds; k++)
-		{
-			const bool on = tm != 0u;
-			const int bit = on ? __ffs(tm) - 1 : 0;
-			tm &= tm - 1u;
-			int yy = 0, xx = bit;
-			while (xx >= W) // at most 31 subtractions, usually 0-3
-			{
-				xx -= W;
-				yy++;
-			}
-			const float fy = (float)(y0 + yy) + 0.5f;
-			float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
-			float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
-			for (int j = 0; j < xx; j++)
-			{
-				e1 += q1.x;
-				e2 += q1.z;
-			}
-			const uint32_t info = (uint32_t)((y0 + yy - tileY0) * MR_TILE + (x0 + xx - tileX0)) | ((uint32_t)slot << 8);
-			pushFragment(fp, wq, keys, qhead, qcount, lane, on, e1, e2, info);
-		}
-	}
-
-	// larger triangles of this batch: a quad of lanes scans each, rows interleaved
-	unsigned large = __ballot_sync(0xffffffffu, have && !masked);
+	// a quad of lanes scans each triangle of the batch, rows interleaved
+	unsigned large = __ballot_sync(0xffffffffu, have);
 	while (large != 0u)
 	{
 		const int q = lane & 3, quad = lane >> 2;
@@ -916,26 +826,30 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	__syncwarp();
 }
 
-// Per-pixel part of phase 2 for tile pixel `pi` (0..255). Warp-convergent: contains shuffles.
-// Returns the pixel's colour and depth (clear values when nothing won); side outputs (winner ids,
-// normals image) are written here.
-__device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsigned long long* keys, int pi, int tileX0, int tileY0, int lane,
+// Per-pixel part of phase 2 for tile pixel `pi` (0..255) whose final depth key is `key`.
+// Warp-convergent: contains shuffles. Returns the pixel's colour and depth (clear values when
+// nothing won); side outputs (winner ids, normals image) are written here.
+__device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned long long key, int pi, int tileX0, int tileY0, int lane,
                                              V3& value, float& zout, bool& store)
 {
 	const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
 	const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
 	const size_t pix = (size_t)py * fp.w + px;
-	const uint32_t win = (inImage && !(fp.debug & 256)) ? (uint32_t)(keys[pi] & 0xffffffffull) : 0u;
+	const uint32_t win = inImage ? (uint32_t)(key & 0xffffffffull) : 0u;
+	const bool attrs = fp.lighting || fp.texturing; // does shading read the corners at all?
 	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-	int4 sa = make_int4(0, 0, 0, 0), sb = sa, sc = sa;
+	float4 s0 = q0, s1 = q0, s2 = q0, s3 = q0, s4 = q0, s5 = q0;
 	int id = -1;
 	if (win != 0u)
 	{
 		id = (int)(win - 1u);
 		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-		const int4* s4 = reinterpret_cast<const int4*>(&fp.srecs[id]);
 		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
-		sa = __ldg(s4); sb = __ldg(s4 + 1); sc = __ldg(s4 + 2);
+		if (attrs)
+		{
+			const float4* c4 = reinterpret_cast<const float4*>(&fp.srecs[id]);
+			s0 = __ldg(c4); s1 = __ldg(c4 + 1); s2 = __ldg(c4 + 2); s3 = __ldg(c4 + 3); s4 = __ldg(c4 + 4); s5 = __ldg(c4 + 5);
+		}
 	}
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a half warp) that share a
 	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
@@ -959,11 +873,11 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsign
 					e1 += q1.x;
 					e2 += q1.z;
 				}
-			const float s1 = __shfl_sync(0xffffffffu, e1, leader), s2 = __shfl_sync(0xffffffffu, e2, leader);
+			const float t1 = __shfl_sync(0xffffffffu, e1, leader), t2 = __shfl_sync(0xffffffffu, e2, leader);
 			if (prefix > 0)
 			{
-				e1 = s1;
-				e2 = s2;
+				e1 = t1;
+				e2 = t2;
 				xcur = tileX0;
 			}
 		}
@@ -992,31 +906,15 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsign
 			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
 			fp.winner[pix] = id;
-		if (fp.debug & 4)
-			value = mk3(k0, k1, k2);
-		else if (__float_as_uint(q3.z) & MR_REC_CLIPPED)
-		{
-			const float3 v = shadeClippedPixel(fp, &fp.srecs[id], id & 1, k0, k1, k2, pix);
-			value = mk3(v.x, v.y, v.z);
-		}
-		else
-		{
-			const MatDev mat = frameMats(fp)[sc.y];
-			Corner c0, c1, c2;
-			if (fp.lighting || (fp.texturing && mat.texOffset >= 0 && mat.texRows > 0))
-			{
-				c0 = fetchCorner(fp, sa.x, sa.w, sb.z);
-				c1 = fetchCorner(fp, sa.y, sb.x, sb.w);
-				c2 = fetchCorner(fp, sa.z, sb.y, sc.x);
-			}
-			else
-			{
-				c0.px = c0.py = c0.pz = c0.nx = c0.ny = c0.nz = c0.u = c0.v = 0.0f;
-				c1 = c0;
-				c2 = c0;
-			}
-			value = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
-		}
+		const MatDev& mat = frameMats(fp)[__float_as_uint(q2.w)];
+		Corner c0, c1, c2;
+		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s1.w;
+		c1.px = s1.x; c1.py = s1.y; c1.pz = s1.z; c1.u = s2.w; c1.v = s3.w;
+		c2.px = s2.x; c2.py = s2.y; c2.pz = s2.z; c2.u = s4.w; c2.v = s5.w;
+		c0.nx = s3.x; c0.ny = s3.y; c0.nz = s3.z;
+		c1.nx = s4.x; c1.ny = s4.y; c1.nz = s4.z;
+		c2.nx = s5.x; c2.ny = s5.y; c2.nz = s5.z;
+		value = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
 	}
 	else if (inImage && !fp.keep)
 	{
@@ -1030,68 +928,55 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, const unsign
 	}
 }
 
-// One tile: phases 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice as
-// many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
+// One tile: phases 0, 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice
+// as many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
 template <int NT>
 __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
 {
+	constexpr int PP = MR_TILE_PIXELS / NT;
 	const int tile = ty * fp.tilesX + tx;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
-	const int total = fp.tileCount[tile];                              // triangles binned to this tile
-	// (independent loads; the counters were written by the previous kernels, so the L1-cached
-	// read-only path is fine and keeps 8160 CTAs from hammering one L2 line)
+	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
+	// ---- phase 0: this tile's keys out of gkeys (independent of the loads below) ----
+	unsigned long long key[PP];
+#pragma unroll
+	for (int pp = 0; pp < PP; pp++)
+	{
+		const int pi = tid + pp * NT;
+		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
+		unsigned long long g = MR_KEY_EMPTY, base = 0ull; // pixels outside the image / strip can never be won
+		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
+		{
+			const size_t pix = (size_t)py * fp.w + px;
+			g = fp.gkeys[pix];
+			base = (unsigned long long)zkey(fp.keep ? fp.depth[pix] : 1e11f) << 32;
+			if (g != MR_KEY_EMPTY)
+				fp.gkeys[pix] = MR_KEY_EMPTY; // ready for the next frame
+		}
+		key[pp] = (g < base) ? g : base;
+	}
+	const int total = fp.tileCount[tile]; // larger triangles binned to this tile
+	// (the counters were written by the previous kernels, so the L1-cached read-only path is fine
+	// and keeps 8160 CTAs from hammering one L2 line)
 	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
 	const unsigned overflowed = __ldg(&fp.ctr->overflow);
 	if (total > fp.binCap && threadIdx.x == 0)
 		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
 	if (overflowed)
-		return; // the overflow list itself overflowed: the host regrows it and re-runs the frame
-	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
+		return; // the overflow list itself overflowed: the host regrows it, clears gkeys and re-runs the frame
 	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
 	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
-	if (total == 0 && !fp.keep)
-	{
-		// empty tile: clear values only (Renderer.cpp:113-119)
-		for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
-		{
-			const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
-			const bool inImage = px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd;
-			const size_t pix = (size_t)py * fp.w + px;
-			if (vec)
-			{
-				storeTileRows(fp, tileX0, tileY0, pi, 0);
-				if (inImage && fp.saveNormals && fp.normals)
-				{
-					float* pn = fp.normals + 3 * pix;
-					pn[0] = 0.0f; pn[1] = 0.0f; pn[2] = 1.0f;
-				}
-				if (inImage && fp.winner)
-					fp.winner[pix] = -1;
-			}
-			else if (inImage)
-				writeClear(fp, pix);
-		}
-		return;
-	}
-	for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
-	{
-		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
-		unsigned long long k0 = 0ull; // pixels outside the image / strip can never be won
-		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
-		{
-			const float d0 = fp.keep ? fp.depth[(size_t)py * fp.w + px] : 1e11f;
-			k0 = (unsigned long long)zkey(d0) << 32;
-		}
-		keys[pi] = k0;
-	}
-	if (tid == 0 && total > 0)
-		atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
-	__syncthreads();
 
-	// ---- phase 1: coverage + depth ----
-	if (!(fp.debug & 8))
+	// ---- phase 1: coverage + depth of the binned triangles ----
+	if (total > 0)
 	{
+#pragma unroll
+		for (int pp = 0; pp < PP; pp++)
+			keys[tid + pp * NT] = key[pp];
+		if (tid == 0)
+			atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
+		__syncthreads();
 		WarpQueue& wq = queues[tid >> 5];
 		const int count = min(total, fp.binCap);
 		const int* bin = fp.bins + (size_t)tile * fp.binCap;
@@ -1124,16 +1009,31 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 			__syncwarp();
 			consumeFragments(fp, wq, keys, qhead, qcount, lane);
 		}
+		__syncthreads();
+#pragma unroll
+		for (int pp = 0; pp < PP; pp++)
+			key[pp] = keys[tid + pp * NT];
 	}
-	__syncthreads();
+
+	// ---- empty tile: clear values only (Renderer.cpp:113-119) ----
+	bool anyWin = false;
+#pragma unroll
+	for (int pp = 0; pp < PP; pp++)
+		anyWin = anyWin || (uint32_t)(key[pp] & 0xffffffffull) != 0u;
+	if (!__syncthreads_or(anyWin) && vec && !(fp.saveNormals && fp.normals) && !fp.winner)
+	{
+		for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
+			storeTileRows(fp, tileX0, tileY0, pi, 0);
+		return;
+	}
 
 	// ---- phase 2: resolve + shade, 256 / NT pixels per thread ----
-	V3 value[MR_TILE_PIXELS / NT];
-	float zout[MR_TILE_PIXELS / NT];
-	bool store[MR_TILE_PIXELS / NT];
+	V3 value[PP];
+	float zout[PP];
+	bool store[PP];
 #pragma unroll
-	for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
-		resolvePixel(fp, keys, tid + pp * NT, tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
+	for (int pp = 0; pp < PP; pp++)
+		resolvePixel(fp, key[pp], tid + pp * NT, tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
 
 	// ---- tile store ----
 	if (vec)
@@ -1141,7 +1041,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		// stage the tile in shared memory (the fragment queues are idle now) and write full rows
 		TileOut* to = reinterpret_cast<TileOut*>(queues);
 #pragma unroll
-		for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+		for (int pp = 0; pp < PP; pp++)
 		{
 			const int pi = tid + pp * NT, r = pi >> 4, c = pi & 15;
 			to->rgb[r][3 * c] = value[pp].x;
@@ -1156,7 +1056,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	else
 	{
 #pragma unroll
-		for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+		for (int pp = 0; pp < PP; pp++)
 			if (store[pp])
 			{
 				const int pi = tid + pp * NT;
@@ -1262,8 +1162,6 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 {
 	const int nTiles = fp.tilesX * fp.tilesY;
 	int vthreads = (fp.nVertInst > nTiles + 1) ? fp.nVertInst : nTiles + 1;
-	if (fp.nNrmInst > vthreads)
-		vthreads = fp.nNrmInst;
 	if (ev) cudaEventRecord(ev[0], stream);
 	k_vertex<<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[1], stream);

@@ -11,11 +11,14 @@
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
 //   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
-//   vpos4[] vnrm4[] float4 per vertex / normal instance: view-space position / normal (loops A, B)
 //   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
 //                  triangle instance index in submission order: the index IS the submission id
 //                  that resolves equal-depth ties
-//   tileCount[] bins[] ovfPairs[]   16x16-tile binning: fixed-capacity bins + global overflow list
+//   srecs[]        96-byte shading record of the same triangle: its three view-space corners
+//   gkeys[]        one 64-bit depth key per pixel: small triangles depth-test straight into it
+//                  (atomicMin in L2); the tile kernel merges, resolves and resets it every frame
+//   tileCount[] bins[] ovfPairs[]   16x16-tile binning of the larger triangles: fixed-capacity
+//                  bins + global overflow list
 #ifndef MR_TYPES_H
 #define MR_TYPES_H
 
@@ -69,29 +72,30 @@ struct __align__(16) MatDev
 
 // 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
 #define MR_REC_CLIPPED 1u // produced by the near-plane clipper
-#define MR_REC_MASKED 2u  // bbox of at most 32 pixels: `mask` holds the exact coverage
+#define MR_KEY_EMPTY 0xffffffffffffffffull // gkeys[] entry no fragment has touched
 struct __align__(16) Rec
 {
 	float p0x, p0y, p2x, p2y; // edge origins (e1 is measured from p2, e2 from p0)
 	float n1x, n1y, n2x, n2y; // scaled edge normals
 	float d0, d1, d2;         // iz[] (perspective) or zz[] (ortho)
-	uint32_t mask;            // MR_REC_MASKED: bit (y-y0)*W + (x-x0) set iff the pixel passes the inside test
+	uint32_t material;        // into mats
 	uint32_t xspan;           // x0 | x1 << 16 : first / last pixel column of the clamped bbox
 	uint32_t yspan;           // y0 | y1 << 16
 	uint32_t flags;
 	uint32_t pad;
 };
 
-// 48-byte shading record of the same triangle: absolute attribute indices, so that the shading
-// pass reaches its inputs in one hop from the record (the winner-only work of paintMesh's loop C).
+// 96-byte shading record of the same triangle: the three corners in view space (for clipper output:
+// the clipped corners), i.e. what the reference's paintTriangle receives (Renderer.cpp:351-380).
+// Shading a pixel reaches everything it needs in one hop from the winner's id.
 struct __align__(16) ShadeRec
 {
-	int ip0, ip1, ip2; // into pos4
-	int in0, in1, in2; // into nrm4
-	int iu0, iu1, iu2; // into uv2, -1: the mesh has no texcoords
-	int material;      // into mats
-	int renderable;
-	int tri;           // triangle index inside the mesh (the clipper path re-derives its corners)
+	float p0[3], u0; // view-space position of corner 0, texcoord u of corner 0
+	float p1[3], v0;
+	float p2[3], u1;
+	float n0[3], v1; // view-space normal of corner 0
+	float n1[3], u2;
+	float n2[3], v2;
 };
 
 struct Counters
@@ -128,7 +132,7 @@ struct FrameParams
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int nRenderables, nVertInst, nTriInst, nNrmInst;
-	int debug; // mr_set_debug flags (4: skip shading, 8: skip phase 1 — profiling experiments only)
+	int debug; // mr_set_debug flags
 	int rasterCtas; // persistent k_raster CTAs (resident CTAs per SM x SM count)
 	int binCap; // entries per tile bin
 	int ovfCap; // entries in the overflow list
@@ -149,8 +153,7 @@ struct FrameParams
 	const int* nrmBlockR; // same for normal instances
 
 	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
-	float4* vpos4;       // per vertex instance: view-space position (reference _vertices)
-	float4* vnrm4;       // per normal instance: view-space normal (reference _normals)
+	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
 	Rec* recs;
 	int* tileCount;      // triangles binned per tile (may exceed binCap: the rest is in ovfPairs)
 	int* bins;           // tilesX*tilesY bins of binCap record indices
