@@ -83,6 +83,7 @@ struct mr_ctx
 
 	int w, h, tilesX, tilesY;
 	int smCount;
+	int rasterCtasPerSm;
 
 	// scene-static device arrays
 	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes;
@@ -113,7 +114,7 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, srecs, tileCount, ovfPairs, bins, ctr, gkeys;
+	DevBuf pv, recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -187,10 +188,18 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev);
 void absorbCounters(mr_ctx* c, const Counters& k)
 {
 	c->stats.triangles_in = (int64_t)k.trianglesIn;
-	c->stats.records = (int64_t)k.records;
-	c->stats.clipped_in = (int64_t)k.clippedIn;
-	c->stats.bin_entries = (int64_t)k.pairTotal;
-	c->stats.zero_coverage = (int64_t)k.zeroCov;
+	unsigned long long rec = 0, clip = 0, pairs = 0, zero = 0;
+	for (int i = 0; i < MR_STAT_SLOTS; i++)
+	{
+		rec += k.records[i];
+		clip += k.clippedIn[i];
+		pairs += k.pairTotal[i];
+		zero += k.zeroCov[i];
+	}
+	c->stats.records = (int64_t)rec;
+	c->stats.clipped_in = (int64_t)clip;
+	c->stats.bin_entries = (int64_t)pairs;
+	c->stats.zero_coverage = (int64_t)zero;
 	c->stats.tiles_x = c->tilesX;
 	c->stats.tiles_y = c->tilesY;
 }
@@ -329,9 +338,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
-	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
-	MR_CUDA(c, c->recs.ensure(sizeof(Rec) * 2 * (size_t)std::max(c->nTriInst, 1)));
-	MR_CUDA(c, c->srecs.ensure(sizeof(ShadeRec) * 2 * (size_t)std::max(c->nTriInst, 1)));
+	MR_CUDA(c, c->pv.ensure(sizeof(float4) * 2 * (size_t)std::max(c->nVertInst, 1)));
+	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
+	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->ctr.ensure(sizeof(Counters) * mr_ctx::kSlots));
 	{
@@ -496,7 +505,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		memcpy(fp.matsInline, md, sizeof(MatDev) * (size_t)f->n_materials);
 	}
 	fp.binCap = c->binCap;
-	fp.rasterCtas = c->smCount * 4; // 64 registers x 256 threads: four CTAs per SM
+	fp.rasterCtas = c->smCount * c->rasterCtasPerSm; // persistent tile CTAs: as many as are resident at once
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
 	fp.pos4 = c->pos4.as<float4>();
 	fp.nrm4 = c->nrm4.as<float4>();
@@ -514,10 +523,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
 	fp.gkeys = c->gkeys.as<unsigned long long>();
-	fp.recs = c->recs.as<Rec>();
+	fp.recs = c->recs.as<float4>();
+	fp.recs1 = c->recs1.as<float4>();
 	fp.tileCount = c->tileCount.as<int>();
 	fp.ovfPairs = c->ovfPairs.as<int2>();
-	fp.srecs = c->srecs.as<ShadeRec>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>() + slotIndex; // per-slot counters: the read-back overlaps the next frame
 	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
@@ -593,6 +602,7 @@ mr_ctx* mr_create(int device, int* status)
 		Bind bind(device);
 		c->smCount = 148;
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
+		c->rasterCtasPerSm = mrk_raster_ctas_per_sm();
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;
@@ -635,7 +645,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->srecs, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)

@@ -9,6 +9,21 @@
 //   k_raster   reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
 #include <math.h>
+#include <stdlib.h>
+
+// experiment switches
+#ifndef MR_EXP
+#define MR_EXP 0 // timing experiments only (break the output)
+#endif
+#ifndef MR_PV32
+#define MR_PV32 0
+#endif
+#ifndef MR_HOIST
+#define MR_HOIST 0
+#endif
+#ifndef MR_EARLY_ATTR
+#define MR_EARLY_ATTR 0
+#endif
 
 namespace {
 
@@ -72,22 +87,24 @@ __device__ __forceinline__ const RDyn* frameRdyn(const FrameParams& fp) { return
 __device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return fp.inlineTables ? fp.matsInline : fp.mats; }
 __device__ __forceinline__ const RStat* frameRstat(const FrameParams& fp) { return fp.inlineTables ? fp.rstatInline : fp.rstat; }
 
-// Renderable that owns instance `inst` (a vertex or triangle instance) of this 256-thread block.
+// Renderable that owns instance `inst` (a vertex or triangle instance) of this NT-thread CTA (NT divides 256).
 // blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
 // and searched there. Must be called by every thread of the block.
 __device__ __forceinline__ int instBase(const RStat& s, int kind) { return kind == 0 ? s.vertBase : kind == 1 ? s.triBase : s.nrmBase; }
 
+template <int NT>
 __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* __restrict__ blockR, int inst, int kind, int* shBases)
 {
 	if (fp.nRenderables == 1)
 		return 0; // nothing to look up (and one dependent load less)
-	const int r0 = __ldg(&blockR[blockIdx.x]), r1 = __ldg(&blockR[blockIdx.x + 1]);
+	const int vblock = (blockIdx.x * NT) >> 8; // the 256-instance block this CTA lies in
+	const int r0 = __ldg(&blockR[vblock]), r1 = __ldg(&blockR[vblock + 1]);
 	if (r0 >= r1)
 		return r0; // the whole block belongs to one renderable
 	const int n = r1 - r0 + 1;
 	if (n <= 256)
 	{
-		for (int i = threadIdx.x; i < n; i += 256)
+		for (int i = threadIdx.x; i < n; i += NT)
 			shBases[i] = instBase(frameRstat(fp)[r0 + i], kind);
 		__syncthreads();
 		int lo = 0, hi = n - 1; // largest i with base[i] <= inst
@@ -126,21 +143,22 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
 		fp.tileCount[vi] = 0;
-	if (vi == 0)
-	{
-		Counters* c = fp.ctr;
-		c->trianglesIn = (unsigned long long)fp.nTriInst; c->records = 0; c->clippedIn = 0; c->pairTotal = 0; c->zeroCov = 0;
-		c->overflow = 0; c->ovfTotal = 0; c->maxTile = 0; c->nextTile = 0;
-	}
+	if (vi < (int)(sizeof(Counters) / 8))
+		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriInst : 0ull; // word 0 = trianglesIn
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return;
-	const int rv = findRenderable(fp, fp.vtxBlockR, vi, 0, shBases);
+	const int rv = findRenderable<256>(fp, fp.vtxBlockR, vi, 0, shBases);
 	if (vi >= fp.nVertInst)
 		return;
 	const RStat& rs = frameRstat(fp)[rv];
 	const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
 	const V3 view = affine(frameRdyn(fp)[rv].mv, p.x, p.y, p.z);
+#if MR_PV32
+	fp.pv[2 * (size_t)vi] = project(fp, view);
+	fp.pv[2 * (size_t)vi + 1] = make_float4(view.x, view.y, view.z, 0.0f);
+#else
 	fp.pv[vi] = project(fp, view);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -232,6 +250,9 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
 				if (z == z) // a NaN depth never passes `z < pixdepth`
 				{
+#if MR_EXP & 1
+					if (z == 12345.0f)
+#endif
 					atomicMin(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
 					any = true;
 				}
@@ -241,14 +262,42 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 	return any;
 }
 
-__device__ __forceinline__ void storeRec(Rec* dst, const float4 a, const float4 b, const float4 c, const Setup& s, int material)
+// Where record `id` = 2 * triangle instance + clipper output lives. Field k (a float4: 0-3 raster
+// record, 4-9 shading record) is at p[k * stride].
+//  * sub-triangle 0 (every unclipped triangle): *plane* layout. The 32 triangles of a setup warp form
+//    a block of 10 planes of 32 float4, so each field is written by one fully coalesced 512-byte
+//    store per warp, and neighbouring winners read neighbouring slots of the same lines.
+//  * sub-triangle 1 (second clipper output, rare): plain 160-byte records in recs1.
+struct RecRef
 {
-	float4* d4 = reinterpret_cast<float4*>(dst);
-	d4[0] = make_float4(a.x, a.y, c.x, c.y);
-	d4[1] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
-	d4[2] = make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material));
-	d4[3] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
-	                    __uint_as_float(s.flags), 0.0f);
+	float4* p;
+	int stride;
+};
+
+__device__ __forceinline__ RecRef recRef(const FrameParams& fp, int id)
+{
+	const int t = id >> 1;
+	RecRef r;
+	if (id & 1)
+	{
+		r.p = fp.recs1 + (size_t)t * MR_REC_FIELDS;
+		r.stride = 1;
+	}
+	else
+	{
+		r.p = fp.recs + (size_t)(t >> 5) * (MR_REC_FIELDS * 32) + (t & 31);
+		r.stride = 32;
+	}
+	return r;
+}
+
+__device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material)
+{
+	d.p[0] = make_float4(a.x, a.y, c.x, c.y);
+	d.p[d.stride] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
+	d.p[2 * d.stride] = make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material));
+	d.p[3 * d.stride] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
+	                                __uint_as_float(s.flags), 0.0f);
 }
 
 // One corner in view space: what paintMesh's loops A/B/C hand to paintTriangle (Renderer.cpp:344-380).
@@ -257,15 +306,14 @@ struct Corner
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
-__device__ __forceinline__ void storeShadeRec(ShadeRec* dst, const Corner& c0, const Corner& c1, const Corner& c2)
+__device__ __forceinline__ void storeShadeRec(const RecRef d, const Corner& c0, const Corner& c1, const Corner& c2)
 {
-	float4* d = reinterpret_cast<float4*>(dst);
-	d[0] = make_float4(c0.px, c0.py, c0.pz, c0.u);
-	d[1] = make_float4(c1.px, c1.py, c1.pz, c0.v);
-	d[2] = make_float4(c2.px, c2.py, c2.pz, c1.u);
-	d[3] = make_float4(c0.nx, c0.ny, c0.nz, c1.v);
-	d[4] = make_float4(c1.nx, c1.ny, c1.nz, c2.u);
-	d[5] = make_float4(c2.nx, c2.ny, c2.nz, c2.v);
+	d.p[4 * d.stride] = make_float4(c0.px, c0.py, c0.pz, c0.u);
+	d.p[5 * d.stride] = make_float4(c1.px, c1.py, c1.pz, c0.v);
+	d.p[6 * d.stride] = make_float4(c2.px, c2.py, c2.pz, c1.u);
+	d.p[7 * d.stride] = make_float4(c0.nx, c0.ny, c0.nz, c1.v);
+	d.p[8 * d.stride] = make_float4(c1.nx, c1.ny, c1.nz, c2.u);
+	d.p[9 * d.stride] = make_float4(c2.nx, c2.ny, c2.nz, c2.v);
 }
 
 // The three view-space corners of triangle `tri` of renderable r: gathers the mesh's positions,
@@ -399,8 +447,9 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 			continue;
 		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
-		storeRec(&fp.recs[id], a, b, c, s, material);
-		storeShadeRec(&fp.srecs[id], o0, o1, o2);
+		const RecRef ref = recRef(fp, id);
+		storeRec(ref, a, b, c, s, material);
+		storeShadeRec(ref, o0, o1, o2);
 		nrec |= 1 << sub;
 	}
 	return nrec;
@@ -419,16 +468,22 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 // The order in which fragments or bin entries arrive does not matter: depth ties are resolved on
 // the record index (submission id) carried in the low word of every depth key.
 // ------------------------------------------------------------------------------------------
-#ifndef MR_SETUP_MINB
-#define MR_SETUP_MINB 4
+#ifndef MR_SETUP_THREADS
+#define MR_SETUP_THREADS 128
 #endif
-__global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
+#ifndef MR_SETUP_MINB
+#define MR_SETUP_MINB (1024 / MR_SETUP_THREADS)
+#endif
+__global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int sh[56];
 	__shared__ int shBases[256];
-	const int t = blockIdx.x * 256 + threadIdx.x;
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const int r = findRenderable(fp, fp.triBlockR, t, 1, shBases);
+	__shared__ int shStat[4]; // records, clipped inputs, zero-coverage drops, warps done
+	if (threadIdx.x < 4)
+		shStat[threadIdx.x] = 0;
+	__syncthreads();
+	const int t = blockIdx.x * MR_SETUP_THREADS + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const int r = findRenderable<MR_SETUP_THREADS>(fp, fp.triBlockR, t, 1, shBases);
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
@@ -438,11 +493,31 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 	{
 		const RStat& rs = frameRstat(fp)[r];
 		const int tri = t - rs.triBase;
+		// all three index streams up front: the normal / texcoord indices are only needed by
+		// survivors, but fetching them now keeps them off the dependent-load chain
 		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
+		const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
 		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
-		const float4 a = fp.pv[rs.vertBase + ia];
-		const float4 b = fp.pv[rs.vertBase + ib];
-		const float4 c = fp.pv[rs.vertBase + ic];
+		const bool hasUv = rs.uvTriBase >= 0;
+#if MR_HOIST
+		const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
+		int iu0 = 0, iu1 = 0, iu2 = 0;
+		if (hasUv)
+		{
+			const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
+			iu0 = __ldg(iu); iu1 = __ldg(iu + 1); iu2 = __ldg(iu + 2);
+		}
+#endif
+#if MR_PV32
+		const float4* va = fp.pv + 2 * (size_t)(rs.vertBase + ia);
+		const float4* vb = fp.pv + 2 * (size_t)(rs.vertBase + ib);
+		const float4* vc = fp.pv + 2 * (size_t)(rs.vertBase + ic);
+#else
+		const float4* va = fp.pv + (size_t)(rs.vertBase + ia);
+		const float4* vb = fp.pv + (size_t)(rs.vertBase + ib);
+		const float4* vc = fp.pv + (size_t)(rs.vertBase + ic);
+#endif
+		const float4 a = *va, b = *vb, c = *vc;
 		const float zn = fp.znear;
 		if (a.z > zn || b.z > zn || c.z > zn) // Renderer.cpp:169-177
 		{
@@ -457,20 +532,78 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
 			if (valid)
 			{
+#define MR_LOAD_ATTRS                                                                                                                      \
+	float4 n0, n1, n2, p0, p1, p2;                                                                                                         \
+	float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;                                                                                 \
+	{                                                                                                                                      \
+		MR_LOAD_IDX2                                                                                                                       \
+		n0 = __ldg(&fp.nrm4[rs.nrmSrcBase + in0]); n1 = __ldg(&fp.nrm4[rs.nrmSrcBase + in1]); n2 = __ldg(&fp.nrm4[rs.nrmSrcBase + in2]); \
+		MR_LOAD_POS                                                                                                                        \
+		if (hasUv)                                                                                                                         \
+		{                                                                                                                                  \
+			t0 = __ldg(&fp.uv2[rs.uvBase + iu0]); t1 = __ldg(&fp.uv2[rs.uvBase + iu1]); t2 = __ldg(&fp.uv2[rs.uvBase + iu2]);             \
+		}                                                                                                                                  \
+	}
+#if MR_HOIST
+#define MR_LOAD_IDX2
+#else
+#define MR_LOAD_IDX2                                                                        \
+	const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);                     \
+	int iu0 = 0, iu1 = 0, iu2 = 0;                                                           \
+	if (hasUv)                                                                               \
+	{                                                                                        \
+		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;                         \
+		iu0 = __ldg(iu); iu1 = __ldg(iu + 1); iu2 = __ldg(iu + 2);                           \
+	}
+#endif
+#if MR_PV32
+#define MR_LOAD_POS p0 = va[1]; p1 = vb[1]; p2 = vc[1]; /* view-space positions (same sectors as a, b, c) */
+#else
+#define MR_LOAD_POS                                                                                                                   \
+	{                                                                                                                                 \
+		const float4 w0 = __ldg(&fp.pos4[rs.posBase + ia]), w1 = __ldg(&fp.pos4[rs.posBase + ib]), w2 = __ldg(&fp.pos4[rs.posBase + ic]); \
+		const RDyn& rdp = frameRdyn(fp)[r];                                                                                           \
+		const V3 q0 = affine(rdp.mv, w0.x, w0.y, w0.z), q1 = affine(rdp.mv, w1.x, w1.y, w1.z), q2 = affine(rdp.mv, w2.x, w2.y, w2.z); \
+		p0 = make_float4(q0.x, q0.y, q0.z, 0.0f); p1 = make_float4(q1.x, q1.y, q1.z, 0.0f); p2 = make_float4(q2.x, q2.y, q2.z, 0.0f); \
+	}
+#endif
+#if MR_EARLY_ATTR
+				// corner attributes: requested before the pixel loop so that they arrive during it
+				MR_LOAD_ATTRS
+#endif
 				if ((s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= MR_SMALL_AREA)
 				{
+#if MR_EXP & 4
+					valid = s.n1x != 12345.0f;
+#else
 					valid = rasterSmall(fp, a, b, c, s, 2 * t);
+#endif
 					nzero = valid ? 0 : 1;
 				}
 				else
 					binned = true;
-			}
-			if (valid)
-			{
-				Corner c0, c1, c2;
-				viewCorners(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
-				storeRec(&fp.recs[2 * (size_t)t], a, b, c, s, frameRdyn(fp)[r].material);
-				storeShadeRec(&fp.srecs[2 * (size_t)t], c0, c1, c2);
+				if (valid)
+				{
+#if !MR_EARLY_ATTR
+					MR_LOAD_ATTRS
+#endif
+					const RDyn& rd = frameRdyn(fp)[r];
+					const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
+#if MR_EXP & 2
+					if (m0.x == 12345.0f)
+#endif
+					{
+					const RecRef ref = recRef(fp, 2 * t);
+					storeRec(ref, a, b, c, s, rd.material);
+					float4* d = ref.p + 4 * ref.stride;
+					d[0] = make_float4(p0.x, p0.y, p0.z, t0.x);
+					d[ref.stride] = make_float4(p1.x, p1.y, p1.z, t0.y);
+					d[2 * ref.stride] = make_float4(p2.x, p2.y, p2.z, t1.x);
+					d[3 * ref.stride] = make_float4(m0.x, m0.y, m0.z, t1.y);
+					d[4 * ref.stride] = make_float4(m1.x, m1.y, m1.z, t2.x);
+					d[5 * ref.stride] = make_float4(m2.x, m2.y, m2.z, t2.y);
+					}
+				}
 			}
 		}
 	}
@@ -538,35 +671,32 @@ __global__ void __launch_bounds__(256, MR_SETUP_MINB) k_setup(const __grid_const
 			if (subs & (1 << sub))
 			{
 				const int id = 2 * (t - lane + src) + sub;
-				const float4 q3 = reinterpret_cast<const float4*>(&fp.recs[id])[3]; // spans written by setupClipped
+				const RecRef ref = recRef(fp, id);
+				const float4 q3 = ref.p[3 * ref.stride]; // spans written by setupClipped
 				const uint32_t xs = __float_as_uint(q3.x), ys = __float_as_uint(q3.y);
 				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16);
 			}
 	}
 
-	// ---- statistics: one atomic per CTA ----
+	// ---- statistics: summed per CTA in shared memory; the last warp to finish sends one RED per
+	// counter (no barrier: finished warps leave at once) ----
 	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + __popc(nrecSlow));
 	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
 	const int nzeroWarp = __reduce_add_sync(0xffffffffu, nzero);
 	if (lane == 0)
 	{
-		sh[32 + wid] = nrecWarp;
-		sh[40 + wid] = nclipWarp;
-		sh[48 + wid] = nzeroWarp;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		int nr = 0, nc = 0, nz = 0;
-		for (int i = 0; i < 8; i++)
+		if (nrecWarp) atomicAdd(&shStat[0], nrecWarp);
+		if (nclipWarp) atomicAdd(&shStat[1], nclipWarp);
+		if (nzeroWarp) atomicAdd(&shStat[2], nzeroWarp);
+		__threadfence_block();
+		if (atomicAdd(&shStat[3], 1) == MR_SETUP_THREADS / 32 - 1)
 		{
-			nr += sh[32 + i];
-			nc += sh[40 + i];
-			nz += sh[48 + i];
+			const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
+			const int nr = atomicAdd(&shStat[0], 0), nc = atomicAdd(&shStat[1], 0), nz = atomicAdd(&shStat[2], 0);
+			if (nr) atomicAdd(&fp.ctr->records[slot], (unsigned long long)nr);
+			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], (unsigned long long)nc);
+			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], (unsigned long long)nz);
 		}
-		if (nr) atomicAdd(&fp.ctr->records, (unsigned long long)nr);
-		if (nc) atomicAdd(&fp.ctr->clippedIn, (unsigned long long)nc);
-		if (nz) atomicAdd(&fp.ctr->zeroCov, (unsigned long long)nz);
 	}
 }
 
@@ -758,8 +888,8 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
 	if (have)
 	{
-		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+		const RecRef ref = recRef(fp, id);
+		q0 = __ldg(ref.p); q1 = __ldg(ref.p + ref.stride); q2 = __ldg(ref.p + 2 * ref.stride); q3 = __ldg(ref.p + 3 * ref.stride);
 		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 	}
 	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
@@ -843,12 +973,14 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	if (win != 0u)
 	{
 		id = (int)(win - 1u);
-		const float4* r4 = reinterpret_cast<const float4*>(&fp.recs[id]);
-		q0 = __ldg(r4); q1 = __ldg(r4 + 1); q2 = __ldg(r4 + 2); q3 = __ldg(r4 + 3);
+		const RecRef ref = recRef(fp, id);
+		const float4* r4 = ref.p;
+		const int st = ref.stride;
+		q0 = __ldg(r4); q1 = __ldg(r4 + st); q2 = __ldg(r4 + 2 * st); q3 = __ldg(r4 + 3 * st);
 		if (attrs)
 		{
-			const float4* c4 = reinterpret_cast<const float4*>(&fp.srecs[id]);
-			s0 = __ldg(c4); s1 = __ldg(c4 + 1); s2 = __ldg(c4 + 2); s3 = __ldg(c4 + 3); s4 = __ldg(c4 + 4); s5 = __ldg(c4 + 5);
+			s0 = __ldg(r4 + 4 * st); s1 = __ldg(r4 + 5 * st); s2 = __ldg(r4 + 6 * st);
+			s3 = __ldg(r4 + 7 * st); s4 = __ldg(r4 + 8 * st); s5 = __ldg(r4 + 9 * st);
 		}
 	}
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a half warp) that share a
@@ -928,43 +1060,65 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	}
 }
 
+// What a CTA fetches for a tile ahead of time: the pixels' depth keys out of gkeys and the number of
+// larger triangles binned to the tile. Loaded one tile ahead, so the round trip to L2 / HBM overlaps
+// the previous tile's shading.
+template <int PP>
+struct TilePre
+{
+	unsigned long long g[PP];
+	int total;
+};
+
+template <int NT>
+__device__ __forceinline__ void fetchTile(const FrameParams& fp, int tileIndex, TilePre<MR_TILE_PIXELS / NT>& pre)
+{
+	const int ty = tileIndex / fp.tilesX, tx = tileIndex - ty * fp.tilesX;
+	const int tileX0 = tx * MR_TILE, tileY0 = (fp.tileRow0 + ty) * MR_TILE;
+#pragma unroll
+	for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
+	{
+		const int pi = threadIdx.x + pp * NT;
+		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
+		pre.g[pp] = MR_KEY_EMPTY;
+		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
+			pre.g[pp] = __ldcs(&fp.gkeys[(size_t)py * fp.w + px]); // read once per frame: streaming
+	}
+	pre.total = fp.tileCount[(fp.tileRow0 + ty) * fp.tilesX + tx];
+}
+
 // One tile: phases 0, 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice
 // as many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
 template <int NT>
-__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
+__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, const TilePre<MR_TILE_PIXELS / NT>& pre,
+                                           unsigned long long ovfTotal, unsigned long long* keys, WarpQueue* queues)
 {
 	constexpr int PP = MR_TILE_PIXELS / NT;
 	const int tile = ty * fp.tilesX + tx;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
-	// ---- phase 0: this tile's keys out of gkeys (independent of the loads below) ----
+	// ---- phase 0: merge the fetched keys with the clear / kept depth, reset gkeys ----
 	unsigned long long key[PP];
 #pragma unroll
 	for (int pp = 0; pp < PP; pp++)
 	{
 		const int pi = tid + pp * NT;
 		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
-		unsigned long long g = MR_KEY_EMPTY, base = 0ull; // pixels outside the image / strip can never be won
+		const unsigned long long g = pre.g[pp];
+		unsigned long long base = 0ull; // pixels outside the image / strip can never be won
 		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
 		{
 			const size_t pix = (size_t)py * fp.w + px;
-			g = fp.gkeys[pix];
 			base = (unsigned long long)zkey(fp.keep ? fp.depth[pix] : 1e11f) << 32;
 			if (g != MR_KEY_EMPTY)
 				fp.gkeys[pix] = MR_KEY_EMPTY; // ready for the next frame
 		}
 		key[pp] = (g < base) ? g : base;
 	}
-	const int total = fp.tileCount[tile]; // larger triangles binned to this tile
-	// (the counters were written by the previous kernels, so the L1-cached read-only path is fine
-	// and keeps 8160 CTAs from hammering one L2 line)
-	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
-	const unsigned overflowed = __ldg(&fp.ctr->overflow);
+	const int total = pre.total; // larger triangles binned to this tile
 	if (total > fp.binCap && threadIdx.x == 0)
 		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
-	if (overflowed)
-		return; // the overflow list itself overflowed: the host regrows it, clears gkeys and re-runs the frame
 	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
 	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
 
@@ -975,7 +1129,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		for (int pp = 0; pp < PP; pp++)
 			keys[tid + pp * NT] = key[pp];
 		if (tid == 0)
-			atomicAdd(&fp.ctr->pairTotal, (unsigned long long)total);
+			atomicAdd(&fp.ctr->pairTotal[tile & (MR_STAT_SLOTS - 1)], (unsigned long long)total);
 		__syncthreads();
 		WarpQueue& wq = queues[tid >> 5];
 		const int count = min(total, fp.binCap);
@@ -1020,6 +1174,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 #pragma unroll
 	for (int pp = 0; pp < PP; pp++)
 		anyWin = anyWin || (uint32_t)(key[pp] & 0xffffffffull) != 0u;
+	// (this barrier also separates the previous tile's staging reads from this tile's staging writes)
 	if (!__syncthreads_or(anyWin) && vec && !(fp.saveNormals && fp.normals) && !fp.winner)
 	{
 		for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
@@ -1068,8 +1223,9 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	}
 }
 
-// One CTA per tile. (A persistent variant with a global tile counter measured 10 % slower: the
-// hardware CTA scheduler already balances 8160 small CTAs well.)
+// Normally one CTA per tile (grid = number of tiles; the loop below runs once). With fewer CTAs than
+// tiles (experiments: fp.rasterCtas) they are persistent, tiles are dealt round-robin and the next
+// tile's keys are requested before the current tile is shaded.
 #ifndef MR_RASTER_THREADS
 #define MR_RASTER_THREADS 128
 #endif
@@ -1078,9 +1234,27 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 #endif
 __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
 {
+	constexpr int NT = MR_RASTER_THREADS;
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
-	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
-	rasterTile<MR_RASTER_THREADS>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
+	__shared__ WarpQueue queues[NT / 32 < 4 ? 4 : NT / 32]; // also >= sizeof(TileOut)
+	const int nT = fp.tilesX * fp.tileRows;
+	int i = blockIdx.x;
+	if (i >= nT)
+		return;
+	TilePre<MR_TILE_PIXELS / NT> pre, cur;
+	fetchTile<NT>(fp, i, pre);
+	// (the counters were written by the previous kernels, so the L1-cached read-only path is fine)
+	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
+	if (__ldg(&fp.ctr->overflow))
+		return; // the overflow list itself overflowed: the host regrows it, clears gkeys and re-runs the frame
+	for (; i < nT; i += gridDim.x)
+	{
+		cur = pre;
+		if (i + (int)gridDim.x < nT)
+			fetchTile<NT>(fp, i + gridDim.x, pre);
+		const int ty = i / fp.tilesX, tx = i - ty * fp.tilesX;
+		rasterTile<NT>(fp, tx, fp.tileRow0 + ty, cur, ovfTotal, keys, queues);
+	}
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1166,13 +1340,22 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	k_vertex<<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[1], stream);
 	if (fp.nTriInst > 0)
-		k_setup<<<(fp.nTriInst + 255) / 256, 256, 0, stream>>>(fp);
+		k_setup<<<(fp.nTriInst + MR_SETUP_THREADS - 1) / MR_SETUP_THREADS, MR_SETUP_THREADS, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);
 	if (ev) cudaEventRecord(ev[4], stream);
 	if (fp.tileRows > 0)
-		k_raster<<<dim3(fp.tilesX, fp.tileRows), MR_RASTER_THREADS, 0, stream>>>(fp);
+		k_raster<<<(fp.rasterCtas > 0) ? min(fp.rasterCtas, fp.tilesX * fp.tileRows) : fp.tilesX * fp.tileRows, MR_RASTER_THREADS, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[5], stream);
+}
+
+int mrk_raster_ctas_per_sm(void)
+{
+	// 0 = one CTA per tile (the hardware CTA scheduler balances uneven tiles better than a static
+	// round-robin over persistent CTAs: measured 46 vs 44 us on the sphere, 255 vs 189 us on the cloud
+	// scene). MR_RASTER_CTAS_PER_SM=n selects n persistent CTAs per SM for experiments.
+	const char* e = getenv("MR_RASTER_CTAS_PER_SM");
+	return (e && atoi(e) > 0) ? atoi(e) : 0;
 }
 
 int mrk_selftest_no_fma(cudaStream_t stream)

@@ -10,7 +10,8 @@
 // Per-frame arrays:
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
-//   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
+//   pv[]           2 x float4 per vertex *instance*: (pixel x, pixel y, view z, depth term) and the
+//                  view-space position (reference _vertices): one 32-byte sector per vertex
 //   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
 //                  triangle instance index in submission order: the index IS the submission id
 //                  that resolves equal-depth ties
@@ -71,6 +72,7 @@ struct __align__(16) MatDev
 };
 
 // 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
+#define MR_REC_FIELDS 10 // float4 fields per record: 4 raster (struct Rec) + 6 shading (struct ShadeRec)
 #define MR_REC_CLIPPED 1u // produced by the near-plane clipper
 #define MR_KEY_EMPTY 0xffffffffffffffffull // gkeys[] entry no fragment has touched
 struct __align__(16) Rec
@@ -98,22 +100,24 @@ struct __align__(16) ShadeRec
 	float n2[3], v2;
 };
 
+#define MR_STAT_SLOTS 32 // statistics are spread over this many slots (summed by the host): no single-address hot spot
 struct Counters
 {
 	// line 0: written by k_vertex / k_setup, only read by k_raster
 	unsigned long long trianglesIn;
-	unsigned long long records;
-	unsigned long long clippedIn;
-	unsigned long long zeroCov;     // set-up triangles with an empty coverage mask (dropped)
 	unsigned long long ovfTotal;    // entries appended to the overflow list (may exceed its capacity)
 	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
 	unsigned int pad0;
-	unsigned long long pad1[10];
+	unsigned long long pad1[13];
 	// line 1 (offset 128): written by k_raster
-	unsigned long long pairTotal;   // (tile, triangle) pairs of the frame (summed by the tile kernel)
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
-	unsigned int nextTile;          // next tile index handed to a persistent k_raster CTA
-	unsigned long long pad3[14];
+	unsigned int pad2;
+	unsigned long long pad3[15];
+	// statistics, one warp-aggregated RED per warp into slot (warp index % MR_STAT_SLOTS)
+	unsigned long long records[MR_STAT_SLOTS];   // set-up triangles that can own a pixel
+	unsigned long long clippedIn[MR_STAT_SLOTS]; // input triangles crossing the near plane
+	unsigned long long zeroCov[MR_STAT_SLOTS];   // set-up small triangles that cover no pixel centre (dropped)
+	unsigned long long pairTotal[MR_STAT_SLOTS]; // (tile, triangle) pairs of the frame (summed by the tile kernel)
 };
 
 #define MR_INLINE_TABLE 32 // renderables / materials that travel inside the kernel parameters
@@ -152,13 +156,13 @@ struct FrameParams
 	const int* triBlockR; // same for triangle instances
 	const int* nrmBlockR; // same for normal instances
 
-	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
+	float4* pv;          // per vertex instance: (pixel x, pixel y, view z, depth term), (view x, y, z, 0)
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
-	Rec* recs;
+	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field k, lane (t & 31)
+	float4* recs1;       // records of sub-triangle 1 (second clipper output): MR_REC_FIELDS float4 per triangle
 	int* tileCount;      // triangles binned per tile (may exceed binCap: the rest is in ovfPairs)
 	int* bins;           // tilesX*tilesY bins of binCap record indices
 	int2* ovfPairs;      // (tile, record) entries that did not fit their bin
-	ShadeRec* srecs;
 	Counters* ctr;
 
 	// Small scenes: the per-frame tables ride in the kernel parameters (no H2D copy per frame).
@@ -177,6 +181,7 @@ struct FrameParams
 // kernel launchers (mr_kernels.cu)
 void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */);
 int mrk_selftest_no_fma(cudaStream_t stream);
+int mrk_raster_ctas_per_sm(void); // resident k_raster CTAs per SM (occupancy query)
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
 void mrk_launch_rgb8(const float* image, uint8_t* out, size_t nFloats, cudaStream_t stream);
