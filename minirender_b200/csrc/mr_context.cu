@@ -83,7 +83,6 @@ struct mr_ctx
 
 	int w, h, tilesX, tilesY;
 	int smCount;
-	int rasterCtasPerSm;
 
 	// scene-static device arrays
 	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes;
@@ -505,7 +504,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 		memcpy(fp.matsInline, md, sizeof(MatDev) * (size_t)f->n_materials);
 	}
 	fp.binCap = c->binCap;
-	fp.rasterCtas = c->smCount * c->rasterCtasPerSm; // persistent tile CTAs: as many as are resident at once
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
 	fp.pos4 = c->pos4.as<float4>();
 	fp.nrm4 = c->nrm4.as<float4>();
@@ -602,7 +600,6 @@ mr_ctx* mr_create(int device, int* status)
 		Bind bind(device);
 		c->smCount = 148;
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
-		c->rasterCtasPerSm = mrk_raster_ctas_per_sm();
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;

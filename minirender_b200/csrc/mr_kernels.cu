@@ -10,6 +10,7 @@
 #include "mr_types.h"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 // experiment switches
 #ifndef MR_EXP
@@ -26,6 +27,13 @@
 #endif
 
 namespace {
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor drains; it must not touch the
+// predecessor's output before pdlWait(). pdlLaunchDependents() in the predecessor lets the
+// successor's CTAs take the SM slots that free up during the predecessor's last wave.
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 struct V3 { float x, y, z; };
 
@@ -139,6 +147,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int shBases[256];
+	pdlLaunchDependents();
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
@@ -212,6 +221,11 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float
 	return true;
 }
 
+// The reference's inside test `!(e1 < 0 || e2 < 0 || k0 < 0)` (Renderer.cpp:245) as one three-way
+// minimum: fminf drops NaN operands exactly where the reference's comparisons are false, and
+// -0 < 0 is false in both forms.
+__device__ __forceinline__ bool insideTest(float e1, float e2, float k0) { return !(fminf(fminf(e1, e2), k0) < 0.0f); }
+
 // Depth of a covered pixel from its edge functions (Renderer.cpp:247-261); d = iz[] or zz[].
 __device__ __forceinline__ float pixelDepth(int persp, float e1, float e2, float d0, float d1, float d2)
 {
@@ -245,7 +259,7 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 		for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x)
 		{
 			const float k0 = 1.0f - e1 - e2;
-			if (!(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f)) // Renderer.cpp:245
+			if (insideTest(e1, e2, k0)) // Renderer.cpp:245
 			{
 				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
 				if (z == z) // a NaN depth never passes `z < pixdepth`
@@ -477,10 +491,12 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int shBases[256];
-	__shared__ int shStat[4]; // records, clipped inputs, zero-coverage drops, warps done
-	if (threadIdx.x < 4)
+	__shared__ int shStat[2]; // packed (records, clipped inputs, zero-coverage drops), warps done
+	if (threadIdx.x < 2)
 		shStat[threadIdx.x] = 0;
 	__syncthreads();
+	pdlLaunchDependents();
+	pdlWait(); // k_vertex's pv[] and zeroed counters
 	const int t = blockIdx.x * MR_SETUP_THREADS + threadIdx.x;
 	const int lane = threadIdx.x & 31;
 	const int r = findRenderable<MR_SETUP_THREADS>(fp, fp.triBlockR, t, 1, shBases);
@@ -678,21 +694,20 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 			}
 	}
 
-	// ---- statistics: summed per CTA in shared memory; the last warp to finish sends one RED per
-	// counter (no barrier: finished warps leave at once) ----
-	const int nrecWarp = __reduce_add_sync(0xffffffffu, (valid ? 1 : 0) + __popc(nrecSlow));
-	const int nclipWarp = __reduce_add_sync(0xffffffffu, nclip);
-	const int nzeroWarp = __reduce_add_sync(0xffffffffu, nzero);
+	// ---- statistics: three 10-bit fields in one word (a CTA sets up at most 256 records), summed per
+	// CTA in shared memory; the last warp to finish sends one RED per counter (no barrier: finished
+	// warps leave at once) ----
+	const int packed = __reduce_add_sync(0xffffffffu, ((valid ? 1 : 0) + __popc(nrecSlow)) | (nclip << 10) | (nzero << 20));
 	if (lane == 0)
 	{
-		if (nrecWarp) atomicAdd(&shStat[0], nrecWarp);
-		if (nclipWarp) atomicAdd(&shStat[1], nclipWarp);
-		if (nzeroWarp) atomicAdd(&shStat[2], nzeroWarp);
+		if (packed)
+			atomicAdd(&shStat[0], packed);
 		__threadfence_block();
-		if (atomicAdd(&shStat[3], 1) == MR_SETUP_THREADS / 32 - 1)
+		if (atomicAdd(&shStat[1], 1) == MR_SETUP_THREADS / 32 - 1)
 		{
 			const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
-			const int nr = atomicAdd(&shStat[0], 0), nc = atomicAdd(&shStat[1], 0), nz = atomicAdd(&shStat[2], 0);
+			const int all = atomicAdd(&shStat[0], 0);
+			const int nr = all & 1023, nc = (all >> 10) & 1023, nz = (all >> 20) & 1023;
 			if (nr) atomicAdd(&fp.ctr->records[slot], (unsigned long long)nr);
 			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], (unsigned long long)nc);
 			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], (unsigned long long)nz);
@@ -862,8 +877,10 @@ __device__ __forceinline__ void storeTileRows(const FrameParams& fp, int tileX0,
 				v = *reinterpret_cast<const float4*>(&to->rgb[row][4 * j]);
 			else
 			{
-				const int c = (4 * j) % 3; // channel of the first of the four floats
-				const float b0 = fp.bg[c], b1 = fp.bg[(c + 1) % 3], b2 = fp.bg[(c + 2) % 3];
+				// channel of the first of the four floats: (4 j) mod 3 == j mod 3
+				const int c = j % 3;
+				const float r = fp.bg[0], g = fp.bg[1], b = fp.bg[2];
+				const float b0 = (c == 0) ? r : (c == 1) ? g : b, b1 = (c == 0) ? g : (c == 1) ? b : r, b2 = (c == 0) ? b : (c == 1) ? r : g;
 				v = make_float4(b0, b1, b2, b0);
 			}
 			*reinterpret_cast<float4*>(fp.image + 3 * ((size_t)y * fp.w + tileX0) + 4 * j) = v;
@@ -934,7 +951,7 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 			for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
 			{
 				const float k0 = 1.0f - e1 - e2;
-				const bool inside = rowOn && cc < ncols && !(e1 < 0.0f || e2 < 0.0f || k0 < 0.0f); // Renderer.cpp:245
+				const bool inside = rowOn && cc < ncols && insideTest(e1, e2, k0); // Renderer.cpp:245
 				pushFragment(fp, wq, keys, qhead, qcount, lane, inside, e1, e2, rowInfo + (uint32_t)cc);
 			}
 		}
@@ -1060,65 +1077,45 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	}
 }
 
-// What a CTA fetches for a tile ahead of time: the pixels' depth keys out of gkeys and the number of
-// larger triangles binned to the tile. Loaded one tile ahead, so the round trip to L2 / HBM overlaps
-// the previous tile's shading.
-template <int PP>
-struct TilePre
-{
-	unsigned long long g[PP];
-	int total;
-};
-
-template <int NT>
-__device__ __forceinline__ void fetchTile(const FrameParams& fp, int tileIndex, TilePre<MR_TILE_PIXELS / NT>& pre)
-{
-	const int ty = tileIndex / fp.tilesX, tx = tileIndex - ty * fp.tilesX;
-	const int tileX0 = tx * MR_TILE, tileY0 = (fp.tileRow0 + ty) * MR_TILE;
-#pragma unroll
-	for (int pp = 0; pp < MR_TILE_PIXELS / NT; pp++)
-	{
-		const int pi = threadIdx.x + pp * NT;
-		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
-		pre.g[pp] = MR_KEY_EMPTY;
-		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
-			pre.g[pp] = __ldcs(&fp.gkeys[(size_t)py * fp.w + px]); // read once per frame: streaming
-	}
-	pre.total = fp.tileCount[(fp.tileRow0 + ty) * fp.tilesX + tx];
-}
-
 // One tile: phases 0, 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice
 // as many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
 template <int NT>
-__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, const TilePre<MR_TILE_PIXELS / NT>& pre,
-                                           unsigned long long ovfTotal, unsigned long long* keys, WarpQueue* queues)
+__device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
 {
 	constexpr int PP = MR_TILE_PIXELS / NT;
 	const int tile = ty * fp.tilesX + tx;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const int tileX0 = tx * MR_TILE, tileY0 = ty * MR_TILE;
-	// ---- phase 0: merge the fetched keys with the clear / kept depth, reset gkeys ----
+	// ---- phase 0: the tile's keys out of gkeys, merged with the clear / kept depth; gkeys reset ----
 	unsigned long long key[PP];
+	const unsigned long long clearKey = (unsigned long long)zkey(1e11f) << 32;
 #pragma unroll
 	for (int pp = 0; pp < PP; pp++)
 	{
 		const int pi = tid + pp * NT;
 		const int px = tileX0 + (pi & 15), py = tileY0 + (pi >> 4);
-		const unsigned long long g = pre.g[pp];
-		unsigned long long base = 0ull; // pixels outside the image / strip can never be won
+		unsigned long long g = MR_KEY_EMPTY, base = 0ull; // pixels outside the image / strip can never be won
 		if (px < fp.w && py < fp.h && py >= fp.rowBegin && py < fp.rowEnd)
 		{
 			const size_t pix = (size_t)py * fp.w + px;
-			base = (unsigned long long)zkey(fp.keep ? fp.depth[pix] : 1e11f) << 32;
+			g = __ldcs(&fp.gkeys[pix]); // read once per frame: streaming
+			base = fp.keep ? (unsigned long long)zkey(fp.depth[pix]) << 32 : clearKey;
 			if (g != MR_KEY_EMPTY)
 				fp.gkeys[pix] = MR_KEY_EMPTY; // ready for the next frame
 		}
 		key[pp] = (g < base) ? g : base;
 	}
-	const int total = pre.total; // larger triangles binned to this tile
-	if (total > fp.binCap && threadIdx.x == 0)
-		atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
+	const int total = fp.tileCount[tile]; // larger triangles binned to this tile
+	unsigned long long ovfTotal = 0ull;
+	if (total > fp.binCap)
+	{
+		// this tile spilled into the overflow list (rare)
+		ovfTotal = __ldg(&fp.ctr->ovfTotal);
+		if (threadIdx.x == 0)
+			atomicMax(&fp.ctr->maxTile, (unsigned)total); // lets the host size the bins for the next frames
+		// if the overflow list itself overflowed, the host regrows it, clears gkeys and re-runs the frame
+	}
 	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
 	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
 
@@ -1223,9 +1220,9 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	}
 }
 
-// Normally one CTA per tile (grid = number of tiles; the loop below runs once). With fewer CTAs than
-// tiles (experiments: fp.rasterCtas) they are persistent, tiles are dealt round-robin and the next
-// tile's keys are requested before the current tile is shaded.
+// One CTA per tile. (Persistent CTAs measured slower twice: with a global tile counter, -10 %, and
+// with a static round-robin plus next-tile prefetch, 46 vs 44 us on the sphere and 255 vs 189 us on
+// the cloud scene — the hardware CTA scheduler balances 8160 uneven tiles better.)
 #ifndef MR_RASTER_THREADS
 #define MR_RASTER_THREADS 128
 #endif
@@ -1234,27 +1231,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 #endif
 __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
 {
-	constexpr int NT = MR_RASTER_THREADS;
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
-	__shared__ WarpQueue queues[NT / 32 < 4 ? 4 : NT / 32]; // also >= sizeof(TileOut)
-	const int nT = fp.tilesX * fp.tileRows;
-	int i = blockIdx.x;
-	if (i >= nT)
-		return;
-	TilePre<MR_TILE_PIXELS / NT> pre, cur;
-	fetchTile<NT>(fp, i, pre);
-	// (the counters were written by the previous kernels, so the L1-cached read-only path is fine)
-	const unsigned long long ovfTotal = __ldg(&fp.ctr->ovfTotal);
-	if (__ldg(&fp.ctr->overflow))
-		return; // the overflow list itself overflowed: the host regrows it, clears gkeys and re-runs the frame
-	for (; i < nT; i += gridDim.x)
-	{
-		cur = pre;
-		if (i + (int)gridDim.x < nT)
-			fetchTile<NT>(fp, i + gridDim.x, pre);
-		const int ty = i / fp.tilesX, tx = i - ty * fp.tilesX;
-		rasterTile<NT>(fp, tx, fp.tileRow0 + ty, cur, ovfTotal, keys, queues);
-	}
+	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
+	pdlWait(); // k_setup's keys, bins and records
+	rasterTile<MR_RASTER_THREADS>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1339,23 +1319,31 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	if (ev) cudaEventRecord(ev[0], stream);
 	k_vertex<<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[1], stream);
+	// k_setup and k_raster may begin while their predecessor drains (unless stage events sit between)
+	cudaLaunchAttribute pdl[1];
+	pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	pdl[0].val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.stream = stream;
+	cfg.attrs = pdl;
+	cfg.numAttrs = (ev || getenv("MR_NO_PDL")) ? 0 : 1;
 	if (fp.nTriInst > 0)
-		k_setup<<<(fp.nTriInst + MR_SETUP_THREADS - 1) / MR_SETUP_THREADS, MR_SETUP_THREADS, 0, stream>>>(fp);
+	{
+		cfg.gridDim = dim3((fp.nTriInst + MR_SETUP_THREADS - 1) / MR_SETUP_THREADS);
+		cfg.blockDim = dim3(MR_SETUP_THREADS);
+		cudaLaunchKernelEx(&cfg, k_setup, fp);
+	}
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);
 	if (ev) cudaEventRecord(ev[4], stream);
 	if (fp.tileRows > 0)
-		k_raster<<<(fp.rasterCtas > 0) ? min(fp.rasterCtas, fp.tilesX * fp.tileRows) : fp.tilesX * fp.tileRows, MR_RASTER_THREADS, 0, stream>>>(fp);
+	{
+		cfg.gridDim = dim3(fp.tilesX, fp.tileRows);
+		cfg.blockDim = dim3(MR_RASTER_THREADS);
+		cudaLaunchKernelEx(&cfg, k_raster, fp);
+	}
 	if (ev) cudaEventRecord(ev[5], stream);
-}
-
-int mrk_raster_ctas_per_sm(void)
-{
-	// 0 = one CTA per tile (the hardware CTA scheduler balances uneven tiles better than a static
-	// round-robin over persistent CTAs: measured 46 vs 44 us on the sphere, 255 vs 189 us on the cloud
-	// scene). MR_RASTER_CTAS_PER_SM=n selects n persistent CTAs per SM for experiments.
-	const char* e = getenv("MR_RASTER_CTAS_PER_SM");
-	return (e && atoi(e) > 0) ? atoi(e) : 0;
 }
 
 int mrk_selftest_no_fma(cudaStream_t stream)

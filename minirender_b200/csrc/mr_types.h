@@ -137,7 +137,6 @@ struct FrameParams
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int nRenderables, nVertInst, nTriInst, nNrmInst;
 	int debug; // mr_set_debug flags
-	int rasterCtas; // persistent k_raster CTAs (resident CTAs per SM x SM count)
 	int binCap; // entries per tile bin
 	int ovfCap; // entries in the overflow list
 
@@ -181,7 +180,6 @@ struct FrameParams
 // kernel launchers (mr_kernels.cu)
 void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */);
 int mrk_selftest_no_fma(cudaStream_t stream);
-int mrk_raster_ctas_per_sm(void); // resident k_raster CTAs per SM (occupancy query)
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
 void mrk_launch_rgb8(const float* image, uint8_t* out, size_t nFloats, cudaStream_t stream);
