@@ -183,6 +183,16 @@ MR_API int mr_read_rgb8(mr_ctx* ctx, uint8_t* host_rgb8 /* h*w*3 */);
 MR_API int mr_read_image_async(mr_ctx* ctx, float* host_rgb);
 MR_API int mr_read_rows_async(mr_ctx* ctx, float* host_rgb, float* host_depth, int row_begin, int row_end);
 
+/* Overlapping the host copy of frame i with the kernels of frame i+1 (a turntable / view batch that
+ * needs every image on the host): with two output slots, successive mr_render calls alternate
+ * between two sets of image/depth buffers. mr_read_image_begin starts the device->host copy of the
+ * newest frame on a separate copy stream (ordered after that frame, `host_rgb` should be
+ * page-locked) and returns a ticket; mr_read_wait blocks until that copy has landed. A slot is not
+ * rendered into again before its pending copy has finished. */
+MR_API int mr_set_output_slots(mr_ctx* ctx, int n /* 1 or 2 */);
+MR_API int mr_read_image_begin(mr_ctx* ctx, float* host_rgb /* h*w*3 */, int* ticket);
+MR_API int mr_read_wait(mr_ctx* ctx, int ticket);
+
 /* Device pointers of the current output buffers (for interop: NCCL gather, checksums). */
 MR_API int mr_device_buffers(mr_ctx* ctx, void** d_image, void** d_depth, void** d_normals);
 /* Overwrite rows [row_begin,row_end) of the output buffers from device memory (strip gather). */

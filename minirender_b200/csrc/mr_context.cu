@@ -120,7 +120,14 @@ struct mr_ctx
 	size_t h2dBytesLastFrame;
 
 	// outputs
-	DevBuf image, depth, normals, winner, scratchOut, flushBuf;
+	// outputs: one or two sets of image/depth buffers (mr_set_output_slots); `image`/`depth` below always
+	// denote the set the newest frame went to
+	DevBuf imageSlot[2], depthSlot[2], normals, winner, scratchOut, flushBuf;
+	int outSlots, outCur;
+	cudaStream_t copy;          // device->host copies that overlap the next frame (mr_read_image_begin)
+	cudaEvent_t frameDone[2];   // render stream: the frame in slot s is complete
+	cudaEvent_t copyDone[2];    // copy stream: the host copy out of slot s is complete
+	bool copyPending[2];
 	void *remoteImage, *remoteDepth;
 	int debugFlags;
 
@@ -133,8 +140,10 @@ struct mr_ctx
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
 	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
-	           remoteDepth(0), debugFlags(0), haveFrame(false)
+	           remoteDepth(0), debugFlags(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
+		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
+		copyPending[0] = copyPending[1] = false;
 		memset(&lastFrame, 0, sizeof(lastFrame));
 		memset(&stats, 0, sizeof(stats));
 	}
@@ -182,7 +191,7 @@ struct Bind
 	}
 };
 
-int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev);
+int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun = false);
 
 void absorbCounters(mr_ctx* c, const Counters& k)
 {
@@ -256,7 +265,7 @@ int finishFrame(mr_ctx* c)
 		f.materials = c->lastMaterials.empty() ? 0 : &c->lastMaterials[0];
 		// the aborted frame left fragments in the depth keys
 		MR_CUDA(c, cudaMemsetAsync(c->gkeys.p, 0xff, (size_t)c->w * c->h * 8, c->stream));
-		int rc = launchFrame(c, &f, 0);
+		int rc = launchFrame(c, &f, 0, true);
 		if (rc)
 			return rc;
 	}
@@ -266,13 +275,16 @@ int finishFrame(mr_ctx* c)
 int ensureOutputs(mr_ctx* c, bool normals, bool winner)
 {
 	const size_t npix = (size_t)c->w * c->h;
-	const bool freshImage = c->image.cap < npix * 12;
-	MR_CUDA(c, c->image.ensure(npix * 12, true));
-	MR_CUDA(c, c->depth.ensure(npix * 4, true));
-	if (freshImage)
+	for (int sl = 0; sl < c->outSlots; sl++)
 	{
-		MR_CUDA(c, cudaMemsetAsync(c->image.p, 0, npix * 12, c->stream));
-		MR_CUDA(c, cudaMemsetAsync(c->depth.p, 0, npix * 4, c->stream));
+		const bool freshImage = c->imageSlot[sl].cap < npix * 12;
+		MR_CUDA(c, c->imageSlot[sl].ensure(npix * 12, true));
+		MR_CUDA(c, c->depthSlot[sl].ensure(npix * 4, true));
+		if (freshImage)
+		{
+			MR_CUDA(c, cudaMemsetAsync(c->imageSlot[sl].p, 0, npix * 12, c->stream));
+			MR_CUDA(c, cudaMemsetAsync(c->depthSlot[sl].p, 0, npix * 4, c->stream));
+		}
 	}
 	// per-pixel depth keys: all MR_KEY_EMPTY between frames (the tile kernel resets what it reads)
 	if (c->gkeys.cap < npix * 8)
@@ -293,7 +305,7 @@ int ensureOutputs(mr_ctx* c, bool normals, bool winner)
 	return MR_OK;
 }
 
-int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
+int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 {
 	const int nR = f->n_renderables;
 	// ---- validate + instance bases ----
@@ -363,6 +375,16 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
 	if (rc)
 		return rc;
+	if (c->outSlots > 1 && !f->keep && !rerun)
+	{
+		// a cleared frame goes to the other output set; a host copy still reading that set must finish first
+		c->outCur = (c->outCur + 1) % c->outSlots;
+		if (c->copyPending[c->outCur])
+		{
+			MR_CUDA(c, cudaStreamWaitEvent(c->stream, c->copyDone[c->outCur], 0));
+			c->copyPending[c->outCur] = false;
+		}
+	}
 
 	// ---- stage per-frame tables in pinned memory, one async copy each ----
 	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
@@ -527,8 +549,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev)
 	fp.ovfPairs = c->ovfPairs.as<int2>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>() + slotIndex; // per-slot counters: the read-back overlaps the next frame
-	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->image.as<float>();
-	fp.depth = (c->remoteDepth && !f->keep) ? (float*)c->remoteDepth : c->depth.as<float>();
+	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->imageSlot[c->outCur].as<float>();
+	fp.depth = (c->remoteDepth && !f->keep) ? (float*)c->remoteDepth : c->depthSlot[c->outCur].as<float>();
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
 	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
 
@@ -603,6 +625,12 @@ mr_ctx* mr_create(int device, int* status)
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;
+		ok = ok && cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) == cudaSuccess;
+		for (int i = 0; i < 2 && ok; i++)
+		{
+			ok = ok && cudaEventCreateWithFlags(&c->frameDone[i], cudaEventDisableTiming) == cudaSuccess;
+			ok = ok && cudaEventCreateWithFlags(&c->copyDone[i], cudaEventDisableTiming) == cudaSuccess;
+		}
 		for (int i = 0; i < mr_ctx::kSlots && ok; i++)
 		{
 			ok = ok && cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
@@ -642,7 +670,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->image, &c->depth, &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)
@@ -661,6 +689,16 @@ void mr_destroy(mr_ctx* c)
 	{
 		cudaStreamSynchronize(c->aux);
 		cudaStreamDestroy(c->aux);
+	}
+	if (c->copy)
+	{
+		cudaStreamSynchronize(c->copy);
+		cudaStreamDestroy(c->copy);
+	}
+	for (int i = 0; i < 2; i++)
+	{
+		if (c->frameDone[i]) cudaEventDestroy(c->frameDone[i]);
+		if (c->copyDone[i]) cudaEventDestroy(c->copyDone[i]);
 	}
 	delete c;
 }
@@ -716,8 +754,11 @@ int mr_set_size(mr_ctx* c, int w, int h)
 	c->tilesY = (h + MR_TILE - 1) / MR_TILE;
 	c->binCap = 0;
 	c->bins.release();
-	c->image.release();
-	c->depth.release();
+	for (int sl = 0; sl < 2; sl++)
+	{
+		c->imageSlot[sl].release();
+		c->depthSlot[sl].release();
+	}
 	c->gkeys.release();
 	c->normals.release();
 	c->winner.release();
@@ -885,7 +926,7 @@ int mr_render_batch(mr_ctx* c, int n, const mr_frame* frames, mr_frame_sink sink
 			rc = finishFrame(c);
 			if (rc)
 				return rc;
-			sink(user, i, c->image.as<float>(), c->depth.as<float>());
+			sink(user, i, c->imageSlot[c->outCur].as<float>(), c->depthSlot[c->outCur].as<float>());
 		}
 	}
 	return MR_OK;
@@ -907,7 +948,7 @@ int mr_read_image(mr_ctx* c, float* host)
 	int rc = finishFrame(c);
 	if (rc)
 		return rc;
-	return readBack(c, host, c->image.p, (size_t)c->w * c->h * 12);
+	return readBack(c, host, c->imageSlot[c->outCur].p, (size_t)c->w * c->h * 12);
 }
 
 int mr_read_depth(mr_ctx* c, float* host)
@@ -918,7 +959,7 @@ int mr_read_depth(mr_ctx* c, float* host)
 	int rc = finishFrame(c);
 	if (rc)
 		return rc;
-	return readBack(c, host, c->depth.p, (size_t)c->w * c->h * 4);
+	return readBack(c, host, c->depthSlot[c->outCur].p, (size_t)c->w * c->h * 4);
 }
 
 int mr_read_normals(mr_ctx* c, float* host)
@@ -959,7 +1000,7 @@ int mr_read_range(mr_ctx* c, const float* P, float znear, float* host)
 		return rc;
 	const size_t bytes = (size_t)c->w * c->h * 12;
 	MR_CUDA(c, c->scratchOut.ensure(bytes));
-	mrk_launch_range(c->depth.as<float>(), c->scratchOut.as<float>(), c->w, c->h, P, c->stream);
+	mrk_launch_range(c->depthSlot[c->outCur].as<float>(), c->scratchOut.as<float>(), c->w, c->h, P, c->stream);
 	MR_CUDA(c, cudaGetLastError());
 	return readBack(c, host, c->scratchOut.p, bytes);
 }
@@ -974,9 +1015,55 @@ int mr_read_rgb8(mr_ctx* c, uint8_t* host)
 		return rc;
 	const size_t n = (size_t)c->w * c->h * 3;
 	MR_CUDA(c, c->scratchOut.ensure(n));
-	mrk_launch_rgb8(c->image.as<float>(), c->scratchOut.as<uint8_t>(), n, c->stream);
+	mrk_launch_rgb8(c->imageSlot[c->outCur].as<float>(), c->scratchOut.as<uint8_t>(), n, c->stream);
 	MR_CUDA(c, cudaGetLastError());
 	return readBack(c, host, c->scratchOut.p, n);
+}
+
+int mr_set_output_slots(mr_ctx* c, int n)
+{
+	if (!c || n < 1 || n > 2)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	int rc = finishFrame(c);
+	if (rc)
+		return rc;
+	MR_CUDA(c, cudaStreamSynchronize(c->copy));
+	c->copyPending[0] = c->copyPending[1] = false;
+	if (n == 1 && c->outCur == 1)
+	{
+		// keep the newest frame addressable as slot 0
+		std::swap(c->imageSlot[0], c->imageSlot[1]);
+		std::swap(c->depthSlot[0], c->depthSlot[1]);
+	}
+	c->outSlots = n;
+	c->outCur = 0;
+	return c->w > 0 ? ensureOutputs(c, false, false) : MR_OK;
+}
+
+int mr_read_image_begin(mr_ctx* c, float* host, int* ticket)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	const int sl = c->outCur;
+	MR_CUDA(c, cudaEventRecord(c->frameDone[sl], c->stream));
+	MR_CUDA(c, cudaStreamWaitEvent(c->copy, c->frameDone[sl], 0));
+	MR_CUDA(c, cudaMemcpyAsync(host, c->imageSlot[sl].p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->copy));
+	MR_CUDA(c, cudaEventRecord(c->copyDone[sl], c->copy));
+	c->copyPending[sl] = true;
+	if (ticket)
+		*ticket = sl;
+	return MR_OK;
+}
+
+int mr_read_wait(mr_ctx* c, int ticket)
+{
+	if (!c || ticket < 0 || ticket > 1)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaEventSynchronize(c->copyDone[ticket]));
+	return MR_OK;
 }
 
 int mr_read_image_async(mr_ctx* c, float* host)
@@ -984,7 +1071,7 @@ int mr_read_image_async(mr_ctx* c, float* host)
 	if (!c || !host)
 		return MR_E_INVALID;
 	Bind bind(c->device);
-	MR_CUDA(c, cudaMemcpyAsync(host, c->image.p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->stream));
+	MR_CUDA(c, cudaMemcpyAsync(host, c->imageSlot[c->outCur].p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->stream));
 	return MR_OK;
 }
 
@@ -995,9 +1082,9 @@ int mr_read_rows_async(mr_ctx* c, float* host_rgb, float* host_depth, int rb, in
 	Bind bind(c->device);
 	const size_t w = (size_t)c->w;
 	if (host_rgb)
-		MR_CUDA(c, cudaMemcpyAsync(host_rgb + 3 * w * rb, c->image.as<float>() + 3 * w * rb, 12 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
+		MR_CUDA(c, cudaMemcpyAsync(host_rgb + 3 * w * rb, c->imageSlot[c->outCur].as<float>() + 3 * w * rb, 12 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
 	if (host_depth)
-		MR_CUDA(c, cudaMemcpyAsync(host_depth + w * rb, c->depth.as<float>() + w * rb, 4 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
+		MR_CUDA(c, cudaMemcpyAsync(host_depth + w * rb, c->depthSlot[c->outCur].as<float>() + w * rb, 4 * w * (re - rb), cudaMemcpyDeviceToHost, c->stream));
 	return MR_OK;
 }
 
@@ -1015,8 +1102,8 @@ int mr_device_buffers(mr_ctx* c, void** image, void** depth, void** normals)
 {
 	if (!c)
 		return MR_E_INVALID;
-	if (image) *image = c->image.p;
-	if (depth) *depth = c->depth.p;
+	if (image) *image = c->imageSlot[c->outCur].p;
+	if (depth) *depth = c->depthSlot[c->outCur].p;
 	if (normals) *normals = c->normals.p;
 	return MR_OK;
 }
@@ -1028,9 +1115,9 @@ int mr_write_rows(mr_ctx* c, const void* img, const void* dep, int rb, int re)
 	Bind bind(c->device);
 	const size_t w = (size_t)c->w;
 	if (img)
-		MR_CUDA(c, cudaMemcpyAsync(c->image.as<float>() + 3 * w * rb, img, 12 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
+		MR_CUDA(c, cudaMemcpyAsync(c->imageSlot[c->outCur].as<float>() + 3 * w * rb, img, 12 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
 	if (dep)
-		MR_CUDA(c, cudaMemcpyAsync(c->depth.as<float>() + w * rb, dep, 4 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
+		MR_CUDA(c, cudaMemcpyAsync(c->depthSlot[c->outCur].as<float>() + w * rb, dep, 4 * w * (re - rb), cudaMemcpyDeviceToDevice, c->stream));
 	return MR_OK;
 }
 
@@ -1046,12 +1133,12 @@ int mr_set_remote_target(mr_ctx* c, void* img, void* dep)
 /* ---- CUDA IPC: lets another rank's tile rasterizer store straight into this framebuffer ---- */
 int mr_ipc_export(mr_ctx* c, void* handles128)
 {
-	if (!c || !handles128 || !c->image.p || !c->depth.p)
+	if (!c || !handles128 || !c->imageSlot[c->outCur].p || !c->depthSlot[c->outCur].p)
 		return MR_E_INVALID;
 	Bind bind(c->device);
 	cudaIpcMemHandle_t h[2];
-	MR_CUDA(c, cudaIpcGetMemHandle(&h[0], c->image.p));
-	MR_CUDA(c, cudaIpcGetMemHandle(&h[1], c->depth.p));
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[0], c->imageSlot[c->outCur].p));
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[1], c->depthSlot[c->outCur].p));
 	memcpy(handles128, h, sizeof(h));
 	return MR_OK;
 }

@@ -157,3 +157,40 @@ def test_render_is_asynchronous_and_repeatable(be):
     for _ in range(12):  # more frames than slots in flight, no read in between
         r.render()
     assert (bits(r.get_depth()) == bits(first)).all()
+
+
+def test_two_output_slots_overlapped_reads_match_blocking_reads(be):
+    """mr_set_output_slots(2) + mr_read_image_begin / mr_read_wait: every frame of a turntable,
+    copied to the host while the next frame renders, equals the blocking read of the same frame."""
+    import torch
+    lib = cabi.load()
+    setup = scenes.SMALL_SCENES["bench_small"](be)
+    r = setup.apply(m.Renderer(be))
+    ctx = r.context_ptr()
+    views = [be.mul(be.translate(0, 0, -3.0 * i), be.rotate_z(0.1 * i)) for i in range(5)]
+
+    want = []
+    for i in range(5):
+        r.set_view(be.mul(setup.view, views[i]))
+        r.render()
+        want.append(r.get_image().copy())
+    h, w = want[0].shape[:2]
+    host = torch.empty((2, h, w, 3), dtype=torch.float32, pin_memory=True)
+    hp = [C.cast(C.c_void_p(host[j].data_ptr()), cabi.F32P) for j in range(2)]
+    assert lib.mr_set_output_slots(ctx, 2) == 0
+    tick = [C.c_int(0), C.c_int(0)]
+    got = []
+    for i in range(5):
+        r.set_view(be.mul(setup.view, views[i]))
+        r.render()
+        assert lib.mr_read_image_begin(ctx, hp[i & 1], C.byref(tick[i & 1])) == 0
+        if i > 0:
+            assert lib.mr_read_wait(ctx, tick[(i - 1) & 1]) == 0
+            got.append(host[(i - 1) & 1].numpy().copy())
+    assert lib.mr_read_wait(ctx, tick[4 & 1]) == 0
+    got.append(host[4 & 1].numpy().copy())
+    assert lib.mr_set_output_slots(ctx, 1) == 0
+    for i in range(5):
+        assert (bits(got[i]) == bits(want[i])).all(), "frame %d differs" % i
+    # back to one slot: the blocking path still sees the newest frame
+    assert (bits(r.get_image()) == bits(want[4])).all()
