@@ -80,6 +80,13 @@ _PRODUCT_ONLY = {
     "mrx_renderer_depth_ptr": (C.POINTER(C.c_float), [C.c_void_p]),
     "mrx_save_ppm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "mrx_load_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mrx_scene_load": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "mrx_scene_node_count": (C.c_int, [C.c_void_p]),
+    "mrx_node_info": (C.c_int, [C.c_void_p, C.c_int, I32P, I32P, F32P]),
+    "mrx_mesh_material": (C.c_int, [C.c_void_p, C.c_int, F32P, I32P, I32P]),
+    "mrx_save_stl": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "mrx_save_xyz": (C.c_int, [C.c_void_p, C.c_int, C.c_int, F32P, C.c_char_p]),
+    "mrx_triangulate": (C.c_int, [I32P, C.c_int, I32P]),
 }
 
 PRIM_CUBE, PRIM_CYLINDER, PRIM_SPHERE = 0, 1, 2
@@ -243,6 +250,31 @@ class Scene:
         iu = np.empty(counts[5], np.int32)
         self.be.check(self.be.lib.mrx_mesh_copy(self.h, node, _fp(pos), _fp(nrm), _fp(uv), _ip(ip), _ip(inr), _ip(iu)), "mrx_mesh_copy")
         return dict(positions=pos, normals=nrm, texcoords=uv, idx_pos=ip, idx_nrm=inr, idx_uv=iu)
+
+    # ---- mesh files (loadMesh: .stl / .obj / .x3d) ----
+    def load(self, filename, parent=-1):
+        """minirender::loadMesh(filename) attached under `parent`. Returns the ids of the loaded
+        subtree's nodes in pre-order (the first one is the subtree's root)."""
+        before = self.be.lib.mrx_scene_node_count(self.h)
+        first = self.be.check(self.be.lib.mrx_scene_load(self.h, parent, os.fsencode(filename)), "mrx_scene_load")
+        assert first == before
+        return list(range(first, self.be.lib.mrx_scene_node_count(self.h)))
+
+    def node_info(self, node):
+        is_mesh, nch = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        xf = np.empty(16, np.float32)
+        self.be.check(self.be.lib.mrx_node_info(self.h, node, _ip(is_mesh), _ip(nch), _fp(xf)), "mrx_node_info")
+        return dict(is_mesh=bool(is_mesh[0]), children=int(nch[0]), transform=xf.reshape(4, 4))
+
+    def mesh_material(self, node):
+        v = np.empty(11, np.float32)
+        tr, tc = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self.be.check(self.be.lib.mrx_mesh_material(self.h, node, _fp(v), _ip(tr), _ip(tc)), "mrx_mesh_material")
+        return dict(diffuse=v[0:3], specular=v[3:6], emissive=v[6:9], shininess=float(v[9]), opacity=float(v[10]),
+                    texture_shape=(int(tr[0]), int(tc[0])))
+
+    def save_stl(self, node, filename):
+        self.be.check(self.be.lib.mrx_save_stl(self.h, node, os.fsencode(filename)), "mrx_save_stl")
 
     def bbox(self):
         out = np.empty(6, np.float32)

@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 CXX_FLAGS = ["-std=c++11", "-O3", "-ffp-contract=off", "-fPIC", "-DMRX_PRODUCT"]
 
 CU_SOURCES = ["csrc/mr_kernels.cu", "csrc/mr_context.cu"]
-CXX_SOURCES = ["host/Scene.cpp", "host/Renderer.cpp", "host/primitives.cpp", "host/io.cpp", "host/mrx_api.cpp"]
+CXX_SOURCES = ["host/Scene.cpp", "host/Renderer.cpp", "host/primitives.cpp", "host/io.cpp", "host/loaders.cpp", "host/mrx_api.cpp"]
 HEADERS = ["csrc/mr_types.h", "host/mrx_api.h", "../include/minirender_b200.h",
            "../include/minirender/Scene.h", "../include/minirender/SceneNode.h", "../include/minirender/Vertex.h",
            "../include/minirender/Material.h", "../include/minirender/Renderer.h",

@@ -543,6 +543,94 @@ int mrx_load_ppm(const char* filename, float* out, int* rows, int* cols)
 	MRX_CATCH(-1)
 }
 
+// Registers a loaded subtree's nodes (pre-order) so that tests can address them by id.
+static void registerTree(SceneBox* sb, const Shared<SceneNode>& n)
+{
+	sb->nodes.push_back(n);
+	for (int i = 0; i < n->children.length(); i++)
+		registerTree(sb, n->children[i]);
+}
+
+int mrx_scene_load(void* scene, int parent, const char* filename)
+{
+	MRX_TRY
+	SceneBox* sb = (SceneBox*)scene;
+	Shared<SceneNode> node = loadMesh(filename);
+	if (!node)
+	{
+		g_error = std::string("cannot load ") + filename;
+		return -1;
+	}
+	if (attach(sb, parent, node))
+		return -1;
+	const int first = (int)sb->nodes.size();
+	registerTree(sb, node);
+	return first;
+	MRX_CATCH(-1)
+}
+
+int mrx_scene_node_count(void* scene) { return (int)((SceneBox*)scene)->nodes.size(); }
+
+int mrx_node_info(void* scene, int node, int32_t* is_mesh, int32_t* n_children, float* transform16)
+{
+	SceneBox* sb = (SceneBox*)scene;
+	if (node < 0 || node >= (int)sb->nodes.size())
+		return -1;
+	SceneNode* n = sb->nodes[node];
+	if (is_mesh) *is_mesh = dynamic_cast<TriMesh*>(n) ? 1 : 0;
+	if (n_children) *n_children = n->children.length();
+	if (transform16) fromMatrix(transform16, n->transform);
+	return 0;
+}
+
+int mrx_mesh_material(void* scene, int node, float* out11, int32_t* tex_rows, int32_t* tex_cols)
+{
+	TriMesh* m = meshOf((SceneBox*)scene, node);
+	if (!m || !m->material)
+		return -1;
+	const Material& a = *m->material;
+	const float v[11] = { a.diffuse.x, a.diffuse.y, a.diffuse.z, a.specular.x, a.specular.y, a.specular.z,
+		                  a.emissive.x, a.emissive.y, a.emissive.z, a.shininess, a.opacity };
+	memcpy(out11, v, sizeof(v));
+	if (tex_rows) *tex_rows = a.texture.rows();
+	if (tex_cols) *tex_cols = a.texture.cols();
+	return 0;
+}
+
+int mrx_save_stl(void* scene, int node, const char* filename)
+{
+	MRX_TRY
+	SceneBox* sb = (SceneBox*)scene;
+	if (!meshOf(sb, node))
+		return -1;
+	Shared<TriMesh> mesh = sb->nodes[node].as<TriMesh>();
+	saveSTL(mesh, filename);
+	return 0;
+	MRX_CATCH(-1)
+}
+
+int mrx_save_xyz(const float* points, int w, int h, const float* m16, const char* filename)
+{
+	MRX_TRY
+	Array2<Vec3> pts(h, w);
+	memcpy(&pts(0, 0), points, sizeof(Vec3) * (size_t)w * h);
+	saveXYZ(pts, filename, toMatrix(m16));
+	return 0;
+	MRX_CATCH(-1)
+}
+
+int mrx_triangulate(const int32_t* in, int n, int32_t* out)
+{
+	Array<int> a;
+	for (int i = 0; i < n; i++)
+		a << in[i];
+	const Array<int> t = triangulateIndices(a);
+	if (out)
+		memcpy(out, t.ptr(), sizeof(int) * t.length());
+	return t.length();
+}
+
 #endif
+
 
 }

@@ -98,6 +98,15 @@ MRX_API const float* mrx_renderer_image_ptr(void* r);
 MRX_API const float* mrx_renderer_depth_ptr(void* r);
 MRX_API int mrx_renderer_synchronize(void* r);
 MRX_API int mrx_save_ppm(const float* image, int w, int h, const char* filename);
+/* mesh files (product only): loadMesh() under `parent`; the loaded subtree's nodes get consecutive ids
+ * in pre-order, the first of which is returned */
+MRX_API int mrx_scene_load(void* scene, int parent, const char* filename);
+MRX_API int mrx_scene_node_count(void* scene);
+MRX_API int mrx_node_info(void* scene, int node, int32_t* is_mesh, int32_t* n_children, float* transform16);
+MRX_API int mrx_mesh_material(void* scene, int node, float* out11, int32_t* tex_rows, int32_t* tex_cols);
+MRX_API int mrx_save_stl(void* scene, int node, const char* filename);
+MRX_API int mrx_save_xyz(const float* points, int w, int h, const float* m16, const char* filename);
+MRX_API int mrx_triangulate(const int32_t* in, int n, int32_t* out);
 MRX_API int mrx_load_ppm(const char* filename, float* out, int* rows, int* cols); /* out may be NULL to query the size */
 
 #ifdef __cplusplus
