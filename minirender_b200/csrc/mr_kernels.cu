@@ -91,16 +91,20 @@ __device__ __forceinline__ uint32_t zkey(float z)
 }
 
 // Per-frame tables: in the kernel parameters for small scenes, in global memory otherwise.
-__device__ __forceinline__ const RDyn* frameRdyn(const FrameParams& fp) { return fp.inlineTables ? fp.rdynInline : fp.rdyn; }
-__device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return fp.inlineTables ? fp.matsInline : fp.mats; }
-__device__ __forceinline__ const RStat* frameRstat(const FrameParams& fp) { return fp.inlineTables ? fp.rstatInline : fp.rstat; }
+// The kernels are compiled once per table mode TM, so that every table access is a plain global
+// load (TM_GLOBAL) or a constant-bank operand of the kernel parameters (TM_INLINE) instead of a
+// generic-address load through a run-time pointer select.
+enum { TM_GLOBAL = 0, TM_INLINE = 1 };
+template <int TM> __device__ __forceinline__ const RDyn* frameRdyn(const FrameParams& fp) { return TM == TM_INLINE ? fp.rdynInline : fp.rdyn; }
+template <int TM> __device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return TM == TM_INLINE ? fp.matsInline : fp.mats; }
+template <int TM> __device__ __forceinline__ const RStat* frameRstat(const FrameParams& fp) { return TM == TM_INLINE ? fp.rstatInline : fp.rstat; }
 
 // Renderable that owns instance `inst` (a vertex or triangle instance) of this NT-thread CTA (NT divides 256).
 // blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
 // and searched there. Must be called by every thread of the block.
 __device__ __forceinline__ int instBase(const RStat& s, int kind) { return kind == 0 ? s.vertBase : kind == 1 ? s.triBase : s.nrmBase; }
 
-template <int NT>
+template <int NT, int TM>
 __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* __restrict__ blockR, int inst, int kind, int* shBases)
 {
 	if (fp.nRenderables == 1)
@@ -113,7 +117,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 	if (n <= 256)
 	{
 		for (int i = threadIdx.x; i < n; i += NT)
-			shBases[i] = instBase(frameRstat(fp)[r0 + i], kind);
+			shBases[i] = instBase(frameRstat<TM>(fp)[r0 + i], kind);
 		__syncthreads();
 		int lo = 0, hi = n - 1; // largest i with base[i] <= inst
 		while (lo < hi)
@@ -130,7 +134,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 	while (lo < hi)
 	{
 		const int mid = (lo + hi + 1) >> 1;
-		if (instBase(frameRstat(fp)[mid], kind) <= inst)
+		if (instBase(frameRstat<TM>(fp)[mid], kind) <= inst)
 			lo = mid;
 		else
 			hi = mid - 1;
@@ -144,6 +148,7 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 // LDG.128 in, STG.128 out, fully coalesced. Also zeroes the per-frame tile counters and statistics.
 // Normals (loop B) are transformed only for the corners of triangles that survive setup (k_setup).
 // ------------------------------------------------------------------------------------------
+template <int TM>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int shBases[256];
@@ -156,12 +161,12 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriInst : 0ull; // word 0 = trianglesIn
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return;
-	const int rv = findRenderable<256>(fp, fp.vtxBlockR, vi, 0, shBases);
+	const int rv = findRenderable<256, TM>(fp, fp.vtxBlockR, vi, 0, shBases);
 	if (vi >= fp.nVertInst)
 		return;
-	const RStat& rs = frameRstat(fp)[rv];
+	const RStat& rs = frameRstat<TM>(fp)[rv];
 	const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
-	const V3 view = affine(frameRdyn(fp)[rv].mv, p.x, p.y, p.z);
+	const V3 view = affine(frameRdyn<TM>(fp)[rv].mv, p.x, p.y, p.z);
 #if MR_PV32
 	fp.pv[2 * (size_t)vi] = project(fp, view);
 	fp.pv[2 * (size_t)vi + 1] = make_float4(view.x, view.y, view.z, 0.0f);
@@ -241,7 +246,7 @@ __device__ __forceinline__ float pixelDepth(int persp, float e1, float e2, float
 // second pass over the triangle. Returns whether any fragment was emitted (if not, the triangle can
 // never own a pixel and needs no records).
 #ifndef MR_SMALL_AREA
-#define MR_SMALL_AREA 32
+#define MR_SMALL_AREA 64
 #endif
 __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 a, const float4 b, const float4 c, const Setup& s, int id)
 {
@@ -334,6 +339,7 @@ __device__ __forceinline__ void storeShadeRec(const RecRef d, const Corner& c0, 
 // normals and texcoords through the three index arrays and transforms them with this frame's
 // modelview / normal matrix — the same expressions, in the same order, as k_vertex / loops A, B.
 // Evaluated only for triangles that survive setup.
+template <int TM>
 __device__ __forceinline__ void viewCorners(const FrameParams& fp, const RStat& rs, int r, int tri, int ia, int ib, int ic,
                                             Corner& c0, Corner& c1, Corner& c2)
 {
@@ -348,7 +354,7 @@ __device__ __forceinline__ void viewCorners(const FrameParams& fp, const RStat& 
 	}
 	const float4 p0 = __ldg(&fp.pos4[rs.posBase + ia]), p1 = __ldg(&fp.pos4[rs.posBase + ib]), p2 = __ldg(&fp.pos4[rs.posBase + ic]);
 	const float4 n0 = __ldg(&fp.nrm4[rs.nrmSrcBase + in0]), n1 = __ldg(&fp.nrm4[rs.nrmSrcBase + in1]), n2 = __ldg(&fp.nrm4[rs.nrmSrcBase + in2]);
-	const RDyn& rd = frameRdyn(fp)[r];
+	const RDyn& rd = frameRdyn<TM>(fp)[r];
 	const V3 v0 = affine(rd.mv, p0.x, p0.y, p0.z), v1 = affine(rd.mv, p1.x, p1.y, p1.z), v2 = affine(rd.mv, p2.x, p2.y, p2.z);
 	const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
 	c0.px = v0.x; c0.py = v0.y; c0.pz = v0.z; c0.nx = m0.x; c0.ny = m0.y; c0.nz = m0.z; c0.u = t0.x; c0.v = t0.y;
@@ -439,12 +445,13 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 // Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up and stores
 // the records (the caller's warp bins them). Returns a bit per stored sub-triangle. Self-contained
 // so that its stack never touches the fast path.
+template <int TM>
 __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
 {
-	const RStat rs = frameRstat(fp)[r];
+	const RStat rs = frameRstat<TM>(fp)[r];
 	Corner v0, v1, v2;
-	viewCorners(fp, rs, r, tri, ia, ib, ic, v0, v1, v2);
-	const int material = frameRdyn(fp)[r].material;
+	viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, v0, v1, v2);
+	const int material = frameRdyn<TM>(fp)[r].material;
 	int nrec = 0;
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
 	for (int sub = 0; sub < 2; sub++)
@@ -488,6 +495,7 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 #ifndef MR_SETUP_MINB
 #define MR_SETUP_MINB (1024 / MR_SETUP_THREADS)
 #endif
+template <int TM>
 __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int shBases[256];
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 	pdlWait(); // k_vertex's pv[] and zeroed counters
 	const int t = blockIdx.x * MR_SETUP_THREADS + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	const int r = findRenderable<MR_SETUP_THREADS>(fp, fp.triBlockR, t, 1, shBases);
+	const int r = findRenderable<MR_SETUP_THREADS, TM>(fp, fp.triBlockR, t, 1, shBases);
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
@@ -507,7 +515,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 	s.flags = 0u;
 	if (t < fp.nTriInst)
 	{
-		const RStat& rs = frameRstat(fp)[r];
+		const RStat& rs = frameRstat<TM>(fp)[r];
 		const int tri = t - rs.triBase;
 		// all three index streams up front: the normal / texcoord indices are only needed by
 		// survivors, but fetching them now keeps them off the dependent-load chain
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 			if (!(a.z > zn && b.z > zn && c.z > zn))
 			{
 				nclip = 1;
-				nrecSlow = setupClipped(fp, t, r, tri, ia, ib, ic);
+				nrecSlow = setupClipped<TM>(fp, t, r, tri, ia, ib, ic);
 			}
 		}
 		else if (setupTriangle(fp, a, b, c, s))
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 #define MR_LOAD_POS                                                                                                                   \
 	{                                                                                                                                 \
 		const float4 w0 = __ldg(&fp.pos4[rs.posBase + ia]), w1 = __ldg(&fp.pos4[rs.posBase + ib]), w2 = __ldg(&fp.pos4[rs.posBase + ic]); \
-		const RDyn& rdp = frameRdyn(fp)[r];                                                                                           \
+		const RDyn& rdp = frameRdyn<TM>(fp)[r];                                                                                           \
 		const V3 q0 = affine(rdp.mv, w0.x, w0.y, w0.z), q1 = affine(rdp.mv, w1.x, w1.y, w1.z), q2 = affine(rdp.mv, w2.x, w2.y, w2.z); \
 		p0 = make_float4(q0.x, q0.y, q0.z, 0.0f); p1 = make_float4(q1.x, q1.y, q1.z, 0.0f); p2 = make_float4(q2.x, q2.y, q2.z, 0.0f); \
 	}
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 #if !MR_EARLY_ATTR
 					MR_LOAD_ATTRS
 #endif
-					const RDyn& rd = frameRdyn(fp)[r];
+					const RDyn& rd = frameRdyn<TM>(fp)[r];
 					const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
 #if MR_EXP & 2
 					if (m0.x == 12345.0f)
@@ -976,6 +984,7 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 // Per-pixel part of phase 2 for tile pixel `pi` (0..255) whose final depth key is `key`.
 // Warp-convergent: contains shuffles. Returns the pixel's colour and depth (clear values when
 // nothing won); side outputs (winner ids, normals image) are written here.
+template <int TM>
 __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned long long key, int pi, int tileX0, int tileY0, int lane,
                                              V3& value, float& zout, bool& store)
 {
@@ -1055,7 +1064,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
 			fp.winner[pix] = id;
-		const MatDev& mat = frameMats(fp)[__float_as_uint(q2.w)];
+		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
 		Corner c0, c1, c2;
 		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s1.w;
 		c1.px = s1.x; c1.py = s1.y; c1.pz = s1.z; c1.u = s2.w; c1.v = s3.w;
@@ -1079,7 +1088,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 
 // One tile: phases 0, 1 and 2, by a CTA of NT threads (128: each thread resolves two pixels; twice
 // as many tiles are then in flight per SM). Called by all threads of the CTA (contains barriers).
-template <int NT>
+template <int NT, int TM>
 __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty, unsigned long long* keys, WarpQueue* queues)
 {
 	constexpr int PP = MR_TILE_PIXELS / NT;
@@ -1185,7 +1194,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	bool store[PP];
 #pragma unroll
 	for (int pp = 0; pp < PP; pp++)
-		resolvePixel(fp, key[pp], tid + pp * NT, tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
+		resolvePixel<TM>(fp, key[pp], tid + pp * NT, tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
 
 	// ---- tile store ----
 	if (vec)
@@ -1229,12 +1238,13 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 #ifndef MR_RASTER_MINB
 #define MR_RASTER_MINB (1024 / MR_RASTER_THREADS)
 #endif
+template <int TM>
 __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(const __grid_constant__ FrameParams fp)
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
 	pdlWait(); // k_setup's keys, bins and records
-	rasterTile<MR_RASTER_THREADS>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
+	rasterTile<MR_RASTER_THREADS, TM>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1317,7 +1327,11 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	const int nTiles = fp.tilesX * fp.tilesY;
 	int vthreads = (fp.nVertInst > nTiles + 1) ? fp.nVertInst : nTiles + 1;
 	if (ev) cudaEventRecord(ev[0], stream);
-	k_vertex<<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
+	const bool inl = fp.inlineTables != 0;
+	if (inl)
+		k_vertex<TM_INLINE><<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
+	else
+		k_vertex<TM_GLOBAL><<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
 	if (ev) cudaEventRecord(ev[1], stream);
 	// k_setup and k_raster may begin while their predecessor drains (unless stage events sit between)
 	cudaLaunchAttribute pdl[1];
@@ -1332,7 +1346,7 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	{
 		cfg.gridDim = dim3((fp.nTriInst + MR_SETUP_THREADS - 1) / MR_SETUP_THREADS);
 		cfg.blockDim = dim3(MR_SETUP_THREADS);
-		cudaLaunchKernelEx(&cfg, k_setup, fp);
+		cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE> : k_setup<TM_GLOBAL>, fp);
 	}
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);
@@ -1341,7 +1355,7 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	{
 		cfg.gridDim = dim3(fp.tilesX, fp.tileRows);
 		cfg.blockDim = dim3(MR_RASTER_THREADS);
-		cudaLaunchKernelEx(&cfg, k_raster, fp);
+		cudaLaunchKernelEx(&cfg, inl ? k_raster<TM_INLINE> : k_raster<TM_GLOBAL>, fp);
 	}
 	if (ev) cudaEventRecord(ev[5], stream);
 }
