@@ -1,3 +1,6 @@
-nvidia-smi -L
-python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -15
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>&1 | tail -3 | cut -c1-900
+nvidia-smi -L | head -2
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 2>&1 | tail -1 | cut -c1-600
+python bench.py --workload strips4k --steps 10 --warmup 3 2>&1 | tail -1 | cut -c1-300
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --workload strips4k --gather peer --steps 10 --warmup 3 2>&1 | tail -1 | cut -c1-300
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --workload strips4k --gather nccl --steps 10 --warmup 3 2>&1 | tail -1 | cut -c1-300

@@ -499,9 +499,9 @@ template <int TM>
 __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
 	__shared__ int shBases[256];
-	__shared__ int shStat[2]; // packed (records, clipped inputs, zero-coverage drops), warps done
-	if (threadIdx.x < 2)
-		shStat[threadIdx.x] = 0;
+	__shared__ unsigned long long shStat; // packed (records, clipped inputs, zero-coverage drops) | warps done << 32
+	if (threadIdx.x == 0)
+		shStat = 0ull;
 	__syncthreads();
 	pdlLaunchDependents();
 	pdlWait(); // k_vertex's pv[] and zeroed counters
@@ -702,20 +702,18 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 			}
 	}
 
-	// ---- statistics: three 10-bit fields in one word (a CTA sets up at most 256 records), summed per
-	// CTA in shared memory; the last warp to finish sends one RED per counter (no barrier: finished
-	// warps leave at once) ----
+	// ---- statistics: three 10-bit fields (a CTA sets up at most 256 records) plus the count of
+	// finished warps in one 64-bit word in shared memory. One atomic per warp; the warp that arrives
+	// last sends one RED per counter (no barrier and no fence: finished warps leave at once) ----
 	const int packed = __reduce_add_sync(0xffffffffu, ((valid ? 1 : 0) + __popc(nrecSlow)) | (nclip << 10) | (nzero << 20));
 	if (lane == 0)
 	{
-		if (packed)
-			atomicAdd(&shStat[0], packed);
-		__threadfence_block();
-		if (atomicAdd(&shStat[1], 1) == MR_SETUP_THREADS / 32 - 1)
+		const unsigned long long mine = (unsigned long long)(unsigned)packed | (1ull << 32);
+		const unsigned long long all = atomicAdd(&shStat, mine) + mine;
+		if ((int)(all >> 32) == MR_SETUP_THREADS / 32)
 		{
 			const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
-			const int all = atomicAdd(&shStat[0], 0);
-			const int nr = all & 1023, nc = (all >> 10) & 1023, nz = (all >> 20) & 1023;
+			const int nr = (int)(all & 1023), nc = (int)((all >> 10) & 1023), nz = (int)((all >> 20) & 1023);
 			if (nr) atomicAdd(&fp.ctr->records[slot], (unsigned long long)nr);
 			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], (unsigned long long)nc);
 			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], (unsigned long long)nz);

@@ -24,7 +24,7 @@ want = {
 }
 res = {}
 for r in rows[2:]:
-    name = r[hdr.index("Kernel Name")].split("::")[-1].split("(")[0]
+    name = r[hdr.index("Kernel Name")].split("::")[-1].split("(")[0].split("<")[0]
     d = {}
     for i, h in enumerate(hdr):
         if h in want:
