@@ -349,7 +349,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
-	MR_CUDA(c, c->pv.ensure(sizeof(float4) * 2 * (size_t)std::max(c->nVertInst, 1)));
+	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
 	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
 	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));

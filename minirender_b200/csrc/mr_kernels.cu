@@ -12,20 +12,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-// experiment switches
-#ifndef MR_EXP
-#define MR_EXP 0 // timing experiments only (break the output)
-#endif
-#ifndef MR_PV32
-#define MR_PV32 0
-#endif
-#ifndef MR_HOIST
-#define MR_HOIST 0
-#endif
-#ifndef MR_EARLY_ATTR
-#define MR_EARLY_ATTR 0
-#endif
-
 namespace {
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-
@@ -167,12 +153,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	const RStat& rs = frameRstat<TM>(fp)[rv];
 	const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
 	const V3 view = affine(frameRdyn<TM>(fp)[rv].mv, p.x, p.y, p.z);
-#if MR_PV32
-	fp.pv[2 * (size_t)vi] = project(fp, view);
-	fp.pv[2 * (size_t)vi + 1] = make_float4(view.x, view.y, view.z, 0.0f);
-#else
 	fp.pv[vi] = project(fp, view);
-#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -269,9 +250,6 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
 				if (z == z) // a NaN depth never passes `z < pixdepth`
 				{
-#if MR_EXP & 1
-					if (z == 12345.0f)
-#endif
 					atomicMin(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
 					any = true;
 				}
@@ -517,31 +495,11 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 	{
 		const RStat& rs = frameRstat<TM>(fp)[r];
 		const int tri = t - rs.triBase;
-		// all three index streams up front: the normal / texcoord indices are only needed by
-		// survivors, but fetching them now keeps them off the dependent-load chain
 		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
-		const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
 		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
-		const bool hasUv = rs.uvTriBase >= 0;
-#if MR_HOIST
-		const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
-		int iu0 = 0, iu1 = 0, iu2 = 0;
-		if (hasUv)
-		{
-			const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
-			iu0 = __ldg(iu); iu1 = __ldg(iu + 1); iu2 = __ldg(iu + 2);
-		}
-#endif
-#if MR_PV32
-		const float4* va = fp.pv + 2 * (size_t)(rs.vertBase + ia);
-		const float4* vb = fp.pv + 2 * (size_t)(rs.vertBase + ib);
-		const float4* vc = fp.pv + 2 * (size_t)(rs.vertBase + ic);
-#else
-		const float4* va = fp.pv + (size_t)(rs.vertBase + ia);
-		const float4* vb = fp.pv + (size_t)(rs.vertBase + ib);
-		const float4* vc = fp.pv + (size_t)(rs.vertBase + ic);
-#endif
-		const float4 a = *va, b = *vb, c = *vc;
+		const float4 a = fp.pv[rs.vertBase + ia];
+		const float4 b = fp.pv[rs.vertBase + ib];
+		const float4 c = fp.pv[rs.vertBase + ic];
 		const float zn = fp.znear;
 		if (a.z > zn || b.z > zn || c.z > zn) // Renderer.cpp:169-177
 		{
@@ -556,78 +514,24 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
 			if (valid)
 			{
-#define MR_LOAD_ATTRS                                                                                                                      \
-	float4 n0, n1, n2, p0, p1, p2;                                                                                                         \
-	float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;                                                                                 \
-	{                                                                                                                                      \
-		MR_LOAD_IDX2                                                                                                                       \
-		n0 = __ldg(&fp.nrm4[rs.nrmSrcBase + in0]); n1 = __ldg(&fp.nrm4[rs.nrmSrcBase + in1]); n2 = __ldg(&fp.nrm4[rs.nrmSrcBase + in2]); \
-		MR_LOAD_POS                                                                                                                        \
-		if (hasUv)                                                                                                                         \
-		{                                                                                                                                  \
-			t0 = __ldg(&fp.uv2[rs.uvBase + iu0]); t1 = __ldg(&fp.uv2[rs.uvBase + iu1]); t2 = __ldg(&fp.uv2[rs.uvBase + iu2]);             \
-		}                                                                                                                                  \
-	}
-#if MR_HOIST
-#define MR_LOAD_IDX2
-#else
-#define MR_LOAD_IDX2                                                                        \
-	const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);                     \
-	int iu0 = 0, iu1 = 0, iu2 = 0;                                                           \
-	if (hasUv)                                                                               \
-	{                                                                                        \
-		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;                         \
-		iu0 = __ldg(iu); iu1 = __ldg(iu + 1); iu2 = __ldg(iu + 2);                           \
-	}
-#endif
-#if MR_PV32
-#define MR_LOAD_POS p0 = va[1]; p1 = vb[1]; p2 = vc[1]; /* view-space positions (same sectors as a, b, c) */
-#else
-#define MR_LOAD_POS                                                                                                                   \
-	{                                                                                                                                 \
-		const float4 w0 = __ldg(&fp.pos4[rs.posBase + ia]), w1 = __ldg(&fp.pos4[rs.posBase + ib]), w2 = __ldg(&fp.pos4[rs.posBase + ic]); \
-		const RDyn& rdp = frameRdyn<TM>(fp)[r];                                                                                           \
-		const V3 q0 = affine(rdp.mv, w0.x, w0.y, w0.z), q1 = affine(rdp.mv, w1.x, w1.y, w1.z), q2 = affine(rdp.mv, w2.x, w2.y, w2.z); \
-		p0 = make_float4(q0.x, q0.y, q0.z, 0.0f); p1 = make_float4(q1.x, q1.y, q1.z, 0.0f); p2 = make_float4(q2.x, q2.y, q2.z, 0.0f); \
-	}
-#endif
-#if MR_EARLY_ATTR
-				// corner attributes: requested before the pixel loop so that they arrive during it
-				MR_LOAD_ATTRS
-#endif
 				if ((s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= MR_SMALL_AREA)
 				{
-#if MR_EXP & 4
-					valid = s.n1x != 12345.0f;
-#else
 					valid = rasterSmall(fp, a, b, c, s, 2 * t);
-#endif
 					nzero = valid ? 0 : 1;
 				}
 				else
 					binned = true;
-				if (valid)
-				{
-#if !MR_EARLY_ATTR
-					MR_LOAD_ATTRS
-#endif
-					const RDyn& rd = frameRdyn<TM>(fp)[r];
-					const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
-#if MR_EXP & 2
-					if (m0.x == 12345.0f)
-#endif
-					{
-					const RecRef ref = recRef(fp, 2 * t);
-					storeRec(ref, a, b, c, s, rd.material);
-					float4* d = ref.p + 4 * ref.stride;
-					d[0] = make_float4(p0.x, p0.y, p0.z, t0.x);
-					d[ref.stride] = make_float4(p1.x, p1.y, p1.z, t0.y);
-					d[2 * ref.stride] = make_float4(p2.x, p2.y, p2.z, t1.x);
-					d[3 * ref.stride] = make_float4(m0.x, m0.y, m0.z, t1.y);
-					d[4 * ref.stride] = make_float4(m1.x, m1.y, m1.z, t2.x);
-					d[5 * ref.stride] = make_float4(m2.x, m2.y, m2.z, t2.y);
-					}
-				}
+			}
+			if (valid)
+			{
+				// The triangle can own pixels: write its records. (Requesting the corner attributes
+				// earlier — before the pixel loop, or the index loads at the top — was measured: the
+				// longer live ranges spill and nothing is gained.)
+				Corner c0, c1, c2;
+				viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
+				const RecRef ref = recRef(fp, 2 * t);
+				storeRec(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material);
+				storeShadeRec(ref, c0, c1, c2);
 			}
 		}
 	}

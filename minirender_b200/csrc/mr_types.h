@@ -10,8 +10,7 @@
 // Per-frame arrays:
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
-//   pv[]           2 x float4 per vertex *instance*: (pixel x, pixel y, view z, depth term) and the
-//                  view-space position (reference _vertices): one 32-byte sector per vertex
+//   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
 //   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
 //                  triangle instance index in submission order: the index IS the submission id
 //                  that resolves equal-depth ties
@@ -155,7 +154,7 @@ struct FrameParams
 	const int* triBlockR; // same for triangle instances
 	const int* nrmBlockR; // same for normal instances
 
-	float4* pv;          // per vertex instance: (pixel x, pixel y, view z, depth term), (view x, y, z, 0)
+	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
 	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field k, lane (t & 31)
 	float4* recs1;       // records of sub-triangle 1 (second clipper output): MR_REC_FIELDS float4 per triangle
