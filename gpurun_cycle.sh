@@ -1,9 +1,9 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for e in 0 1; do
+if [ $e = 1 ]; then export MR_NO_CLUSTER_CULL=1; echo "no cluster cull"; fi
 python tools/stage_probe.py sphere 0 | grep flags
 python tools/stage_probe.py bench 0 | grep flags
 python tools/stage_probe.py cloud 0 | grep flags
-for e in 0 1; do
-if [ $e = 1 ]; then export MR_NO_PDL=1; echo "no pdl"; fi
 python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:

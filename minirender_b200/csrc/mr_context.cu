@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,7 +87,8 @@ struct mr_ctx
 	int smCount;
 
 	// scene-static device arrays
-	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes;
+	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes, clusters, triBlockCl, clusterVis;
+	std::vector<int> hostClusterBase; // first cluster of every mesh
 	std::vector<MeshDev> hostMeshes;
 	std::vector<int> hostNrmCount; // normals per mesh
 	std::vector<int> texOffset, texRows, texCols;
@@ -310,7 +313,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	const int nR = f->n_renderables;
 	// ---- validate + instance bases ----
 	std::vector<RStat> rs((size_t)nR);
-	long long vb = 0, tb = 0, nb = 0;
+	long long vb = 0, tb = 0, nb = 0, triReal = 0;
 	bool sameStructure = (c->structureSerial == c->sceneSerial) && ((int)c->structureKey.size() == nR);
 	for (int i = 0; i < nR; i++)
 	{
@@ -328,8 +331,13 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		rs[i].nrmSrcBase = hm.nrmBase;
 		rs[i].uvBase = hm.uvBase;
 		rs[i].uvTriBase = hm.hasUV ? hm.uvTriBase : -1;
+		rs[i].clusterBase = c->hostClusterBase[r.mesh];
+		rs[i].nTri = hm.nTri;
+		rs[i].triBaseReal = (int)triReal;
+		rs[i].pad = 0;
 		vb += hm.nPos;
-		tb += hm.nTri;
+		tb += ((long long)hm.nTri + MR_CLUSTER - 1) / MR_CLUSTER * MR_CLUSTER; // whole clusters per renderable
+		triReal += hm.nTri;
 		nb += c->hostNrmCount[r.mesh];
 		if (sameStructure && c->structureKey[i] != r.mesh)
 			sameStructure = false;
@@ -348,6 +356,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
+	const int nCB = c->nTriInst / MR_CLUSTER;
+	MR_CUDA(c, c->triBlockCl.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
+	MR_CUDA(c, c->clusterVis.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
 	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
@@ -391,9 +402,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)(nVB + 1);
 	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)(nTB + 1);
 	const size_t szNB = sameStructure ? 0 : sizeof(int) * (size_t)(nNB + 1);
+	const size_t szCB = sameStructure ? 0 : sizeof(int) * (size_t)nCB;
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
-	const size_t total = szStat + szVB + szTB + szNB + szDyn + szMat + 64;
+	const size_t total = szStat + szVB + szTB + szNB + szCB + szDyn + szMat + 64;
 	const int slotIndex = c->slotNext;
 	{
 		const int rc0 = retireSlot(c, slotIndex); // normally long finished
@@ -442,6 +454,15 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		nbr[nNB] = std::max(nR - 1, 0);
 		if (szNB) MR_CUDA(c, cudaMemcpyAsync(c->nrmBlockR.p, sp + off, szNB, cudaMemcpyHostToDevice, c->stream));
 		off += szNB;
+		int* cbr = (int*)(sp + off);
+		for (int i = 0; i < nR; i++)
+		{
+			const int b0 = rs[i].triBase / MR_CLUSTER, b1 = (i + 1 < nR ? rs[i + 1].triBase : c->nTriInst) / MR_CLUSTER;
+			for (int b = b0; b < b1; b++)
+				cbr[b] = i;
+		}
+		if (szCB) MR_CUDA(c, cudaMemcpyAsync(c->triBlockCl.p, sp + off, szCB, cudaMemcpyHostToDevice, c->stream));
+		off += szCB;
 		c->structureKey.resize((size_t)nR);
 		for (int i = 0; i < nR; i++)
 			c->structureKey[i] = f->renderables[i].mesh;
@@ -454,7 +475,25 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		memcpy(rd[i].mv, f->renderables[i].modelview, sizeof(float) * 12);
 		memcpy(rd[i].nm, f->renderables[i].normalmat, sizeof(float) * 12);
 		rd[i].material = f->renderables[i].material;
-		rd[i].pad[0] = rd[i].pad[1] = rd[i].pad[2] = 0;
+		{
+			// Is the modelview a similarity (uniform scale x rotation) with positive determinant? Then a
+			// cluster's normal cone is still a cone in view space and its bounding radius scales by s.
+			const float* m = rd[i].mv;
+			const double c0[3] = { m[0], m[4], m[8] }, c1[3] = { m[1], m[5], m[9] }, c2[3] = { m[2], m[6], m[10] };
+			const double l0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], l1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
+			             l2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+			const double d01 = c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2], d02 = c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2],
+			             d12 = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
+			const double det = c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c0[1] * (c1[0] * c2[2] - c1[2] * c2[0]) + c0[2] * (c1[0] * c2[1] - c1[1] * c2[0]);
+			const double lmax = std::max(l0, std::max(l1, l2)), lmin = std::min(l0, std::min(l1, l2));
+			const double tol = 1e-4 * lmax;
+			const bool similar = lmax > 0 && (lmax - lmin) <= tol && fabs(d01) <= tol && fabs(d02) <= tol && fabs(d12) <= tol && lmax == lmax;
+			rd[i].cullFlags = (similar && det > 0) ? 1 : 0;
+			// the largest stretch of the linear part: s for a similarity, the Frobenius norm otherwise
+			const double stretch = similar ? sqrt(lmax) : sqrt(l0 + l1 + l2);
+			rd[i].radiusScale = (stretch == stretch) ? (float)(stretch * 1.0001) : INFINITY;
+			rd[i].pad = 0;
+		}
 	}
 	const bool inlineTables = nR <= MR_INLINE_TABLE && f->n_materials <= MR_INLINE_TABLE;
 	if (szDyn && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->rdyn.p, rd, szDyn, cudaMemcpyHostToDevice, c->stream));
@@ -481,7 +520,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
 	if (szMat && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
+	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + szCB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -508,6 +547,35 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.tileRow0 = rb >> MR_TILE_SHIFT;
 	fp.tileRows = (re > rb) ? ((re + MR_TILE - 1) >> MR_TILE_SHIFT) - fp.tileRow0 : 0;
 	fp.persp = f->projection[15] == 0.0f;
+	{
+		// Cluster culling needs the standard perspective form (w_clip = -z_view, x and y not mirrored).
+		const float* P = f->projection;
+		const bool standard = fp.persp && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f && P[0] > 0.0f && P[5] > 0.0f;
+		fp.cullClusters = (standard && !getenv("MR_NO_CLUSTER_CULL")) ? 1 : 0;
+		if (fp.cullClusters)
+		{
+			// Columns / rows this frame can touch, widened by 1.5 pixels, as NDC bounds; each bound is a plane
+			// through the eye: (x_ndc >= xl) <=> (row0 - xl * row3) . p >= 0 for points in front of the camera.
+			const float xl = -1.0f - 3.0f / (float)c->w, xr = 1.0f + 3.0f / (float)c->w;
+			const float yt = 1.0f - 2.0f * ((float)rb - 1.5f) / (float)c->h, yb = 1.0f - 2.0f * ((float)re + 1.5f) / (float)c->h;
+			const float sgn[4] = { 1.0f, -1.0f, 1.0f, -1.0f }, bound[4] = { xl, xr, yb, yt };
+			for (int k = 0; k < 4; k++)
+			{
+				const float* row = P + 4 * (k / 2);
+				double n[4];
+				for (int j = 0; j < 4; j++)
+					n[j] = sgn[k] * ((double)row[j] - (double)bound[k] * (double)P[12 + j]);
+				const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+				if (!(len > 0))
+				{
+					fp.cullClusters = 0;
+					break;
+				}
+				for (int j = 0; j < 4; j++)
+					fp.cullPlanes[k][j] = (float)(n[j] / len);
+			}
+		}
+	}
 	fp.lightIsPoint = f->light_is_point;
 	fp.lighting = f->lighting;
 	fp.texturing = f->texturing;
@@ -516,6 +584,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.nRenderables = nR;
 	fp.nVertInst = c->nVertInst;
 	fp.nTriInst = c->nTriInst;
+	fp.nTriReal = (int)triReal;
 	fp.nNrmInst = c->nNrmInst;
 	fp.debug = c->debugFlags;
 	fp.inlineTables = inlineTables ? 1 : 0;
@@ -540,6 +609,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.mats = c->mats.as<MatDev>();
 	fp.vtxBlockR = c->vtxBlockR.as<int>();
 	fp.triBlockR = c->triBlockR.as<int>();
+	fp.triBlockCl = c->triBlockCl.as<int>();
+	fp.clusters = c->clusters.as<float4>();
+	fp.clusterVis = c->clusterVis.as<int>();
 	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
 	fp.gkeys = c->gkeys.as<unsigned long long>();
@@ -583,6 +655,90 @@ int readBack(mr_ctx* c, void* host, const void* dev, size_t bytes)
 	MR_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
 	MR_CUDA(c, cudaStreamSynchronize(c->stream));
 	return MR_OK;
+}
+
+// Cull clusters of one mesh: for every MR_CLUSTER consecutive triangles, a bounding sphere of their
+// vertices and a cone around their geometric normals, (b - a) x (c - a). k_setup drops a whole CTA
+// of triangles when the sphere lies outside the rows / columns of the frame or nearer than the near
+// plane, or when every normal of the cone points away from the eye — only triangles the reference
+// itself discards (off-screen reject Renderer.cpp:202, near test :169-177, area cull :205-210),
+// decided with generous margins, so the image does not change.
+void buildClusters(const mr_mesh_desc& m, float* out /* 8 floats per cluster */)
+{
+	const double kMargin = 0.07; // radians (4 degrees) added to the cone half-angle
+	const int nCl = (m.n_triangles + MR_CLUSTER - 1) / MR_CLUSTER;
+	for (int k = 0; k < nCl; k++)
+	{
+		const int t0 = k * MR_CLUSTER, t1 = std::min(m.n_triangles, t0 + MR_CLUSTER);
+		double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, sum[3] = { 0, 0, 0 };
+		bool finite = true;
+		for (int t = t0; t < t1; t++)
+		{
+			const float* v[3];
+			for (int j = 0; j < 3; j++)
+			{
+				v[j] = m.positions + 3 * (size_t)m.idx_pos[3 * (size_t)t + j];
+				for (int a = 0; a < 3; a++)
+				{
+					const double x = v[j][a];
+					if (!(x == x) || x > 1e30 || x < -1e30)
+						finite = false;
+					lo[a] = std::min(lo[a], x);
+					hi[a] = std::max(hi[a], x);
+				}
+			}
+			const double e1[3] = { (double)v[1][0] - v[0][0], (double)v[1][1] - v[0][1], (double)v[1][2] - v[0][2] };
+			const double e2[3] = { (double)v[2][0] - v[0][0], (double)v[2][1] - v[0][1], (double)v[2][2] - v[0][2] };
+			const double n[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+			const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+			if (len > 0 && len == len) // a zero-area triangle has no facing (and never draws)
+				for (int a = 0; a < 3; a++)
+					sum[a] += n[a] / len;
+		}
+		float* o = out + 8 * (size_t)k;
+		if (!finite)
+		{
+			o[0] = o[1] = o[2] = 0.0f; o[3] = INFINITY; // never culled
+			o[4] = o[5] = 0.0f; o[6] = 1.0f; o[7] = 2.0f;
+			continue;
+		}
+		const double c[3] = { 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2]) };
+		double r2 = 0;
+		for (int t = t0; t < t1; t++)
+			for (int j = 0; j < 3; j++)
+			{
+				const float* v = m.positions + 3 * (size_t)m.idx_pos[3 * (size_t)t + j];
+				const double d[3] = { v[0] - c[0], v[1] - c[1], v[2] - c[2] };
+				r2 = std::max(r2, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+			}
+		o[0] = (float)c[0]; o[1] = (float)c[1]; o[2] = (float)c[2];
+		o[3] = (float)(sqrt(r2) * 1.001 + 1e-30) + fabsf((float)c[0]) * 1e-6f + fabsf((float)c[1]) * 1e-6f + fabsf((float)c[2]) * 1e-6f;
+		const double sl = sqrt(sum[0] * sum[0] + sum[1] * sum[1] + sum[2] * sum[2]);
+		o[4] = o[5] = 0.0f; o[6] = 1.0f; o[7] = 2.0f; // no usable cone unless shown otherwise
+		if (sl > 1e-6)
+		{
+			const double ax[3] = { sum[0] / sl, sum[1] / sl, sum[2] / sl };
+			double cosMin = 1.0;
+			for (int t = t0; t < t1; t++)
+			{
+				const float* v0 = m.positions + 3 * (size_t)m.idx_pos[3 * (size_t)t];
+				const float* v1 = m.positions + 3 * (size_t)m.idx_pos[3 * (size_t)t + 1];
+				const float* v2 = m.positions + 3 * (size_t)m.idx_pos[3 * (size_t)t + 2];
+				const double e1[3] = { (double)v1[0] - v0[0], (double)v1[1] - v0[1], (double)v1[2] - v0[2] };
+				const double e2[3] = { (double)v2[0] - v0[0], (double)v2[1] - v0[1], (double)v2[2] - v0[2] };
+				const double n[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+				const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+				if (len > 0 && len == len)
+					cosMin = std::min(cosMin, (n[0] * ax[0] + n[1] * ax[1] + n[2] * ax[2]) / len);
+			}
+			const double alpha = acos(std::max(-1.0, std::min(1.0, cosMin))) + kMargin;
+			if (alpha < 1.5) // below ~86 degrees: a cone that can ever face away as a whole
+			{
+				o[4] = (float)ax[0]; o[5] = (float)ax[1]; o[6] = (float)ax[2];
+				o[7] = (float)sin(alpha);
+			}
+		}
+	}
 }
 
 }
@@ -668,7 +824,7 @@ void mr_destroy(mr_ctx* c)
 	Bind bind(c->device);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
-	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->rstat,
+	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->clusters, &c->triBlockCl, &c->clusterVis, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
 		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
@@ -882,9 +1038,24 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 	}
 	if (s->n_meshes)
 		MR_CUDA(c, cudaMemcpyAsync(c->meshes.p, md.data(), sizeof(MeshDev) * md.size(), cudaMemcpyHostToDevice, c->stream));
+	// cull clusters (host pass over the triangles, once per upload)
+	std::vector<int> clusterBase((size_t)s->n_meshes);
+	size_t nClusters = 0;
+	for (int i = 0; i < s->n_meshes; i++)
+	{
+		clusterBase[i] = (int)nClusters;
+		nClusters += (size_t)(s->meshes[i].n_triangles + MR_CLUSTER - 1) / MR_CLUSTER;
+	}
+	std::vector<float> clusters(8 * std::max<size_t>(nClusters, 1), 0.0f);
+	for (int i = 0; i < s->n_meshes; i++)
+		if (s->meshes[i].n_triangles > 0)
+			buildClusters(s->meshes[i], clusters.data() + 8 * (size_t)clusterBase[i]);
+	MR_CUDA(c, c->clusters.ensure(sizeof(float) * clusters.size()));
+	MR_CUDA(c, cudaMemcpyAsync(c->clusters.p, clusters.data(), sizeof(float) * clusters.size(), cudaMemcpyHostToDevice, c->stream));
 	MR_CUDA(c, cudaGetLastError());
 	MR_CUDA(c, cudaStreamSynchronize(c->stream)); // host arrays are only borrowed for this call
 	c->hostMeshes.swap(md);
+	c->hostClusterBase.swap(clusterBase);
 	c->hostNrmCount.resize((size_t)s->n_meshes);
 	for (int i = 0; i < s->n_meshes; i++)
 		c->hostNrmCount[i] = s->meshes[i].n_normals;

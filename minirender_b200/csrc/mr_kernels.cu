@@ -128,6 +128,49 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 	return lo;
 }
 
+// Cluster culling (evaluated by k_vertex, one thread per k_setup CTA). Cluster `ci` = MR_CLUSTER
+// consecutive triangle instances of one renderable = MR_CLUSTER consecutive triangles of its mesh,
+// for which mr_upload_scene stored a bounding sphere and a cone around the geometric normals.
+// Returns false when no triangle of the cluster can reach a pixel of this frame:
+//  * every vertex nearer than the near plane: the reference drops such triangles (Renderer.cpp:169-177);
+//  * the sphere outside the columns / rows the frame can touch (widened by 1.5 px): off-screen reject
+//    (Renderer.cpp:202) or, for strip rendering, another rank's rows;
+//  * every normal of the cone facing away from the eye: area cull (Renderer.cpp:205-210).
+// Only triangles the reference discards itself are dropped, with generous margins, so the image
+// does not change.
+template <int TM>
+__device__ __forceinline__ bool clusterVisible(const FrameParams& fp, int ci)
+{
+	const int r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
+	const RStat& rs = frameRstat<TM>(fp)[r];
+	const float4* cl = fp.clusters + 2 * (size_t)(rs.clusterBase + (ci * MR_CLUSTER - rs.triBase) / MR_CLUSTER);
+	const float4 cs = __ldg(cl), ca = __ldg(cl + 1);
+	const RDyn& rd = frameRdyn<TM>(fp)[r];
+	const V3 c = affine(rd.mv, cs.x, cs.y, cs.z);
+	const float R = cs.w * rd.radiusScale;
+	const float slack = 1e-4f * (fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + R) + 1e-6f;
+	bool cull = c.z - R > fp.znear + slack;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		cull = cull || (fp.cullPlanes[k][0] * c.x + fp.cullPlanes[k][1] * c.y + fp.cullPlanes[k][2] * c.z + fp.cullPlanes[k][3] < -(R + slack));
+	// The eye is the origin of view space; p ranges over the bounding sphere, n over the normal cone:
+	// all back-facing <=> angle(eye->centre, axis) + cone half-angle (+ margin) + angular radius < 90 degrees
+	if ((rd.cullFlags & 1) && ca.w < 1.5f)
+	{
+		const float d = sqrtf(c.x * c.x + c.y * c.y + c.z * c.z);
+		if (d > R + slack)
+		{
+			const float inv = 1.0f / (rd.radiusScale * d); // the axis goes through the similarity's linear part
+			const float tdot = (c.x * (rd.mv[0] * ca.x + rd.mv[1] * ca.y + rd.mv[2] * ca.z) + c.y * (rd.mv[4] * ca.x + rd.mv[5] * ca.y + rd.mv[6] * ca.z) +
+			                    c.z * (rd.mv[8] * ca.x + rd.mv[9] * ca.y + rd.mv[10] * ca.z)) * inv;
+			const float sinB = R / d, cosB = sqrtf(fmaxf(1.0f - sinB * sinB, 0.0f));
+			const float cosA = sqrtf(fmaxf(1.0f - ca.w * ca.w, 0.0f));
+			cull = cull || (tdot > ca.w * cosB + cosA * sinB + 1e-3f);
+		}
+	}
+	return !cull;
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel 1: vertex transform + projection (reference loop A, Renderer.cpp:344-345, and the
 // per-vertex part of paintTriangle, :186-196, :223-224). Thread i handles vertex instance i:
@@ -144,7 +187,9 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	if (vi <= nTiles)
 		fp.tileCount[vi] = 0;
 	if (vi < (int)(sizeof(Counters) / 8))
-		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriInst : 0ull; // word 0 = trianglesIn
+		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriReal : 0ull; // word 0 = trianglesIn
+	if (fp.cullClusters && vi < fp.nTriInst / MR_CLUSTER)
+		fp.clusterVis[vi] = clusterVisible<TM>(fp, vi) ? 1 : 0;
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return;
 	const int rv = findRenderable<256, TM>(fp, fp.vtxBlockR, vi, 0, shBases);
@@ -288,13 +333,13 @@ __device__ __forceinline__ RecRef recRef(const FrameParams& fp, int id)
 	return r;
 }
 
-__device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material)
+__device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission)
 {
 	d.p[0] = make_float4(a.x, a.y, c.x, c.y);
 	d.p[d.stride] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
 	d.p[2 * d.stride] = make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material));
 	d.p[3 * d.stride] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
-	                                __uint_as_float(s.flags), 0.0f);
+	                                __uint_as_float(s.flags), __uint_as_float((uint32_t)submission));
 }
 
 // One corner in view space: what paintMesh's loops A/B/C hand to paintTriangle (Renderer.cpp:344-380).
@@ -447,7 +492,7 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
 		const RecRef ref = recRef(fp, id);
-		storeRec(ref, a, b, c, s, material);
+		storeRec(ref, a, b, c, s, material, 2 * (rs.triBaseReal + tri) + sub);
 		storeShadeRec(ref, o0, o1, o2);
 		nrec |= 1 << sub;
 	}
@@ -473,30 +518,40 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 #ifndef MR_SETUP_MINB
 #define MR_SETUP_MINB (1024 / MR_SETUP_THREADS)
 #endif
+static_assert(MR_SETUP_THREADS == MR_CLUSTER, "one k_setup CTA per cull cluster");
 template <int TM>
 __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
 {
-	__shared__ int shBases[256];
 	__shared__ unsigned long long shStat; // packed (records, clipped inputs, zero-coverage drops) | warps done << 32
 	if (threadIdx.x == 0)
 		shStat = 0ull;
 	__syncthreads();
 	pdlLaunchDependents();
-	pdlWait(); // k_vertex's pv[] and zeroed counters
+	// This CTA = one cluster of MR_CLUSTER consecutive triangles of one renderable (instance bases are
+	// padded to whole clusters, so no search is needed).
+	const int r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[blockIdx.x]);
+	const RStat& rs = frameRstat<TM>(fp)[r];
 	const int t = blockIdx.x * MR_SETUP_THREADS + threadIdx.x;
+	const int tri = t - rs.triBase;
 	const int lane = threadIdx.x & 31;
-	const int r = findRenderable<MR_SETUP_THREADS, TM>(fp, fp.triBlockR, t, 1, shBases);
+	// the triangle's vertex indices are requested before the cluster test, so that the test's own loads
+	// do not add a round trip to the dependent chain of the clusters that survive it
+	int ia = 0, ib = 0, ic = 0;
+	if (tri < rs.nTri)
+	{
+		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
+		ia = __ldg(ix); ib = __ldg(ix + 1); ic = __ldg(ix + 2);
+	}
+	pdlWait(); // k_vertex's pv[], cluster verdicts and zeroed counters
+	if (fp.cullClusters && fp.clusterVis[blockIdx.x] == 0)
+		return; // the whole cluster is off screen, nearer than the near plane or facing away (clusterVisible())
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
 	s.x0 = s.x1 = s.y0 = s.y1 = 0;
 	s.flags = 0u;
-	if (t < fp.nTriInst)
+	if (tri < rs.nTri)
 	{
-		const RStat& rs = frameRstat<TM>(fp)[r];
-		const int tri = t - rs.triBase;
-		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
-		const int ia = __ldg(ix), ib = __ldg(ix + 1), ic = __ldg(ix + 2);
 		const float4 a = fp.pv[rs.vertBase + ia];
 		const float4 b = fp.pv[rs.vertBase + ib];
 		const float4 c = fp.pv[rs.vertBase + ic];
@@ -530,7 +585,7 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 				Corner c0, c1, c2;
 				viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
 				const RecRef ref = recRef(fp, 2 * t);
-				storeRec(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material);
+				storeRec(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material, 2 * (rs.triBaseReal + tri));
 				storeShadeRec(ref, c0, c1, c2);
 			}
 		}
@@ -965,7 +1020,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 		else
 			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
-			fp.winner[pix] = id;
+			fp.winner[pix] = (int)__float_as_uint(q3.w); // the reference's submission index (instance ids are padded per renderable)
 		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
 		Corner c0, c1, c2;
 		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s1.w;
@@ -1228,6 +1283,8 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 {
 	const int nTiles = fp.tilesX * fp.tilesY;
 	int vthreads = (fp.nVertInst > nTiles + 1) ? fp.nVertInst : nTiles + 1;
+	if (fp.nTriInst / MR_CLUSTER > vthreads)
+		vthreads = fp.nTriInst / MR_CLUSTER;
 	if (ev) cudaEventRecord(ev[0], stream);
 	const bool inl = fp.inlineTables != 0;
 	if (inl)

@@ -38,16 +38,23 @@ struct MeshDev
 	int nPos, nTri, hasUV;
 };
 
+#define MR_CLUSTER 128 // triangles per cull cluster = triangles per k_setup CTA
+
 struct __align__(16) RStat // per renderable, changes only when the flattened structure changes
 {
-	int vertBase;   // first vertex instance (into pv / vpos4)
-	int triBase;    // first triangle instance (submission order)
+	int vertBase;   // first vertex instance (into pv)
+	int triBase;    // first triangle instance (submission order); a multiple of MR_CLUSTER: every
+	                // k_setup CTA lies inside one renderable and maps onto one cluster of its mesh
 	int nrmBase;    // first normal instance (into vnrm4)
 	int idxBase;    // the mesh's first triangle in idxPos / idxNrm
 	int posBase;    // the mesh's first vertex in pos4
 	int nrmSrcBase; // the mesh's first normal in nrm4
 	int uvBase;     // the mesh's first texcoord in uv2
 	int uvTriBase;  // the mesh's first triangle in idxUv, -1: no texcoords
+	int clusterBase; // the mesh's first cluster in clusters[]
+	int nTri;        // triangles of the mesh (instances beyond it are padding)
+	int triBaseReal; // first triangle instance counted without padding (the reference's submission index)
+	int pad;
 };
 
 struct __align__(16) RDyn // per renderable, per frame
@@ -55,7 +62,9 @@ struct __align__(16) RDyn // per renderable, per frame
 	float mv[12]; // modelview, row-major 3x4
 	float nm[12]; // normal matrix, row-major 3x4
 	int material;
-	int pad[3];
+	int cullFlags;     // bit 0: the modelview is a similarity with positive determinant (normal cones stay cones)
+	float radiusScale; // upper bound of the modelview's stretch: scales a cluster's bounding radius
+	int pad;
 };
 
 struct __align__(16) MatDev
@@ -83,7 +92,7 @@ struct __align__(16) Rec
 	uint32_t xspan;           // x0 | x1 << 16 : first / last pixel column of the clamped bbox
 	uint32_t yspan;           // y0 | y1 << 16
 	uint32_t flags;
-	uint32_t pad;
+	uint32_t submission; // 2 * unpadded triangle instance + clipper output: the id mr_read_winner_ids reports
 };
 
 // 96-byte shading record of the same triangle: the three corners in view space (for clipper output:
@@ -150,6 +159,14 @@ struct FrameParams
 	const RStat* rstat;
 	const RDyn* rdyn;
 	const MatDev* mats;
+	// Cluster culling (k_setup): per mesh cluster of MR_CLUSTER triangles, two float4 in object space:
+	// (bounding-sphere centre, radius), (normal-cone axis, sin(cone half-angle + margin) or 2 = no cone)
+	const float4* clusters;
+	const int* triBlockCl; // renderable of every k_setup CTA (MR_CLUSTER triangle instances)
+	int* clusterVis;       // per k_setup CTA: 0 = culled this frame (written by k_vertex)
+	int nTriReal;          // triangles submitted (nTriInst counts the per-renderable padding too)
+	int cullClusters;      // 0: off (orthographic or non-standard projection)
+	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
 	const int* vtxBlockR; // renderable that owns the first vertex instance of each 256-block
 	const int* triBlockR; // same for triangle instances
 	const int* nrmBlockR; // same for normal instances

@@ -34,8 +34,11 @@ def test_golden_through_c_abi(ctx, name):
         assert np.abs(ctx.read_normals() - want["normals"]).max() <= 1e-5
 
 
-def test_strips_union_is_byte_identical(be):
-    setup = scenes.SMALL_SCENES["cloud_small"](be)
+@pytest.mark.parametrize("scene", ["cloud_small", "culling0", "culling2"])
+def test_strips_union_is_byte_identical(be, scene):
+    """Strip rendering also narrows the cluster-culling planes to the strip's rows: the union of the
+    strips must still be the whole frame, bit for bit."""
+    setup = scenes.SMALL_SCENES[scene](be)
     r = setup.apply(m.Renderer(be))
     r.render()
     full_i, full_d = r.get_image(), r.get_depth()
