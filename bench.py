@@ -395,6 +395,8 @@ def run_strips(args, rank, local_rank, world):
     if world > 1 and args.gather == "nccl":
         img, dep = sharding.device_tensors(lib, ctx, H4, W4, torch.device("cuda", local_rank))
 
+    token = torch.zeros(1, device="cuda")
+
     def frame(i):
         r.set_view(scenes.sphere_view(be, i, d=330.0))
         r.render()
@@ -403,8 +405,9 @@ def run_strips(args, rank, local_rank, world):
                 r.synchronize()
                 sharding.gather_strips(img, dep, H4, rank, world, dist, dst=0)
             else:
-                r.synchronize()
-                dist.barrier()  # every strip has landed in rank 0's framebuffer
+                # every strip has landed in rank 0's framebuffer once all ranks have passed this
+                # stream-ordered all-reduce (enqueued behind the frame's kernels; no host sync)
+                dist.all_reduce(token)
 
     K, Wm = max(1, args.steps), max(3, args.warmup)
     for i in range(Wm):

@@ -87,7 +87,7 @@ struct mr_ctx
 	int smCount;
 
 	// scene-static device arrays
-	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes, clusters, triBlockCl, clusterVis;
+	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes, clusters, triBlockCl, clusterVis, visList, visCount;
 	std::vector<int> hostClusterBase; // first cluster of every mesh
 	std::vector<MeshDev> hostMeshes;
 	std::vector<int> hostNrmCount; // normals per mesh
@@ -117,6 +117,7 @@ struct mr_ctx
 
 	// scratch
 	DevBuf pv, recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
+	float lastVisFrac; // clusters that survived culling in the newest retired frame (fraction; < 0: unknown)
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -142,7 +143,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), lastVisFrac(-1.0f), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -211,6 +212,8 @@ void absorbCounters(mr_ctx* c, const Counters& k)
 	c->stats.clipped_in = (int64_t)clip;
 	c->stats.bin_entries = (int64_t)pairs;
 	c->stats.zero_coverage = (int64_t)zero;
+	if (k.clusters > 0)
+		c->lastVisFrac = (float)k.visible / (float)k.clusters;
 	c->stats.tiles_x = c->tilesX;
 	c->stats.tiles_y = c->tilesY;
 }
@@ -358,7 +361,13 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	const int nCB = c->nTriInst / MR_CLUSTER;
 	MR_CUDA(c, c->triBlockCl.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
+	MR_CUDA(c, c->visList.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
 	MR_CUDA(c, c->clusterVis.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
+	if (!c->visCount.p)
+	{
+		MR_CUDA(c, c->visCount.ensure(256, true));
+		MR_CUDA(c, cudaMemsetAsync(c->visCount.p, 0, 256, c->stream));
+	}
 	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
@@ -611,7 +620,19 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.triBlockR = c->triBlockR.as<int>();
 	fp.triBlockCl = c->triBlockCl.as<int>();
 	fp.clusters = c->clusters.as<float4>();
+	fp.visList = c->visList.as<int>();
 	fp.clusterVis = c->clusterVis.as<int>();
+	fp.visCount = c->visCount.as<int>();
+	{
+		const char* e = getenv("MR_SETUP_CTAS_PER_SM");
+		// Most clusters expected to survive culling: one CTA per cluster. Most culled (a strip of a frame,
+		// or what the newest finished frame reported): a few persistent CTAs per SM.
+		// (also when the scene is made of many small meshes: their padded clusters are mostly empty and
+		// one CTA each is bound by the launch rate, not by work)
+		const bool mostlyCulled = fp.cullClusters && (fp.tileRows < fp.tilesY || (c->lastVisFrac >= 0.0f && c->lastVisFrac < 0.5f) ||
+		                                              (double)triReal < 0.75 * (double)c->nTriInst);
+		fp.setupCtas = (e && atoi(e) > 0) ? c->smCount * atoi(e) : mostlyCulled ? c->smCount * 16 : 0x7fffffff;
+	}
 	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
 	fp.gkeys = c->gkeys.as<unsigned long long>();
@@ -824,7 +845,7 @@ void mr_destroy(mr_ctx* c)
 	Bind bind(c->device);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
-	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->clusters, &c->triBlockCl, &c->clusterVis, &c->rstat,
+	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->clusters, &c->triBlockCl, &c->clusterVis, &c->visList, &c->visCount, &c->rstat,
 		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
 		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)

@@ -8,6 +8,7 @@
 //              plus the exact coverage mask of small triangles (loops D/E :238-249 without depth)
 //   k_raster   reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -188,8 +189,26 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		fp.tileCount[vi] = 0;
 	if (vi < (int)(sizeof(Counters) / 8))
 		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriReal : 0ull; // word 0 = trianglesIn
-	if (fp.cullClusters && vi < fp.nTriInst / MR_CLUSTER)
-		fp.clusterVis[vi] = clusterVisible<TM>(fp, vi) ? 1 : 0;
+	if (fp.cullClusters && blockIdx.x * 256 < fp.nTriInst / MR_CLUSTER)
+	{
+		// the verdict of every cluster, as a flag (k_setup with one CTA per cluster) and appended to
+		// visList (persistent k_setup; one atomic per warp; the order of the list is irrelevant: ids
+		// come from the cluster index)
+		const bool vis = vi < fp.nTriInst / MR_CLUSTER && clusterVisible<TM>(fp, vi);
+		if (vi < fp.nTriInst / MR_CLUSTER)
+			fp.clusterVis[vi] = vis ? 1 : 0;
+		const unsigned m = __ballot_sync(0xffffffffu, vis);
+		if (m != 0u)
+		{
+			const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+			int base = 0;
+			if (lane == leader)
+				base = atomicAdd(fp.visCount, __popc(m));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (vis)
+				fp.visList[base + __popc(m & ((1u << lane) - 1u))] = vi;
+		}
+	}
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return;
 	const int rv = findRenderable<256, TM>(fp, fp.vtxBlockR, vi, 0, shBases);
@@ -518,39 +537,50 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 #ifndef MR_SETUP_MINB
 #define MR_SETUP_MINB (1024 / MR_SETUP_THREADS)
 #endif
-static_assert(MR_SETUP_THREADS == MR_CLUSTER, "one k_setup CTA per cull cluster");
-template <int TM>
-__global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
+static_assert(MR_SETUP_THREADS == MR_CLUSTER, "one cull cluster per k_setup CTA iteration");
+
+// One cluster: MR_CLUSTER consecutive triangle instances of one renderable (instance bases are padded
+// to whole clusters, so the cluster index gives the renderable without a search), one per thread.
+// acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
+struct ClusterTri // what a thread works on within cluster ci
 {
-	__shared__ unsigned long long shStat; // packed (records, clipped inputs, zero-coverage drops) | warps done << 32
-	if (threadIdx.x == 0)
-		shStat = 0ull;
-	__syncthreads();
-	pdlLaunchDependents();
-	// This CTA = one cluster of MR_CLUSTER consecutive triangles of one renderable (instance bases are
-	// padded to whole clusters, so no search is needed).
-	const int r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[blockIdx.x]);
-	const RStat& rs = frameRstat<TM>(fp)[r];
-	const int t = blockIdx.x * MR_SETUP_THREADS + threadIdx.x;
-	const int tri = t - rs.triBase;
-	const int lane = threadIdx.x & 31;
-	// the triangle's vertex indices are requested before the cluster test, so that the test's own loads
-	// do not add a round trip to the dependent chain of the clusters that survive it
-	int ia = 0, ib = 0, ic = 0;
-	if (tri < rs.nTri)
+	int r;            // renderable
+	const RStat* rs;
+	int t, tri;       // triangle instance (padded numbering), triangle within the mesh
+	bool active;      // false: padding behind the mesh's last triangle
+	int ia, ib, ic;   // its vertex indices
+};
+
+template <int TM>
+__device__ __forceinline__ ClusterTri locateAndLoadIndices(const FrameParams& fp, int ci)
+{
+	ClusterTri k;
+	k.r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
+	k.rs = &frameRstat<TM>(fp)[k.r];
+	k.t = ci * MR_CLUSTER + (int)threadIdx.x;
+	k.tri = k.t - k.rs->triBase;
+	k.active = k.tri < k.rs->nTri;
+	k.ia = k.ib = k.ic = 0;
+	if (k.active)
 	{
-		const int* ix = fp.idxPos + (size_t)(rs.idxBase + tri) * 3;
-		ia = __ldg(ix); ib = __ldg(ix + 1); ic = __ldg(ix + 2);
+		const int* ix = fp.idxPos + (size_t)(k.rs->idxBase + k.tri) * 3;
+		k.ia = __ldg(ix); k.ib = __ldg(ix + 1); k.ic = __ldg(ix + 2);
 	}
-	pdlWait(); // k_vertex's pv[], cluster verdicts and zeroed counters
-	if (fp.cullClusters && fp.clusterVis[blockIdx.x] == 0)
-		return; // the whole cluster is off screen, nearer than the near plane or facing away (clusterVisible())
+	return k;
+}
+
+template <int TM>
+__device__ __forceinline__ void setupCluster(const FrameParams& fp, const ClusterTri& k, int lane, unsigned long long& acc)
+{
+	const int r = k.r, t = k.t, tri = k.tri, ia = k.ia, ib = k.ib, ic = k.ic;
+	const RStat& rs = *k.rs;
+	const bool active = k.active;
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	Setup s;
 	s.x0 = s.x1 = s.y0 = s.y1 = 0;
 	s.flags = 0u;
-	if (tri < rs.nTri)
+	if (active)
 	{
 		const float4 a = fp.pv[rs.vertBase + ia];
 		const float4 b = fp.pv[rs.vertBase + ib];
@@ -661,21 +691,78 @@ __global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const
 			}
 	}
 
-	// ---- statistics: three 10-bit fields (a CTA sets up at most 256 records) plus the count of
-	// finished warps in one 64-bit word in shared memory. One atomic per warp; the warp that arrives
-	// last sends one RED per counter (no barrier and no fence: finished warps leave at once) ----
-	const int packed = __reduce_add_sync(0xffffffffu, ((valid ? 1 : 0) + __popc(nrecSlow)) | (nclip << 10) | (nzero << 20));
+	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
+}
+
+// Two forms, chosen by the host per frame (each its own kernel: with both bodies inlined into one,
+// the instruction cache misses cost the many-small-meshes scene 15 us):
+//  * PERSIST = false, one CTA per cluster of the frame — when most clusters are expected to survive.
+//    The hardware balances the CTAs (a static round-robin cost the 20-object bench scene 6 us).
+//  * PERSIST = true, a few CTAs per SM, CTA b takes entries b, b + G, ... of the visible list that
+//    k_vertex built — when most clusters are culled: launching 78 000 CTAs only to have 85 % of them
+//    exit is bound by the CTA launch rate (4K, 10 M triangles, strip 1 of 8: k_setup 97 -> 37 us).
+template <int TM, bool PERSIST>
+__global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
+{
+	__shared__ unsigned long long shStat[2]; // summed acc of the CTA's threads; warps done
+	if (threadIdx.x < 2)
+		shStat[threadIdx.x] = 0ull;
+	__syncthreads();
+	pdlLaunchDependents();
+	const int lane = threadIdx.x & 31;
+	const int nCl = fp.nTriInst / MR_CLUSTER;
+	unsigned long long acc = 0ull;
+	if (!PERSIST)
+	{
+		// one CTA per cluster: the vertex indices (scene-static) are requested before waiting for
+		// k_vertex, so the verdict's round trip does not lengthen the surviving clusters' chain; a
+		// culled cluster's CTA exits on its flag
+		const ClusterTri k = locateAndLoadIndices<TM>(fp, blockIdx.x);
+		pdlWait(); // k_vertex's pv[], cluster verdicts and zeroed counters
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+		{
+			fp.ctr->visible = fp.cullClusters ? (unsigned)*fp.visCount : (unsigned)nCl;
+			fp.ctr->clusters = (unsigned)nCl;
+		}
+		if (!fp.cullClusters || fp.clusterVis[blockIdx.x] != 0)
+			setupCluster<TM>(fp, k, lane, acc);
+	}
+	else
+	{
+		// persistent CTAs walk the list of visible clusters
+		pdlWait();
+		const int nVis = fp.cullClusters ? *fp.visCount : nCl;
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+		{
+			fp.ctr->visible = (unsigned)nVis;
+			fp.ctr->clusters = (unsigned)nCl;
+		}
+		for (int i = blockIdx.x; i < nVis; i += gridDim.x)
+		{
+			const ClusterTri k = locateAndLoadIndices<TM>(fp, fp.cullClusters ? fp.visList[i] : i);
+			setupCluster<TM>(fp, k, lane, acc);
+		}
+	}
+
+	// ---- statistics: one shared-memory atomic per warp; the warp that arrives last sends one RED per
+	// counter (no barrier and no fence: finished warps leave at once). Fields are 20 bits wide: a CTA
+	// sets up at most a few thousand triangles ----
+	unsigned long long sum = acc;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		sum += __shfl_xor_sync(0xffffffffu, sum, o);
 	if (lane == 0)
 	{
-		const unsigned long long mine = (unsigned long long)(unsigned)packed | (1ull << 32);
-		const unsigned long long all = atomicAdd(&shStat, mine) + mine;
-		if ((int)(all >> 32) == MR_SETUP_THREADS / 32)
+		// the arrival count rides in the top bits of the same word, so one atomic both adds and tells
+		const unsigned long long mine = sum + (1ull << 60);
+		const unsigned long long all = atomicAdd(&shStat[0], mine) + mine;
+		if ((int)(all >> 60) == MR_SETUP_THREADS / 32)
 		{
 			const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
-			const int nr = (int)(all & 1023), nc = (int)((all >> 10) & 1023), nz = (int)((all >> 20) & 1023);
-			if (nr) atomicAdd(&fp.ctr->records[slot], (unsigned long long)nr);
-			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], (unsigned long long)nc);
-			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], (unsigned long long)nz);
+			const unsigned long long nr = all & 0xfffffull, nc = (all >> 20) & 0xfffffull, nz = (all >> 40) & 0xfffffull;
+			if (nr) atomicAdd(&fp.ctr->records[slot], nr);
+			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], nc);
+			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], nz);
 		}
 	}
 }
@@ -1201,6 +1288,8 @@ __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(co
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
 	pdlWait(); // k_setup's keys, bins and records
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+		*fp.visCount = 0; // k_setup has consumed the visible-cluster list: ready for the next frame's k_vertex
 	rasterTile<MR_RASTER_THREADS, TM>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
 }
 
@@ -1303,9 +1392,14 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	cfg.numAttrs = (ev || getenv("MR_NO_PDL")) ? 0 : 1;
 	if (fp.nTriInst > 0)
 	{
-		cfg.gridDim = dim3((fp.nTriInst + MR_SETUP_THREADS - 1) / MR_SETUP_THREADS);
+		const int nCl = fp.nTriInst / MR_CLUSTER;
+		const bool persist = fp.setupCtas < nCl;
+		cfg.gridDim = dim3(std::max(1, persist ? fp.setupCtas : nCl));
 		cfg.blockDim = dim3(MR_SETUP_THREADS);
-		cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE> : k_setup<TM_GLOBAL>, fp);
+		if (persist)
+			cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE, true> : k_setup<TM_GLOBAL, true>, fp);
+		else
+			cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE, false> : k_setup<TM_GLOBAL, false>, fp);
 	}
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (ev) cudaEventRecord(ev[3], stream);

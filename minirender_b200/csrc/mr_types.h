@@ -116,7 +116,8 @@ struct Counters
 	unsigned long long ovfTotal;    // entries appended to the overflow list (may exceed its capacity)
 	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
 	unsigned int pad0;
-	unsigned long long pad1[13];
+	unsigned int visible, clusters; // k_setup: clusters that survived culling / clusters of the frame (sizes the next frame's grid)
+	unsigned long long pad1[12];
 	// line 1 (offset 128): written by k_raster
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
 	unsigned int pad2;
@@ -163,7 +164,10 @@ struct FrameParams
 	// (bounding-sphere centre, radius), (normal-cone axis, sin(cone half-angle + margin) or 2 = no cone)
 	const float4* clusters;
 	const int* triBlockCl; // renderable of every k_setup CTA (MR_CLUSTER triangle instances)
-	int* clusterVis;       // per k_setup CTA: 0 = culled this frame (written by k_vertex)
+	int* clusterVis;       // per cluster: 0 = culled this frame (written by k_vertex)
+	int* visList;          // clusters that can reach a pixel of this frame (written by k_vertex, any order)
+	int* visCount;         // their number; zeroed again by k_raster once k_setup has consumed the list
+	int setupCtas;         // persistent k_setup CTAs
 	int nTriReal;          // triangles submitted (nTriInst counts the per-renderable padding too)
 	int cullClusters;      // 0: off (orthographic or non-standard projection)
 	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
