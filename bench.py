@@ -437,6 +437,7 @@ def run_strips(args, rank, local_rank, world):
                           "steps": K, "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "mtri_per_s": st.triangles_in / ms / 1e3, "mpix_per_s": W4 * H4 / ms / 1e3,
+                          "ms_per_step_device": dev_ms / K, "ms_per_step_host_wall": wall * 1000.0 / K,
                           "config": {"workload": "configs[2]: 3840x2160, createSphere(100,2237,2237) = 10.0M triangles, 256x256 float texture, "
                                                  "strips of whole tile rows per rank (sort-first: every rank sets up all triangles)",
                                      "gather": args.gather if world > 1 else "none", "l2": "working set (> 1 GB) exceeds the L2"},
