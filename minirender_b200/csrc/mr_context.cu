@@ -96,10 +96,10 @@ struct mr_ctx
 	unsigned sceneSerial;
 
 	// per-frame tables
-	DevBuf rstat, rdyn, mats, vtxBlockR, triBlockR, nrmBlockR;
+	DevBuf rstat, rdyn, mats, vtxBlockR;
 	std::vector<int> structureKey; // mesh id per renderable of the tables currently on the device
 	unsigned structureSerial;
-	int nVertInst, nTriInst, nNrmInst;
+	int nVertInst, nTriInst;
 	// per-frame host staging + counters, a ring so that mr_render never waits for the GPU
 	struct Slot
 	{
@@ -349,8 +349,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		return setError(c, MR_E_INVALID, "frame too large: %lld vertex instances, %lld triangle instances", vb, tb);
 	c->nVertInst = (int)vb;
 	c->nTriInst = (int)tb;
-	c->nNrmInst = (int)nb;
-	const int nVB = (c->nVertInst + 255) / 256, nTB = (c->nTriInst + 255) / 256, nNB = (c->nNrmInst + 255) / 256;
+	const int nVB = (c->nVertInst + 255) / 256;
 
 	// ---- device buffers ----
 	const int nTiles = c->tilesX * c->tilesY;
@@ -358,7 +357,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->rdyn.ensure(sizeof(RDyn) * (size_t)std::max(nR, 1)));
 	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
 	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
-	MR_CUDA(c, c->triBlockR.ensure(sizeof(int) * (size_t)(nTB + 1)));
 	const int nCB = c->nTriInst / MR_CLUSTER;
 	MR_CUDA(c, c->triBlockCl.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
 	MR_CUDA(c, c->visList.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
@@ -368,7 +366,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		MR_CUDA(c, c->visCount.ensure(256, true));
 		MR_CUDA(c, cudaMemsetAsync(c->visCount.p, 0, 256, c->stream));
 	}
-	MR_CUDA(c, c->nrmBlockR.ensure(sizeof(int) * (size_t)(nNB + 1)));
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
 	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
@@ -409,12 +406,10 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	// ---- stage per-frame tables in pinned memory, one async copy each ----
 	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
 	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)(nVB + 1);
-	const size_t szTB = sameStructure ? 0 : sizeof(int) * (size_t)(nTB + 1);
-	const size_t szNB = sameStructure ? 0 : sizeof(int) * (size_t)(nNB + 1);
 	const size_t szCB = sameStructure ? 0 : sizeof(int) * (size_t)nCB;
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
-	const size_t total = szStat + szVB + szTB + szNB + szCB + szDyn + szMat + 64;
+	const size_t total = szStat + szVB + szCB + szDyn + szMat + 64;
 	const int slotIndex = c->slotNext;
 	{
 		const int rc0 = retireSlot(c, slotIndex); // normally long finished
@@ -441,28 +436,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		vbr[nVB] = std::max(nR - 1, 0); // sentinel: upper bound of the last block's renderable range
 		if (szVB) MR_CUDA(c, cudaMemcpyAsync(c->vtxBlockR.p, sp + off, szVB, cudaMemcpyHostToDevice, c->stream));
 		off += szVB;
-		int* tbr = (int*)(sp + off);
-		for (int b = 0, r = 0; b < nTB; b++)
-		{
-			const int first = b * 256;
-			while (r + 1 < nR && first >= rs[r + 1].triBase)
-				r++;
-			tbr[b] = r;
-		}
-		tbr[nTB] = std::max(nR - 1, 0);
-		if (szTB) MR_CUDA(c, cudaMemcpyAsync(c->triBlockR.p, sp + off, szTB, cudaMemcpyHostToDevice, c->stream));
-		off += szTB;
-		int* nbr = (int*)(sp + off);
-		for (int b = 0, r = 0; b < nNB; b++)
-		{
-			const int first = b * 256;
-			while (r + 1 < nR && first >= rs[r + 1].nrmBase)
-				r++;
-			nbr[b] = r;
-		}
-		nbr[nNB] = std::max(nR - 1, 0);
-		if (szNB) MR_CUDA(c, cudaMemcpyAsync(c->nrmBlockR.p, sp + off, szNB, cudaMemcpyHostToDevice, c->stream));
-		off += szNB;
 		int* cbr = (int*)(sp + off);
 		for (int i = 0; i < nR; i++)
 		{
@@ -529,7 +502,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
 	if (szMat && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	c->h2dBytesLastFrame = szStat + szVB + szTB + szNB + szCB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
+	c->h2dBytesLastFrame = szStat + szVB + szCB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -594,7 +567,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.nVertInst = c->nVertInst;
 	fp.nTriInst = c->nTriInst;
 	fp.nTriReal = (int)triReal;
-	fp.nNrmInst = c->nNrmInst;
 	fp.debug = c->debugFlags;
 	fp.inlineTables = inlineTables ? 1 : 0;
 	if (inlineTables)
@@ -617,7 +589,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.rdyn = c->rdyn.as<RDyn>();
 	fp.mats = c->mats.as<MatDev>();
 	fp.vtxBlockR = c->vtxBlockR.as<int>();
-	fp.triBlockR = c->triBlockR.as<int>();
 	fp.triBlockCl = c->triBlockCl.as<int>();
 	fp.clusters = c->clusters.as<float4>();
 	fp.visList = c->visList.as<int>();
@@ -633,7 +604,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		                                              (double)triReal < 0.75 * (double)c->nTriInst);
 		fp.setupCtas = (e && atoi(e) > 0) ? c->smCount * atoi(e) : mostlyCulled ? c->smCount * 16 : 0x7fffffff;
 	}
-	fp.nrmBlockR = c->nrmBlockR.as<int>();
 	fp.pv = c->pv.as<float4>();
 	fp.gkeys = c->gkeys.as<unsigned long long>();
 	fp.recs = c->recs.as<float4>();
@@ -846,8 +816,8 @@ void mr_destroy(mr_ctx* c)
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->clusters, &c->triBlockCl, &c->clusterVis, &c->visList, &c->visCount, &c->rstat,
-		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->triBlockR, &c->pv, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->nrmBlockR, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->pv, &c->recs, &c->tileCount,
+		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)

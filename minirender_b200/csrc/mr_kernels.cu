@@ -1410,6 +1410,8 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 		cfg.blockDim = dim3(MR_RASTER_THREADS);
 		cudaLaunchKernelEx(&cfg, inl ? k_raster<TM_INLINE> : k_raster<TM_GLOBAL>, fp);
 	}
+	else
+		cudaMemsetAsync(fp.visCount, 0, sizeof(int), stream); // k_raster normally resets the visible-cluster count
 	if (ev) cudaEventRecord(ev[5], stream);
 }
 

@@ -144,7 +144,7 @@ struct FrameParams
 	int tileRow0, tileRows; // tile rows covered by this frame (strip rendering)
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
-	int nRenderables, nVertInst, nTriInst, nNrmInst;
+	int nRenderables, nVertInst, nTriInst;
 	int debug; // mr_set_debug flags
 	int binCap; // entries per tile bin
 	int ovfCap; // entries in the overflow list
@@ -172,8 +172,6 @@ struct FrameParams
 	int cullClusters;      // 0: off (orthographic or non-standard projection)
 	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
 	const int* vtxBlockR; // renderable that owns the first vertex instance of each 256-block
-	const int* triBlockR; // same for triangle instances
-	const int* nrmBlockR; // same for normal instances
 
 	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)

@@ -197,3 +197,20 @@ def test_two_output_slots_overlapped_reads_match_blocking_reads(be):
         assert (bits(got[i]) == bits(want[i])).all(), "frame %d differs" % i
     # back to one slot: the blocking path still sees the newest frame
     assert (bits(r.get_image()) == bits(want[4])).all()
+
+
+def test_row_range_outside_the_image_renders_nothing_and_leaves_no_state(be):
+    """A strip that lies outside the image launches no tile kernel; the frames after it must be
+    unaffected (per-frame scratch such as the visible-cluster list is reset either way)."""
+    setup = scenes.SMALL_SCENES["culling0"](be)
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    want_i, want_d = r.get_image().copy(), r.get_depth().copy()
+    for _ in range(3):
+        r.set_row_range(setup.height + 100, setup.height + 200)
+        r.render()
+    r.synchronize()
+    r.set_row_range(0, 0)
+    r.render()
+    assert (bits(r.get_depth()) == bits(want_d)).all()
+    assert (bits(r.get_image()) == bits(want_i)).all()
