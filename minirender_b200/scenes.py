@@ -286,7 +286,7 @@ def soup_scene(be, width=256, height=192, seed=0, tris=400, nan_fraction=0.02):
 
 
 
-def culling_scene(be, width=480, height=270, variant=0):
+def culling_scene(be, width=480, height=270, variant=0, tess=1.0):
     """Finely tessellated spheres (many 128-triangle clusters each) under the transforms that decide
     whether cluster culling may use normal cones: rotation + uniform scale (cones on), a mirror
     (negative determinant: the inside of the sphere is what the reference draws), a non-uniform
@@ -294,15 +294,16 @@ def culling_scene(be, width=480, height=270, variant=0):
     and meshes straddling the near plane and every screen edge."""
     sc = api.Scene(be, ambient=0.2)
     blue = sc.add_material(diffuse=(0.3, 0.4, 0.9), shininess=25.0)
-    sc.add_sphere(30.0, 40, 80, xf=be.mul(be.translate(-70, 10, 0), be.rotate_vec(0.3, 0.2, 0.5), be.scale(1.7, 1.7, 1.7)), material=blue)
-    sc.add_sphere(30.0, 40, 80, xf=be.mul(be.translate(60, -20, 10), be.scale(-1.0, 1.0, 1.0)))               # mirrored
-    sc.add_sphere(25.0, 40, 80, xf=be.mul(be.translate(0, 60, -30), be.rotate_z(f32(0.4)), be.scale(2.5, 0.6, 1.2)))  # non-uniform
+    q = lambda n: max(4, int(round(n * tess)))  # tessellation scale (the committed golden uses a coarse one)
+    sc.add_sphere(30.0, q(40), q(80), xf=be.mul(be.translate(-70, 10, 0), be.rotate_vec(0.3, 0.2, 0.5), be.scale(1.7, 1.7, 1.7)), material=blue)
+    sc.add_sphere(30.0, q(40), q(80), xf=be.mul(be.translate(60, -20, 10), be.scale(-1.0, 1.0, 1.0)))               # mirrored
+    sc.add_sphere(25.0, q(40), q(80), xf=be.mul(be.translate(0, 60, -30), be.rotate_z(f32(0.4)), be.scale(2.5, 0.6, 1.2)))  # non-uniform
     shear = np.eye(4, dtype=np.float32); shear[0, 1] = 0.8; shear[2, 0] = -0.5
-    sc.add_sphere(20.0, 30, 60, xf=be.mul(be.translate(10, -70, 20), shear))
-    sc.add_sphere(400.0, 60, 120, xf=be.scale(1.0, -1.0, 1.0),
+    sc.add_sphere(20.0, q(30), q(60), xf=be.mul(be.translate(10, -70, 20), shear))
+    sc.add_sphere(400.0, q(60), q(120), xf=be.scale(1.0, -1.0, 1.0),
                   material=sc.add_material(diffuse=(0.5, 0.5, 0.4), shininess=0.0))                          # camera inside, mirrored: its inside shows
-    sc.add_sphere(30.0, 40, 80, xf=be.translate(150, 0, 160))                                                # around the near plane
-    sc.add_cylinder(20.0, 300.0, 64, 40, True, xf=be.mul(be.translate(-150, 0, 0), be.rotate_x(f32(1.2))))  # across the screen edge
+    sc.add_sphere(30.0, q(40), q(80), xf=be.translate(150, 0, 160))                                                # around the near plane
+    sc.add_cylinder(20.0, 300.0, q(64), q(40), True, xf=be.mul(be.translate(-150, 0, 0), be.rotate_x(f32(1.2))))  # across the screen edge
     d = [200.0, 120.0, 320.0][variant % 3]
     view = be.mul(be.translate(0, 0, -d), be.rotate_x(f32(-0.9 + 0.3 * variant)), be.rotate_z(f32(0.5 * variant)))
     return Setup("culling%d" % variant, sc, width, height, frustum(be, width, height, 50.0, 10.0, 3000.0), view, point_light=(variant == 1),

@@ -31,6 +31,7 @@ GOLDEN = {
     "textured": lambda be: scenes.textured_scene(be, width=144, height=96),
     "big_triangles": lambda be: scenes.big_triangles_scene(be, width=100, height=75, count=10),
     "soup_nan": lambda be: scenes.soup_scene(be, width=96, height=72, seed=4, tris=150, nan_fraction=0.05),
+    "culling": lambda be: scenes.culling_scene(be, width=160, height=90, variant=2, tess=0.4),
     "bench_tiny": lambda be: scenes.bench_scene(be, width=160, height=90, objects=3, m=16, n=16),
 }
 
