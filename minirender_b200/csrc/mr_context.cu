@@ -360,7 +360,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	const int nCB = c->nTriInst / MR_CLUSTER;
 	MR_CUDA(c, c->triBlockCl.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
 	MR_CUDA(c, c->visList.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
-	MR_CUDA(c, c->clusterVis.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
+	MR_CUDA(c, c->clusterVis.ensure(sizeof(unsigned) * ((size_t)nCB / 32 + 16))); // k_vertex writes whole 256-cluster blocks
 	if (!c->visCount.p)
 	{
 		MR_CUDA(c, c->visCount.ensure(256, true));
@@ -592,7 +592,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.triBlockCl = c->triBlockCl.as<int>();
 	fp.clusters = c->clusters.as<float4>();
 	fp.visList = c->visList.as<int>();
-	fp.clusterVis = c->clusterVis.as<int>();
+	fp.clusterVis = c->clusterVis.as<unsigned>();
 	fp.visCount = c->visCount.as<int>();
 	{
 		const char* e = getenv("MR_SETUP_CTAS_PER_SM");

@@ -164,7 +164,7 @@ struct FrameParams
 	// (bounding-sphere centre, radius), (normal-cone axis, sin(cone half-angle + margin) or 2 = no cone)
 	const float4* clusters;
 	const int* triBlockCl; // renderable of every k_setup CTA (MR_CLUSTER triangle instances)
-	int* clusterVis;       // per cluster: 0 = culled this frame (written by k_vertex)
+	unsigned* clusterVis;  // a bit per cluster: 0 = culled this frame (written by k_vertex, one word per warp)
 	int* visList;          // clusters that can reach a pixel of this frame (written by k_vertex, any order)
 	int* visCount;         // their number; zeroed again by k_raster once k_setup has consumed the list
 	int setupCtas;         // persistent k_setup CTAs
