@@ -369,7 +369,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
 	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
-	MR_CUDA(c, c->tileCount.ensure(sizeof(int) * (size_t)(nTiles + 1)));
+	MR_CUDA(c, c->tileCount.ensure(sizeof(int2) * (size_t)(nTiles + 1)));
 	MR_CUDA(c, c->ctr.ensure(sizeof(Counters) * mr_ctx::kSlots));
 	{
 		// Bin capacity: a power of two, at least 256 and at least 8x the mean triangles per tile,
@@ -579,6 +579,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
 	fp.pos4 = c->pos4.as<float4>();
 	fp.nrm4 = c->nrm4.as<float4>();
+	fp.nNrmSrc = (int)std::min<size_t>(c->nrm4.cap / sizeof(float4), 0x7fffffff);
 	fp.uv2 = c->uv2.as<float2>();
 	fp.idxPos = c->idxPos.as<int>();
 	fp.idxNrm = c->idxNrm.as<int>();
@@ -608,7 +609,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.gkeys = c->gkeys.as<unsigned long long>();
 	fp.recs = c->recs.as<float4>();
 	fp.recs1 = c->recs1.as<float4>();
-	fp.tileCount = c->tileCount.as<int>();
+	fp.tileCount = c->tileCount.as<int2>();
 	fp.ovfPairs = c->ovfPairs.as<int2>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>() + slotIndex; // per-slot counters: the read-back overlaps the next frame

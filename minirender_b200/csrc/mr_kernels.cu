@@ -22,6 +22,19 @@ namespace {
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
+// Software prefetch (no destination register: costs an issue slot, no register pressure).
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef MR_PREFETCH_NIDX
+#define MR_PREFETCH_NIDX 1 // k_setup: 1 = a triangle's normal / texcoord indices into L2 while it is set up, 2 = into L1
+#endif
+#ifndef MR_PREFETCH_ATTR
+#define MR_PREFETCH_ATTR 0 // k_setup: 1 = a set-up triangle's normals into L2 before its pixel loop, 2 = into L1
+#endif
+#ifndef MR_PREFETCH_NRM
+#define MR_PREFETCH_NRM 0 // k_vertex: 1 = the scene's normals into L2 for k_setup
+#endif
+
 struct V3 { float x, y, z; };
 
 __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 	const int vi = blockIdx.x * 256 + threadIdx.x;
 	const int nTiles = fp.tilesX * fp.tilesY;
 	if (vi <= nTiles)
-		fp.tileCount[vi] = 0;
+		fp.tileCount[vi] = make_int2(0, 0);
 	if (vi < (int)(sizeof(Counters) / 8))
 		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriReal : 0ull; // word 0 = trianglesIn
 	if (fp.cullClusters && blockIdx.x * 256 < fp.nTriInst / MR_CLUSTER)
@@ -209,6 +222,10 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 				fp.visList[base + __popc(m & ((1u << lane) - 1u))] = vi;
 		}
 	}
+#if MR_PREFETCH_NRM
+	if (vi < fp.nNrmSrc)
+		prefetchL2(fp.nrm4 + vi);
+#endif
 	if (blockIdx.x * 256 >= fp.nVertInst)
 		return;
 	const int rv = findRenderable<256, TM>(fp, fp.vtxBlockR, vi, 0, shBases);
@@ -480,7 +497,7 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 	{
 		const int row = k / nx;
 		const int tile = (ty0 + row) * fp.tilesX + tx0 + k - row * nx;
-		binStore(fp, tile, atomicAdd(&fp.tileCount[tile], 1), id);
+		binStore(fp, tile, atomicAdd(&fp.tileCount[tile].x, 1), id);
 	}
 }
 
@@ -570,6 +587,16 @@ __device__ __forceinline__ ClusterTri locateAndLoadIndices(const FrameParams& fp
 	{
 		const int* ix = fp.idxPos + (size_t)(k.rs->idxBase + k.tri) * 3;
 		k.ia = __ldg(ix); k.ib = __ldg(ix + 1); k.ic = __ldg(ix + 2);
+#if MR_PREFETCH_NIDX
+		// the survivors' second chain of dependent loads starts at these indices
+		const int* in = fp.idxNrm + (size_t)(k.rs->idxBase + k.tri) * 3;
+		if (MR_PREFETCH_NIDX == 2) prefetchL1(in); else prefetchL2(in);
+		if (k.rs->uvTriBase >= 0)
+		{
+			const int* iu = fp.idxUv + (size_t)(k.rs->uvTriBase + k.tri) * 3;
+			if (MR_PREFETCH_NIDX == 2) prefetchL1(iu); else prefetchL2(iu);
+		}
+#endif
 	}
 	return k;
 }
@@ -602,6 +629,17 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 		else if (setupTriangle(fp, a, b, c, s))
 		{
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
+#if MR_PREFETCH_ATTR
+			if (valid)
+			{
+				// the normals come from DRAM: ask for them now, the pixel loop hides the round trip
+				const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
+				const float4* nb = fp.nrm4 + rs.nrmSrcBase;
+				const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
+				if (MR_PREFETCH_ATTR == 2) { prefetchL1(nb + in0); prefetchL1(nb + in1); prefetchL1(nb + in2); }
+				else { prefetchL2(nb + in0); prefetchL2(nb + in1); prefetchL2(nb + in2); }
+			}
+#endif
 			if (valid)
 			{
 				if ((s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= MR_SMALL_AREA)
@@ -626,6 +664,25 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 		}
 	}
 	__syncwarp();
+
+	// ---- tiles that may have received fragments of this warp's small triangles: the tiles of the union
+	// of their bboxes get their "touched" word set (plain idempotent stores, a handful per warp). The tile
+	// kernel does not even read the depth keys of a tile nothing has touched. ----
+	{
+		const bool emitted = valid && !binned;
+		const int ya = max(s.y0, fp.rowBegin), yb = min(s.y1, fp.rowEnd - 1);
+		const int tx0 = __reduce_min_sync(0xffffffffu, emitted ? (s.x0 >> MR_TILE_SHIFT) : 0x7fff);
+		const int tx1 = __reduce_max_sync(0xffffffffu, emitted ? (s.x1 >> MR_TILE_SHIFT) : -1);
+		const int ty0 = __reduce_min_sync(0xffffffffu, emitted ? (ya >> MR_TILE_SHIFT) : 0x7fff);
+		const int ty1 = __reduce_max_sync(0xffffffffu, emitted ? (yb >> MR_TILE_SHIFT) : -1);
+		if (tx1 >= tx0)
+		{
+			// 8 x 4 tiles per pass (a warp of neighbouring small triangles spans a few tiles)
+			for (int ty = ty0 + (lane >> 3); ty <= ty1; ty += 4)
+				for (int tx = tx0 + (lane & 7); tx <= tx1; tx += 8)
+					fp.tileCount[ty * fp.tilesX + tx].y = 1;
+		}
+	}
 
 	// ---- binning of the larger triangles: up to MR_SEG_PER_LANE tiles each, warp-aggregated ----
 	if (__any_sync(0xffffffffu, binned))
@@ -656,7 +713,7 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 				{
 					tileOf[k] = tile;
 					if (lane == leadOf[k])
-						baseOf[k] = atomicAdd(&fp.tileCount[tile], __popc(peers));
+						baseOf[k] = atomicAdd(&fp.tileCount[tile].x, __popc(peers));
 				}
 			}
 		}
@@ -1216,6 +1273,15 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
 	// the common case: every pixel of the tile belongs to this frame (no per-pixel bounds tests)
 	const bool full = PP == 2 && NT == 128 && vec && tileY0 >= fp.rowBegin && tileY0 + MR_TILE <= fp.rowEnd && tileY0 + MR_TILE <= fp.h;
+	// x: larger triangles binned to this tile, y: fragments of small triangles may have reached its keys
+	const int2 tinfo = fp.tileCount[tile];
+	const int total = tinfo.x;
+	if (full && tinfo.x == 0 && tinfo.y == 0 && !(fp.saveNormals && fp.normals) && !fp.winner)
+	{
+		// nothing has touched this tile: clear values only (Renderer.cpp:113-119), its keys are not even read
+		storeFullTile128<true>(fp, tileX0, tileY0, tid, 0);
+		return;
+	}
 	// ---- phase 0: the tile's keys out of gkeys, merged with the clear / kept depth; gkeys reset ----
 	unsigned long long key[PP];
 	const unsigned long long clearKey = (unsigned long long)zkey(1e11f) << 32;
@@ -1248,7 +1314,6 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 			key[pp] = (g < base) ? g : base;
 		}
 	}
-	const int total = fp.tileCount[tile]; // larger triangles binned to this tile
 	unsigned long long ovfTotal = 0ull;
 	if (total > fp.binCap)
 	{

@@ -168,6 +168,7 @@ struct FrameParams
 	int* visList;          // clusters that can reach a pixel of this frame (written by k_vertex, any order)
 	int* visCount;         // their number; zeroed again by k_raster once k_setup has consumed the list
 	int setupCtas;         // persistent k_setup CTAs
+	int nNrmSrc;           // float4 elements of nrm4 that may be prefetched
 	int nTriReal;          // triangles submitted (nTriInst counts the per-renderable padding too)
 	int cullClusters;      // 0: off (orthographic or non-standard projection)
 	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
@@ -177,7 +178,8 @@ struct FrameParams
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
 	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field k, lane (t & 31)
 	float4* recs1;       // records of sub-triangle 1 (second clipper output): MR_REC_FIELDS float4 per triangle
-	int* tileCount;      // triangles binned per tile (may exceed binCap: the rest is in ovfPairs)
+	int2* tileCount;     // per tile: x = triangles binned (may exceed binCap: the rest is in ovfPairs),
+	                     // y = nonzero if fragments of small triangles may have reached the tile's gkeys
 	int* bins;           // tilesX*tilesY bins of binCap record indices
 	int2* ovfPairs;      // (tile, record) entries that did not fit their bin
 	Counters* ctr;
