@@ -677,10 +677,17 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 		const int ty1 = __reduce_max_sync(0xffffffffu, emitted ? (yb >> MR_TILE_SHIFT) : -1);
 		if (tx1 >= tx0)
 		{
-			// 8 x 4 tiles per pass (a warp of neighbouring small triangles spans a few tiles)
-			for (int ty = ty0 + (lane >> 3); ty <= ty1; ty += 4)
-				for (int tx = tx0 + (lane & 7); tx <= tx1; tx += 8)
+			// 8 x 4 tiles per pass; a warp of neighbouring small triangles spans a few tiles: one pass
+			const int tx = tx0 + (lane & 7), ty = ty0 + (lane >> 3);
+			if (tx1 - tx0 < 8 && ty1 - ty0 < 4)
+			{
+				if (tx <= tx1 && ty <= ty1)
 					fp.tileCount[ty * fp.tilesX + tx].y = 1;
+			}
+			else
+				for (int y = ty; y <= ty1; y += 4)
+					for (int x = tx; x <= tx1; x += 8)
+						fp.tileCount[y * fp.tilesX + x].y = 1;
 		}
 	}
 
@@ -1040,9 +1047,7 @@ __device__ __forceinline__ float4 clearRgb4(const FrameParams& fp, int j)
 {
 	// channel of the first of the four floats: (4 j) mod 3 == j mod 3; j / 3 == (11 j) >> 5 for j < 12
 	const int c = j - 3 * ((j * 11) >> 5);
-	const float r = fp.bg[0], g = fp.bg[1], b = fp.bg[2];
-	const float b0 = (c == 0) ? r : (c == 1) ? g : b, b1 = (c == 0) ? g : (c == 1) ? b : r, b2 = (c == 0) ? b : (c == 1) ? r : g;
-	return make_float4(b0, b1, b2, b0);
+	return make_float4(fp.bgPattern[c], fp.bgPattern[c + 1], fp.bgPattern[c + 2], fp.bgPattern[c + 3]); // r g b r g b, indexed in the constant bank
 }
 
 template <bool CLEAR>
@@ -1272,7 +1277,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	// float4 row stores need 16-byte aligned rows and a tile that lies fully inside the image width
 	const bool vec = ((fp.w & 3) == 0) && (tileX0 + MR_TILE <= fp.w) && !fp.keep;
 	// the common case: every pixel of the tile belongs to this frame (no per-pixel bounds tests)
-	const bool full = PP == 2 && NT == 128 && vec && tileY0 >= fp.rowBegin && tileY0 + MR_TILE <= fp.rowEnd && tileY0 + MR_TILE <= fp.h;
+	const bool full = PP == 2 && NT == 128 && tx < fp.fullTx && ty >= fp.fullTy0 && ty < fp.fullTy1;
 	// x: larger triangles binned to this tile, y: fragments of small triangles may have reached its keys
 	const int2 tinfo = fp.tileCount[tile];
 	const int total = tinfo.x;

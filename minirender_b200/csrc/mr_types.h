@@ -142,6 +142,10 @@ struct FrameParams
 	int w, h;
 	int tilesX, tilesY;
 	int tileRow0, tileRows; // tile rows covered by this frame (strip rendering)
+	// Tiles tx < fullTx, fullTy0 <= ty < fullTy1 lie fully inside the image and the strip and may be stored as
+	// whole float4 rows (width a multiple of 4, not an accumulating frame): no per-pixel bounds tests there.
+	int fullTx, fullTy0, fullTy1;
+	float bgPattern[6];     // r g b r g b
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int nRenderables, nVertInst, nTriInst;
