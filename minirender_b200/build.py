@@ -69,6 +69,8 @@ def build_product(force=False, verbose=False):
         o = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
         if force or _newer(o, [s] + headers):
             _run([NVCC] + NVCC_FLAGS + EXTRA + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o], log)
+            if src.endswith("mr_kernels.cu") and not EXTRA:
+                check_wide_ops(o)
         objs.append(o)
     for src in CXX_SOURCES:
         s = os.path.join(PKG, src)
@@ -81,6 +83,30 @@ def build_product(force=False, verbose=False):
     if verbose:
         sys.stdout.write("".join(log))
     return LIB
+
+
+def check_wide_ops(obj):
+    """ptxas 12.9 was seen to assemble a `st.global.v8.f32` (Blackwell 256-bit store) as a plain 32-bit STG
+    in one out-of-line function, which silently drops 28 of 32 bytes. Count the wide instructions the
+    kernels are written to contain, so that a miscompile fails the build instead of a parity test."""
+    dump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(dump):
+        return
+    sass = subprocess.run([dump, "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
+    counts, fn = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            counts[fn] = [0, 0]
+        elif fn and "STG.E.ENL2.256" in line:
+            counts[fn][0] += 1
+        elif fn and "LDG.E.ENL2.256" in line:
+            counts[fn][1] += 1
+    for fn, (st, ld) in counts.items():
+        if "k_setup" in fn and st != 5:
+            raise RuntimeError("k_setup: expected 5 STG.256 (record pairs), found %d in %s" % (st, fn))
+        if "k_raster" in fn and (st != 3 or ld < 10):
+            raise RuntimeError("k_raster: expected 3 STG.256 / >= 10 LDG.256, found %d / %d in %s" % (st, ld, fn))
 
 
 def build_oracle():

@@ -529,11 +529,11 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.tileRow0 = rb >> MR_TILE_SHIFT;
 	fp.tileRows = (re > rb) ? ((re + MR_TILE - 1) >> MR_TILE_SHIFT) - fp.tileRow0 : 0;
 	{
-		const bool vecOk = (c->w & 3) == 0 && !f->keep;
+		const bool vecOk = (c->w & 7) == 0 && !f->keep;
 		fp.fullTx = vecOk ? c->w >> MR_TILE_SHIFT : 0;
 		fp.fullTy0 = (rb + MR_TILE - 1) >> MR_TILE_SHIFT;
 		fp.fullTy1 = std::min(re, c->h) >> MR_TILE_SHIFT;
-		for (int k = 0; k < 6; k++)
+		for (int k = 0; k < 12; k++)
 			fp.bgPattern[k] = f->background[k % 3];
 	}
 	fp.persp = f->projection[15] == 0.0f;

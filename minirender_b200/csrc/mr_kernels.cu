@@ -340,15 +340,48 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 	return any;
 }
 
-// Where record `id` = 2 * triangle instance + clipper output lives. Field k (a float4: 0-3 raster
-// record, 4-9 shading record) is at p[k * stride].
+// Where record `id` = 2 * triangle instance + clipper output lives. A record is 10 float4 fields (0-3
+// raster record, 4-9 shading record) moved as 5 *pairs* of 32 bytes: Blackwell's 256-bit global loads and
+// stores (LDG.256 / STG.256) carry one pair per instruction, and a pair is exactly one DRAM / L2 sector.
+// Pair j (fields 2j, 2j+1) is at p[j * stride].
 //  * sub-triangle 0 (every unclipped triangle): *plane* layout. The 32 triangles of a setup warp form
-//    a block of 10 planes of 32 float4, so each field is written by one fully coalesced 512-byte
-//    store per warp, and neighbouring winners read neighbouring slots of the same lines.
+//    a block of 5 planes of 32 pairs, so each pair is written by one fully coalesced 1 KB store per warp,
+//    and neighbouring winners read neighbouring sectors of the same lines.
 //  * sub-triangle 1 (second clipper output, rare): plain 160-byte records in recs1.
+struct __align__(32) F8
+{
+	float4 a, b;
+};
+
+__device__ __forceinline__ F8 ldPair(const F8* p) // read-only path (records are written by an earlier kernel)
+{
+	F8 r;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+	             : "l"(p));
+	return r;
+}
+
+// WIDE = false: two 16-byte stores. (ptxas 12.9 assembles st.global.v8 inside the out-of-line near-plane
+// path as a plain 32-bit STG — found through the clipping parity test — so that rare path keeps float4 stores;
+// minirender_b200/build.py counts the wide instructions in the SASS after every compile.)
+template <bool WIDE>
+__device__ __forceinline__ void stPair(F8* p, const float4 a, const float4 b)
+{
+	if (WIDE)
+		asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+		             "f"(b.z), "f"(b.w)
+		             : "memory");
+	else
+	{
+		reinterpret_cast<float4*>(p)[0] = a;
+		reinterpret_cast<float4*>(p)[1] = b;
+	}
+}
+
 struct RecRef
 {
-	float4* p;
+	F8* p;
 	int stride;
 };
 
@@ -358,24 +391,24 @@ __device__ __forceinline__ RecRef recRef(const FrameParams& fp, int id)
 	RecRef r;
 	if (id & 1)
 	{
-		r.p = fp.recs1 + (size_t)t * MR_REC_FIELDS;
+		r.p = reinterpret_cast<F8*>(fp.recs1) + (size_t)t * (MR_REC_FIELDS / 2);
 		r.stride = 1;
 	}
 	else
 	{
-		r.p = fp.recs + (size_t)(t >> 5) * (MR_REC_FIELDS * 32) + (t & 31);
+		r.p = reinterpret_cast<F8*>(fp.recs) + (size_t)(t >> 5) * (MR_REC_FIELDS / 2 * 32) + (t & 31);
 		r.stride = 32;
 	}
 	return r;
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission)
 {
-	d.p[0] = make_float4(a.x, a.y, c.x, c.y);
-	d.p[d.stride] = make_float4(s.n1x, s.n1y, s.n2x, s.n2y);
-	d.p[2 * d.stride] = make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material));
-	d.p[3 * d.stride] = make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
-	                                __uint_as_float(s.flags), __uint_as_float((uint32_t)submission));
+	stPair<WIDE>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
+	stPair<WIDE>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
+	       make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
+	                   __uint_as_float(s.flags), __uint_as_float((uint32_t)submission)));
 }
 
 // One corner in view space: what paintMesh's loops A/B/C hand to paintTriangle (Renderer.cpp:344-380).
@@ -384,14 +417,12 @@ struct Corner
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
+template <bool WIDE>
 __device__ __forceinline__ void storeShadeRec(const RecRef d, const Corner& c0, const Corner& c1, const Corner& c2)
 {
-	d.p[4 * d.stride] = make_float4(c0.px, c0.py, c0.pz, c0.u);
-	d.p[5 * d.stride] = make_float4(c1.px, c1.py, c1.pz, c0.v);
-	d.p[6 * d.stride] = make_float4(c2.px, c2.py, c2.pz, c1.u);
-	d.p[7 * d.stride] = make_float4(c0.nx, c0.ny, c0.nz, c1.v);
-	d.p[8 * d.stride] = make_float4(c1.nx, c1.ny, c1.nz, c2.u);
-	d.p[9 * d.stride] = make_float4(c2.nx, c2.ny, c2.nz, c2.v);
+	stPair<WIDE>(d.p + 2 * d.stride, make_float4(c0.px, c0.py, c0.pz, c0.u), make_float4(c1.px, c1.py, c1.pz, c0.v));
+	stPair<WIDE>(d.p + 3 * d.stride, make_float4(c2.px, c2.py, c2.pz, c1.u), make_float4(c0.nx, c0.ny, c0.nz, c1.v));
+	stPair<WIDE>(d.p + 4 * d.stride, make_float4(c1.nx, c1.ny, c1.nz, c2.u), make_float4(c2.nx, c2.ny, c2.nz, c2.v));
 }
 
 // The three view-space corners of triangle `tri` of renderable r: gathers the mesh's positions,
@@ -505,7 +536,7 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 // the records (the caller's warp bins them). Returns a bit per stored sub-triangle. Self-contained
 // so that its stack never touches the fast path.
 template <int TM>
-__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic)
+__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic, uint2* spans)
 {
 	const RStat rs = frameRstat<TM>(fp)[r];
 	Corner v0, v1, v2;
@@ -528,8 +559,9 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
 		const RecRef ref = recRef(fp, id);
-		storeRec(ref, a, b, c, s, material, 2 * (rs.triBaseReal + tri) + sub);
-		storeShadeRec(ref, o0, o1, o2);
+		storeRec<false>(ref, a, b, c, s, material, 2 * (rs.triBaseReal + tri) + sub);
+		storeShadeRec<false>(ref, o0, o1, o2);
+		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
 		nrec |= 1 << sub;
 	}
 	return nrec;
@@ -609,6 +641,8 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 	const bool active = k.active;
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
+	uint2 clipSpans[2]; // bbox spans of the clipper's output triangles (the warp bins them below)
+	clipSpans[0] = clipSpans[1] = make_uint2(0u, 0u);
 	Setup s;
 	s.x0 = s.x1 = s.y0 = s.y1 = 0;
 	s.flags = 0u;
@@ -623,7 +657,7 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 			if (!(a.z > zn && b.z > zn && c.z > zn))
 			{
 				nclip = 1;
-				nrecSlow = setupClipped<TM>(fp, t, r, tri, ia, ib, ic);
+				nrecSlow = setupClipped<TM>(fp, t, r, tri, ia, ib, ic, clipSpans);
 			}
 		}
 		else if (setupTriangle(fp, a, b, c, s))
@@ -658,8 +692,8 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 				Corner c0, c1, c2;
 				viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
 				const RecRef ref = recRef(fp, 2 * t);
-				storeRec(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material, 2 * (rs.triBaseReal + tri));
-				storeShadeRec(ref, c0, c1, c2);
+				storeRec<true>(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material, 2 * (rs.triBaseReal + tri));
+				storeShadeRec<true>(ref, c0, c1, c2);
 			}
 		}
 	}
@@ -753,9 +787,7 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 			if (subs & (1 << sub))
 			{
 				const int id = 2 * (t - lane + src) + sub;
-				const RecRef ref = recRef(fp, id);
-				const float4 q3 = ref.p[3 * ref.stride]; // spans written by setupClipped
-				const uint32_t xs = __float_as_uint(q3.x), ys = __float_as_uint(q3.y);
+				const uint32_t xs = __shfl_sync(0xffffffffu, clipSpans[sub].x, src), ys = __shfl_sync(0xffffffffu, clipSpans[sub].y, src);
 				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16);
 			}
 	}
@@ -1001,8 +1033,9 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 // Tile output staging: 16 rows x (48 rgb floats + 16 depth floats); written to HBM as float4 rows.
 struct TileOut
 {
-	float rgb[MR_TILE][MR_TILE * 3];
-	float z[MR_TILE][MR_TILE];
+	// per pixel row: 48 rgb floats then 16 depth floats = 8 sectors of 32 bytes, in the order the tile store
+	// sends them out; rows padded to 72 floats (keeps 32-byte alignment, spreads the rows over the banks)
+	float px[MR_TILE][72];
 };
 
 // Writes a tile's rows to the framebuffer as float4: 12 per row of rgb (192 B), 4 per row of depth
@@ -1016,7 +1049,7 @@ __device__ __forceinline__ void storeTileRows(const FrameParams& fp, int tileX0,
 		{
 			float4 v;
 			if (to)
-				v = *reinterpret_cast<const float4*>(&to->rgb[row][4 * j]);
+				v = *reinterpret_cast<const float4*>(&to->px[row][4 * j]);
 			else
 			{
 				// channel of the first of the four floats: (4 j) mod 3 == j mod 3
@@ -1033,43 +1066,35 @@ __device__ __forceinline__ void storeTileRows(const FrameParams& fp, int tileX0,
 		const int t = tid - MR_TILE * 12, row = t >> 2, j = t & 3, y = tileY0 + row;
 		if (y < fp.h && y >= fp.rowBegin && y < fp.rowEnd)
 		{
-			const float4 v = to ? *reinterpret_cast<const float4*>(&to->z[row][4 * j]) : make_float4(1e11f, 1e11f, 1e11f, 1e11f);
+			const float4 v = to ? *reinterpret_cast<const float4*>(&to->px[row][48 + 4 * j]) : make_float4(1e11f, 1e11f, 1e11f, 1e11f);
 			*reinterpret_cast<float4*>(fp.depth + (size_t)y * fp.w + tileX0 + 4 * j) = v;
 		}
 	}
 }
 
 // The same for a tile that lies fully inside the image and the strip (almost every tile), by a CTA of
-// 128 threads, two float4 each and no bounds tests or divisions: rows of 12 rgb float4 (192 B) are
-// covered by (thread >> 3, thread & 7) and (thread >> 2, 8 + (thread & 3)), the 4 depth float4 of a row
-// by threads 64..127.
-__device__ __forceinline__ float4 clearRgb4(const FrameParams& fp, int j)
-{
-	// channel of the first of the four floats: (4 j) mod 3 == j mod 3; j / 3 == (11 j) >> 5 for j < 12
-	const int c = j - 3 * ((j * 11) >> 5);
-	return make_float4(fp.bgPattern[c], fp.bgPattern[c + 1], fp.bgPattern[c + 2], fp.bgPattern[c + 3]); // r g b r g b, indexed in the constant bank
-}
-
+// 128 threads: a tile is 16 rows x (6 sectors of rgb + 2 sectors of depth) = 128 sectors of 32 bytes, one
+// 256-bit store (STG.256) per thread, no bounds tests. Needs an image width that is a multiple of 8.
 template <bool CLEAR>
 __device__ __forceinline__ void storeFullTile128(const FrameParams& fp, int tileX0, int tileY0, int tid, const TileOut* to)
 {
+	const int row = tid >> 3, j = tid & 7;
+	const size_t pix = (size_t)(tileY0 + row) * fp.w + tileX0;
+	float* dst = (j < 6) ? fp.image + 3 * pix + 8 * j : fp.depth + pix + 8 * (j - 6);
+	float4 v0, v1;
+	if (CLEAR)
 	{
-		const int row = tid >> 3, j = tid & 7;
-		const float4 v = CLEAR ? clearRgb4(fp, j) : *reinterpret_cast<const float4*>(&to->rgb[row][4 * j]);
-		*reinterpret_cast<float4*>(fp.image + 3 * ((size_t)(tileY0 + row) * fp.w + tileX0) + 4 * j) = v;
-	}
-	if (tid < 64)
-	{
-		const int row = tid >> 2, j = 8 + (tid & 3);
-		const float4 v = CLEAR ? clearRgb4(fp, j) : *reinterpret_cast<const float4*>(&to->rgb[row][4 * j]);
-		*reinterpret_cast<float4*>(fp.image + 3 * ((size_t)(tileY0 + row) * fp.w + tileX0) + 4 * j) = v;
+		// rgb sector j starts at float 8 j of the row: channel (8 j) mod 3 = (2 j) mod 3; bgPattern = r g b r g b ...
+		const int c = (2 * j) % 3;
+		v0 = (j < 6) ? make_float4(fp.bgPattern[c], fp.bgPattern[c + 1], fp.bgPattern[c + 2], fp.bgPattern[c + 3]) : make_float4(1e11f, 1e11f, 1e11f, 1e11f);
+		v1 = (j < 6) ? make_float4(fp.bgPattern[c + 4], fp.bgPattern[c + 5], fp.bgPattern[c + 6], fp.bgPattern[c + 7]) : v0;
 	}
 	else
 	{
-		const int row = (tid - 64) >> 2, j = tid & 3;
-		const float4 v = CLEAR ? make_float4(1e11f, 1e11f, 1e11f, 1e11f) : *reinterpret_cast<const float4*>(&to->z[row][4 * j]);
-		*reinterpret_cast<float4*>(fp.depth + (size_t)(tileY0 + row) * fp.w + tileX0 + 4 * j) = v;
+		v0 = *reinterpret_cast<const float4*>(&to->px[row][8 * j]);
+		v1 = *reinterpret_cast<const float4*>(&to->px[row][8 * j + 4]);
 	}
+	stPair<true>(reinterpret_cast<F8*>(dst), v0, v1);
 }
 
 // Phase 1 for one batch of up to 32 binned triangles (a lane each; `have` lanes hold record `id`).
@@ -1081,7 +1106,8 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	if (have)
 	{
 		const RecRef ref = recRef(fp, id);
-		q0 = __ldg(ref.p); q1 = __ldg(ref.p + ref.stride); q2 = __ldg(ref.p + 2 * ref.stride); q3 = __ldg(ref.p + 3 * ref.stride);
+		const F8 f01 = ldPair(ref.p), f23 = ldPair(ref.p + ref.stride);
+		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b;
 		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 	}
 	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
@@ -1170,13 +1196,14 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	{
 		id = (int)(win - 1u);
 		const RecRef ref = recRef(fp, id);
-		const float4* r4 = ref.p;
+		const F8* r8 = ref.p;
 		const int st = ref.stride;
-		q0 = __ldg(r4); q1 = __ldg(r4 + st); q2 = __ldg(r4 + 2 * st); q3 = __ldg(r4 + 3 * st);
+		const F8 f01 = ldPair(r8), f23 = ldPair(r8 + st);
+		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b;
 		if (attrs)
 		{
-			s0 = __ldg(r4 + 4 * st); s1 = __ldg(r4 + 5 * st); s2 = __ldg(r4 + 6 * st);
-			s3 = __ldg(r4 + 7 * st); s4 = __ldg(r4 + 8 * st); s5 = __ldg(r4 + 9 * st);
+			const F8 f45 = ldPair(r8 + 2 * st), f67 = ldPair(r8 + 3 * st), f89 = ldPair(r8 + 4 * st);
+			s0 = f45.a; s1 = f45.b; s2 = f67.a; s3 = f67.b; s4 = f89.a; s5 = f89.b;
 		}
 	}
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a warp covers 2 or 4 rows) that share a
@@ -1408,11 +1435,11 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		if (PP == 2)
 		{
 			const int pi = 2 * tid, r = pi >> 4, c = pi & 15; // c even: 24 contiguous, 8-byte aligned bytes of rgb
-			float2* d = reinterpret_cast<float2*>(&to->rgb[r][3 * c]);
+			float2* d = reinterpret_cast<float2*>(&to->px[r][3 * c]);
 			d[0] = make_float2(value[0].x, value[0].y);
 			d[1] = make_float2(value[0].z, value[PP - 1].x);
 			d[2] = make_float2(value[PP - 1].y, value[PP - 1].z);
-			*reinterpret_cast<float2*>(&to->z[r][c]) = make_float2(zout[0], zout[PP - 1]);
+			*reinterpret_cast<float2*>(&to->px[r][48 + c]) = make_float2(zout[0], zout[PP - 1]);
 		}
 		else
 		{
@@ -1420,10 +1447,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 			for (int pp = 0; pp < PP; pp++)
 			{
 				const int pi = tilePixel<NT>(tid, pp), r = pi >> 4, c = pi & 15;
-				to->rgb[r][3 * c] = value[pp].x;
-				to->rgb[r][3 * c + 1] = value[pp].y;
-				to->rgb[r][3 * c + 2] = value[pp].z;
-				to->z[r][c] = zout[pp];
+				to->px[r][3 * c] = value[pp].x;
+				to->px[r][3 * c + 1] = value[pp].y;
+				to->px[r][3 * c + 2] = value[pp].z;
+				to->px[r][48 + c] = zout[pp];
 			}
 		}
 		__syncthreads();

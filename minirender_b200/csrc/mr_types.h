@@ -143,9 +143,9 @@ struct FrameParams
 	int tilesX, tilesY;
 	int tileRow0, tileRows; // tile rows covered by this frame (strip rendering)
 	// Tiles tx < fullTx, fullTy0 <= ty < fullTy1 lie fully inside the image and the strip and may be stored as
-	// whole float4 rows (width a multiple of 4, not an accumulating frame): no per-pixel bounds tests there.
+	// whole 32-byte sectors (width a multiple of 8, not an accumulating frame): no per-pixel bounds tests there.
 	int fullTx, fullTy0, fullTy1;
-	float bgPattern[6];     // r g b r g b
+	float bgPattern[12];    // r g b r g b ...
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int nRenderables, nVertInst, nTriInst;
@@ -180,7 +180,7 @@ struct FrameParams
 
 	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
-	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field k, lane (t & 31)
+	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field pair j, lane (t & 31), 32 bytes each
 	float4* recs1;       // records of sub-triangle 1 (second clipper output): MR_REC_FIELDS float4 per triangle
 	int2* tileCount;     // per tile: x = triangles binned (may exceed binCap: the rest is in ovfPairs),
 	                     // y = nonzero if fragments of small triangles may have reached the tile's gkeys
