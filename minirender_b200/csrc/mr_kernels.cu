@@ -1034,8 +1034,9 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 struct TileOut
 {
 	// per pixel row: 48 rgb floats then 16 depth floats = 8 sectors of 32 bytes, in the order the tile store
-	// sends them out; rows padded to 72 floats (keeps 32-byte alignment, spreads the rows over the banks)
-	float px[MR_TILE][72];
+	// sends them out; rows padded to 80 floats: 32-byte aligned, and 80 mod 32 = 16 puts the 8-byte staging
+	// stores of two neighbouring rows (a half warp) on disjoint banks
+	float px[MR_TILE][80];
 };
 
 // Writes a tile's rows to the framebuffer as float4: 12 per row of rgb (192 B), 4 per row of depth
