@@ -42,6 +42,17 @@ def test_abi_version_and_no_cpu_fallback():
             r.render()
 
 
+def test_kernels_contain_the_wide_memory_instructions():
+    """The record and tile paths are written with Blackwell's 256-bit global accesses; ptxas was seen to
+    assemble one of them as a 32-bit store (see build.check_wide_ops). The built object must carry them."""
+    import shutil
+    from minirender_b200 import build
+    obj = os.path.join(build.OBJ_DIR, "mr_kernels.cu.o")
+    if not os.path.exists(obj) or not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("no kernel object / cuobjdump here (prebuilt library only)")
+    build.check_wide_ops(obj)
+
+
 def test_ctypes_struct_sizes_match_header(tmp_path):
     """sizeof of every descriptor as the C compiler sees include/minirender_b200.h."""
     import subprocess
