@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FramePar
 		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriReal : 0ull; // word 0 = trianglesIn
 	if (fp.cullClusters && blockIdx.x * 256 < fp.nTriInst / MR_CLUSTER)
 	{
-		// the verdict of every cluster, as a flag (k_setup with one CTA per cluster) and appended to
+		// the verdict of every cluster, as a bit of the mask (k_setup with one CTA per cluster) and appended to
 		// visList (persistent k_setup; one atomic per warp; the order of the list is irrelevant: ids
 		// come from the cluster index)
 		const bool vis = vi < fp.nTriInst / MR_CLUSTER && clusterVisible<TM>(fp, vi);
@@ -1030,7 +1030,8 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 	return value;
 }
 
-// Tile output staging: 16 rows x (48 rgb floats + 16 depth floats); written to HBM as float4 rows.
+// Tile output staging: 16 rows x (48 rgb floats + 16 depth floats); written to HBM as 32-byte sectors
+// (full tiles) or float4 rows.
 struct TileOut
 {
 	// per pixel row: 48 rgb floats then 16 depth floats = 8 sectors of 32 bytes, in the order the tile store

@@ -11,10 +11,10 @@
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
 //   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
-//   recs[]         one 64-byte raster record per set-up triangle, at index 2*t+sub where t is the
-//                  triangle instance index in submission order: the index IS the submission id
-//                  that resolves equal-depth ties
-//   srecs[]        96-byte shading record of the same triangle: its three view-space corners
+//   recs[]         one 160-byte record per set-up triangle (10 float4 fields: 4 raster, 6 shading = its
+//                  three view-space corners), at index 2*t+sub where t is the triangle instance index in
+//                  submission order: the index IS the submission id that resolves equal-depth ties.
+//                  Stored as five 32-byte pairs (256-bit accesses), in planes of 32 triangles
 //   gkeys[]        one 64-bit depth key per pixel: small triangles depth-test straight into it
 //                  (atomicMin in L2); the tile kernel merges, resolves and resets it every frame
 //   tileCount[] bins[] ovfPairs[]   16x16-tile binning of the larger triangles: fixed-capacity
