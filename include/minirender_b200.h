@@ -220,6 +220,10 @@ MR_API int mr_get_stats(mr_ctx* ctx, mr_stats* out);
 /* Evict the L2 cache by writing a 256 MiB scratch buffer on the context's stream (benchmark
  * hygiene: cold-cache timing between steps). */
 MR_API int mr_flush_l2(mr_ctx* ctx);
+/* Benchmark aid: the next mr_render records these two CUDA events (cudaEvent_t) on the render stream
+ * immediately before its first and after its last kernel launch, so that a device-time bracket contains the
+ * frame's kernels and nothing of the caller's host work. One shot: cleared by that mr_render. */
+MR_API int mr_set_timing_events(mr_ctx* ctx, void* cuda_event_start, void* cuda_event_stop);
 /* Render `frame` `repeats` times with CUDA events between the stages; fills mr_stats.ms_kernel
  * with the averages. With mr_set_debug flag 2 the L2 is flushed before every repeat. */
 MR_API int mr_profile_frame(mr_ctx* ctx, const mr_frame* frame, int repeats);

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "mr_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mr_host_unregister": (C.c_int, [C.c_void_p]),
     "mr_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
+    "mr_set_timing_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mr_set_output_slots": (C.c_int, [C.c_void_p, C.c_int]),
     "mr_read_image_begin": (C.c_int, [C.c_void_p, F32P, C.POINTER(C.c_int)]),
     "mr_read_wait": (C.c_int, [C.c_void_p, C.c_int]),

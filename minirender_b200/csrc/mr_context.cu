@@ -134,6 +134,7 @@ struct mr_ctx
 	bool copyPending[2];
 	void *remoteImage, *remoteDepth;
 	int debugFlags;
+	cudaEvent_t timingStart, timingStop; // mr_set_timing_events: recorded around the next frame's launches
 
 	// last frame (kept for overflow re-runs and profiling)
 	mr_frame lastFrame;
@@ -144,7 +145,7 @@ struct mr_ctx
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
 	           structureSerial(~0u), lastVisFrac(-1.0f), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
-	           remoteDepth(0), debugFlags(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
+	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
 		copyPending[0] = copyPending[1] = false;
@@ -626,7 +627,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
 	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
 
-	mrk_launch_frame(fp, c->stream, ev);
+	mrk_launch_frame(fp, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop);
+	if (!ev)
+		c->timingStart = c->timingStop = 0;
 	MR_CUDA(c, cudaGetLastError());
 	MR_CUDA(c, cudaEventRecord(slot.kernelsDone, c->stream));
 	MR_CUDA(c, cudaStreamWaitEvent(c->aux, slot.kernelsDone, 0));
@@ -879,6 +882,15 @@ int mr_set_stream(mr_ctx* c, void* s)
 		MR_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		c->ownStream = true;
 	}
+	return MR_OK;
+}
+
+int mr_set_timing_events(mr_ctx* c, void* start, void* stop)
+{
+	if (!c)
+		return MR_E_INVALID;
+	c->timingStart = (cudaEvent_t)start;
+	c->timingStop = (cudaEvent_t)stop;
 	return MR_OK;
 }
 

@@ -1572,8 +1572,9 @@ __global__ void k_selftest(const float* in, float* out)
 
 }
 
-void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* ev)
+void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* ev, cudaEvent_t bracketStart, cudaEvent_t bracketStop)
 {
+	if (bracketStart) cudaEventRecord(bracketStart, stream);
 	const int nTiles = fp.tilesX * fp.tilesY;
 	int vthreads = (fp.nVertInst > nTiles + 1) ? fp.nVertInst : nTiles + 1;
 	if (fp.nTriInst / MR_CLUSTER > vthreads)
@@ -1617,6 +1618,7 @@ void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* e
 	else
 		cudaMemsetAsync(fp.visCount, 0, sizeof(int), stream); // k_raster normally resets the visible-cluster count
 	if (ev) cudaEventRecord(ev[5], stream);
+	if (bracketStop) cudaEventRecord(bracketStop, stream);
 }
 
 int mrk_selftest_no_fma(cudaStream_t stream)

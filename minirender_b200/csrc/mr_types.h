@@ -202,7 +202,8 @@ struct FrameParams
 };
 
 // kernel launchers (mr_kernels.cu)
-void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */);
+void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */, cudaEvent_t bracketStart = 0,
+                      cudaEvent_t bracketStop = 0);
 int mrk_selftest_no_fma(cudaStream_t stream);
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
