@@ -9,7 +9,10 @@ Blinn-Phong, untextured), one turntable frame per step.
 N > 1 (under torchrun, one rank per GPU): the multi-view batch of BASELINE.json configs[4] —
 every rank owns a replica of the scene and renders its own views; no data-path collective
 (weak scaling). The timed region is bracketed by a barrier + device sync, per-rank device time is
-measured with CUDA events on the stream the kernels run on, and the job time is the max over ranks.
+measured with CUDA events on the stream the kernels run on (recorded by the library immediately
+around each frame's launches, mr_set_timing_events), and the job time is the max over ranks. Before
+the timed region every rank renders untimed for a quarter of a second on top of the W warm-up steps,
+so that no GPU is still at idle clocks.
 
 One JSON line on stdout (rank 0). `value` = frames/s with the scene resident in HBM and the L2
 flushed between timed steps; `e2e` = frames/s through the drop-in Renderer API with host buffers
@@ -51,46 +54,87 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled while the render loops run: NVML polled every millisecond from
+    a thread (the timed region of the default run is ~8 ms long, too short for `nvidia-smi -lms`), with
+    `nvidia-smi` every 20 ms as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc, self.nvml, self.stopping = index, uuid, [], None, None, False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode()) if self.uuid else None
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, h, float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h, mx = self.nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stopping:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append([time.perf_counter(), sm, mx, 0.0] + ["Active" if bits & b else "Not Active" for _, b in names])
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def stop(self, t_load0=None, t0=None, t1=None):
+        """Samples between t_load0 (start of the untimed render loop that precedes the timed region) and
+        t1 (end of the timed region) are 'under load'; those between t0 and t1 fell inside the timed region."""
+        self.stopping = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        elif not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
+        sm, mx, reasons, inside = [], [], set(), []
+        for r in list(self.rows):
+            t, r = r[0], r[1:]
+            if t_load0 is not None and not (t_load0 <= t <= t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
                 continue
+            if t0 is not None and t0 <= t <= t1:
+                inside.append(float(r[0]))
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(inside)) if inside else (float(np.median(sm)) if sm else None), "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside),
+                "source": "NVML polled every ms" if self.nvml else "nvidia-smi -lms 20",
+                "window": "sm_mhz = median of the samples inside the timed region (of all samples under load if none fell inside); "
+                          "reasons over the untimed quarter-second render loop and the timed region"}
 
 
 def build_scene(be, frame=0):
@@ -186,6 +230,13 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     lib = cabi.load()
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
+    if rank == 0:
+        sampler.start()  # up and sampling long before the render loops begin
     be = m.Backend()
     setup = build_scene(be)
     r = setup.apply(m.Renderer(be))
@@ -234,10 +285,7 @@ def run_ours(args, rank, local_rank, world):
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     for e in starts + stops:
         e.record(stream)  # creates the underlying cudaEvent_t
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     for i in range(K):
         r.set_view(view_of(W + i))
@@ -246,7 +294,7 @@ def run_ours(args, rank, local_rank, world):
         r.render()
     barrier()
     wall_dev_loop = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_ramp, wall0, time.perf_counter()) if rank == 0 else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     dev_ms = sum(step_ms)
 

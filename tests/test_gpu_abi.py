@@ -214,3 +214,29 @@ def test_row_range_outside_the_image_renders_nothing_and_leaves_no_state(be):
     r.render()
     assert (bits(r.get_depth()) == bits(want_d)).all()
     assert (bits(r.get_image()) == bits(want_i)).all()
+
+
+def test_timing_events_bracket_one_frame(be):
+    """mr_set_timing_events: the next mr_render records the caller's two CUDA events around its own
+    launches (bench.py's device-time bracket); one shot."""
+    torch = pytest.importorskip("torch")
+    lib = cabi.load()
+    setup = scenes.SMALL_SCENES["bench_small"](be)
+    r = setup.apply(m.Renderer(be))
+    ctx = r.context_ptr()
+    stream = torch.cuda.Stream()
+    assert lib.mr_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
+    r.render()
+    r.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); e1.record(stream)  # creates the cudaEvent_t handles
+    torch.cuda.synchronize()
+    assert lib.mr_set_timing_events(ctx, C.c_void_p(e0.cuda_event), C.c_void_p(e1.cuda_event)) == 0
+    r.render()
+    r.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert 0.001 < ms < 50.0
+    r.render()  # not armed again: the events keep their values
+    r.synchronize()
+    assert e0.elapsed_time(e1) == ms
+    assert lib.mr_set_stream(ctx, None) == 0
