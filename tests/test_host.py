@@ -116,6 +116,55 @@ def test_prepare_flattens_in_submission_order(be):
     assert f["znear"] == pytest.approx(-10.0, rel=1e-5) and f["ambient"] == pytest.approx(0.2)
 
 
+def _descriptors(r):
+    r.prepare()
+    f = cabi.frame_to_dict(r.frame_desc_ptr())
+    meshes, textures = cabi.scene_to_lists(r.scene_desc_ptr())
+    return f, meshes, textures
+
+
+def _same_descriptors(a, b):
+    fa, ma, ta = a
+    fb, mb, tb = b
+    assert len(fa["renderables"]) == len(fb["renderables"]) and fa["materials"] == fb["materials"]
+    for x, y in zip(fa["renderables"], fb["renderables"]):
+        assert x["mesh"] == y["mesh"] and x["material"] == y["material"]
+        assert (x["modelview"].view(np.uint32) == y["modelview"].view(np.uint32)).all()
+        assert (x["normalmat"].view(np.uint32) == y["normalmat"].view(np.uint32)).all()
+    assert len(ma) == len(mb) and len(ta) == len(tb)
+    for x, y in zip(ma, mb):
+        assert sorted(x) == sorted(y)
+        for k in x:
+            assert np.array_equal(x[k], y[k])
+
+
+def test_prepare_structure_cache_follows_scene_edits(be):
+    """describe() remembers which entry used which mesh / material between frames; every edit of the scene
+    (materials' values, transforms, new nodes, instances) must show up exactly as in a renderer that has
+    never seen the scene before."""
+    setup = scenes.ties_scene(be)
+    sc = setup.scene
+    reused = setup.apply(m.Renderer(be))
+    _descriptors(reused)                      # warm: the cache now describes the initial structure
+
+    def fresh():
+        return _descriptors(setup.apply(m.Renderer(be)))
+
+    _same_descriptors(_descriptors(reused), fresh())                    # unchanged scene, cached path
+    sc.set_transform(1, be.mul(be.translate(3, 1, -2), be.rotate_z(0.4)))
+    _same_descriptors(_descriptors(reused), fresh())                    # transform edit, cached path
+    mid = sc.add_material(diffuse=(0.1, 0.9, 0.2), shininess=3.0)
+    extra = sc.add_cube(7.0, xf=be.translate(-20, 5, 0), material=mid)  # new node + new material: structure changes
+    _same_descriptors(_descriptors(reused), fresh())
+    sc.add_instance(extra)                                              # an instance of an existing mesh
+    _same_descriptors(_descriptors(reused), fresh())
+    sc.update_material(mid, diffuse=(0.9, 0.1, 0.1), shininess=20.0)    # same structure, new values
+    got = _descriptors(reused)
+    _same_descriptors(got, fresh())
+    assert any(abs(mt["shininess"] - 20.0) < 1e-6 for mt in got[0]["materials"])
+    assert len(_descriptors(reused)[0]["renderables"]) == len(fresh()[0]["renderables"]) > 7
+
+
 def test_ppm_roundtrip(be, tmp_path):
     rng = np.random.default_rng(0)
     img = rng.uniform(-0.2, 1.2, (13, 17, 3)).astype(np.float32)
