@@ -383,7 +383,10 @@ static void describe(Renderer::Impl& s, const Array<Renderable>& list, const Mat
 	}
 	catch (...)
 	{
-		s.cacheMeshOf.clear(); // do not trust the cache after a rejected mesh
+		// do not trust the cache after a rejected mesh
+		s.cacheMeshOf.clear(); s.cacheMatOf.clear(); s.cacheMeshId.clear(); s.cacheMatId.clear();
+		s.cacheUniqMesh.clear(); s.cacheUniqMat.clear();
+		s.meshes.clear();
 		throw;
 	}
 	for (size_t k = 0; k < s.cacheUniqMat.size(); k++)
