@@ -148,7 +148,7 @@ typedef struct mr_stats
 	int32_t regrows;           /* times a queue had to be regrown and the frame re-run */
 	int32_t kernels_launched;  /* kernel launches issued for the frame */
 	float   ms_kernel[8];      /* per-stage device time of the last mr_profile_frame:
-	                              0 vertex, 1 setup+scan, 2 (unused), 3 scatter, 4 raster, 5 whole frame */
+	                              1 geometry (k_geom), 4 tile resolve + shade (k_raster), 5 whole frame; others 0 */
 	int64_t h2d_bytes;         /* host->device bytes the last mr_render copied (per-frame tables) */
 } mr_stats;
 

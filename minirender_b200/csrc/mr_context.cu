@@ -87,19 +87,19 @@ struct mr_ctx
 	int smCount;
 
 	// scene-static device arrays
-	DevBuf pos4, nrm4, uv2, idxPos, idxNrm, idxUv, texels, meshes, clusters, triBlockCl, clusterVis, visList, visCount;
+	DevBuf meshlets, meshletDir, texels, clusters, triBlockCl, visEntries, geomSync;
+	int geomVertCap, geomTeams, geomGrid, geomSmem; // shape of k_geom for this scene's meshlets
 	std::vector<int> hostClusterBase; // first cluster of every mesh
 	std::vector<MeshDev> hostMeshes;
-	std::vector<int> hostNrmCount; // normals per mesh
 	std::vector<int> texOffset, texRows, texCols;
 	bool haveScene;
 	unsigned sceneSerial;
 
 	// per-frame tables
-	DevBuf rstat, rdyn, mats, vtxBlockR;
+	DevBuf rstat, rdyn, mats;
 	std::vector<int> structureKey; // mesh id per renderable of the tables currently on the device
 	unsigned structureSerial;
-	int nVertInst, nTriInst;
+	int nTriInst;
 	// per-frame host staging + counters, a ring so that mr_render never waits for the GPU
 	struct Slot
 	{
@@ -116,8 +116,9 @@ struct mr_ctx
 	int slotNewest; // slot of the most recent frame (-1: none)
 
 	// scratch
-	DevBuf pv, recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
-	float lastVisFrac; // clusters that survived culling in the newest retired frame (fraction; < 0: unknown)
+	DevBuf recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
+	bool slotOverflowed; // a frame older than the newest one overflowed its spill list (async readers are told)
+	bool noClusterCull, noPdl; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -132,6 +133,7 @@ struct mr_ctx
 	cudaEvent_t frameDone[2];   // render stream: the frame in slot s is complete
 	cudaEvent_t copyDone[2];    // copy stream: the host copy out of slot s is complete
 	bool copyPending[2];
+	int copyRing[2];            // frame-ring slot of the frame whose image the pending copy of output set s reads
 	void *remoteImage, *remoteDepth;
 	int debugFlags;
 	cudaEvent_t timingStart, timingStop; // mr_set_timing_events: recorded around the next frame's launches
@@ -144,11 +146,12 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), lastVisFrac(-1.0f), nVertInst(0), nTriInst(0), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), geomVertCap(0), geomTeams(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
 		copyPending[0] = copyPending[1] = false;
+		copyRing[0] = copyRing[1] = -1;
 		memset(&lastFrame, 0, sizeof(lastFrame));
 		memset(&stats, 0, sizeof(stats));
 	}
@@ -213,8 +216,6 @@ void absorbCounters(mr_ctx* c, const Counters& k)
 	c->stats.clipped_in = (int64_t)clip;
 	c->stats.bin_entries = (int64_t)pairs;
 	c->stats.zero_coverage = (int64_t)zero;
-	if (k.clusters > 0)
-		c->lastVisFrac = (float)k.visible / (float)k.clusters;
 	c->stats.tiles_x = c->tilesX;
 	c->stats.tiles_y = c->tilesY;
 }
@@ -317,7 +318,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	const int nR = f->n_renderables;
 	// ---- validate + instance bases ----
 	std::vector<RStat> rs((size_t)nR);
-	long long vb = 0, tb = 0, nb = 0, triReal = 0;
+	long long tb = 0, triReal = 0;
 	bool sameStructure = (c->structureSerial == c->sceneSerial) && ((int)c->structureKey.size() == nR);
 	for (int i = 0; i < nR; i++)
 	{
@@ -327,51 +328,46 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		if (r.material < 0 || r.material >= f->n_materials)
 			return setError(c, MR_E_INVALID, "renderable %d: material index %d out of range", i, r.material);
 		const MeshDev& hm = c->hostMeshes[r.mesh];
-		rs[i].vertBase = (int)vb;
 		rs[i].triBase = (int)tb;
-		rs[i].nrmBase = (int)nb;
-		rs[i].idxBase = hm.triBase;
-		rs[i].posBase = hm.posBase;
-		rs[i].nrmSrcBase = hm.nrmBase;
-		rs[i].uvBase = hm.uvBase;
-		rs[i].uvTriBase = hm.hasUV ? hm.uvTriBase : -1;
-		rs[i].clusterBase = c->hostClusterBase[r.mesh];
+		rs[i].clusterBase = hm.clusterBase;
 		rs[i].nTri = hm.nTri;
 		rs[i].triBaseReal = (int)triReal;
-		rs[i].pad = 0;
-		vb += hm.nPos;
 		tb += ((long long)hm.nTri + MR_CLUSTER - 1) / MR_CLUSTER * MR_CLUSTER; // whole clusters per renderable
 		triReal += hm.nTri;
-		nb += c->hostNrmCount[r.mesh];
 		if (sameStructure && c->structureKey[i] != r.mesh)
 			sameStructure = false;
 	}
-	if (vb > 0x3fffffffLL || tb > 0x3fffffffLL || nb > 0x3fffffffLL)
-		return setError(c, MR_E_INVALID, "frame too large: %lld vertex instances, %lld triangle instances", vb, tb);
-	c->nVertInst = (int)vb;
+	if (tb > 0x3fffffffLL)
+		return setError(c, MR_E_INVALID, "frame too large: %lld triangle instances", tb);
 	c->nTriInst = (int)tb;
-	const int nVB = (c->nVertInst + 255) / 256;
 
 	// ---- device buffers ----
 	const int nTiles = c->tilesX * c->tilesY;
 	MR_CUDA(c, c->rstat.ensure(sizeof(RStat) * (size_t)std::max(nR, 1)));
 	MR_CUDA(c, c->rdyn.ensure(sizeof(RDyn) * (size_t)std::max(nR, 1)));
 	MR_CUDA(c, c->mats.ensure(sizeof(MatDev) * (size_t)std::max(f->n_materials, 1)));
-	MR_CUDA(c, c->vtxBlockR.ensure(sizeof(int) * (size_t)(nVB + 1)));
 	const int nCB = c->nTriInst / MR_CLUSTER;
 	MR_CUDA(c, c->triBlockCl.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
-	MR_CUDA(c, c->visList.ensure(sizeof(int) * (size_t)std::max(nCB, 1)));
-	MR_CUDA(c, c->clusterVis.ensure(sizeof(unsigned) * ((size_t)nCB / 32 + 16))); // k_vertex writes whole 256-cluster blocks
-	if (!c->visCount.p)
+	MR_CUDA(c, c->visEntries.ensure(sizeof(GeomEntry) * (size_t)std::max(nCB, 1)));
+	if (!c->geomSync.p)
 	{
-		MR_CUDA(c, c->visCount.ensure(256, true));
-		MR_CUDA(c, cudaMemsetAsync(c->visCount.p, 0, 256, c->stream));
+		MR_CUDA(c, c->geomSync.ensure(256, true));
+		MR_CUDA(c, cudaMemsetAsync(c->geomSync.p, 0, 256, c->stream));
 	}
-	MR_CUDA(c, c->pv.ensure(sizeof(float4) * (size_t)std::max(c->nVertInst, 1)));
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
 	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
-	MR_CUDA(c, c->tileCount.ensure(sizeof(int2) * (size_t)(nTiles + 1)));
-	MR_CUDA(c, c->ctr.ensure(sizeof(Counters) * mr_ctx::kSlots));
+	if (c->tileCount.cap < sizeof(int2) * (size_t)(nTiles + 1))
+	{
+		// all zero between frames: k_raster resets the entries it reads
+		MR_CUDA(c, c->tileCount.ensure(sizeof(int2) * (size_t)(nTiles + 1)));
+		MR_CUDA(c, cudaMemsetAsync(c->tileCount.p, 0, c->tileCount.cap, c->stream));
+	}
+	if (!c->ctr.p)
+	{
+		// a frame's statistics start from zero: k_raster clears the next frame's slot
+		MR_CUDA(c, c->ctr.ensure(sizeof(Counters) * mr_ctx::kSlots, true));
+		MR_CUDA(c, cudaMemsetAsync(c->ctr.p, 0, sizeof(Counters) * mr_ctx::kSlots, c->stream));
+	}
 	{
 		// Bin capacity: a power of two, at least 256 and at least 8x the mean triangles per tile,
 		// within a 1 GiB budget for the bin array; doubled on demand when tiles spill a lot.
@@ -394,28 +390,34 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	if (rc)
 		return rc;
 	if (c->outSlots > 1 && !f->keep && !rerun)
+		c->outCur = (c->outCur + 1) % c->outSlots; // a cleared frame goes to the other output set
+	if (c->copyPending[c->outCur])
 	{
-		// a cleared frame goes to the other output set; a host copy still reading that set must finish first
-		c->outCur = (c->outCur + 1) % c->outSlots;
-		if (c->copyPending[c->outCur])
-		{
-			MR_CUDA(c, cudaStreamWaitEvent(c->stream, c->copyDone[c->outCur], 0));
-			c->copyPending[c->outCur] = false;
-		}
+		// a host copy still reading the target set must finish before the kernels write into it
+		MR_CUDA(c, cudaStreamWaitEvent(c->stream, c->copyDone[c->outCur], 0));
+		c->copyPending[c->outCur] = false;
 	}
 
 	// ---- stage per-frame tables in pinned memory, one async copy each ----
 	const size_t szStat = sameStructure ? 0 : sizeof(RStat) * (size_t)nR;
-	const size_t szVB = sameStructure ? 0 : sizeof(int) * (size_t)(nVB + 1);
 	const size_t szCB = sameStructure ? 0 : sizeof(int) * (size_t)nCB;
 	const size_t szDyn = sizeof(RDyn) * (size_t)nR;
 	const size_t szMat = sizeof(MatDev) * (size_t)f->n_materials;
-	const size_t total = szStat + szVB + szCB + szDyn + szMat + 64;
+	const size_t total = szStat + szCB + szDyn + szMat + 64;
 	const int slotIndex = c->slotNext;
 	{
-		const int rc0 = retireSlot(c, slotIndex); // normally long finished
+		// this frame's slot and the next one (whose statistics this frame's k_raster clears) must have
+		// delivered their counters; both are normally long finished
+		const int rc0 = retireSlot(c, slotIndex);
 		if (rc0 < 0)
 			return rc0;
+		if (rc0 > 0)
+			c->slotOverflowed = true;
+		const int rc1 = retireSlot(c, (slotIndex + 1) % mr_ctx::kSlots);
+		if (rc1 < 0)
+			return rc1;
+		if (rc1 > 0)
+			c->slotOverflowed = true;
 	}
 	mr_ctx::Slot& slot = c->slots[slotIndex];
 	MR_CUDA(c, slot.stage.ensure(total));
@@ -426,17 +428,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		memcpy(sp + off, rs.data(), szStat);
 		if (szStat) MR_CUDA(c, cudaMemcpyAsync(c->rstat.p, sp + off, szStat, cudaMemcpyHostToDevice, c->stream));
 		off += szStat;
-		int* vbr = (int*)(sp + off);
-		for (int b = 0, r = 0; b < nVB; b++)
-		{
-			const int first = b * 256;
-			while (r + 1 < nR && first >= rs[r + 1].vertBase)
-				r++;
-			vbr[b] = r;
-		}
-		vbr[nVB] = std::max(nR - 1, 0); // sentinel: upper bound of the last block's renderable range
-		if (szVB) MR_CUDA(c, cudaMemcpyAsync(c->vtxBlockR.p, sp + off, szVB, cudaMemcpyHostToDevice, c->stream));
-		off += szVB;
 		int* cbr = (int*)(sp + off);
 		for (int i = 0; i < nR; i++)
 		{
@@ -503,7 +494,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		md[i].pad[0] = md[i].pad[1] = md[i].pad[2] = 0;
 	}
 	if (szMat && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->mats.p, md, szMat, cudaMemcpyHostToDevice, c->stream));
-	c->h2dBytesLastFrame = szStat + szVB + szCB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
+	c->h2dBytesLastFrame = szStat + szCB + (inlineTables ? 0 : szDyn + szMat) + sizeof(FrameParams);
 
 	// ---- frame parameters ----
 	FrameParams fp;
@@ -542,7 +533,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		// Cluster culling needs the standard perspective form (w_clip = -z_view, x and y not mirrored).
 		const float* P = f->projection;
 		const bool standard = fp.persp && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f && P[0] > 0.0f && P[5] > 0.0f;
-		fp.cullClusters = (standard && !getenv("MR_NO_CLUSTER_CULL")) ? 1 : 0;
+		fp.cullClusters = (standard && !c->noClusterCull) ? 1 : 0;
 		if (fp.cullClusters)
 		{
 			// Columns / rows this frame can touch, widened by 1.5 pixels, as NDC bounds; each bound is a plane
@@ -573,7 +564,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.saveNormals = f->save_normals;
 	fp.keep = f->keep;
 	fp.nRenderables = nR;
-	fp.nVertInst = c->nVertInst;
 	fp.nTriInst = c->nTriInst;
 	fp.nTriReal = (int)triReal;
 	fp.debug = c->debugFlags;
@@ -586,35 +576,18 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	}
 	fp.binCap = c->binCap;
 	fp.ovfCap = (int)std::min<size_t>(c->ovfCap, 0x7fffffff);
-	fp.pos4 = c->pos4.as<float4>();
-	fp.nrm4 = c->nrm4.as<float4>();
-	fp.nNrmSrc = (int)std::min<size_t>(c->nrm4.cap / sizeof(float4), 0x7fffffff);
-	fp.uv2 = c->uv2.as<float2>();
-	fp.idxPos = c->idxPos.as<int>();
-	fp.idxNrm = c->idxNrm.as<int>();
-	fp.idxUv = c->idxUv.as<int>();
+	fp.meshlets = c->meshlets.as<unsigned char>();
+	fp.meshletDir = c->meshletDir.as<MeshletDir>();
 	fp.texels = c->texels.as<float4>();
-	fp.meshes = c->meshes.as<MeshDev>();
 	fp.rstat = c->rstat.as<RStat>();
 	fp.rdyn = c->rdyn.as<RDyn>();
 	fp.mats = c->mats.as<MatDev>();
-	fp.vtxBlockR = c->vtxBlockR.as<int>();
 	fp.triBlockCl = c->triBlockCl.as<int>();
 	fp.clusters = c->clusters.as<float4>();
-	fp.visList = c->visList.as<int>();
-	fp.clusterVis = c->clusterVis.as<unsigned>();
-	fp.visCount = c->visCount.as<int>();
-	{
-		const char* e = getenv("MR_SETUP_CTAS_PER_SM");
-		// Most clusters expected to survive culling: one CTA per cluster. Most culled (a strip of a frame,
-		// or what the newest finished frame reported): a few persistent CTAs per SM.
-		// (also when the scene is made of many small meshes: their padded clusters are mostly empty and
-		// one CTA each is bound by the launch rate, not by work)
-		const bool mostlyCulled = fp.cullClusters && (fp.tileRows < fp.tilesY || (c->lastVisFrac >= 0.0f && c->lastVisFrac < 0.5f) ||
-		                                              (double)triReal < 0.75 * (double)c->nTriInst);
-		fp.setupCtas = (e && atoi(e) > 0) ? c->smCount * atoi(e) : mostlyCulled ? c->smCount * 16 : 0x7fffffff;
-	}
-	fp.pv = c->pv.as<float4>();
+	fp.geomTeams = c->geomTeams;
+	fp.geomVertCap = c->geomVertCap;
+	fp.visEntries = c->visEntries.as<GeomEntry>();
+	fp.geomSync = c->geomSync.as<int>();
 	fp.gkeys = c->gkeys.as<unsigned long long>();
 	fp.recs = c->recs.as<float4>();
 	fp.recs1 = c->recs1.as<float4>();
@@ -622,12 +595,13 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.ovfPairs = c->ovfPairs.as<int2>();
 	fp.bins = c->bins.as<int>();
 	fp.ctr = c->ctr.as<Counters>() + slotIndex; // per-slot counters: the read-back overlaps the next frame
+	fp.ctrNext = c->ctr.as<Counters>() + (slotIndex + 1) % mr_ctx::kSlots;
 	fp.image = (c->remoteImage && !f->keep) ? (float*)c->remoteImage : c->imageSlot[c->outCur].as<float>();
 	fp.depth = (c->remoteDepth && !f->keep) ? (float*)c->remoteDepth : c->depthSlot[c->outCur].as<float>();
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
 	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
 
-	mrk_launch_frame(fp, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop);
+	mrk_launch_frame(fp, c->geomGrid, c->geomSmem, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop, !c->noPdl);
 	if (!ev)
 		c->timingStart = c->timingStop = 0;
 	MR_CUDA(c, cudaGetLastError());
@@ -638,7 +612,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	slot.pending = true;
 	c->slotNewest = slotIndex;
 	c->slotNext = (slotIndex + 1) % mr_ctx::kSlots;
-	c->stats.kernels_launched = (c->nTriInst > 0) ? 3 : 2;
+	c->stats.kernels_launched = (fp.tileRows > 0) ? 2 : 1;
 	return MR_OK;
 }
 
@@ -658,6 +632,78 @@ int readBack(mr_ctx* c, void* host, const void* dev, size_t bytes)
 	MR_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
 	MR_CUDA(c, cudaStreamSynchronize(c->stream));
 	return MR_OK;
+}
+
+// Meshlets of one mesh: for every MR_CLUSTER consecutive triangles, the distinct (position, normal, texcoord)
+// index triples of their corners in order of first use ("local corners": what paintMesh's loop C gathers,
+// Renderer.cpp:351-380, deduplicated), stored as two float4 planes, and the triangles as three 10-bit local
+// indices each. Appends the blobs to `blob` (16-byte aligned), fills dir[] and raises maxNv.
+void buildMeshlets(const mr_mesh_desc& m, bool hasUV, std::vector<unsigned char>& blob, MeshletDir* dir, int& maxNv)
+{
+	const int nCl = (m.n_triangles + MR_CLUSTER - 1) / MR_CLUSTER;
+	// open-addressing table of the cluster's corners; entries of older clusters are recognised by their stamp
+	enum { kTable = 1024 };
+	struct Slot { int ip, in, iu, local, stamp; };
+	std::vector<Slot> table((size_t)kTable);
+	for (int i = 0; i < kTable; i++)
+		table[i].stamp = -1;
+	float verts[MR_MESHLET_MAX_VERTS][8];
+	uint32_t idx[MR_CLUSTER];
+	for (int k = 0; k < nCl; k++)
+	{
+		const int t0 = k * MR_CLUSTER, t1 = std::min(m.n_triangles, t0 + MR_CLUSTER);
+		int nv = 0;
+		memset(idx, 0, sizeof(idx));
+		for (int t = t0; t < t1; t++)
+		{
+			uint32_t packed = 0;
+			for (int j = 0; j < 3; j++)
+			{
+				const size_t corner = 3 * (size_t)t + j;
+				const int ip = m.idx_pos[corner], in = m.idx_nrm[corner], iu = hasUV ? m.idx_uv[corner] : -1;
+				uint32_t h = ((uint32_t)ip * 2654435761u) ^ ((uint32_t)in * 40503u) ^ ((uint32_t)iu * 2246822519u);
+				h = (h ^ (h >> 15)) & (kTable - 1);
+				int local = -1;
+				for (;; h = (h + 1) & (kTable - 1))
+				{
+					Slot& sl = table[h];
+					if (sl.stamp != k)
+					{
+						sl.stamp = k; sl.ip = ip; sl.in = in; sl.iu = iu; sl.local = nv;
+						local = nv;
+						const float* p = m.positions + 3 * (size_t)ip;
+						const float* n = m.normals + 3 * (size_t)in;
+						float* o = verts[nv++];
+						o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+						o[3] = n[0]; o[4] = n[1]; o[5] = n[2];
+						o[6] = hasUV ? m.texcoords[2 * (size_t)iu] : 0.0f;
+						o[7] = hasUV ? m.texcoords[2 * (size_t)iu + 1] : 0.0f;
+						break;
+					}
+					if (sl.ip == ip && sl.in == in && sl.iu == iu)
+					{
+						local = sl.local;
+						break;
+					}
+				}
+				packed |= (uint32_t)local << (10 * j);
+			}
+			idx[t - t0] = packed;
+		}
+		const size_t at = blob.size(); // a multiple of 16: every blob is
+		blob.resize(at + (size_t)MR_MESHLET_BYTES(nv));
+		float* p0 = reinterpret_cast<float*>(blob.data() + at);
+		float* p1 = p0 + 4 * (size_t)nv;
+		for (int v = 0; v < nv; v++)
+		{
+			p0[4 * v] = verts[v][0]; p0[4 * v + 1] = verts[v][1]; p0[4 * v + 2] = verts[v][2]; p0[4 * v + 3] = verts[v][3];
+			p1[4 * v] = verts[v][4]; p1[4 * v + 1] = verts[v][5]; p1[4 * v + 2] = verts[v][6]; p1[4 * v + 3] = verts[v][7];
+		}
+		memcpy(p1 + 4 * (size_t)nv, idx, sizeof(idx));
+		dir[k].off16 = (uint32_t)(at / 16);
+		dir[k].nv = (uint32_t)nv;
+		maxNv = std::max(maxNv, nv);
+	}
 }
 
 // Cull clusters of one mesh: for every MR_CLUSTER consecutive triangles, a bounding sphere of their
@@ -781,6 +827,8 @@ mr_ctx* mr_create(int device, int* status)
 		Bind bind(device);
 		c->smCount = 148;
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
+		c->noClusterCull = getenv("MR_NO_CLUSTER_CULL") != 0; // verification switches, read once
+		c->noPdl = getenv("MR_NO_PDL") != 0;
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;
@@ -827,8 +875,8 @@ void mr_destroy(mr_ctx* c)
 	Bind bind(c->device);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
-	DevBuf* bufs[] = { &c->pos4, &c->nrm4, &c->uv2, &c->idxPos, &c->idxNrm, &c->idxUv, &c->texels, &c->meshes, &c->clusters, &c->triBlockCl, &c->clusterVis, &c->visList, &c->visCount, &c->rstat,
-		               &c->rdyn, &c->mats, &c->vtxBlockR, &c->pv, &c->recs, &c->tileCount,
+	DevBuf* bufs[] = { &c->meshlets, &c->meshletDir, &c->texels, &c->clusters, &c->triBlockCl, &c->visEntries, &c->geomSync, &c->rstat,
+		               &c->rdyn, &c->mats, &c->recs, &c->tileCount,
 		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
@@ -944,7 +992,8 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 		return rc;
 	// ---- validate and lay out ----
 	std::vector<MeshDev> md((size_t)s->n_meshes);
-	long long nPos = 0, nNrm = 0, nUv = 0, nTri = 0, nUvTri = 0;
+	long long nTri = 0;
+	size_t nClusters = 0;
 	for (int i = 0; i < s->n_meshes; i++)
 	{
 		const mr_mesh_desc& m = s->meshes[i];
@@ -962,24 +1011,14 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 			if (hasUV && (unsigned)m.idx_uv[k] >= (unsigned)m.n_texcoords)
 				return setError(c, MR_E_INVALID, "mesh %d: texcoord index %d out of range at corner %lld", i, m.idx_uv[k], k);
 		}
-		md[i].posBase = (int)nPos;
-		md[i].nrmBase = (int)nNrm;
-		md[i].uvBase = (int)nUv;
-		md[i].triBase = (int)nTri;
-		md[i].uvTriBase = hasUV ? (int)nUvTri : -1;
-		md[i].nPos = m.n_positions;
+		md[i].clusterBase = (int)nClusters;
 		md[i].nTri = m.n_triangles;
 		md[i].hasUV = hasUV;
-		nPos += m.n_positions;
-		nNrm += m.n_normals;
+		md[i].pad = 0;
 		nTri += m.n_triangles;
-		if (hasUV)
-		{
-			nUv += m.n_texcoords;
-			nUvTri += m.n_triangles;
-		}
+		nClusters += (size_t)(m.n_triangles + MR_CLUSTER - 1) / MR_CLUSTER;
 	}
-	if (nPos > 0x3fffffffLL || nNrm > 0x3fffffffLL || nTri > 0x2aaaaaaaLL)
+	if (nTri > 0x2aaaaaaaLL)
 		return setError(c, MR_E_INVALID, "scene too large for 32-bit indexing");
 	long long nTexel = 0;
 	std::vector<int> to((size_t)s->n_textures), tr((size_t)s->n_textures), tc((size_t)s->n_textures);
@@ -996,51 +1035,46 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 	if (nTexel > 0x3fffffffLL)
 		return setError(c, MR_E_INVALID, "textures too large");
 
-	MR_CUDA(c, c->pos4.ensure(sizeof(float4) * (size_t)std::max(nPos, 1LL)));
-	MR_CUDA(c, c->nrm4.ensure(sizeof(float4) * (size_t)std::max(nNrm, 1LL)));
-	MR_CUDA(c, c->uv2.ensure(sizeof(float2) * (size_t)std::max(nUv, 1LL)));
-	MR_CUDA(c, c->idxPos.ensure(sizeof(int) * 3 * (size_t)std::max(nTri, 1LL)));
-	MR_CUDA(c, c->idxNrm.ensure(sizeof(int) * 3 * (size_t)std::max(nTri, 1LL)));
-	MR_CUDA(c, c->idxUv.ensure(sizeof(int) * 3 * (size_t)std::max(nUvTri, 1LL)));
-	MR_CUDA(c, c->texels.ensure(sizeof(float4) * (size_t)std::max(nTexel, 1LL)));
-	MR_CUDA(c, c->meshes.ensure(sizeof(MeshDev) * (size_t)std::max(s->n_meshes, 1)));
-
-	// packed xyz / rgb arrays go through a device staging buffer and are widened to float4 there
-	size_t maxRaw = 0;
+	// ---- meshlets + cull clusters (host pass over the triangles, once per upload) ----
+	std::vector<unsigned char> blob;
+	std::vector<MeshletDir> dir(std::max<size_t>(nClusters, 1));
+	std::vector<float> clusters(8 * std::max<size_t>(nClusters, 1), 0.0f);
+	int maxNv = 4;
 	for (int i = 0; i < s->n_meshes; i++)
-		maxRaw = std::max(maxRaw, sizeof(float) * 3 * (size_t)std::max(s->meshes[i].n_positions, s->meshes[i].n_normals));
+		if (s->meshes[i].n_triangles > 0)
+		{
+			buildMeshlets(s->meshes[i], md[i].hasUV != 0, blob, dir.data() + md[i].clusterBase, maxNv);
+			buildClusters(s->meshes[i], clusters.data() + 8 * (size_t)md[i].clusterBase);
+		}
+	if (blob.size() / 16 > 0xffffffffULL)
+		return setError(c, MR_E_INVALID, "scene too large: %zu bytes of meshlets", blob.size());
+	const int nvCap = (maxNv + 3) & ~3;
+	int teams = 0, grid = 0, smem = 0;
+	if (mrk_geom_config(nvCap, c->smCount, &teams, &grid, &smem) != 0)
+	{
+		cudaGetLastError();
+		return setError(c, MR_E_CUDA, "k_geom does not fit this device (meshlets of %d corners)", nvCap);
+	}
+	c->geomVertCap = nvCap;
+	c->geomTeams = teams;
+	c->geomGrid = grid;
+	c->geomSmem = smem;
+
+	MR_CUDA(c, c->meshlets.ensure(std::max<size_t>(blob.size(), 16)));
+	MR_CUDA(c, c->meshletDir.ensure(sizeof(MeshletDir) * dir.size()));
+	MR_CUDA(c, c->clusters.ensure(sizeof(float) * clusters.size()));
+	MR_CUDA(c, c->texels.ensure(sizeof(float4) * (size_t)std::max(nTexel, 1LL)));
+	if (!blob.empty())
+		MR_CUDA(c, cudaMemcpyAsync(c->meshlets.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+	MR_CUDA(c, cudaMemcpyAsync(c->meshletDir.p, dir.data(), sizeof(MeshletDir) * dir.size(), cudaMemcpyHostToDevice, c->stream));
+	MR_CUDA(c, cudaMemcpyAsync(c->clusters.p, clusters.data(), sizeof(float) * clusters.size(), cudaMemcpyHostToDevice, c->stream));
+
+	// packed rgb texel arrays go through a device staging buffer and are widened to float4 there
+	size_t maxRaw = 0;
 	for (int i = 0; i < s->n_textures; i++)
 		maxRaw = std::max(maxRaw, sizeof(float) * 3 * (size_t)s->textures[i].rows * s->textures[i].cols);
 	MR_CUDA(c, c->scratchOut.ensure(std::max<size_t>(maxRaw, 16)));
 	float* raw = c->scratchOut.as<float>();
-	for (int i = 0; i < s->n_meshes; i++)
-	{
-		const mr_mesh_desc& m = s->meshes[i];
-		if (m.n_positions)
-		{
-			MR_CUDA(c, cudaMemcpyAsync(raw, m.positions, sizeof(float) * 3 * (size_t)m.n_positions, cudaMemcpyHostToDevice, c->stream));
-			mrk_launch_pack(c->pos4.as<float4>() + md[i].posBase, raw, m.n_positions, 3, 1.0f, c->stream);
-		}
-		if (m.n_normals)
-		{
-			MR_CUDA(c, cudaMemcpyAsync(raw, m.normals, sizeof(float) * 3 * (size_t)m.n_normals, cudaMemcpyHostToDevice, c->stream));
-			mrk_launch_pack(c->nrm4.as<float4>() + md[i].nrmBase, raw, m.n_normals, 3, 0.0f, c->stream);
-		}
-		if (md[i].hasUV)
-		{
-			MR_CUDA(c, cudaMemcpyAsync(c->uv2.as<float2>() + md[i].uvBase, m.texcoords, sizeof(float) * 2 * (size_t)m.n_texcoords,
-			                           cudaMemcpyHostToDevice, c->stream));
-			MR_CUDA(c, cudaMemcpyAsync(c->idxUv.as<int>() + 3 * (size_t)md[i].uvTriBase, m.idx_uv, sizeof(int) * 3 * (size_t)m.n_triangles,
-			                           cudaMemcpyHostToDevice, c->stream));
-		}
-		if (m.n_triangles)
-		{
-			MR_CUDA(c, cudaMemcpyAsync(c->idxPos.as<int>() + 3 * (size_t)md[i].triBase, m.idx_pos, sizeof(int) * 3 * (size_t)m.n_triangles,
-			                           cudaMemcpyHostToDevice, c->stream));
-			MR_CUDA(c, cudaMemcpyAsync(c->idxNrm.as<int>() + 3 * (size_t)md[i].triBase, m.idx_nrm, sizeof(int) * 3 * (size_t)m.n_triangles,
-			                           cudaMemcpyHostToDevice, c->stream));
-		}
-	}
 	for (int i = 0; i < s->n_textures; i++)
 	{
 		const mr_texture_desc& t = s->textures[i];
@@ -1048,29 +1082,9 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 		MR_CUDA(c, cudaMemcpyAsync(raw, t.texels, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
 		mrk_launch_pack(c->texels.as<float4>() + to[i], raw, (int)n, 3, 0.0f, c->stream);
 	}
-	if (s->n_meshes)
-		MR_CUDA(c, cudaMemcpyAsync(c->meshes.p, md.data(), sizeof(MeshDev) * md.size(), cudaMemcpyHostToDevice, c->stream));
-	// cull clusters (host pass over the triangles, once per upload)
-	std::vector<int> clusterBase((size_t)s->n_meshes);
-	size_t nClusters = 0;
-	for (int i = 0; i < s->n_meshes; i++)
-	{
-		clusterBase[i] = (int)nClusters;
-		nClusters += (size_t)(s->meshes[i].n_triangles + MR_CLUSTER - 1) / MR_CLUSTER;
-	}
-	std::vector<float> clusters(8 * std::max<size_t>(nClusters, 1), 0.0f);
-	for (int i = 0; i < s->n_meshes; i++)
-		if (s->meshes[i].n_triangles > 0)
-			buildClusters(s->meshes[i], clusters.data() + 8 * (size_t)clusterBase[i]);
-	MR_CUDA(c, c->clusters.ensure(sizeof(float) * clusters.size()));
-	MR_CUDA(c, cudaMemcpyAsync(c->clusters.p, clusters.data(), sizeof(float) * clusters.size(), cudaMemcpyHostToDevice, c->stream));
 	MR_CUDA(c, cudaGetLastError());
 	MR_CUDA(c, cudaStreamSynchronize(c->stream)); // host arrays are only borrowed for this call
 	c->hostMeshes.swap(md);
-	c->hostClusterBase.swap(clusterBase);
-	c->hostNrmCount.resize((size_t)s->n_meshes);
-	for (int i = 0; i < s->n_meshes; i++)
-		c->hostNrmCount[i] = s->meshes[i].n_normals;
 	c->texOffset.swap(to);
 	c->texRows.swap(tr);
 	c->texCols.swap(tc);
@@ -1235,6 +1249,7 @@ int mr_read_image_begin(mr_ctx* c, float* host, int* ticket)
 	MR_CUDA(c, cudaMemcpyAsync(host, c->imageSlot[sl].p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->copy));
 	MR_CUDA(c, cudaEventRecord(c->copyDone[sl], c->copy));
 	c->copyPending[sl] = true;
+	c->copyRing[sl] = c->slotNewest;
 	if (ticket)
 		*ticket = sl;
 	return MR_OK;
@@ -1246,6 +1261,20 @@ int mr_read_wait(mr_ctx* c, int ticket)
 		return MR_E_INVALID;
 	Bind bind(c->device);
 	MR_CUDA(c, cudaEventSynchronize(c->copyDone[ticket]));
+	// The copied frame's counters follow its kernels on the side stream: a frame that overflowed its spill list
+	// is incomplete and must not be taken for good (the capacities have been raised: render it again).
+	bool overflowed = c->slotOverflowed;
+	c->slotOverflowed = false;
+	if (c->copyRing[ticket] >= 0)
+	{
+		const int rc = retireSlot(c, c->copyRing[ticket]);
+		c->copyRing[ticket] = -1;
+		if (rc < 0)
+			return rc;
+		overflowed = overflowed || rc > 0;
+	}
+	if (overflowed)
+		return setError(c, MR_E_OVERFLOW, "a pipelined frame overflowed its spill list (capacities raised): render it again");
 	return MR_OK;
 }
 
@@ -1386,8 +1415,8 @@ int mr_profile_frame(mr_ctx* c, const mr_frame* f, int repeats)
 	rc = finishFrame(c);
 	if (rc)
 		return rc;
-	cudaEvent_t ev[6];
-	for (int i = 0; i < 6; i++)
+	cudaEvent_t ev[3];
+	for (int i = 0; i < 3; i++)
 		MR_CUDA(c, cudaEventCreate(&ev[i]));
 	float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	for (int it = 0; it < repeats; it++)
@@ -1398,17 +1427,15 @@ int mr_profile_frame(mr_ctx* c, const mr_frame* f, int repeats)
 		if (rc)
 			break;
 		MR_CUDA(c, cudaStreamSynchronize(c->stream));
-		for (int i = 0; i < 5; i++)
-		{
-			float ms = 0;
-			cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-			acc[i] += ms;
-		}
 		float ms = 0;
-		cudaEventElapsedTime(&ms, ev[0], ev[5]);
+		cudaEventElapsedTime(&ms, ev[0], ev[1]);
+		acc[1] += ms; // k_geom
+		cudaEventElapsedTime(&ms, ev[1], ev[2]);
+		acc[4] += ms; // k_raster
+		cudaEventElapsedTime(&ms, ev[0], ev[2]);
 		acc[5] += ms;
 	}
-	for (int i = 0; i < 6; i++)
+	for (int i = 0; i < 3; i++)
 		cudaEventDestroy(ev[i]);
 	for (int i = 0; i < 8; i++)
 		c->stats.ms_kernel[i] = acc[i] / repeats;

@@ -3,10 +3,10 @@
 // for bit, so every multiply and add below rounds separately, in the reference's association.
 // IEEE division and square root are nvcc's defaults (-prec-div=true -prec-sqrt=true -ftz=false).
 //
-//   k_vertex   reference loop A            src/Renderer.cpp:344-345 + htransform :13-20, :195-196
-//   k_setup    reference loop C + setup    src/Renderer.cpp:351-380, :163-224, clipTriangle :131-161,
-//              plus the exact coverage mask of small triangles (loops D/E :238-249 without depth)
-//   k_raster   reference loops D/E + shade src/Renderer.cpp:236-305, clear :113-119
+//   k_geom     reference loops A, B, C     src/Renderer.cpp:344-380 + htransform :13-20, :195-196,
+//              setup + clipping            :163-224, clipTriangle :131-161,
+//              loops D/E of small triangles :238-269 (depth test = 64-bit atomicMin per covered pixel)
+//   k_raster   loops D/E of the larger triangles, resolve + shade src/Renderer.cpp:236-305, clear :113-119
 #include "mr_types.h"
 #include <algorithm>
 #include <math.h>
@@ -21,19 +21,6 @@ namespace {
 // successor's CTAs take the SM slots that free up during the predecessor's last wave.
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-
-// Software prefetch (no destination register: costs an issue slot, no register pressure).
-__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#ifndef MR_PREFETCH_NIDX
-#define MR_PREFETCH_NIDX 1 // k_setup: 1 = a triangle's normal / texcoord indices into L2 while it is set up, 2 = into L1
-#endif
-#ifndef MR_PREFETCH_ATTR
-#define MR_PREFETCH_ATTR 0 // k_setup: 1 = a set-up triangle's normals into L2 before its pixel loop, 2 = into L1
-#endif
-#ifndef MR_PREFETCH_NRM
-#define MR_PREFETCH_NRM 0 // k_vertex: 1 = the scene's normals into L2 for k_setup
-#endif
 
 struct V3 { float x, y, z; };
 
@@ -99,50 +86,7 @@ template <int TM> __device__ __forceinline__ const RDyn* frameRdyn(const FramePa
 template <int TM> __device__ __forceinline__ const MatDev* frameMats(const FrameParams& fp) { return TM == TM_INLINE ? fp.matsInline : fp.mats; }
 template <int TM> __device__ __forceinline__ const RStat* frameRstat(const FrameParams& fp) { return TM == TM_INLINE ? fp.rstatInline : fp.rstat; }
 
-// Renderable that owns instance `inst` (a vertex or triangle instance) of this NT-thread CTA (NT divides 256).
-// blockR[b] / blockR[b+1] bracket the candidates; their base offsets are staged in shared memory
-// and searched there. Must be called by every thread of the block.
-__device__ __forceinline__ int instBase(const RStat& s, int kind) { return kind == 0 ? s.vertBase : kind == 1 ? s.triBase : s.nrmBase; }
-
-template <int NT, int TM>
-__device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* __restrict__ blockR, int inst, int kind, int* shBases)
-{
-	if (fp.nRenderables == 1)
-		return 0; // nothing to look up (and one dependent load less)
-	const int vblock = (blockIdx.x * NT) >> 8; // the 256-instance block this CTA lies in
-	const int r0 = __ldg(&blockR[vblock]), r1 = __ldg(&blockR[vblock + 1]);
-	if (r0 >= r1)
-		return r0; // the whole block belongs to one renderable
-	const int n = r1 - r0 + 1;
-	if (n <= 256)
-	{
-		for (int i = threadIdx.x; i < n; i += NT)
-			shBases[i] = instBase(frameRstat<TM>(fp)[r0 + i], kind);
-		__syncthreads();
-		int lo = 0, hi = n - 1; // largest i with base[i] <= inst
-		while (lo < hi)
-		{
-			const int mid = (lo + hi + 1) >> 1;
-			if (shBases[mid] <= inst)
-				lo = mid;
-			else
-				hi = mid - 1;
-		}
-		return r0 + lo;
-	}
-	int lo = r0, hi = r1; // pathological: more than 256 renderables inside one block
-	while (lo < hi)
-	{
-		const int mid = (lo + hi + 1) >> 1;
-		if (instBase(frameRstat<TM>(fp)[mid], kind) <= inst)
-			lo = mid;
-		else
-			hi = mid - 1;
-	}
-	return lo;
-}
-
-// Cluster culling (evaluated by k_vertex, one thread per k_setup CTA). Cluster `ci` = MR_CLUSTER
+// Cluster culling (k_geom's first phase, one thread per cluster of the frame). Cluster `ci` = MR_CLUSTER
 // consecutive triangle instances of one renderable = MR_CLUSTER consecutive triangles of its mesh,
 // for which mr_upload_scene stored a bounding sphere and a cone around the geometric normals.
 // Returns false when no triangle of the cluster can reach a pixel of this frame:
@@ -152,14 +96,8 @@ __device__ __forceinline__ int findRenderable(const FrameParams& fp, const int* 
 //  * every normal of the cone facing away from the eye: area cull (Renderer.cpp:205-210).
 // Only triangles the reference discards itself are dropped, with generous margins, so the image
 // does not change.
-template <int TM>
-__device__ __forceinline__ bool clusterVisible(const FrameParams& fp, int ci)
+__device__ __forceinline__ bool clusterVisible(const FrameParams& fp, const RDyn& rd, const float4 cs, const float4 ca)
 {
-	const int r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
-	const RStat& rs = frameRstat<TM>(fp)[r];
-	const float4* cl = fp.clusters + 2 * (size_t)(rs.clusterBase + (ci * MR_CLUSTER - rs.triBase) / MR_CLUSTER);
-	const float4 cs = __ldg(cl), ca = __ldg(cl + 1);
-	const RDyn& rd = frameRdyn<TM>(fp)[r];
 	const V3 c = affine(rd.mv, cs.x, cs.y, cs.z);
 	const float R = cs.w * rd.radiusScale;
 	const float slack = 1e-4f * (fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + R) + 1e-6f;
@@ -183,58 +121,6 @@ __device__ __forceinline__ bool clusterVisible(const FrameParams& fp, int ci)
 		}
 	}
 	return !cull;
-}
-
-// ------------------------------------------------------------------------------------------
-// Kernel 1: vertex transform + projection (reference loop A, Renderer.cpp:344-345, and the
-// per-vertex part of paintTriangle, :186-196, :223-224). Thread i handles vertex instance i:
-// LDG.128 in, STG.128 out, fully coalesced. Also zeroes the per-frame tile counters and statistics.
-// Normals (loop B) are transformed only for the corners of triangles that survive setup (k_setup).
-// ------------------------------------------------------------------------------------------
-template <int TM>
-__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameParams fp)
-{
-	__shared__ int shBases[256];
-	pdlLaunchDependents();
-	const int vi = blockIdx.x * 256 + threadIdx.x;
-	const int nTiles = fp.tilesX * fp.tilesY;
-	if (vi <= nTiles)
-		fp.tileCount[vi] = make_int2(0, 0);
-	if (vi < (int)(sizeof(Counters) / 8))
-		reinterpret_cast<unsigned long long*>(fp.ctr)[vi] = (vi == 0) ? (unsigned long long)fp.nTriReal : 0ull; // word 0 = trianglesIn
-	if (fp.cullClusters && blockIdx.x * 256 < fp.nTriInst / MR_CLUSTER)
-	{
-		// the verdict of every cluster, as a bit of the mask (k_setup with one CTA per cluster) and appended to
-		// visList (persistent k_setup; one atomic per warp; the order of the list is irrelevant: ids
-		// come from the cluster index)
-		const bool vis = vi < fp.nTriInst / MR_CLUSTER && clusterVisible<TM>(fp, vi);
-		const unsigned m = __ballot_sync(0xffffffffu, vis);
-		if ((threadIdx.x & 31) == 0)
-			fp.clusterVis[vi >> 5] = m; // a bit per cluster: the whole frame's verdicts are a few L1 lines for k_setup
-		if (m != 0u)
-		{
-			const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-			int base = 0;
-			if (lane == leader)
-				base = atomicAdd(fp.visCount, __popc(m));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (vis)
-				fp.visList[base + __popc(m & ((1u << lane) - 1u))] = vi;
-		}
-	}
-#if MR_PREFETCH_NRM
-	if (vi < fp.nNrmSrc)
-		prefetchL2(fp.nrm4 + vi);
-#endif
-	if (blockIdx.x * 256 >= fp.nVertInst)
-		return;
-	const int rv = findRenderable<256, TM>(fp, fp.vtxBlockR, vi, 0, shBases);
-	if (vi >= fp.nVertInst)
-		return;
-	const RStat& rs = frameRstat<TM>(fp)[rv];
-	const float4 p = __ldg(&fp.pos4[rs.posBase + (vi - rs.vertBase)]);
-	const V3 view = affine(frameRdyn<TM>(fp)[rv].mv, p.x, p.y, p.z);
-	fp.pv[vi] = project(fp, view);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -302,6 +188,9 @@ __device__ __forceinline__ float pixelDepth(int persp, float e1, float e2, float
 	return k0 * d0 + e1 * d1 + e2 * d2 + 0.0f * 1.0f; // :261
 }
 
+// 64-bit minimum without a return value (RED, fire and forget: the warp does not wait for L2)
+__device__ __forceinline__ void redMin64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.min.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
 // Small triangle (bbox of at most MR_SMALL_AREA pixel centres): the reference's loops D/E
 // (Renderer.cpp:238-269) run right here by the setup thread; the depth test of every covered pixel
 // is one 64-bit atomicMin on the pixel's key in gkeys (fire-and-forget RED in L2). No binning, no
@@ -331,7 +220,7 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
 				if (z == z) // a NaN depth never passes `z < pixdepth`
 				{
-					atomicMin(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
+					redMin64(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
 					any = true;
 				}
 			}
@@ -417,39 +306,14 @@ struct Corner
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
+// The shading half of a record: the three corners as k_geom keeps them in shared memory,
+// B = (view x, y, z, u), C = (view normal x, y, z, v): pairs (B0 B1) (B2 C0) (C1 C2).
 template <bool WIDE>
-__device__ __forceinline__ void storeShadeRec(const RecRef d, const Corner& c0, const Corner& c1, const Corner& c2)
+__device__ __forceinline__ void storeShadeRec(const RecRef d, const float4 B0, const float4 B1, const float4 B2, const float4 C0, const float4 C1, const float4 C2)
 {
-	stPair<WIDE>(d.p + 2 * d.stride, make_float4(c0.px, c0.py, c0.pz, c0.u), make_float4(c1.px, c1.py, c1.pz, c0.v));
-	stPair<WIDE>(d.p + 3 * d.stride, make_float4(c2.px, c2.py, c2.pz, c1.u), make_float4(c0.nx, c0.ny, c0.nz, c1.v));
-	stPair<WIDE>(d.p + 4 * d.stride, make_float4(c1.nx, c1.ny, c1.nz, c2.u), make_float4(c2.nx, c2.ny, c2.nz, c2.v));
-}
-
-// The three view-space corners of triangle `tri` of renderable r: gathers the mesh's positions,
-// normals and texcoords through the three index arrays and transforms them with this frame's
-// modelview / normal matrix — the same expressions, in the same order, as k_vertex / loops A, B.
-// Evaluated only for triangles that survive setup.
-template <int TM>
-__device__ __forceinline__ void viewCorners(const FrameParams& fp, const RStat& rs, int r, int tri, int ia, int ib, int ic,
-                                            Corner& c0, Corner& c1, Corner& c2)
-{
-	const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
-	const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
-	float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;
-	if (rs.uvTriBase >= 0)
-	{
-		const int* iu = fp.idxUv + (size_t)(rs.uvTriBase + tri) * 3;
-		const int iu0 = __ldg(iu), iu1 = __ldg(iu + 1), iu2 = __ldg(iu + 2);
-		t0 = __ldg(&fp.uv2[rs.uvBase + iu0]); t1 = __ldg(&fp.uv2[rs.uvBase + iu1]); t2 = __ldg(&fp.uv2[rs.uvBase + iu2]);
-	}
-	const float4 p0 = __ldg(&fp.pos4[rs.posBase + ia]), p1 = __ldg(&fp.pos4[rs.posBase + ib]), p2 = __ldg(&fp.pos4[rs.posBase + ic]);
-	const float4 n0 = __ldg(&fp.nrm4[rs.nrmSrcBase + in0]), n1 = __ldg(&fp.nrm4[rs.nrmSrcBase + in1]), n2 = __ldg(&fp.nrm4[rs.nrmSrcBase + in2]);
-	const RDyn& rd = frameRdyn<TM>(fp)[r];
-	const V3 v0 = affine(rd.mv, p0.x, p0.y, p0.z), v1 = affine(rd.mv, p1.x, p1.y, p1.z), v2 = affine(rd.mv, p2.x, p2.y, p2.z);
-	const V3 m0 = affine(rd.nm, n0.x, n0.y, n0.z), m1 = affine(rd.nm, n1.x, n1.y, n1.z), m2 = affine(rd.nm, n2.x, n2.y, n2.z);
-	c0.px = v0.x; c0.py = v0.y; c0.pz = v0.z; c0.nx = m0.x; c0.ny = m0.y; c0.nz = m0.z; c0.u = t0.x; c0.v = t0.y;
-	c1.px = v1.x; c1.py = v1.y; c1.pz = v1.z; c1.nx = m1.x; c1.ny = m1.y; c1.nz = m1.z; c1.u = t1.x; c1.v = t1.y;
-	c2.px = v2.x; c2.py = v2.y; c2.pz = v2.z; c2.nx = m2.x; c2.ny = m2.y; c2.nz = m2.z; c2.u = t2.x; c2.v = t2.y;
+	stPair<WIDE>(d.p + 2 * d.stride, B0, B1);
+	stPair<WIDE>(d.p + 3 * d.stride, B2, C0);
+	stPair<WIDE>(d.p + 4 * d.stride, C1, C2);
 }
 
 // reference clip(), Renderer.cpp:121-129
@@ -532,16 +396,21 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 	}
 }
 
-// Near-plane path of k_setup (rare): rebuilds the corners in view space, clips, sets up and stores
-// the records (the caller's warp bins them). Returns a bit per stored sub-triangle. Self-contained
-// so that its stack never touches the fast path.
-template <int TM>
-__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, int tri, int ia, int ib, int ic, uint2* spans)
+__device__ __forceinline__ Corner cornerOf(const float4 B, const float4 C)
 {
-	const RStat rs = frameRstat<TM>(fp)[r];
-	Corner v0, v1, v2;
-	viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, v0, v1, v2);
-	const int material = frameRdyn<TM>(fp)[r].material;
+	Corner c;
+	c.px = B.x; c.py = B.y; c.pz = B.z; c.u = B.w;
+	c.nx = C.x; c.ny = C.y; c.nz = C.z; c.v = C.w;
+	return c;
+}
+
+// Near-plane path of k_geom (rare): clips the triangle's view-space corners, sets up and stores the
+// records of the one or two output triangles (the caller's warp bins them). Returns a bit per stored
+// sub-triangle. Out of line so that its stack never touches the fast path.
+__device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int material, int submission, const float4* sB, const float4* sC, int i0, int i1, int i2,
+                                         uint2* spans)
+{
+	const Corner v0 = cornerOf(sB[i0], sC[i0]), v1 = cornerOf(sB[i1], sC[i1]), v2 = cornerOf(sB[i2], sC[i2]);
 	int nrec = 0;
 	const int tyLo = fp.tileRow0, tyHi = fp.tileRow0 + fp.tileRows - 1;
 	for (int sub = 0; sub < 2; sub++)
@@ -559,8 +428,9 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
 		const RecRef ref = recRef(fp, id);
-		storeRec<false>(ref, a, b, c, s, material, 2 * (rs.triBaseReal + tri) + sub);
-		storeShadeRec<false>(ref, o0, o1, o2);
+		storeRec<false>(ref, a, b, c, s, material, submission + sub);
+		storeShadeRec<false>(ref, make_float4(o0.px, o0.py, o0.pz, o0.u), make_float4(o1.px, o1.py, o1.pz, o1.u), make_float4(o2.px, o2.py, o2.pz, o2.u),
+		                     make_float4(o0.nx, o0.ny, o0.nz, o0.v), make_float4(o1.nx, o1.ny, o1.nz, o1.v), make_float4(o2.nx, o2.ny, o2.nz, o2.v));
 		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
 		nrec |= 1 << sub;
 	}
@@ -568,77 +438,86 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int r, in
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 2: near test, clip, setup, and either direct rasterization (small triangles) or binning.
-// One thread per triangle instance t. A surviving triangle's records are written at index 2t
-// (clipper outputs at 2t and 2t+1): the index is the submission id.
-//  * bbox of at most MR_SMALL_AREA pixel centres: rasterSmall() depth-tests its covered pixels
-//    straight into gkeys; the triangle never enters a bin.
-//  * larger: appended to the bin of every 16x16 tile its bbox touches. Bins have a fixed capacity
-//    per tile (fp.binCap); the position comes from the tile counter with one atomic per distinct
-//    tile per warp (__match_any_sync: neighbouring triangles mostly share a tile), and the rare
-//    entries beyond the capacity go to a global overflow list.
+// Kernel 1: geometry. Persistent CTAs of MR_GEOM_TEAMS teams of 128 threads.
+//
+// Phase 0, cull: one thread per cluster of the frame (CTA b takes clusters b*NT .. b*NT+NT-1, strided by the
+//   grid) evaluates clusterVisible(); survivors are appended to the frame's work list as self-contained
+//   128-byte GeomEntry records (renderable matrices included). The CTAs then meet at a grid-wide counter:
+//   the list is complete before anyone pops from it.
+// Phase 1: a team pops one entry at a time from the global list (one atomic per cluster: perfect balance
+//   across SMs whatever survives where) and processes that cluster of MR_CLUSTER triangles entirely out of
+//   shared memory:
+//     load      its meshlet blob (the cluster's distinct corners + 10-bit local indices, ~4.7 KB for a grid
+//               mesh) arrives by one cp.async.bulk, completion on the team's mbarrier; the copy for cluster
+//               k+1 is issued as soon as cluster k's corners are transformed, so it overlaps k's triangles;
+//     vertex    thread v transforms corner v: modelview (loop A, Renderer.cpp:344-345), htransform + pixel
+//               coordinates + depth term (:13-20, :186-196, :223-224), normal matrix (loop B, :347-348);
+//               results go to the team's shared memory as three float4 planes;
+//     triangle  thread j sets up triangle j from shared memory (near test, clip path, reject, cull, edge
+//               normals, spans: Renderer.cpp:163-224). bbox of at most MR_SMALL_AREA pixel centres: the
+//               reference's loops D/E run right here, the depth test being one 64-bit atomicMin per covered
+//               pixel on gkeys; larger: binned to the 16x16 tiles of its bbox for k_raster. A triangle that
+//               can own a pixel writes its record (index 2t: the index is the submission id) as five
+//               coalesced 32-byte pairs.
+//   The pop for cluster k+2, the entry read for k+1 and the bulk copy for k+1 are all issued by the team's
+//   first warp right after the vertex phase of cluster k and consumed one iteration later: no dependent
+//   global load sits on a team's critical path. Everything a frame needs zeroed between frames (tile
+//   counters, list counters, the next frame's statistics) is reset by k_raster.
 // The order in which fragments or bin entries arrive does not matter: depth ties are resolved on
 // the record index (submission id) carried in the low word of every depth key.
 // ------------------------------------------------------------------------------------------
-#ifndef MR_SETUP_THREADS
-#define MR_SETUP_THREADS 128
-#endif
-#ifndef MR_SETUP_MINB
-#define MR_SETUP_MINB (1024 / MR_SETUP_THREADS)
-#endif
-static_assert(MR_SETUP_THREADS == MR_CLUSTER, "one cull cluster per k_setup CTA iteration");
-// 1: a one-CTA-per-cluster k_setup requests its (scene-static) vertex indices before it waits for
-// k_vertex and looks at its verdict; 0: verdict first, so that culled CTAs load nothing.
-#ifndef MR_SETUP_INDICES_FIRST
-#define MR_SETUP_INDICES_FIRST 0
+#define MR_GEOM_TEAMS 4
+#define MR_GEOM_THREADS (MR_GEOM_TEAMS * MR_CLUSTER)
+#ifndef MR_GEOM_MINB
+#define MR_GEOM_MINB 2
 #endif
 
-// One cluster: MR_CLUSTER consecutive triangle instances of one renderable (instance bases are padded
-// to whole clusters, so the cluster index gives the renderable without a search), one per thread.
-// acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
-struct ClusterTri // what a thread works on within cluster ci
+struct GeomShared // fixed part of k_geom's dynamic shared memory
 {
-	int r;            // renderable
-	const RStat* rs;
-	int t, tri;       // triangle instance (padded numbering), triangle within the mesh
-	bool active;      // false: padding behind the mesh's last triangle
-	int ia, ib, ic;   // its vertex indices
+	GeomEntry entry[MR_GEOM_TEAMS][2]; // the cluster a team works on (k & 1) and the next one
+	unsigned long long full[MR_GEOM_TEAMS]; // mbarrier: the team's meshlet (or the news that there is none) has arrived
+	unsigned long long stat;
+	int nVis;
 };
+#define MR_GEOM_FIXED_BYTES ((int)((sizeof(GeomShared) + 127) / 128 * 128))
+#define MR_GEOM_TEAM_BYTES(nvCap) (MR_MESHLET_BYTES(nvCap) + 2 * ((nvCap) * 48 + MR_CLUSTER * 4))
 
-template <int TM>
-__device__ __forceinline__ ClusterTri locateAndLoadIndices(const FrameParams& fp, int ci)
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* b, uint32_t bytes)
 {
-	ClusterTri k;
-	k.r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
-	k.rs = &frameRstat<TM>(fp)[k.r];
-	k.t = ci * MR_CLUSTER + (int)threadIdx.x;
-	k.tri = k.t - k.rs->triBase;
-	k.active = k.tri < k.rs->nTri;
-	k.ia = k.ib = k.ic = 0;
-	if (k.active)
-	{
-		const int* ix = fp.idxPos + (size_t)(k.rs->idxBase + k.tri) * 3;
-		k.ia = __ldg(ix); k.ib = __ldg(ix + 1); k.ic = __ldg(ix + 2);
-#if MR_PREFETCH_NIDX
-		// the survivors' second chain of dependent loads starts at these indices
-		const int* in = fp.idxNrm + (size_t)(k.rs->idxBase + k.tri) * 3;
-		if (MR_PREFETCH_NIDX == 2) prefetchL1(in); else prefetchL2(in);
-		if (k.rs->uvTriBase >= 0)
-		{
-			const int* iu = fp.idxUv + (size_t)(k.rs->uvTriBase + k.tri) * 3;
-			if (MR_PREFETCH_NIDX == 2) prefetchL1(iu); else prefetchL2(iu);
-		}
-#endif
-	}
-	return k;
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(b)), "r"(bytes) : "memory");
 }
-
-template <int TM>
-__device__ __forceinline__ void setupCluster(const FrameParams& fp, const ClusterTri& k, int lane, unsigned long long& acc)
+__device__ __forceinline__ void mbarArrive(unsigned long long* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(b)) : "memory"); }
+__device__ __forceinline__ void mbarWait(unsigned long long* b, uint32_t parity)
 {
-	const int r = k.r, t = k.t, tri = k.tri, ia = k.ia, ib = k.ib, ic = k.ic;
-	const RStat& rs = *k.rs;
-	const bool active = k.active;
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"MR_WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra MR_DONE_%=;\n"
+		"bra MR_WAIT_%=;\n"
+		"MR_DONE_%=:\n"
+		"}" ::"r"(smemAddr(b)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
+	             "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void teamBarrier(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(MR_CLUSTER) : "memory"); }
+__device__ __forceinline__ int ldAcquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// Triangle phase of one cluster for one thread (triangle tt of the cluster); see k_geom.
+// acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
+__device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEntry& e, const float4* __restrict__ sA, const float4* __restrict__ sB,
+                                             const float4* __restrict__ sC, const uint32_t* __restrict__ sIdx, int tt, int lane, unsigned long long& acc)
+{
+	const int t = e.ci * MR_CLUSTER + tt; // triangle instance (padded numbering): 2t is its record index
+	const int tri = e.triFirst + tt;      // triangle within the mesh
+	const bool active = tri < e.nTri;     // false: padding behind the mesh's last triangle
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
 	uint2 clipSpans[2]; // bbox spans of the clipper's output triangles (the warp bins them below)
@@ -648,32 +527,21 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 	s.flags = 0u;
 	if (active)
 	{
-		const float4 a = fp.pv[rs.vertBase + ia];
-		const float4 b = fp.pv[rs.vertBase + ib];
-		const float4 c = fp.pv[rs.vertBase + ic];
+		const uint32_t ix = sIdx[tt];
+		const int i0 = ix & 1023u, i1 = (ix >> 10) & 1023u, i2 = ix >> 20;
+		const float4 a = sA[i0], b = sA[i1], c = sA[i2];
 		const float zn = fp.znear;
 		if (a.z > zn || b.z > zn || c.z > zn) // Renderer.cpp:169-177
 		{
 			if (!(a.z > zn && b.z > zn && c.z > zn))
 			{
 				nclip = 1;
-				nrecSlow = setupClipped<TM>(fp, t, r, tri, ia, ib, ic, clipSpans);
+				nrecSlow = setupClipped(fp, t, e.material, 2 * (e.subBase + tri), sB, sC, i0, i1, i2, clipSpans);
 			}
 		}
 		else if (setupTriangle(fp, a, b, c, s))
 		{
 			valid = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1) >= max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0);
-#if MR_PREFETCH_ATTR
-			if (valid)
-			{
-				// the normals come from DRAM: ask for them now, the pixel loop hides the round trip
-				const int* in = fp.idxNrm + (size_t)(rs.idxBase + tri) * 3;
-				const float4* nb = fp.nrm4 + rs.nrmSrcBase;
-				const int in0 = __ldg(in), in1 = __ldg(in + 1), in2 = __ldg(in + 2);
-				if (MR_PREFETCH_ATTR == 2) { prefetchL1(nb + in0); prefetchL1(nb + in1); prefetchL1(nb + in2); }
-				else { prefetchL2(nb + in0); prefetchL2(nb + in1); prefetchL2(nb + in2); }
-			}
-#endif
 			if (valid)
 			{
 				if ((s.x1 - s.x0 + 1) * (s.y1 - s.y0 + 1) <= MR_SMALL_AREA)
@@ -686,14 +554,10 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 			}
 			if (valid)
 			{
-				// The triangle can own pixels: write its records. (Requesting the corner attributes
-				// earlier — before the pixel loop, or the index loads at the top — was measured: the
-				// longer live ranges spill and nothing is gained.)
-				Corner c0, c1, c2;
-				viewCorners<TM>(fp, rs, r, tri, ia, ib, ic, c0, c1, c2);
+				// The triangle can own pixels: its record = raster half + its three view-space corners as they lie in shared memory
 				const RecRef ref = recRef(fp, 2 * t);
-				storeRec<true>(ref, a, b, c, s, frameRdyn<TM>(fp)[r].material, 2 * (rs.triBaseReal + tri));
-				storeShadeRec<true>(ref, c0, c1, c2);
+				storeRec<true>(ref, a, b, c, s, e.material, 2 * (e.subBase + tri));
+				storeShadeRec<true>(ref, sB[i0], sB[i1], sB[i2], sC[i0], sC[i1], sC[i2]);
 			}
 		}
 	}
@@ -795,97 +659,202 @@ __device__ __forceinline__ void setupCluster(const FrameParams& fp, const Cluste
 	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
 }
 
-// Two forms, chosen by the host per frame (each its own kernel: with both bodies inlined into one,
-// the instruction cache misses cost the many-small-meshes scene 15 us):
-//  * PERSIST = false, one CTA per cluster of the frame — when most clusters are expected to survive.
-//    The hardware balances the CTAs (a static round-robin cost the 20-object bench scene 6 us).
-//  * PERSIST = true, a few CTAs per SM, CTA b takes entries b, b + G, ... of the visible list that
-//    k_vertex built — when most clusters are culled: launching 78 000 CTAs only to have 85 % of them
-//    exit is bound by the CTA launch rate (4K, 10 M triangles, strip 1 of 8: k_setup 97 -> 37 us).
-template <int TM, bool PERSIST>
-__global__ void __launch_bounds__(MR_SETUP_THREADS, MR_SETUP_MINB) k_setup(const __grid_constant__ FrameParams fp)
+template <int TM>
+__global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __grid_constant__ FrameParams fp)
 {
-	__shared__ unsigned long long shStat[2]; // summed acc of the CTA's threads; warps done
-	pdlLaunchDependents();
-	const int lane = threadIdx.x & 31;
+	extern __shared__ __align__(128) unsigned char geomSmem[];
+	GeomShared& gs = *reinterpret_cast<GeomShared*>(geomSmem);
+	const int tid = threadIdx.x, team = tid >> 7, tt = tid & (MR_CLUSTER - 1), lane = tid & 31;
+	const int nvCap = fp.geomVertCap;
 	const int nCl = fp.nTriInst / MR_CLUSTER;
-	unsigned long long acc = 0ull;
-	if (!PERSIST)
+	int* const sync = fp.geomSync;
+
+	pdlLaunchDependents(); // k_raster's CTAs may take the SMs this kernel's CTAs leave (they wait for the whole grid)
+	if (tid == 0)
 	{
-		// One CTA per cluster. A culled cluster's CTA must cost next to nothing (on a closed mesh that is
-		// every other CTA): the verdicts are a bit mask of a few 128-byte lines, resident in the SM's L1
-		// after its first CTAs, and a culled CTA leaves before it loads or reduces anything.
-#if MR_SETUP_INDICES_FIRST
-		const ClusterTri k = locateAndLoadIndices<TM>(fp, blockIdx.x);
-#endif
-		pdlWait(); // k_vertex's pv[], cluster verdicts and zeroed counters
-		if (blockIdx.x == 0 && threadIdx.x == 0)
-		{
-			fp.ctr->visible = fp.cullClusters ? (unsigned)*fp.visCount : (unsigned)nCl;
-			fp.ctr->clusters = (unsigned)nCl;
-		}
-		if (fp.cullClusters && ((fp.clusterVis[blockIdx.x >> 5] >> (blockIdx.x & 31)) & 1u) == 0u)
-			return;
-#if !MR_SETUP_INDICES_FIRST
-		const ClusterTri k = locateAndLoadIndices<TM>(fp, blockIdx.x);
-#endif
-		if (threadIdx.x < 2)
-			shStat[threadIdx.x] = 0ull;
-		__syncthreads();
-		setupCluster<TM>(fp, k, lane, acc);
+		for (int i = 0; i < MR_GEOM_TEAMS; i++)
+			mbarInit(&gs.full[i], 1);
+		gs.stat = 0ull;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	else
+
+	// ---- phase 0: cull (Renderer.cpp:169-177, :202, :205-210 decided per cluster) ----
+	for (int base = blockIdx.x * MR_GEOM_THREADS; base < nCl; base += gridDim.x * MR_GEOM_THREADS)
 	{
-		// persistent CTAs walk the list of visible clusters
-		if (threadIdx.x < 2)
-			shStat[threadIdx.x] = 0ull;
-		__syncthreads();
-		pdlWait();
-		const int nVis = fp.cullClusters ? *fp.visCount : nCl;
-		if (blockIdx.x == 0 && threadIdx.x == 0)
+		const int ci = base + tid;
+		bool vis = false;
+		int r = 0;
+		RStat rs;
+		rs.triBase = rs.clusterBase = rs.nTri = rs.triBaseReal = 0;
+		int meshCluster = 0;
+		if (ci < nCl)
 		{
-			fp.ctr->visible = (unsigned)nVis;
+			r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
+			rs = frameRstat<TM>(fp)[r];
+			meshCluster = rs.clusterBase + (ci * MR_CLUSTER - rs.triBase) / MR_CLUSTER;
+			vis = true;
+			if (fp.cullClusters)
+			{
+				const float4* cl = fp.clusters + 2 * (size_t)meshCluster;
+				vis = clusterVisible(fp, frameRdyn<TM>(fp)[r], __ldg(cl), __ldg(cl + 1));
+			}
+		}
+		const unsigned m = __ballot_sync(0xffffffffu, vis);
+		if (m != 0u)
+		{
+			const int leader = __ffs(m) - 1;
+			int at = 0;
+			if (lane == leader)
+				at = atomicAdd(&sync[1], __popc(m));
+			at = __shfl_sync(0xffffffffu, at, leader) + __popc(m & ((1u << lane) - 1u));
+			if (vis)
+			{
+				const MeshletDir d = fp.meshletDir[meshCluster];
+				const RDyn& rd = frameRdyn<TM>(fp)[r];
+				uint4* o = reinterpret_cast<uint4*>(fp.visEntries + at);
+				o[0] = make_uint4((uint32_t)ci, d.nv, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
+				o[1] = make_uint4((uint32_t)rs.nTri, (uint32_t)rs.triBaseReal, (uint32_t)rd.material, 0u);
+#pragma unroll
+				for (int k = 0; k < 3; k++)
+				{
+					o[2 + k] = make_uint4(__float_as_uint(rd.mv[4 * k]), __float_as_uint(rd.mv[4 * k + 1]), __float_as_uint(rd.mv[4 * k + 2]), __float_as_uint(rd.mv[4 * k + 3]));
+					o[5 + k] = make_uint4(__float_as_uint(rd.nm[4 * k]), __float_as_uint(rd.nm[4 * k + 1]), __float_as_uint(rd.nm[4 * k + 2]), __float_as_uint(rd.nm[4 * k + 3]));
+				}
+			}
+		}
+	}
+	// every CTA's entries must be visible before anyone pops: a grid-wide arrival counter (all CTAs are
+	// resident: the grid is sized from the occupancy of this kernel and launched cooperatively)
+	__threadfence();
+	__syncthreads();
+	if (tid == 0)
+	{
+		atomicAdd(&sync[2], 1);
+		while (ldAcquire(&sync[2]) < (int)gridDim.x)
+			;
+		const int n = ldAcquire(&sync[1]);
+		gs.nVis = n;
+		if (blockIdx.x == 0)
+		{
+			fp.ctr->trianglesIn = (unsigned long long)fp.nTriReal;
+			fp.ctr->visible = (unsigned)n;
 			fp.ctr->clusters = (unsigned)nCl;
 		}
-		for (int i = blockIdx.x; i < nVis; i += gridDim.x)
+	}
+	__syncthreads();
+	const int nVis = gs.nVis;
+
+	// ---- phase 1 ----
+	unsigned long long acc = 0ull;
+	if (team < fp.geomTeams)
+	{
+		unsigned char* const teamMem = geomSmem + MR_GEOM_FIXED_BYTES + (size_t)team * MR_GEOM_TEAM_BYTES(nvCap);
+		unsigned char* const raw = teamMem;
+		const int scrBytes = nvCap * 48 + MR_CLUSTER * 4;
+		const uint32_t* const visWords = reinterpret_cast<const uint32_t*>(fp.visEntries);
+		const bool loader = tt < 32; // the team's first warp pops work and issues the copies
+		int popIdx = 0x7fffffff;     // (lane 0) list index popped for the cluster after next
+		uint32_t entryWord = 0u;     // word `lane` of the next cluster's entry
+		if (loader)
 		{
-			const ClusterTri k = locateAndLoadIndices<TM>(fp, fp.cullClusters ? fp.visList[i] : i);
-			setupCluster<TM>(fp, k, lane, acc);
+			int i0 = 0, i1 = 0;
+			if (lane == 0)
+			{
+				i0 = atomicAdd(&sync[0], 1);
+				i1 = atomicAdd(&sync[0], 1);
+				popIdx = atomicAdd(&sync[0], 1);
+			}
+			i0 = __shfl_sync(0xffffffffu, i0, 0);
+			i1 = __shfl_sync(0xffffffffu, i1, 0);
+			const uint32_t none = (lane == 0) ? 0xffffffffu : 0u;
+			const uint32_t w0 = (i0 < nVis) ? __ldcg(visWords + (size_t)i0 * 32 + lane) : none;
+			entryWord = (i1 < nVis) ? __ldcg(visWords + (size_t)i1 * 32 + lane) : none;
+			reinterpret_cast<uint32_t*>(&gs.entry[team][0])[lane] = w0;
+			__syncwarp();
+			if (lane == 0)
+			{
+				const GeomEntry& n = gs.entry[team][0];
+				if (n.ci >= 0)
+				{
+					mbarExpectTx(&gs.full[team], (uint32_t)MR_MESHLET_BYTES(n.nv));
+					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), &gs.full[team]);
+				}
+				else
+					mbarArrive(&gs.full[team]);
+			}
+		}
+		for (int k = 0;; k++)
+		{
+			mbarWait(&gs.full[team], (uint32_t)(k & 1));
+			const GeomEntry& e = gs.entry[team][k & 1];
+			if (e.ci < 0)
+				break;
+			const int nv = e.nv;
+			float4* const sA = reinterpret_cast<float4*>(teamMem + MR_MESHLET_BYTES(nvCap) + (size_t)(k & 1) * scrBytes);
+			float4* const sB = sA + nvCap;
+			float4* const sC = sB + nvCap;
+			uint32_t* const sIdx = reinterpret_cast<uint32_t*>(sC + nvCap);
+
+			// ---- vertex phase: loops A and B of paintMesh for the cluster's corners, plus their projection ----
+			{
+				const float4* const raw0 = reinterpret_cast<const float4*>(raw);
+				const float4* const raw1 = raw0 + nv;
+				sIdx[tt] = reinterpret_cast<const uint32_t*>(raw1 + nv)[tt];
+				for (int v = tt; v < nv; v += MR_CLUSTER)
+				{
+					const float4 q0 = raw0[v], q1 = raw1[v]; // (px py pz nx) (ny nz u v)
+					const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
+					const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
+					sA[v] = project(fp, view);
+					sB[v] = make_float4(view.x, view.y, view.z, q1.z);
+					sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
+				}
+			}
+			teamBarrier(team); // corners complete; the meshlet buffer is free again
+
+			// ---- the loader warp prepares the next cluster: entry (read one iteration ago) into shared memory,
+			// bulk copy issued, entry after next requested, another index popped ----
+			if (loader)
+			{
+				reinterpret_cast<uint32_t*>(&gs.entry[team][(k + 1) & 1])[lane] = entryWord;
+				const int i2 = __shfl_sync(0xffffffffu, popIdx, 0);
+				__syncwarp();
+				if (lane == 0)
+				{
+					const GeomEntry& n = gs.entry[team][(k + 1) & 1];
+					if (n.ci >= 0)
+					{
+						mbarExpectTx(&gs.full[team], (uint32_t)MR_MESHLET_BYTES(n.nv));
+						bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), &gs.full[team]);
+					}
+					else
+						mbarArrive(&gs.full[team]);
+					popIdx = atomicAdd(&sync[0], 1);
+				}
+				entryWord = (i2 < nVis) ? __ldcg(visWords + (size_t)i2 * 32 + lane) : ((lane == 0) ? 0xffffffffu : 0u);
+			}
+
+			// ---- triangle phase ----
+			geomTriangle(fp, e, sA, sB, sC, sIdx, tt, lane, acc);
 		}
 	}
 
-	// ---- statistics: one shared-memory atomic per warp; the warp that arrives last sends one RED per
-	// counter (no barrier and no fence: finished warps leave at once). Fields are 20 bits wide: a CTA
-	// sets up at most a few thousand triangles ----
-	unsigned long long sum;
-	if (!PERSIST)
-	{
-		// one cluster per thread: every field of acc is at most 2, so the three fit 10-bit fields of one
-		// word and the warp sum is a single REDUX
-		const unsigned packed = (unsigned)(acc & 0x3ffull) | ((unsigned)((acc >> 20) & 0x3ffull) << 10) | ((unsigned)((acc >> 40) & 0x3ffull) << 20);
-		const unsigned w = __reduce_add_sync(0xffffffffu, packed);
-		sum = (unsigned long long)(w & 0x3ffu) | ((unsigned long long)((w >> 10) & 0x3ffu) << 20) | ((unsigned long long)(w >> 20) << 40);
-	}
-	else
-	{
-		sum = acc;
+	// ---- statistics: one shared-memory atomic per warp, one RED per counter per CTA ----
+	unsigned long long sum = acc;
 #pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
-			sum += __shfl_xor_sync(0xffffffffu, sum, o);
-	}
-	if (lane == 0)
+	for (int o = 16; o > 0; o >>= 1)
+		sum += __shfl_xor_sync(0xffffffffu, sum, o);
+	if (lane == 0 && sum != 0ull)
+		atomicAdd(&gs.stat, sum);
+	__syncthreads();
+	if (tid == 0)
 	{
-		// the arrival count rides in the top bits of the same word, so one atomic both adds and tells
-		const unsigned long long mine = sum + (1ull << 60);
-		const unsigned long long all = atomicAdd(&shStat[0], mine) + mine;
-		if ((int)(all >> 60) == MR_SETUP_THREADS / 32)
-		{
-			const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
-			const unsigned long long nr = all & 0xfffffull, nc = (all >> 20) & 0xfffffull, nz = (all >> 40) & 0xfffffull;
-			if (nr) atomicAdd(&fp.ctr->records[slot], nr);
-			if (nc) atomicAdd(&fp.ctr->clippedIn[slot], nc);
-			if (nz) atomicAdd(&fp.ctr->zeroCov[slot], nz);
-		}
+		const unsigned long long all = gs.stat;
+		const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
+		const unsigned long long nr = all & 0xfffffull, nc = (all >> 20) & 0xfffffull, nz = (all >> 40) & 0xfffffull;
+		if (nr) atomicAdd(&fp.ctr->records[slot], nr);
+		if (nc) atomicAdd(&fp.ctr->clippedIn[slot], nc);
+		if (nz) atomicAdd(&fp.ctr->zeroCov[slot], nz);
 	}
 }
 
@@ -1268,9 +1237,10 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 			fp.winner[pix] = (int)__float_as_uint(q3.w); // the reference's submission index (instance ids are padded per renderable)
 		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
 		Corner c0, c1, c2;
-		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s1.w;
-		c1.px = s1.x; c1.py = s1.y; c1.pz = s1.z; c1.u = s2.w; c1.v = s3.w;
-		c2.px = s2.x; c2.py = s2.y; c2.pz = s2.z; c2.u = s4.w; c2.v = s5.w;
+		// record pairs 2-4 = (B0 B1) (B2 C0) (C1 C2), B = (view position, u), C = (view normal, v)
+		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s3.w;
+		c1.px = s1.x; c1.py = s1.y; c1.pz = s1.z; c1.u = s1.w; c1.v = s4.w;
+		c2.px = s2.x; c2.py = s2.y; c2.pz = s2.z; c2.u = s2.w; c2.v = s5.w;
 		c0.nx = s3.x; c0.ny = s3.y; c0.nz = s3.z;
 		c1.nx = s4.x; c1.ny = s4.y; c1.nz = s4.z;
 		c2.nx = s5.x; c2.ny = s5.y; c2.nz = s5.z;
@@ -1411,7 +1381,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	for (int pp = 0; pp < PP; pp++)
 		anyWin = anyWin || (uint32_t)(key[pp] & 0xffffffffull) != 0u;
 	// (this barrier also separates the previous tile's staging reads from this tile's staging writes)
-	if (!__syncthreads_or(anyWin) && vec && !(fp.saveNormals && fp.normals) && !fp.winner)
+	const bool anyWinTile = __syncthreads_or(anyWin);
+	if (tid == 0 && (tinfo.x | tinfo.y) != 0)
+		fp.tileCount[tile] = make_int2(0, 0); // every thread has read it: ready for the next frame
+	if (!anyWinTile && vec && !(fp.saveNormals && fp.normals) && !fp.winner)
 	{
 		if (full)
 			storeFullTile128<true>(fp, tileX0, tileY0, tid, 0);
@@ -1491,9 +1464,16 @@ __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(co
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
-	pdlWait(); // k_setup's keys, bins and records
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-		*fp.visCount = 0; // k_setup has consumed the visible-cluster list: ready for the next frame's k_vertex
+	pdlWait(); // k_geom's keys, bins and records
+	if (blockIdx.x == 0 && blockIdx.y == 0)
+	{
+		// k_geom is done with its work list and this frame's statistics are where they belong:
+		// the list counters and the next frame's statistics start from zero
+		if (threadIdx.x < 4)
+			fp.geomSync[threadIdx.x] = 0;
+		for (int i = threadIdx.x; i < (int)(sizeof(Counters) / 8); i += MR_RASTER_THREADS)
+			reinterpret_cast<unsigned long long*>(fp.ctrNext)[i] = 0ull;
+	}
 	rasterTile<MR_RASTER_THREADS, TM>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
 }
 
@@ -1572,52 +1552,83 @@ __global__ void k_selftest(const float* in, float* out)
 
 }
 
-void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* ev, cudaEvent_t bracketStart, cudaEvent_t bracketStop)
+// Shape of k_geom for meshlets of up to nvCap corners: teams per CTA (fewer when a team's shared memory is
+// large), dynamic shared memory per CTA, and a grid of as many CTAs as are resident at once (the cull phase
+// ends in a grid-wide rendezvous).
+int mrk_geom_config(int nvCap, int smCount, int* teams, int* grid, int* smemBytes)
+{
+	int dev = 0, smemMax = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+		return -1;
+	const int perTeam = MR_GEOM_TEAM_BYTES(nvCap);
+	int nt = MR_GEOM_TEAMS;
+	// two CTAs per SM when their teams fit half of the SM's shared memory; else one CTA with as many teams as fit
+	const int half = (smemMax + 1024) / 2 - 2048;
+	if (MR_GEOM_FIXED_BYTES + nt * perTeam > half)
+		while (nt > 1 && MR_GEOM_FIXED_BYTES + nt * perTeam > smemMax)
+			nt--;
+	const int bytes = MR_GEOM_FIXED_BYTES + nt * perTeam;
+	if (bytes > smemMax)
+		return -1;
+	int perSm = 0;
+	for (int tm = 0; tm < 2; tm++)
+	{
+		const void* fn = tm ? (const void*)k_geom<TM_INLINE> : (const void*)k_geom<TM_GLOBAL>;
+		if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+			return -1;
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, MR_GEOM_THREADS, bytes) != cudaSuccess || n < 1)
+			return -1;
+		perSm = tm ? std::min(perSm, n) : n;
+	}
+	*teams = nt;
+	*grid = smCount * std::min(perSm, MR_GEOM_MINB);
+	*smemBytes = bytes;
+	return 0;
+}
+
+void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* ev, cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl)
 {
 	if (bracketStart) cudaEventRecord(bracketStart, stream);
-	const int nTiles = fp.tilesX * fp.tilesY;
-	int vthreads = (fp.nVertInst > nTiles + 1) ? fp.nVertInst : nTiles + 1;
-	if (fp.nTriInst / MR_CLUSTER > vthreads)
-		vthreads = fp.nTriInst / MR_CLUSTER;
 	if (ev) cudaEventRecord(ev[0], stream);
 	const bool inl = fp.inlineTables != 0;
-	if (inl)
-		k_vertex<TM_INLINE><<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
-	else
-		k_vertex<TM_GLOBAL><<<(vthreads + 255) / 256, 256, 0, stream>>>(fp);
-	if (ev) cudaEventRecord(ev[1], stream);
-	// k_setup and k_raster may begin while their predecessor drains (unless stage events sit between)
-	cudaLaunchAttribute pdl[1];
-	pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	pdl[0].val.programmaticStreamSerializationAllowed = 1;
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.stream = stream;
-	cfg.attrs = pdl;
-	cfg.numAttrs = (ev || getenv("MR_NO_PDL")) ? 0 : 1;
-	if (fp.nTriInst > 0)
+	cudaLaunchAttribute attr[1];
+	cfg.attrs = attr;
 	{
-		const int nCl = fp.nTriInst / MR_CLUSTER;
-		const bool persist = fp.setupCtas < nCl;
-		cfg.gridDim = dim3(std::max(1, persist ? fp.setupCtas : nCl));
-		cfg.blockDim = dim3(MR_SETUP_THREADS);
-		if (persist)
-			cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE, true> : k_setup<TM_GLOBAL, true>, fp);
+		// all CTAs of k_geom must be resident (grid-wide rendezvous after the cull phase): cooperative launch
+		attr[0].id = cudaLaunchAttributeCooperative;
+		attr[0].val.cooperative = 1;
+		cfg.numAttrs = 1;
+		cfg.gridDim = dim3(std::max(1, geomGrid));
+		cfg.blockDim = dim3(MR_GEOM_THREADS);
+		cfg.dynamicSmemBytes = (size_t)geomSmem;
+		if (inl)
+			cudaLaunchKernelEx(&cfg, k_geom<TM_INLINE>, fp);
 		else
-			cudaLaunchKernelEx(&cfg, inl ? k_setup<TM_INLINE, false> : k_setup<TM_GLOBAL, false>, fp);
+			cudaLaunchKernelEx(&cfg, k_geom<TM_GLOBAL>, fp);
 	}
-	if (ev) cudaEventRecord(ev[2], stream);
-	if (ev) cudaEventRecord(ev[3], stream);
-	if (ev) cudaEventRecord(ev[4], stream);
+	if (ev) cudaEventRecord(ev[1], stream);
 	if (fp.tileRows > 0)
 	{
+		// k_raster may become resident while k_geom drains (unless stage events sit between)
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.numAttrs = (ev || !pdl) ? 0 : 1;
 		cfg.gridDim = dim3(fp.tilesX, fp.tileRows);
 		cfg.blockDim = dim3(MR_RASTER_THREADS);
+		cfg.dynamicSmemBytes = 0;
 		cudaLaunchKernelEx(&cfg, inl ? k_raster<TM_INLINE> : k_raster<TM_GLOBAL>, fp);
 	}
 	else
-		cudaMemsetAsync(fp.visCount, 0, sizeof(int), stream); // k_raster normally resets the visible-cluster count
-	if (ev) cudaEventRecord(ev[5], stream);
+	{
+		// k_raster normally resets the work-list counters and the next frame's statistics
+		cudaMemsetAsync(fp.geomSync, 0, 4 * sizeof(int), stream);
+		cudaMemsetAsync(fp.ctrNext, 0, sizeof(Counters), stream);
+	}
+	if (ev) cudaEventRecord(ev[2], stream);
 	if (bracketStop) cudaEventRecord(bracketStop, stream);
 }
 

@@ -1,16 +1,16 @@
 // Device-side data model of the B200 rasterization pipeline (shared by kernels and host code).
 //
 // Scene-static arrays (uploaded by mr_upload_scene, resident in HBM):
-//   pos4[]   float4 per mesh vertex   (x,y,z,1)      -- one LDG.128 per vertex, 16 B aligned
-//   nrm4[]   float4 per mesh normal   (x,y,z,0)
-//   uv2[]    float2 per texcoord
-//   idxPos[] idxNrm[] idxUv[]  int per triangle corner (3 per triangle)
-//   texels[] float4 per texel (r,g,b,0), all textures concatenated
-//   MeshDev[] per mesh: base offsets into the arrays above
+//   meshlets[]    one blob per MR_CLUSTER consecutive triangles of a mesh: the distinct (position, normal,
+//                 texcoord) corners of those triangles as two float4 planes, then one packed word of three
+//                 10-bit local indices per triangle. A blob is what one team of k_geom pulls into shared
+//                 memory with a single cp.async.bulk; meshletDir[] gives offset and vertex count
+//   clusters[]    bounding sphere + normal cone of the same triangles (cluster culling)
+//   texels[]      float4 per texel (r,g,b,0), all textures concatenated
 // Per-frame arrays:
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
-//   pv[]           float4 per vertex *instance*: (pixel x, pixel y, view z, depth term)
+//   visEntries[]   one GeomEntry per cluster that survived culling (k_geom's work list)
 //   recs[]         one 160-byte record per set-up triangle (10 float4 fields: 4 raster, 6 shading = its
 //                  three view-space corners), at index 2*t+sub where t is the triangle instance index in
 //                  submission order: the index IS the submission id that resolves equal-depth ties.
@@ -30,31 +30,36 @@
 #define MR_TILE_PIXELS 256
 #define MR_SEG_PER_LANE 4 // tiles per triangle binned on the warp-aggregated fast path
 
-struct MeshDev
+struct MeshDev // host-side bookkeeping of one uploaded mesh
 {
-	int posBase, nrmBase, uvBase; // into pos4 / nrm4 / uv2
-	int triBase;                  // first triangle in idxPos/idxNrm (units: triangles)
-	int uvTriBase;                // first triangle in idxUv, or -1 when the mesh has no uv stream
-	int nPos, nTri, hasUV;
+	int clusterBase; // its first cluster in clusters[] / meshletDir[]
+	int nTri;
+	int hasUV;
+	int pad;
 };
 
-#define MR_CLUSTER 128 // triangles per cull cluster = triangles per k_setup CTA
+#define MR_CLUSTER 128 // triangles per cluster = per meshlet = per k_geom team iteration
+
+// Meshlet blob of one cluster (scene-static, built by mr_upload_scene): nv distinct corners
+//   plane 0: nv x float4 (px, py, pz, nx)      object-space position, normal x
+//   plane 1: nv x float4 (ny, nz, u, v)        normal y z, texcoord (0,0 when the mesh has none)
+//   index  : MR_CLUSTER x uint32               i0 | i1 << 10 | i2 << 20 (local corner indices; padding triangles: 0)
+// Blobs start at multiples of 16 bytes and are a multiple of 16 bytes long (cp.async.bulk).
+#define MR_MESHLET_MAX_VERTS (3 * MR_CLUSTER)
+#define MR_MESHLET_BYTES(nv) ((nv) * 32 + MR_CLUSTER * 4)
+struct MeshletDir
+{
+	uint32_t off16; // blob offset into meshlets[] in units of 16 bytes
+	uint32_t nv;
+};
 
 struct __align__(16) RStat // per renderable, changes only when the flattened structure changes
 {
-	int vertBase;   // first vertex instance (into pv)
-	int triBase;    // first triangle instance (submission order); a multiple of MR_CLUSTER: every
-	                // k_setup CTA lies inside one renderable and maps onto one cluster of its mesh
-	int nrmBase;    // first normal instance (into vnrm4)
-	int idxBase;    // the mesh's first triangle in idxPos / idxNrm
-	int posBase;    // the mesh's first vertex in pos4
-	int nrmSrcBase; // the mesh's first normal in nrm4
-	int uvBase;     // the mesh's first texcoord in uv2
-	int uvTriBase;  // the mesh's first triangle in idxUv, -1: no texcoords
-	int clusterBase; // the mesh's first cluster in clusters[]
+	int triBase;     // first triangle instance (submission order); a multiple of MR_CLUSTER: every
+	                 // cluster lies inside one renderable and maps onto one meshlet of its mesh
+	int clusterBase; // the mesh's first cluster in clusters[] / meshletDir[]
 	int nTri;        // triangles of the mesh (instances beyond it are padding)
 	int triBaseReal; // first triangle instance counted without padding (the reference's submission index)
-	int pad;
 };
 
 struct __align__(16) RDyn // per renderable, per frame
@@ -65,6 +70,22 @@ struct __align__(16) RDyn // per renderable, per frame
 	int cullFlags;     // bit 0: the modelview is a similarity with positive determinant (normal cones stay cones)
 	float radiusScale; // upper bound of the modelview's stretch: scales a cluster's bounding radius
 	int pad;
+};
+
+// One unit of work of k_geom: a cluster that survived culling, with everything a team needs to process it
+// (so that popping it is a single 128-byte read). Written by k_geom's own cull phase.
+struct __align__(128) GeomEntry
+{
+	int ci;          // cluster: triangle instances [ci * MR_CLUSTER, (ci + 1) * MR_CLUSTER); -1 = no more work
+	int nv;          // corners in its meshlet
+	uint32_t off16;  // meshlet blob offset (16-byte units)
+	int triFirst;    // its first triangle within the mesh
+	int nTri;        // triangles of the mesh
+	int subBase;     // RStat::triBaseReal
+	int material;
+	int pad;
+	float mv[12];
+	float nm[12];
 };
 
 struct __align__(16) MatDev
@@ -111,12 +132,12 @@ struct __align__(16) ShadeRec
 #define MR_STAT_SLOTS 32 // statistics are spread over this many slots (summed by the host): no single-address hot spot
 struct Counters
 {
-	// line 0: written by k_vertex / k_setup, only read by k_raster
+	// line 0: written by k_geom, only read by k_raster
 	unsigned long long trianglesIn;
 	unsigned long long ovfTotal;    // entries appended to the overflow list (may exceed its capacity)
 	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
 	unsigned int pad0;
-	unsigned int visible, clusters; // k_setup: clusters that survived culling / clusters of the frame (sizes the next frame's grid)
+	unsigned int visible, clusters; // k_geom: clusters that survived culling / clusters of the frame
 	unsigned long long pad1[12];
 	// line 1 (offset 128): written by k_raster
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
@@ -148,45 +169,41 @@ struct FrameParams
 	float bgPattern[12];    // r g b r g b ...
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
-	int nRenderables, nVertInst, nTriInst;
+	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags
 	int binCap; // entries per tile bin
 	int ovfCap; // entries in the overflow list
 
-	const float4* pos4;
-	const float4* nrm4;
-	const float2* uv2;
-	const int* idxPos;
-	const int* idxNrm;
-	const int* idxUv;
+	const unsigned char* meshlets; // meshlet blobs (see MeshletDir)
+	const MeshletDir* meshletDir;  // per mesh cluster
 	const float4* texels;
-	const MeshDev* meshes;
 	const RStat* rstat;
 	const RDyn* rdyn;
 	const MatDev* mats;
-	// Cluster culling (k_setup): per mesh cluster of MR_CLUSTER triangles, two float4 in object space:
+	// Cluster culling: per mesh cluster of MR_CLUSTER triangles, two float4 in object space:
 	// (bounding-sphere centre, radius), (normal-cone axis, sin(cone half-angle + margin) or 2 = no cone)
 	const float4* clusters;
-	const int* triBlockCl; // renderable of every k_setup CTA (MR_CLUSTER triangle instances)
-	unsigned* clusterVis;  // a bit per cluster: 0 = culled this frame (written by k_vertex, one word per warp)
-	int* visList;          // clusters that can reach a pixel of this frame (written by k_vertex, any order)
-	int* visCount;         // their number; zeroed again by k_raster once k_setup has consumed the list
-	int setupCtas;         // persistent k_setup CTAs
-	int nNrmSrc;           // float4 elements of nrm4 that may be prefetched
+	const int* triBlockCl; // renderable of every cluster of the frame (MR_CLUSTER triangle instances)
 	int nTriReal;          // triangles submitted (nTriInst counts the per-renderable padding too)
-	int cullClusters;      // 0: off (orthographic or non-standard projection)
+	int cullClusters;      // 0: off (orthographic or non-standard projection): every cluster is processed
 	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
-	const int* vtxBlockR; // renderable that owns the first vertex instance of each 256-block
 
-	float4* pv;          // per vertex instance: pixel x, pixel y, view z, depth term
+	// k_geom: persistent CTAs of geomTeams teams (128 threads each); a team's shared memory holds one meshlet
+	// (geomVertCap corners) and two sets of transformed corners
+	int geomTeams, geomVertCap;
+	GeomEntry* visEntries; // work list of the frame: clusters that survived culling (any order)
+	int* geomSync;         // [0] entries popped, [1] entries appended, [2] CTAs that finished culling; zeroed by k_raster
+
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
 	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field pair j, lane (t & 31), 32 bytes each
 	float4* recs1;       // records of sub-triangle 1 (second clipper output): MR_REC_FIELDS float4 per triangle
 	int2* tileCount;     // per tile: x = triangles binned (may exceed binCap: the rest is in ovfPairs),
-	                     // y = nonzero if fragments of small triangles may have reached the tile's gkeys
+	                     // y = nonzero if fragments of small triangles may have reached the tile's gkeys.
+	                     // All zero between frames: the tile kernel resets what it reads
 	int* bins;           // tilesX*tilesY bins of binCap record indices
 	int2* ovfPairs;      // (tile, record) entries that did not fit their bin
-	Counters* ctr;
+	Counters* ctr;       // this frame's counters (zero when the frame starts)
+	Counters* ctrNext;   // the next frame's: zeroed by k_raster
 
 	// Small scenes: the per-frame tables ride in the kernel parameters (no H2D copy per frame).
 	// rdyn / mats point at these arrays then (set up on the device: see frameTables()).
@@ -202,8 +219,9 @@ struct FrameParams
 };
 
 // kernel launchers (mr_kernels.cu)
-void mrk_launch_frame(const FrameParams& fp, cudaStream_t stream, cudaEvent_t* stageEvents /* 6 or NULL */, cudaEvent_t bracketStart = 0,
-                      cudaEvent_t bracketStop = 0);
+int mrk_geom_config(int nvCap, int smCount, int* teams, int* grid, int* smemBytes);
+void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* stageEvents /* 3 or NULL */,
+                      cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl);
 int mrk_selftest_no_fma(cudaStream_t stream);
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);

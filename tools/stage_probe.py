@@ -14,5 +14,5 @@ for flags in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(
     lib.mr_set_debug(ctx, (flags & ~1024) | (0 if flags & 1024 else 2))
     assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 30) == 0
     st = cabi.Stats(); lib.mr_get_stats(ctx, C.byref(st)); ms = list(st.ms_kernel)
-    print("%s flags %2d: vertex %.1f setup %.1f raster %.1f frame %.1f us | records %d pairs %d zero %d" % (
-        name, flags, ms[0]*1e3, ms[1]*1e3, ms[4]*1e3, ms[5]*1e3, st.records, st.bin_entries, st.zero_coverage))
+    print("%s flags %2d: geom %.1f raster %.1f frame %.1f us | records %d pairs %d zero %d" % (
+        name, flags, ms[1]*1e3, ms[4]*1e3, ms[5]*1e3, st.records, st.bin_entries, st.zero_coverage))
