@@ -88,7 +88,7 @@ struct mr_ctx
 
 	// scene-static device arrays
 	DevBuf meshlets, meshletDir, texels, clusters, triBlockCl, visEntries, geomSync;
-	int geomVertCap, geomTeams, geomGrid, geomSmem; // shape of k_geom for this scene's meshlets
+	int geomVertCap, geomGrid, geomSmem; // shape of k_geom for this scene's meshlets
 	std::vector<int> hostClusterBase; // first cluster of every mesh
 	std::vector<MeshDev> hostMeshes;
 	std::vector<int> texOffset, texRows, texCols;
@@ -146,7 +146,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), geomVertCap(0), geomTeams(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -584,7 +584,6 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.mats = c->mats.as<MatDev>();
 	fp.triBlockCl = c->triBlockCl.as<int>();
 	fp.clusters = c->clusters.as<float4>();
-	fp.geomTeams = c->geomTeams;
 	fp.geomVertCap = c->geomVertCap;
 	fp.visEntries = c->visEntries.as<GeomEntry>();
 	fp.geomSync = c->geomSync.as<int>();
@@ -1049,14 +1048,13 @@ int mr_upload_scene(mr_ctx* c, const mr_scene_desc* s)
 	if (blob.size() / 16 > 0xffffffffULL)
 		return setError(c, MR_E_INVALID, "scene too large: %zu bytes of meshlets", blob.size());
 	const int nvCap = (maxNv + 3) & ~3;
-	int teams = 0, grid = 0, smem = 0;
-	if (mrk_geom_config(nvCap, c->smCount, &teams, &grid, &smem) != 0)
+	int grid = 0, smem = 0;
+	if (mrk_geom_config(nvCap, c->smCount, &grid, &smem) != 0)
 	{
 		cudaGetLastError();
 		return setError(c, MR_E_CUDA, "k_geom does not fit this device (meshlets of %d corners)", nvCap);
 	}
 	c->geomVertCap = nvCap;
-	c->geomTeams = teams;
 	c->geomGrid = grid;
 	c->geomSmem = smem;
 

@@ -438,49 +438,64 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1: geometry. Persistent CTAs of MR_GEOM_TEAMS teams of 128 threads.
+// Kernel 1: geometry. Persistent CTAs of MR_GEOM_WARPS warps; a warp is the unit that works: no block or
+// team barrier anywhere in the main loop.
 //
-// Phase 0, cull: one thread per cluster of the frame (CTA b takes clusters b*NT .. b*NT+NT-1, strided by the
-//   grid) evaluates clusterVisible(); survivors are appended to the frame's work list as self-contained
+// Phase 0, cull: one thread per cluster of the frame (a cluster = MR_CLUSTER = 32 consecutive triangles of a
+//   renderable) evaluates clusterVisible(); survivors are appended to the frame's work list as self-contained
 //   128-byte GeomEntry records (renderable matrices included). The CTAs then meet at a grid-wide counter:
 //   the list is complete before anyone pops from it.
-// Phase 1: a team pops one entry at a time from the global list (one atomic per cluster: perfect balance
-//   across SMs whatever survives where) and processes that cluster of MR_CLUSTER triangles entirely out of
-//   shared memory:
-//     load      its meshlet blob (the cluster's distinct corners + 10-bit local indices, ~4.7 KB for a grid
-//               mesh) arrives by one cp.async.bulk, completion on the team's mbarrier; the copy for cluster
+// Phase 1: a warp takes one entry at a time from the global list (its first two by position, the rest by one
+//   atomic each: perfect balance across SMs whatever survives where) and processes that cluster entirely out
+//   of shared memory:
+//     load      its meshlet blob (the cluster's distinct corners + 10-bit local indices, ~1.2 KB for a grid
+//               mesh) arrives by one cp.async.bulk, completion on the warp's mbarrier; the copy for cluster
 //               k+1 is issued as soon as cluster k's corners are transformed, so it overlaps k's triangles;
-//     vertex    thread v transforms corner v: modelview (loop A, Renderer.cpp:344-345), htransform + pixel
-//               coordinates + depth term (:13-20, :186-196, :223-224), normal matrix (loop B, :347-348);
-//               results go to the team's shared memory as three float4 planes;
-//     triangle  thread j sets up triangle j from shared memory (near test, clip path, reject, cull, edge
+//     vertex    lane v transforms corner v (v + 32, ...): modelview (loop A, Renderer.cpp:344-345), htransform +
+//               pixel coordinates + depth term (:13-20, :186-196, :223-224), normal matrix (loop B, :347-348);
+//               results go to the warp's shared memory as three float4 planes;
+//     triangle  lane j sets up triangle j from shared memory (near test, clip path, reject, cull, edge
 //               normals, spans: Renderer.cpp:163-224). bbox of at most MR_SMALL_AREA pixel centres: the
-//               reference's loops D/E run right here, the depth test being one 64-bit atomicMin per covered
+//               reference's loops D/E run right here, the depth test being one 64-bit RED.MIN per covered
 //               pixel on gkeys; larger: binned to the 16x16 tiles of its bbox for k_raster. A triangle that
 //               can own a pixel writes its record (index 2t: the index is the submission id) as five
 //               coalesced 32-byte pairs.
-//   The pop for cluster k+2, the entry read for k+1 and the bulk copy for k+1 are all issued by the team's
-//   first warp right after the vertex phase of cluster k and consumed one iteration later: no dependent
-//   global load sits on a team's critical path. Everything a frame needs zeroed between frames (tile
-//   counters, list counters, the next frame's statistics) is reset by k_raster.
+//   The pop for cluster k+2, the entry read for k+1 and the bulk copy for k+1 are all issued right after the
+//   vertex phase of cluster k and consumed one iteration later: no dependent global load sits on a warp's
+//   critical path. Everything a frame needs zeroed between frames (tile counters, list counters, the next
+//   frame's statistics) is reset by k_raster.
 // The order in which fragments or bin entries arrive does not matter: depth ties are resolved on
 // the record index (submission id) carried in the low word of every depth key.
 // ------------------------------------------------------------------------------------------
-#define MR_GEOM_TEAMS 4
-#define MR_GEOM_THREADS (MR_GEOM_TEAMS * MR_CLUSTER)
+#ifndef MR_GEOM_WARPS
+#define MR_GEOM_WARPS 16
+#endif
+#define MR_GEOM_THREADS (MR_GEOM_WARPS * 32)
 #ifndef MR_GEOM_MINB
 #define MR_GEOM_MINB 2
 #endif
+static_assert(MR_CLUSTER == 32, "a cluster is what one warp sets up at a time");
 
+// Work distribution. The frame's work list is cut into chunks of MR_GEOM_CHUNK entries; a CTA holds a small ring of
+// chunk numbers in shared memory and its warps draw tickets from a shared-memory counter: ticket t = entry t % CHUNK
+// of the chunk in ring slot t / CHUNK. Chunks 0 and 1 of a CTA are fixed by its position; the warp that draws the
+// first ticket of a slot fetches the chunk for two slots ahead with ONE global atomic (a single-address atomic per
+// cluster would serialise in L2: ~5 cycles each, measured as the whole kernel's bound), and stores it into the ring
+// an iteration later, when the result has long arrived. Balance across SMs stays dynamic at chunk granularity.
+#define MR_GEOM_CHUNK 32
+#define MR_GEOM_RING 4
 struct GeomShared // fixed part of k_geom's dynamic shared memory
 {
-	GeomEntry entry[MR_GEOM_TEAMS][2]; // the cluster a team works on (k & 1) and the next one
-	unsigned long long full[MR_GEOM_TEAMS]; // mbarrier: the team's meshlet (or the news that there is none) has arrived
+	GeomEntry entry[MR_GEOM_WARPS][2]; // the cluster a warp works on (k & 1) and the next one
+	unsigned long long full[MR_GEOM_WARPS]; // mbarrier: the warp's meshlet (or the news that there is none) has arrived
+	unsigned long long ring[MR_GEOM_RING];  // slot number << 32 | chunk number (as written by the fetching warp)
 	unsigned long long stat;
+	unsigned ticket;
 	int nVis;
 };
 #define MR_GEOM_FIXED_BYTES ((int)((sizeof(GeomShared) + 127) / 128 * 128))
-#define MR_GEOM_TEAM_BYTES(nvCap) (MR_MESHLET_BYTES(nvCap) + 2 * ((nvCap) * 48 + MR_CLUSTER * 4))
+// per warp: the meshlet as loaded, the transformed corners (3 float4 planes), a copy of the local indices
+#define MR_GEOM_WARP_BYTES(nvCap) (MR_MESHLET_BYTES(nvCap) + (nvCap) * 48 + MR_CLUSTER * 4)
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(unsigned long long* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(b)), "r"(count) : "memory"); }
@@ -507,16 +522,43 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
 	             "r"(smemAddr(bar)) : "memory");
 }
-__device__ __forceinline__ void teamBarrier(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(MR_CLUSTER) : "memory"); }
 __device__ __forceinline__ int ldAcquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-// Triangle phase of one cluster for one thread (triangle tt of the cluster); see k_geom.
+// Draws the next work-list index for the calling lane (lane 0 of a warp). If the ticket opens a new ring slot, the
+// chunk for two slots ahead is requested: `fetch` receives the atomic's result (to be stored by ringStore() one
+// iteration later), `fetchSlot` its slot. Returns an index >= nVis when the list is exhausted.
+__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nChunks, int firstDynamic, int& fetch, int& fetchSlot)
+{
+	const unsigned t = atomicAdd(&gs.ticket, 1u);
+	const unsigned slot = t / MR_GEOM_CHUNK, within = t % MR_GEOM_CHUNK;
+	if (within == 0u)
+	{
+		fetch = atomicAdd(&sync[0], 1); // consumed by ringStore(), not here
+		fetchSlot = (int)slot + 2;
+	}
+	volatile unsigned long long* cell = &gs.ring[slot % MR_GEOM_RING];
+	unsigned long long v = *cell;
+	while ((unsigned)(v >> 32) != slot) // the fetch for this slot was issued two chunks ago: normally long there
+		v = *cell;
+	const int chunk = (int)(unsigned)v;
+	return (chunk < nChunks) ? chunk * MR_GEOM_CHUNK + (int)within : 0x7fffffff;
+}
+__device__ __forceinline__ void ringStore(GeomShared& gs, int firstDynamic, int& fetch, int& fetchSlot)
+{
+	if (fetchSlot >= 0)
+	{
+		*(volatile unsigned long long*)&gs.ring[fetchSlot % MR_GEOM_RING] = ((unsigned long long)(unsigned)fetchSlot << 32) | (unsigned)(firstDynamic + fetch);
+		fetchSlot = -1;
+	}
+}
+
+// Triangle phase of one cluster for one lane (triangle `lane` of the cluster); see k_geom.
 // acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
 __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEntry& e, const float4* __restrict__ sA, const float4* __restrict__ sB,
-                                             const float4* __restrict__ sC, const uint32_t* __restrict__ sIdx, int tt, int lane, unsigned long long& acc)
+                                             const float4* __restrict__ sC, const uint32_t* __restrict__ sIdx, int lane, unsigned long long& acc)
 {
-	const int t = e.ci * MR_CLUSTER + tt; // triangle instance (padded numbering): 2t is its record index
-	const int tri = e.triFirst + tt;      // triangle within the mesh
+	const int t = e.ci * MR_CLUSTER + lane; // triangle instance (padded numbering): 2t is its record index
+	const int tri = e.triFirst + lane;      // triangle within the mesh
 	const bool active = tri < e.nTri;     // false: padding behind the mesh's last triangle
 	bool valid = false, binned = false;
 	int nclip = 0, nrecSlow = 0, nzero = 0;
@@ -527,7 +569,7 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 	s.flags = 0u;
 	if (active)
 	{
-		const uint32_t ix = sIdx[tt];
+		const uint32_t ix = sIdx[lane];
 		const int i0 = ix & 1023u, i1 = (ix >> 10) & 1023u, i2 = ix >> 20;
 		const float4 a = sA[i0], b = sA[i1], c = sA[i2];
 		const float zn = fp.znear;
@@ -664,7 +706,7 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 {
 	extern __shared__ __align__(128) unsigned char geomSmem[];
 	GeomShared& gs = *reinterpret_cast<GeomShared*>(geomSmem);
-	const int tid = threadIdx.x, team = tid >> 7, tt = tid & (MR_CLUSTER - 1), lane = tid & 31;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int nvCap = fp.geomVertCap;
 	const int nCl = fp.nTriInst / MR_CLUSTER;
 	int* const sync = fp.geomSync;
@@ -672,12 +714,16 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	pdlLaunchDependents(); // k_raster's CTAs may take the SMs this kernel's CTAs leave (they wait for the whole grid)
 	if (tid == 0)
 	{
-		for (int i = 0; i < MR_GEOM_TEAMS; i++)
+		for (int i = 0; i < MR_GEOM_WARPS; i++)
 			mbarInit(&gs.full[i], 1);
 		gs.stat = 0ull;
+		gs.ticket = 0u;
+		// the CTA's first two chunks by position; later ones are fetched from sync[0], which counts from chunk 2 * grid
+		gs.ring[0] = (0ull << 32) | (unsigned)blockIdx.x;
+		gs.ring[1] = (1ull << 32) | (unsigned)(blockIdx.x + gridDim.x);
+		gs.ring[2] = gs.ring[3] = ~0ull;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-
 	// ---- phase 0: cull (Renderer.cpp:169-177, :202, :205-210 decided per cluster) ----
 	for (int base = blockIdx.x * MR_GEOM_THREADS; base < nCl; base += gridDim.x * MR_GEOM_THREADS)
 	{
@@ -686,18 +732,17 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 		int r = 0;
 		RStat rs;
 		rs.triBase = rs.clusterBase = rs.nTri = rs.triBaseReal = 0;
-		int meshCluster = 0;
+		MeshletDir d;
+		d.off16 = d.nv = 0u;
 		if (ci < nCl)
 		{
 			r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
 			rs = frameRstat<TM>(fp)[r];
-			meshCluster = rs.clusterBase + (ci * MR_CLUSTER - rs.triBase) / MR_CLUSTER;
-			vis = true;
-			if (fp.cullClusters)
-			{
-				const float4* cl = fp.clusters + 2 * (size_t)meshCluster;
-				vis = clusterVisible(fp, frameRdyn<TM>(fp)[r], __ldg(cl), __ldg(cl + 1));
-			}
+			const int meshCluster = rs.clusterBase + (ci * MR_CLUSTER - rs.triBase) / MR_CLUSTER;
+			const float4* cl = fp.clusters + 2 * (size_t)meshCluster;
+			const float4 cs = __ldg(cl), ca = __ldg(cl + 1);
+			d = fp.meshletDir[meshCluster]; // requested together with the bounds
+			vis = !fp.cullClusters || clusterVisible(fp, frameRdyn<TM>(fp)[r], cs, ca);
 		}
 		const unsigned m = __ballot_sync(0xffffffffu, vis);
 		if (m != 0u)
@@ -709,7 +754,6 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 			at = __shfl_sync(0xffffffffu, at, leader) + __popc(m & ((1u << lane) - 1u));
 			if (vis)
 			{
-				const MeshletDir d = fp.meshletDir[meshCluster];
 				const RDyn& rd = frameRdyn<TM>(fp)[r];
 				uint4* o = reinterpret_cast<uint4*>(fp.visEntries + at);
 				o[0] = make_uint4((uint32_t)ci, d.nv, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
@@ -744,63 +788,60 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	__syncthreads();
 	const int nVis = gs.nVis;
 
-	// ---- phase 1 ----
+	// ---- phase 1: every warp on its own ----
 	unsigned long long acc = 0ull;
-	if (team < fp.geomTeams)
 	{
-		unsigned char* const teamMem = geomSmem + MR_GEOM_FIXED_BYTES + (size_t)team * MR_GEOM_TEAM_BYTES(nvCap);
-		unsigned char* const raw = teamMem;
-		const int scrBytes = nvCap * 48 + MR_CLUSTER * 4;
+		unsigned char* const warpMem = geomSmem + MR_GEOM_FIXED_BYTES + (size_t)warp * MR_GEOM_WARP_BYTES(nvCap);
+		unsigned char* const raw = warpMem;
+		float4* const sA = reinterpret_cast<float4*>(warpMem + MR_MESHLET_BYTES(nvCap));
+		float4* const sB = sA + nvCap;
+		float4* const sC = sB + nvCap;
+		uint32_t* const sIdx = reinterpret_cast<uint32_t*>(sC + nvCap);
+		unsigned long long* const full = &gs.full[warp];
 		const uint32_t* const visWords = reinterpret_cast<const uint32_t*>(fp.visEntries);
-		const bool loader = tt < 32; // the team's first warp pops work and issues the copies
-		int popIdx = 0x7fffffff;     // (lane 0) list index popped for the cluster after next
-		uint32_t entryWord = 0u;     // word `lane` of the next cluster's entry
-		if (loader)
+		const uint32_t none = (lane == 0) ? 0xffffffffu : 0u; // word `lane` of an entry that says "no more work"
+		const int nChunks = (nVis + MR_GEOM_CHUNK - 1) / MR_GEOM_CHUNK, firstDynamic = 2 * (int)gridDim.x;
+		int fetch = 0, fetchSlot = -1; // (lane 0) a chunk request in flight for ring slot fetchSlot
+		uint32_t entryWord;            // word `lane` of the next cluster's entry
 		{
 			int i0 = 0, i1 = 0;
 			if (lane == 0)
 			{
-				i0 = atomicAdd(&sync[0], 1);
-				i1 = atomicAdd(&sync[0], 1);
-				popIdx = atomicAdd(&sync[0], 1);
+				i0 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
+				i1 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
 			}
 			i0 = __shfl_sync(0xffffffffu, i0, 0);
 			i1 = __shfl_sync(0xffffffffu, i1, 0);
-			const uint32_t none = (lane == 0) ? 0xffffffffu : 0u;
 			const uint32_t w0 = (i0 < nVis) ? __ldcg(visWords + (size_t)i0 * 32 + lane) : none;
 			entryWord = (i1 < nVis) ? __ldcg(visWords + (size_t)i1 * 32 + lane) : none;
-			reinterpret_cast<uint32_t*>(&gs.entry[team][0])[lane] = w0;
+			reinterpret_cast<uint32_t*>(&gs.entry[warp][0])[lane] = w0;
 			__syncwarp();
 			if (lane == 0)
 			{
-				const GeomEntry& n = gs.entry[team][0];
+				const GeomEntry& n = gs.entry[warp][0];
 				if (n.ci >= 0)
 				{
-					mbarExpectTx(&gs.full[team], (uint32_t)MR_MESHLET_BYTES(n.nv));
-					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), &gs.full[team]);
+					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
+					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
 				}
 				else
-					mbarArrive(&gs.full[team]);
+					mbarArrive(full);
 			}
 		}
 		for (int k = 0;; k++)
 		{
-			mbarWait(&gs.full[team], (uint32_t)(k & 1));
-			const GeomEntry& e = gs.entry[team][k & 1];
+			mbarWait(full, (uint32_t)(k & 1));
+			const GeomEntry& e = gs.entry[warp][k & 1];
 			if (e.ci < 0)
 				break;
 			const int nv = e.nv;
-			float4* const sA = reinterpret_cast<float4*>(teamMem + MR_MESHLET_BYTES(nvCap) + (size_t)(k & 1) * scrBytes);
-			float4* const sB = sA + nvCap;
-			float4* const sC = sB + nvCap;
-			uint32_t* const sIdx = reinterpret_cast<uint32_t*>(sC + nvCap);
 
 			// ---- vertex phase: loops A and B of paintMesh for the cluster's corners, plus their projection ----
 			{
 				const float4* const raw0 = reinterpret_cast<const float4*>(raw);
 				const float4* const raw1 = raw0 + nv;
-				sIdx[tt] = reinterpret_cast<const uint32_t*>(raw1 + nv)[tt];
-				for (int v = tt; v < nv; v += MR_CLUSTER)
+				sIdx[lane] = reinterpret_cast<const uint32_t*>(raw1 + nv)[lane];
+				for (int v = lane; v < nv; v += 32)
 				{
 					const float4 q0 = raw0[v], q1 = raw1[v]; // (px py pz nx) (ny nz u v)
 					const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
@@ -810,33 +851,33 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 					sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
 				}
 			}
-			teamBarrier(team); // corners complete; the meshlet buffer is free again
-
-			// ---- the loader warp prepares the next cluster: entry (read one iteration ago) into shared memory,
-			// bulk copy issued, entry after next requested, another index popped ----
-			if (loader)
+			// ---- the next cluster: its entry (read one iteration ago) into shared memory, its bulk copy issued
+			// (the meshlet buffer is free again), the entry after next requested, another index popped ----
+			reinterpret_cast<uint32_t*>(&gs.entry[warp][(k + 1) & 1])[lane] = entryWord;
+			__syncwarp(); // corners complete, every lane is done with the meshlet buffer
+			int i2 = 0;
+			if (lane == 0)
 			{
-				reinterpret_cast<uint32_t*>(&gs.entry[team][(k + 1) & 1])[lane] = entryWord;
-				const int i2 = __shfl_sync(0xffffffffu, popIdx, 0);
-				__syncwarp();
-				if (lane == 0)
+				const GeomEntry& n = gs.entry[warp][(k + 1) & 1];
+				if (n.ci >= 0)
 				{
-					const GeomEntry& n = gs.entry[team][(k + 1) & 1];
-					if (n.ci >= 0)
-					{
-						mbarExpectTx(&gs.full[team], (uint32_t)MR_MESHLET_BYTES(n.nv));
-						bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), &gs.full[team]);
-					}
-					else
-						mbarArrive(&gs.full[team]);
-					popIdx = atomicAdd(&sync[0], 1);
+					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
+					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
 				}
-				entryWord = (i2 < nVis) ? __ldcg(visWords + (size_t)i2 * 32 + lane) : ((lane == 0) ? 0xffffffffu : 0u);
+				else
+					mbarArrive(full);
+				ringStore(gs, firstDynamic, fetch, fetchSlot); // last iteration's chunk request has arrived
+				i2 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
 			}
+			i2 = __shfl_sync(0xffffffffu, i2, 0);
+			entryWord = (i2 < nVis) ? __ldcg(visWords + (size_t)i2 * 32 + lane) : none;
 
 			// ---- triangle phase ----
-			geomTriangle(fp, e, sA, sB, sC, sIdx, tt, lane, acc);
+			geomTriangle(fp, e, sA, sB, sC, sIdx, lane, acc);
+			__syncwarp(); // the corners may be overwritten by the next cluster's
 		}
+		if (lane == 0)
+			ringStore(gs, firstDynamic, fetch, fetchSlot); // a request still in flight must reach the ring: others may wait for it
 	}
 
 	// ---- statistics: one shared-memory atomic per warp, one RED per counter per CTA ----
@@ -1552,22 +1593,14 @@ __global__ void k_selftest(const float* in, float* out)
 
 }
 
-// Shape of k_geom for meshlets of up to nvCap corners: teams per CTA (fewer when a team's shared memory is
-// large), dynamic shared memory per CTA, and a grid of as many CTAs as are resident at once (the cull phase
-// ends in a grid-wide rendezvous).
-int mrk_geom_config(int nvCap, int smCount, int* teams, int* grid, int* smemBytes)
+// Shape of k_geom for meshlets of up to nvCap corners: dynamic shared memory per CTA and a grid of as many
+// CTAs as are resident at once (the cull phase ends in a grid-wide rendezvous).
+int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes)
 {
 	int dev = 0, smemMax = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
 		return -1;
-	const int perTeam = MR_GEOM_TEAM_BYTES(nvCap);
-	int nt = MR_GEOM_TEAMS;
-	// two CTAs per SM when their teams fit half of the SM's shared memory; else one CTA with as many teams as fit
-	const int half = (smemMax + 1024) / 2 - 2048;
-	if (MR_GEOM_FIXED_BYTES + nt * perTeam > half)
-		while (nt > 1 && MR_GEOM_FIXED_BYTES + nt * perTeam > smemMax)
-			nt--;
-	const int bytes = MR_GEOM_FIXED_BYTES + nt * perTeam;
+	const int bytes = MR_GEOM_FIXED_BYTES + MR_GEOM_WARPS * MR_GEOM_WARP_BYTES(nvCap);
 	if (bytes > smemMax)
 		return -1;
 	int perSm = 0;
@@ -1581,7 +1614,6 @@ int mrk_geom_config(int nvCap, int smCount, int* teams, int* grid, int* smemByte
 			return -1;
 		perSm = tm ? std::min(perSm, n) : n;
 	}
-	*teams = nt;
 	*grid = smCount * std::min(perSm, MR_GEOM_MINB);
 	*smemBytes = bytes;
 	return 0;

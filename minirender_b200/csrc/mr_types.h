@@ -38,7 +38,7 @@ struct MeshDev // host-side bookkeeping of one uploaded mesh
 	int pad;
 };
 
-#define MR_CLUSTER 128 // triangles per cluster = per meshlet = per k_geom team iteration
+#define MR_CLUSTER 32 // triangles per cluster = per meshlet = what one warp of k_geom sets up at a time
 
 // Meshlet blob of one cluster (scene-static, built by mr_upload_scene): nv distinct corners
 //   plane 0: nv x float4 (px, py, pz, nx)      object-space position, normal x
@@ -188,9 +188,8 @@ struct FrameParams
 	int cullClusters;      // 0: off (orthographic or non-standard projection): every cluster is processed
 	float cullPlanes[4][4]; // view-space planes (unit normal, offset) bounding the rows / columns this frame can touch
 
-	// k_geom: persistent CTAs of geomTeams teams (128 threads each); a team's shared memory holds one meshlet
-	// (geomVertCap corners) and two sets of transformed corners
-	int geomTeams, geomVertCap;
+	// k_geom: persistent CTAs; a warp's shared memory holds one meshlet (geomVertCap corners) and its transformed corners
+	int geomVertCap;
 	GeomEntry* visEntries; // work list of the frame: clusters that survived culling (any order)
 	int* geomSync;         // [0] entries popped, [1] entries appended, [2] CTAs that finished culling; zeroed by k_raster
 
@@ -219,7 +218,7 @@ struct FrameParams
 };
 
 // kernel launchers (mr_kernels.cu)
-int mrk_geom_config(int nvCap, int smCount, int* teams, int* grid, int* smemBytes);
+int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes);
 void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* stageEvents /* 3 or NULL */,
                       cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl);
 int mrk_selftest_no_fma(cudaStream_t stream);
