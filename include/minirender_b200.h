@@ -150,6 +150,8 @@ typedef struct mr_stats
 	float   ms_kernel[8];      /* per-stage device time of the last mr_profile_frame:
 	                              1 geometry (k_geom), 4 tile resolve + shade (k_raster), 5 whole frame; others 0 */
 	int64_t h2d_bytes;         /* host->device bytes the last mr_render copied (per-frame tables) */
+	int64_t clusters;          /* 32-triangle clusters of the frame ... */
+	int64_t clusters_visible;  /* ... and how many of them survived cluster culling */
 } mr_stats;
 
 MR_API int mr_abi_version(void);
@@ -212,7 +214,10 @@ MR_API int mr_host_unregister(void* host);
 
 /* Verification aid: with flags & 1, mr_render also records for every pixel the submission id of
  * the triangle that owns it (2 * triangle instance index + clip sub-triangle, -1 = background),
- * which is what equal-depth ties are resolved on. Read it back with mr_read_winner_ids. */
+ * which is what equal-depth ties are resolved on. Read it back with mr_read_winner_ids.
+ * flags & 4 turns cluster culling off and flags & 8 the standard-perspective vertex path (every cluster is set up /
+ * every corner goes through the general htransform): the image must not change, which is what the tests use them for.
+ * (The environment variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ do the same for a whole process.) */
 MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 

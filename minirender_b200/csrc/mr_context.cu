@@ -118,7 +118,7 @@ struct mr_ctx
 	// scratch
 	DevBuf recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
 	bool slotOverflowed; // a frame older than the newest one overflowed its spill list (async readers are told)
-	bool noClusterCull, noPdl; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
+	bool noClusterCull, noPdl, noStdProj; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -146,7 +146,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -216,6 +216,8 @@ void absorbCounters(mr_ctx* c, const Counters& k)
 	c->stats.clipped_in = (int64_t)clip;
 	c->stats.bin_entries = (int64_t)pairs;
 	c->stats.zero_coverage = (int64_t)zero;
+	c->stats.clusters = (int64_t)k.clusters;
+	c->stats.clusters_visible = (int64_t)k.visible;
 	c->stats.tiles_x = c->tilesX;
 	c->stats.tiles_y = c->tilesY;
 }
@@ -351,8 +353,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	MR_CUDA(c, c->visEntries.ensure(sizeof(GeomEntry) * (size_t)std::max(nCB, 1)));
 	if (!c->geomSync.p)
 	{
-		MR_CUDA(c, c->geomSync.ensure(256, true));
-		MR_CUDA(c, cudaMemsetAsync(c->geomSync.p, 0, 256, c->stream));
+		MR_CUDA(c, c->geomSync.ensure(sizeof(int) * 3 * MR_SYNC_STRIDE, true));
+		MR_CUDA(c, cudaMemsetAsync(c->geomSync.p, 0, sizeof(int) * 3 * MR_SYNC_STRIDE, c->stream));
 	}
 	MR_CUDA(c, c->recs.ensure(sizeof(float4) * MR_REC_FIELDS * 32 * (size_t)((c->nTriInst + 31) / 32 + 1)));
 	MR_CUDA(c, c->recs1.ensure(sizeof(float4) * MR_REC_FIELDS * (size_t)std::max(c->nTriInst, 1)));
@@ -530,10 +532,17 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	}
 	fp.persp = f->projection[15] == 0.0f;
 	{
-		// Cluster culling needs the standard perspective form (w_clip = -z_view, x and y not mirrored).
 		const float* P = f->projection;
-		const bool standard = fp.persp && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f && P[0] > 0.0f && P[5] > 0.0f;
-		fp.cullClusters = (standard && !c->noClusterCull) ? 1 : 0;
+		fp.stdProj = (fp.persp && P[1] == 0.0f && P[3] == 0.0f && P[4] == 0.0f && P[7] == 0.0f && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f &&
+		              f->znear < 0.0f && !c->noStdProj && !(c->debugFlags & 8)) ? 1 : 0;
+	}
+	{
+		// Cluster culling needs the standard perspective form (w_clip = -z_view, x and y not mirrored
+		const float* P = f->projection;
+		// ... and no translation in clip x / y: the bounds below are planes through the eye)
+		const bool standard = fp.persp && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f && P[3] == 0.0f && P[7] == 0.0f &&
+		                      (double)P[0] * P[5] - (double)P[1] * P[4] > 0.0;
+		fp.cullClusters = (standard && !c->noClusterCull && !(c->debugFlags & 4)) ? 1 : 0;
 		if (fp.cullClusters)
 		{
 			// Columns / rows this frame can touch, widened by 1.5 pixels, as NDC bounds; each bound is a plane
@@ -699,8 +708,13 @@ void buildMeshlets(const mr_mesh_desc& m, bool hasUV, std::vector<unsigned char>
 			p1[4 * v] = verts[v][4]; p1[4 * v + 1] = verts[v][5]; p1[4 * v + 2] = verts[v][6]; p1[4 * v + 3] = verts[v][7];
 		}
 		memcpy(p1 + 4 * (size_t)nv, idx, sizeof(idx));
+		bool finite = true;
+		for (int v = 0; v < nv && finite; v++)
+			for (int a = 0; a < 3; a++)
+				if (!(fabsf(verts[v][a]) <= 3.0e38f)) // NaN or infinite
+					finite = false;
 		dir[k].off16 = (uint32_t)(at / 16);
-		dir[k].nv = (uint32_t)nv;
+		dir[k].nv = (uint32_t)nv | (finite ? 0u : (MR_MESHLET_NONFINITE << 16));
 		maxNv = std::max(maxNv, nv);
 	}
 }
@@ -828,6 +842,7 @@ mr_ctx* mr_create(int device, int* status)
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
 		c->noClusterCull = getenv("MR_NO_CLUSTER_CULL") != 0; // verification switches, read once
 		c->noPdl = getenv("MR_NO_PDL") != 0;
+		c->noStdProj = getenv("MR_NO_STD_PROJ") != 0;
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;

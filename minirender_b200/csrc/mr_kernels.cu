@@ -67,6 +67,24 @@ __device__ __forceinline__ float4 project(const FrameParams& fp, V3 view)
 	return o;
 }
 
+// The same for the standard perspective matrix (fp.stdProj: rows (a 0 b 0) (0 c d 0) (. . . .) (0 0 -1 0), near plane in
+// front of the eye) and finite x, y: the structural zeros contribute +-0 terms only, which change nothing but the sign
+// of a zero sum, and the trailing `+ 0.0f` (the reference's + m[3]) settles that the same way; w = -z makes the depth
+// term -1/z the very reciprocal htransform computes (IEEE division is sign-symmetric), except at z = +-0, where such a
+// corner is in front of the near plane and the triangle takes the clip path, which projects its own corners.
+__device__ __forceinline__ float4 projectStd(const FrameParams& fp, V3 view)
+{
+	const float iw = 1.0f / (0.0f - view.z);
+	const float nx = (fp.P[0] * view.x + fp.P[2] * view.z + 0.0f) * iw;
+	const float ny = (fp.P[5] * view.y + fp.P[6] * view.z + 0.0f) * iw;
+	float4 o;
+	o.x = (1.0f + nx) * (fp.wf / 2.0f);
+	o.y = (1.0f - ny) * (fp.hf / 2.0f);
+	o.z = view.z;
+	o.w = iw;
+	return o;
+}
+
 // order-preserving float -> uint map (so that atomicMin on the key is a depth test);
 // -0 is folded onto +0 because the reference's `z < pixdepth` treats them as equal
 __device__ __forceinline__ uint32_t zkey(float z)
@@ -438,16 +456,15 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1: geometry. Persistent CTAs of MR_GEOM_WARPS warps; a warp is the unit that works: no block or
-// team barrier anywhere in the main loop.
+// Kernel 1: geometry. Persistent CTAs of MR_GEOM_WARPS warps; in the main loop a warp works on its own: no
+// block-wide barrier.
 //
 // Phase 0, cull: one thread per cluster of the frame (a cluster = MR_CLUSTER = 32 consecutive triangles of a
-//   renderable) evaluates clusterVisible(); survivors are appended to the frame's work list as self-contained
-//   128-byte GeomEntry records (renderable matrices included). The CTAs then meet at a grid-wide counter:
-//   the list is complete before anyone pops from it.
-// Phase 1: a warp takes one entry at a time from the global list (its first two by position, the rest by one
-//   atomic each: perfect balance across SMs whatever survives where) and processes that cluster entirely out
-//   of shared memory:
+//   renderable; slices of 32 clusters are dealt to the warps of the grid round-robin, so every SM gets its share)
+//   evaluates clusterVisible(); survivors are appended to the frame's work list as self-contained 128-byte
+//   GeomEntry records (renderable matrices included), one global atomic per CTA. The CTAs then meet at a
+//   grid-wide counter: the list is complete before anyone takes from it.
+// Phase 1: a warp takes one entry at a time and processes that cluster entirely out of shared memory:
 //     load      its meshlet blob (the cluster's distinct corners + 10-bit local indices, ~1.2 KB for a grid
 //               mesh) arrives by one cp.async.bulk, completion on the warp's mbarrier; the copy for cluster
 //               k+1 is issued as soon as cluster k's corners are transformed, so it overlaps k's triangles;
@@ -460,38 +477,40 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 //               pixel on gkeys; larger: binned to the 16x16 tiles of its bbox for k_raster. A triangle that
 //               can own a pixel writes its record (index 2t: the index is the submission id) as five
 //               coalesced 32-byte pairs.
-//   The pop for cluster k+2, the entry read for k+1 and the bulk copy for k+1 are all issued right after the
-//   vertex phase of cluster k and consumed one iteration later: no dependent global load sits on a warp's
-//   critical path. Everything a frame needs zeroed between frames (tile counters, list counters, the next
-//   frame's statistics) is reset by k_raster.
+//   Work distribution: the list is cut into chunks of MR_GEOM_CHUNK entries. The warps of a CTA draw tickets from
+//   a shared-memory counter; ticket t is entry t % CHUNK of the CTA's chunk number t / CHUNK. A CTA's first chunk
+//   is fixed by its position; the warp that draws the first ticket of a later chunk fetches its number with ONE
+//   global atomic (a single-address atomic per cluster would serialise in L2, ~5 cycles each: measured as the
+//   whole kernel's bound) after the previous chunk's number has arrived, so a CTA's chunk numbers grow with its
+//   tickets and the first ticket behind the end of the list tells a warp that it is done. A CTA never holds more
+//   than one chunk (one cluster per warp) ahead of what it works on: balance across SMs stays dynamic to the end.
+//   The entry of cluster k+1 is read while cluster k is processed and its bulk copy issued right after k's vertex
+//   phase: no dependent global load sits on a warp's critical path.
+// Everything a frame needs zeroed between frames (tile counters, list counters, the next frame's statistics)
+// is reset by k_raster.
 // The order in which fragments or bin entries arrive does not matter: depth ties are resolved on
 // the record index (submission id) carried in the low word of every depth key.
 // ------------------------------------------------------------------------------------------
 #ifndef MR_GEOM_WARPS
-#define MR_GEOM_WARPS 16
+#define MR_GEOM_WARPS 8 // x 2 CTAs per SM: as fast as twice as many (measured), without register spills, and a cluster takes half as long
 #endif
 #define MR_GEOM_THREADS (MR_GEOM_WARPS * 32)
 #ifndef MR_GEOM_MINB
 #define MR_GEOM_MINB 2
 #endif
 static_assert(MR_CLUSTER == 32, "a cluster is what one warp sets up at a time");
-
-// Work distribution. The frame's work list is cut into chunks of MR_GEOM_CHUNK entries; a CTA holds a small ring of
-// chunk numbers in shared memory and its warps draw tickets from a shared-memory counter: ticket t = entry t % CHUNK
-// of the chunk in ring slot t / CHUNK. Chunks 0 and 1 of a CTA are fixed by its position; the warp that draws the
-// first ticket of a slot fetches the chunk for two slots ahead with ONE global atomic (a single-address atomic per
-// cluster would serialise in L2: ~5 cycles each, measured as the whole kernel's bound), and stores it into the ring
-// an iteration later, when the result has long arrived. Balance across SMs stays dynamic at chunk granularity.
-#define MR_GEOM_CHUNK 32
+#define MR_GEOM_CHUNK 8
 #define MR_GEOM_RING 4
+
 struct GeomShared // fixed part of k_geom's dynamic shared memory
 {
-	GeomEntry entry[MR_GEOM_WARPS][2]; // the cluster a warp works on (k & 1) and the next one
+	GeomEntry entry[MR_GEOM_WARPS][2];      // the cluster a warp works on (k & 1) and the next one
 	unsigned long long full[MR_GEOM_WARPS]; // mbarrier: the warp's meshlet (or the news that there is none) has arrived
-	unsigned long long ring[MR_GEOM_RING];  // slot number << 32 | chunk number (as written by the fetching warp)
+	unsigned long long ring[MR_GEOM_RING];  // chunk slot number << 32 | chunk number
 	unsigned long long stat;
 	unsigned ticket;
 	int nVis;
+	int cullCount, cullBase; // survivors of this CTA in the current cull round, and where they go in the list
 };
 #define MR_GEOM_FIXED_BYTES ((int)((sizeof(GeomShared) + 127) / 128 * 128))
 // per warp: the meshlet as loaded, the transformed corners (3 float4 planes), a copy of the local indices
@@ -524,32 +543,25 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ int ldAcquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-// Draws the next work-list index for the calling lane (lane 0 of a warp). If the ticket opens a new ring slot, the
-// chunk for two slots ahead is requested: `fetch` receives the atomic's result (to be stored by ringStore() one
-// iteration later), `fetchSlot` its slot. Returns an index >= nVis when the list is exhausted.
-__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nChunks, int firstDynamic, int& fetch, int& fetchSlot)
+// The next work-list index for the calling lane (lane 0 of a warp), or 0x7fffffff when the list is exhausted; see k_geom.
+__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int firstDynamic)
 {
 	const unsigned t = atomicAdd(&gs.ticket, 1u);
 	const unsigned slot = t / MR_GEOM_CHUNK, within = t % MR_GEOM_CHUNK;
-	if (within == 0u)
+	volatile unsigned long long* ring = gs.ring;
+	if (within == 0u && slot > 0u)
 	{
-		fetch = atomicAdd(&sync[0], 1); // consumed by ringStore(), not here
-		fetchSlot = (int)slot + 2;
+		// this warp fetches the chunk for everybody, once the previous chunk's number is known (keeps them ordered)
+		while ((unsigned)(ring[(slot - 1u) % MR_GEOM_RING] >> 32) != slot - 1u)
+			;
+		const int c = firstDynamic + atomicAdd(&sync[0], 1);
+		ring[slot % MR_GEOM_RING] = ((unsigned long long)slot << 32) | (unsigned)c;
 	}
-	volatile unsigned long long* cell = &gs.ring[slot % MR_GEOM_RING];
-	unsigned long long v = *cell;
-	while ((unsigned)(v >> 32) != slot) // the fetch for this slot was issued two chunks ago: normally long there
-		v = *cell;
-	const int chunk = (int)(unsigned)v;
-	return (chunk < nChunks) ? chunk * MR_GEOM_CHUNK + (int)within : 0x7fffffff;
-}
-__device__ __forceinline__ void ringStore(GeomShared& gs, int firstDynamic, int& fetch, int& fetchSlot)
-{
-	if (fetchSlot >= 0)
-	{
-		*(volatile unsigned long long*)&gs.ring[fetchSlot % MR_GEOM_RING] = ((unsigned long long)(unsigned)fetchSlot << 32) | (unsigned)(firstDynamic + fetch);
-		fetchSlot = -1;
-	}
+	unsigned long long v = ring[slot % MR_GEOM_RING];
+	while ((unsigned)(v >> 32) != slot)
+		v = ring[slot % MR_GEOM_RING];
+	const long long idx = (long long)(unsigned)v * MR_GEOM_CHUNK + within;
+	return idx < (long long)nVis ? (int)idx : 0x7fffffff;
 }
 
 // Triangle phase of one cluster for one lane (triangle `lane` of the cluster); see k_geom.
@@ -701,6 +713,18 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
 }
 
+#ifdef MR_TIMELINE
+// Experiment build only: per-warp time stamps (globaltimer, ns) of k_geom's phases, read back by mr_debug_timeline().
+#define MR_TL_SLOTS 8
+__device__ unsigned long long g_timeline[1024 * MR_GEOM_WARPS * MR_TL_SLOTS];
+__device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MR_TL(slot) do { if (lane == 0 && blockIdx.x < 1024) g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + (slot)] = globalTimer(); } while (0)
+#define MR_TL_ADD(slot, v) do { if (lane == 0 && blockIdx.x < 1024) g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + (slot)] += (v); } while (0)
+#else
+#define MR_TL(slot) do { } while (0)
+#define MR_TL_ADD(slot, v) do { } while (0)
+#endif
+
 template <int TM>
 __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __grid_constant__ FrameParams fp)
 {
@@ -709,32 +733,40 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int nvCap = fp.geomVertCap;
 	const int nCl = fp.nTriInst / MR_CLUSTER;
-	int* const sync = fp.geomSync;
+	int* const syncChunks = fp.geomSync;
+	int* const syncTail = fp.geomSync + MR_SYNC_STRIDE;
+	int* const syncArrived = fp.geomSync + 2 * MR_SYNC_STRIDE;
 
 	pdlLaunchDependents(); // k_raster's CTAs may take the SMs this kernel's CTAs leave (they wait for the whole grid)
+	MR_TL(0); // kernel entered
 	if (tid == 0)
 	{
 		for (int i = 0; i < MR_GEOM_WARPS; i++)
 			mbarInit(&gs.full[i], 1);
 		gs.stat = 0ull;
 		gs.ticket = 0u;
-		// the CTA's first two chunks by position; later ones are fetched from sync[0], which counts from chunk 2 * grid
-		gs.ring[0] = (0ull << 32) | (unsigned)blockIdx.x;
-		gs.ring[1] = (1ull << 32) | (unsigned)(blockIdx.x + gridDim.x);
-		gs.ring[2] = gs.ring[3] = ~0ull;
+		gs.cullCount = 0;
+		gs.ring[0] = (0ull << 32) | (unsigned)blockIdx.x; // the CTA's first chunk by position; sync[0] counts from chunk `grid`
+		for (int i = 1; i < MR_GEOM_RING; i++)
+			gs.ring[i] = ~0ull;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	// ---- phase 0: cull (Renderer.cpp:169-177, :202, :205-210 decided per cluster) ----
-	for (int base = blockIdx.x * MR_GEOM_THREADS; base < nCl; base += gridDim.x * MR_GEOM_THREADS)
+	__syncthreads();
+
+	// ---- phase 0: cull (Renderer.cpp:169-177, :202, :205-210 decided per cluster). Slice s = clusters 32 s .. 32 s + 31
+	// goes to warp (s / grid) % WARPS of CTA s % grid ----
+	const int nSlices = (nCl + 31) >> 5;
+	for (int round = 0; round * (int)gridDim.x * MR_GEOM_WARPS < nSlices; round++) // (block-uniform)
 	{
-		const int ci = base + tid;
+		const int slice = (round * MR_GEOM_WARPS + warp) * (int)gridDim.x + (int)blockIdx.x;
+		const int ci = slice * 32 + lane;
 		bool vis = false;
 		int r = 0;
 		RStat rs;
 		rs.triBase = rs.clusterBase = rs.nTri = rs.triBaseReal = 0;
 		MeshletDir d;
 		d.off16 = d.nv = 0u;
-		if (ci < nCl)
+		if (slice < nSlices && ci < nCl)
 		{
 			r = (fp.nRenderables == 1) ? 0 : __ldg(&fp.triBlockCl[ci]);
 			rs = frameRstat<TM>(fp)[r];
@@ -744,39 +776,45 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 			d = fp.meshletDir[meshCluster]; // requested together with the bounds
 			vis = !fp.cullClusters || clusterVisible(fp, frameRdyn<TM>(fp)[r], cs, ca);
 		}
+		// where the survivors go: a shared-memory atomic per warp, one global atomic per CTA
 		const unsigned m = __ballot_sync(0xffffffffu, vis);
-		if (m != 0u)
+		int at = 0;
+		if (lane == 0 && m != 0u)
+			at = atomicAdd(&gs.cullCount, __popc(m));
+		at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+		__syncthreads();
+		if (tid == 0)
 		{
-			const int leader = __ffs(m) - 1;
-			int at = 0;
-			if (lane == leader)
-				at = atomicAdd(&sync[1], __popc(m));
-			at = __shfl_sync(0xffffffffu, at, leader) + __popc(m & ((1u << lane) - 1u));
-			if (vis)
-			{
-				const RDyn& rd = frameRdyn<TM>(fp)[r];
-				uint4* o = reinterpret_cast<uint4*>(fp.visEntries + at);
-				o[0] = make_uint4((uint32_t)ci, d.nv, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
-				o[1] = make_uint4((uint32_t)rs.nTri, (uint32_t)rs.triBaseReal, (uint32_t)rd.material, 0u);
+			const int n = gs.cullCount;
+			gs.cullBase = n > 0 ? atomicAdd(syncTail, n) : 0;
+			gs.cullCount = 0;
+		}
+		__syncthreads();
+		if (vis)
+		{
+			const RDyn& rd = frameRdyn<TM>(fp)[r];
+			uint4* o = reinterpret_cast<uint4*>(fp.visEntries + gs.cullBase + at);
+			o[0] = make_uint4((uint32_t)ci, d.nv & 0xffffu, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
+			o[1] = make_uint4((uint32_t)rs.nTri, (uint32_t)rs.triBaseReal, (uint32_t)rd.material, d.nv >> 16);
 #pragma unroll
-				for (int k = 0; k < 3; k++)
-				{
-					o[2 + k] = make_uint4(__float_as_uint(rd.mv[4 * k]), __float_as_uint(rd.mv[4 * k + 1]), __float_as_uint(rd.mv[4 * k + 2]), __float_as_uint(rd.mv[4 * k + 3]));
-					o[5 + k] = make_uint4(__float_as_uint(rd.nm[4 * k]), __float_as_uint(rd.nm[4 * k + 1]), __float_as_uint(rd.nm[4 * k + 2]), __float_as_uint(rd.nm[4 * k + 3]));
-				}
+			for (int k = 0; k < 3; k++)
+			{
+				o[2 + k] = make_uint4(__float_as_uint(rd.mv[4 * k]), __float_as_uint(rd.mv[4 * k + 1]), __float_as_uint(rd.mv[4 * k + 2]), __float_as_uint(rd.mv[4 * k + 3]));
+				o[5 + k] = make_uint4(__float_as_uint(rd.nm[4 * k]), __float_as_uint(rd.nm[4 * k + 1]), __float_as_uint(rd.nm[4 * k + 2]), __float_as_uint(rd.nm[4 * k + 3]));
 			}
 		}
 	}
-	// every CTA's entries must be visible before anyone pops: a grid-wide arrival counter (all CTAs are
-	// resident: the grid is sized from the occupancy of this kernel and launched cooperatively)
+	// every CTA's entries must be visible before anyone takes from the list: a grid-wide arrival counter (all CTAs
+	// are resident: the grid is sized from the occupancy of this kernel and launched cooperatively)
 	__threadfence();
+	MR_TL(1); // own clusters culled
 	__syncthreads();
 	if (tid == 0)
 	{
-		atomicAdd(&sync[2], 1);
-		while (ldAcquire(&sync[2]) < (int)gridDim.x)
+		atomicAdd(syncArrived, 1);
+		while (ldAcquire(syncArrived) < (int)gridDim.x)
 			;
-		const int n = ldAcquire(&sync[1]);
+		const int n = ldAcquire(syncTail);
 		gs.nVis = n;
 		if (blockIdx.x == 0)
 		{
@@ -787,6 +825,11 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	}
 	__syncthreads();
 	const int nVis = gs.nVis;
+	MR_TL(2); // work list complete
+#ifdef MR_TIMELINE
+	if (lane == 0 && blockIdx.x < 1024)
+		g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 5] = g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 6] = 0ull;
+#endif
 
 	// ---- phase 1: every warp on its own ----
 	unsigned long long acc = 0ull;
@@ -800,15 +843,14 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 		unsigned long long* const full = &gs.full[warp];
 		const uint32_t* const visWords = reinterpret_cast<const uint32_t*>(fp.visEntries);
 		const uint32_t none = (lane == 0) ? 0xffffffffu : 0u; // word `lane` of an entry that says "no more work"
-		const int nChunks = (nVis + MR_GEOM_CHUNK - 1) / MR_GEOM_CHUNK, firstDynamic = 2 * (int)gridDim.x;
-		int fetch = 0, fetchSlot = -1; // (lane 0) a chunk request in flight for ring slot fetchSlot
-		uint32_t entryWord;            // word `lane` of the next cluster's entry
+		const int firstDynamic = (int)gridDim.x;
+		uint32_t entryWord; // word `lane` of the next cluster's entry
 		{
 			int i0 = 0, i1 = 0;
 			if (lane == 0)
 			{
-				i0 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
-				i1 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
+				i0 = geomPop(gs, syncChunks, nVis, firstDynamic);
+				i1 = (i0 < nVis) ? geomPop(gs, syncChunks, nVis, firstDynamic) : i0;
 			}
 			i0 = __shfl_sync(0xffffffffu, i0, 0);
 			i1 = __shfl_sync(0xffffffffu, i1, 0);
@@ -824,16 +866,22 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
 					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
 				}
-				else
-					mbarArrive(full);
 			}
 		}
 		for (int k = 0;; k++)
 		{
-			mbarWait(full, (uint32_t)(k & 1));
 			const GeomEntry& e = gs.entry[warp][k & 1];
 			if (e.ci < 0)
 				break;
+#ifdef MR_TIMELINE
+			const unsigned long long tw0 = globalTimer();
+#endif
+			mbarWait(full, (uint32_t)(k & 1));
+#ifdef MR_TIMELINE
+			MR_TL_ADD(5, globalTimer() - tw0); // time spent waiting for meshlets
+			if (k == 0) MR_TL(3);              // first meshlet there
+			MR_TL_ADD(6, 1ull);                // iterations
+#endif
 			const int nv = e.nv;
 
 			// ---- vertex phase: loops A and B of paintMesh for the cluster's corners, plus their projection ----
@@ -841,21 +889,32 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 				const float4* const raw0 = reinterpret_cast<const float4*>(raw);
 				const float4* const raw1 = raw0 + nv;
 				sIdx[lane] = reinterpret_cast<const uint32_t*>(raw1 + nv)[lane];
-				for (int v = lane; v < nv; v += 32)
-				{
-					const float4 q0 = raw0[v], q1 = raw1[v]; // (px py pz nx) (ny nz u v)
-					const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
-					const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
-					sA[v] = project(fp, view);
-					sB[v] = make_float4(view.x, view.y, view.z, q1.z);
-					sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
-				}
+				if (fp.stdProj && !(e.flags & MR_MESHLET_NONFINITE))
+					for (int v = lane; v < nv; v += 32)
+					{
+						const float4 q0 = raw0[v], q1 = raw1[v]; // (px py pz nx) (ny nz u v)
+						const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
+						const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
+						sA[v] = projectStd(fp, view);
+						sB[v] = make_float4(view.x, view.y, view.z, q1.z);
+						sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
+					}
+				else
+					for (int v = lane; v < nv; v += 32)
+					{
+						const float4 q0 = raw0[v], q1 = raw1[v];
+						const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
+						const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
+						sA[v] = project(fp, view);
+						sB[v] = make_float4(view.x, view.y, view.z, q1.z);
+						sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
+					}
 			}
 			// ---- the next cluster: its entry (read one iteration ago) into shared memory, its bulk copy issued
-			// (the meshlet buffer is free again), the entry after next requested, another index popped ----
+			// (the meshlet buffer is free again), another index drawn and that entry requested ----
 			reinterpret_cast<uint32_t*>(&gs.entry[warp][(k + 1) & 1])[lane] = entryWord;
 			__syncwarp(); // corners complete, every lane is done with the meshlet buffer
-			int i2 = 0;
+			int i2 = 0x7fffffff;
 			if (lane == 0)
 			{
 				const GeomEntry& n = gs.entry[warp][(k + 1) & 1];
@@ -863,11 +922,8 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 				{
 					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
 					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
+					i2 = geomPop(gs, syncChunks, nVis, firstDynamic);
 				}
-				else
-					mbarArrive(full);
-				ringStore(gs, firstDynamic, fetch, fetchSlot); // last iteration's chunk request has arrived
-				i2 = geomPop(gs, sync, nChunks, firstDynamic, fetch, fetchSlot);
 			}
 			i2 = __shfl_sync(0xffffffffu, i2, 0);
 			entryWord = (i2 < nVis) ? __ldcg(visWords + (size_t)i2 * 32 + lane) : none;
@@ -876,10 +932,9 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 			geomTriangle(fp, e, sA, sB, sC, sIdx, lane, acc);
 			__syncwarp(); // the corners may be overwritten by the next cluster's
 		}
-		if (lane == 0)
-			ringStore(gs, firstDynamic, fetch, fetchSlot); // a request still in flight must reach the ring: others may wait for it
 	}
 
+	MR_TL(4); // warp out of work
 	// ---- statistics: one shared-memory atomic per warp, one RED per counter per CTA ----
 	unsigned long long sum = acc;
 #pragma unroll
@@ -1510,8 +1565,8 @@ __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(co
 	{
 		// k_geom is done with its work list and this frame's statistics are where they belong:
 		// the list counters and the next frame's statistics start from zero
-		if (threadIdx.x < 4)
-			fp.geomSync[threadIdx.x] = 0;
+		if (threadIdx.x < 3)
+			fp.geomSync[threadIdx.x * MR_SYNC_STRIDE] = 0;
 		for (int i = threadIdx.x; i < (int)(sizeof(Counters) / 8); i += MR_RASTER_THREADS)
 			reinterpret_cast<unsigned long long*>(fp.ctrNext)[i] = 0ull;
 	}
@@ -1594,7 +1649,7 @@ __global__ void k_selftest(const float* in, float* out)
 }
 
 // Shape of k_geom for meshlets of up to nvCap corners: dynamic shared memory per CTA and a grid of as many
-// CTAs as are resident at once (the cull phase ends in a grid-wide rendezvous).
+// CTAs as are resident at once (they are persistent: work comes from the frame's slice counter).
 int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes)
 {
 	int dev = 0, smemMax = 0;
@@ -1657,12 +1712,20 @@ void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStr
 	else
 	{
 		// k_raster normally resets the work-list counters and the next frame's statistics
-		cudaMemsetAsync(fp.geomSync, 0, 4 * sizeof(int), stream);
+		cudaMemsetAsync(fp.geomSync, 0, 3 * MR_SYNC_STRIDE * sizeof(int), stream);
 		cudaMemsetAsync(fp.ctrNext, 0, sizeof(Counters), stream);
 	}
 	if (ev) cudaEventRecord(ev[2], stream);
 	if (bracketStop) cudaEventRecord(bracketStop, stream);
 }
+
+#ifdef MR_TIMELINE
+extern "C" __attribute__((visibility("default"))) int mr_debug_timeline(unsigned long long* out, int nWords)
+{
+	const size_t n = std::min((size_t)nWords, sizeof(g_timeline) / 8);
+	return cudaMemcpyFromSymbol(out, g_timeline, n * 8) == cudaSuccess ? (int)n : -1;
+}
+#endif
 
 int mrk_selftest_no_fma(cudaStream_t stream)
 {

@@ -10,7 +10,6 @@
 // Per-frame arrays:
 //   RStat[]/RDyn[] per renderable (flattened scene entry): mesh + instance bases / matrices
 //   MatDev[]       materials
-//   visEntries[]   one GeomEntry per cluster that survived culling (k_geom's work list)
 //   recs[]         one 160-byte record per set-up triangle (10 float4 fields: 4 raster, 6 shading = its
 //                  three view-space corners), at index 2*t+sub where t is the triangle instance index in
 //                  submission order: the index IS the submission id that resolves equal-depth ties.
@@ -47,10 +46,11 @@ struct MeshDev // host-side bookkeeping of one uploaded mesh
 // Blobs start at multiples of 16 bytes and are a multiple of 16 bytes long (cp.async.bulk).
 #define MR_MESHLET_MAX_VERTS (3 * MR_CLUSTER)
 #define MR_MESHLET_BYTES(nv) ((nv) * 32 + MR_CLUSTER * 4)
+#define MR_MESHLET_NONFINITE 1u // a corner position of the meshlet is NaN or infinite
 struct MeshletDir
 {
 	uint32_t off16; // blob offset into meshlets[] in units of 16 bytes
-	uint32_t nv;
+	uint32_t nv;    // corners | MR_MESHLET_* flags << 16
 };
 
 struct __align__(16) RStat // per renderable, changes only when the flattened structure changes
@@ -72,8 +72,8 @@ struct __align__(16) RDyn // per renderable, per frame
 	int pad;
 };
 
-// One unit of work of k_geom: a cluster that survived culling, with everything a team needs to process it
-// (so that popping it is a single 128-byte read). Written by k_geom's own cull phase.
+// One unit of work of k_geom: a cluster that survived culling, with everything a warp needs to process it
+// (so that taking it is a single 128-byte read). Written by k_geom's own cull phase.
 struct __align__(128) GeomEntry
 {
 	int ci;          // cluster: triangle instances [ci * MR_CLUSTER, (ci + 1) * MR_CLUSTER); -1 = no more work
@@ -83,7 +83,7 @@ struct __align__(128) GeomEntry
 	int nTri;        // triangles of the mesh
 	int subBase;     // RStat::triBaseReal
 	int material;
-	int pad;
+	uint32_t flags;  // MR_MESHLET_*
 	float mv[12];
 	float nm[12];
 };
@@ -129,6 +129,7 @@ struct __align__(16) ShadeRec
 	float n2[3], v2;
 };
 
+#define MR_SYNC_STRIDE 256 // ints between k_geom's global counters
 #define MR_STAT_SLOTS 32 // statistics are spread over this many slots (summed by the host): no single-address hot spot
 struct Counters
 {
@@ -169,6 +170,7 @@ struct FrameParams
 	float bgPattern[12];    // r g b r g b ...
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
+	int stdProj; // standard perspective matrix with the near plane in front of the eye: projectStd() applies
 	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags
 	int binCap; // entries per tile bin
@@ -191,7 +193,8 @@ struct FrameParams
 	// k_geom: persistent CTAs; a warp's shared memory holds one meshlet (geomVertCap corners) and its transformed corners
 	int geomVertCap;
 	GeomEntry* visEntries; // work list of the frame: clusters that survived culling (any order)
-	int* geomSync;         // [0] entries popped, [1] entries appended, [2] CTAs that finished culling; zeroed by k_raster
+	int* geomSync;         // three counters MR_SYNC_STRIDE ints apart (own L2 lines): [0] chunks of the list handed out,
+	                       // [1] entries appended, [2] CTAs that finished culling; zeroed by k_raster
 
 	unsigned long long* gkeys; // per pixel: orderable z << 32 | record index + 1 (MR_KEY_EMPTY: untouched)
 	float4* recs;        // records of sub-triangle 0 in plane layout: block (t >> 5), field pair j, lane (t & 31), 32 bytes each

@@ -326,3 +326,47 @@ SMALL_SCENES = {
     "bench_small_tex": lambda be: bench_scene(be, width=300, height=170, objects=3, m=30, n=30, usetex=True),
     "cloud_small": lambda be: cloud_scene(be, width=480, height=270, groups=8, per_group=12, extent=70.0),
 }
+
+
+def fuzz_scene(be, seed, width=384, height=216):
+    """Randomised stress scene for the shortcuts that must not change the image (cluster culling, the
+    standard-perspective vertex path): finely tessellated primitives under random translation / rotation /
+    scale, some sheared, some mirrored, some enclosing the camera or crossing the near plane and the
+    screen edges; perspective (symmetric or off-centre) or orthographic projection."""
+    rng = np.random.default_rng(1000 + seed)
+    sc = api.Scene(be, ambient=float(rng.uniform(0.05, 0.3)))
+    n_obj = int(rng.integers(3, 8))
+    for k in range(n_obj):
+        t = (rng.uniform(-1, 1, 3) * np.array([160, 110, 160])).astype(f32)
+        xf = be.mul(be.translate(*t), be.rotate_vec(*rng.uniform(-2, 2, 3).astype(f32)))
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            s = f32(rng.uniform(0.3, 3.0)); xf = be.mul(xf, be.scale(s, s, s))                       # similarity
+        elif kind == 1:
+            xf = be.mul(xf, be.scale(*rng.uniform(0.3, 3.0, 3).astype(f32)))                        # non-uniform
+        elif kind == 2:
+            s = rng.uniform(0.5, 2.0, 3).astype(f32); s[int(rng.integers(0, 3))] *= f32(-1); xf = be.mul(xf, be.scale(*s))  # mirrored
+        elif kind == 3:
+            sh = np.eye(4, dtype=f32); sh[int(rng.integers(0, 3)), int(rng.integers(0, 3))] += f32(rng.uniform(-1.2, 1.2)); xf = be.mul(xf, sh)
+        mat = sc.add_material(diffuse=rng.random(3).astype(f32), shininess=float(rng.choice([0.0, 7.0, 12.5])))
+        shape = rng.integers(0, 4)
+        if shape == 0:
+            sc.add_sphere(float(rng.uniform(10, 60)), int(rng.integers(8, 50)), int(rng.integers(8, 90)), xf=xf, material=mat)
+        elif shape == 1:
+            sc.add_cylinder(float(rng.uniform(5, 30)), float(rng.uniform(20, 300)), int(rng.integers(6, 64)), int(rng.integers(1, 30)), True, xf=xf, material=mat)
+        elif shape == 2:
+            sc.add_cube(float(rng.uniform(10, 80)), xf=xf, material=mat)
+        else:
+            sc.add_sphere(float(rng.uniform(200, 500)), int(rng.integers(10, 60)), int(rng.integers(10, 120)), xf=xf, material=mat)  # may enclose the camera
+    d = float(rng.uniform(20, 350))
+    view = be.mul(be.translate(float(rng.uniform(-30, 30)), float(rng.uniform(-30, 30)), -d), be.rotate_x(f32(rng.uniform(-1.5, 0.5))), be.rotate_z(f32(rng.uniform(0, 6.28))))
+    mode = seed % 4
+    if mode == 0:
+        proj = frustum(be, width, height, float(rng.uniform(20, 80)), float(rng.uniform(1, 30)), 5000.0)
+    elif mode == 1:
+        proj = be.projection(api.PROJ_PERSPECTIVE6, -8.0 * rng.uniform(0.5, 1.5), 6.0 * rng.uniform(0.5, 1.5), -3.0, 5.0, 10.0, 4000.0)  # off-centre
+    elif mode == 2:
+        proj = be.projection(api.PROJ_ORTHO6, -200, 200, -120, 120, 1.0, 1500.0)
+    else:
+        proj = frustum(be, width, height, 35.0, 10.0, 7000.0)
+    return Setup("fuzz%d" % seed, sc, width, height, proj, view, point_light=bool(seed & 1), light=(40.0, 90.0, 150.0) if seed & 1 else (-0.4, 0.6, 1.0))
