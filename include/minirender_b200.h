@@ -215,9 +215,10 @@ MR_API int mr_host_unregister(void* host);
 /* Verification aid: with flags & 1, mr_render also records for every pixel the submission id of
  * the triangle that owns it (2 * triangle instance index + clip sub-triangle, -1 = background),
  * which is what equal-depth ties are resolved on. Read it back with mr_read_winner_ids.
- * flags & 4 turns cluster culling off and flags & 8 the standard-perspective vertex path (every cluster is set up /
- * every corner goes through the general htransform): the image must not change, which is what the tests use them for.
- * (The environment variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ do the same for a whole process.) */
+ * flags & 4 turns cluster culling off, flags & 8 the standard-perspective vertex path and flags & 16 the tight scan of
+ * small triangles (every cluster is set up / every corner goes through the general htransform / every pixel centre of
+ * the reference's loops is tested): the image must not change, which is what the tests use them for. (The environment
+ * variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ / MR_NO_TIGHT_SCAN do the same for a whole process.) */
 MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 

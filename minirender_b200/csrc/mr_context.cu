@@ -118,7 +118,7 @@ struct mr_ctx
 	// scratch
 	DevBuf recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
 	bool slotOverflowed; // a frame older than the newest one overflowed its spill list (async readers are told)
-	bool noClusterCull, noPdl, noStdProj; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
+	bool noClusterCull, noPdl, noStdProj, noTightScan; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -146,7 +146,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), noTightScan(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -531,6 +531,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 			fp.bgPattern[k] = f->background[k % 3];
 	}
 	fp.persp = f->projection[15] == 0.0f;
+	fp.tightScan = (c->noTightScan || (c->debugFlags & 16)) ? 0 : 1;
 	{
 		const float* P = f->projection;
 		fp.stdProj = (fp.persp && P[1] == 0.0f && P[3] == 0.0f && P[4] == 0.0f && P[7] == 0.0f && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f &&
@@ -843,6 +844,7 @@ mr_ctx* mr_create(int device, int* status)
 		c->noClusterCull = getenv("MR_NO_CLUSTER_CULL") != 0; // verification switches, read once
 		c->noPdl = getenv("MR_NO_PDL") != 0;
 		c->noStdProj = getenv("MR_NO_STD_PROJ") != 0;
+		c->noTightScan = getenv("MR_NO_TIGHT_SCAN") != 0;
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
 		c->ownStream = ok;
 		ok = ok && cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) == cudaSuccess;

@@ -148,9 +148,30 @@ __device__ __forceinline__ bool clusterVisible(const FrameParams& fp, const RDyn
 struct Setup
 {
 	float n1x, n1y, n2x, n2y;
-	int x0, x1, y0, y1;
+	int x0, x1, y0, y1; // the reference's pixel loops: columns x0..x1, rows y0..y1 (the clamped bbox)
 	uint32_t flags;
+	uint32_t skip;      // MR_SKIP_*: outermost column / row of the loops that provably holds no covered pixel
 };
+#define MR_SKIP_L 1u
+#define MR_SKIP_R 2u
+#define MR_SKIP_T 4u
+#define MR_SKIP_B 8u
+
+// Tight scan. The reference's loops start at the pixel centre floor(min) + 0.5 and end at floor(max) + 0.5, i.e. they
+// visit centres up to half a pixel OUTSIDE the triangle's bounding box on every side, where no pixel is covered - in
+// exact arithmetic. In float arithmetic a centre farther than MR_TIGHT_DELTA outside the box is still rejected by the
+// reference's own test (Renderer.cpp:245) whenever the triangle is not a sliver:
+//   * a centre q at distance >= d outside the box has a true barycentric <= -d / (2 L), L = box extent + 1 >= |q - p_i|
+//     (sum_i k_i (x_i - q_x) = 0 with every x_i - q_x in [d, L], sum k_i = 1, at most two k_i negative);
+//   * the computed e1, e2, k0 differ from the true barycentrics by less than 2^-19 S^2 + 2^-14.9 S, S = L^2 / area:
+//     area carries a relative error <= 2^-21 S (cancellation of two products of magnitude <= L^2), which scales every
+//     barycentric (|k_i| <= sqrt(2) S inside the scanned box); row start and <= 64 chain additions add
+//     <= 2^-16 S (each rounding is 2^-24 of a partial sum <= 2 |n| L, |n| L <= sqrt(2) S).
+// With 2^-18 S^2 + 2^-12 S as the error bound (2x / 7x the above), the outermost column or row is skipped only when
+// (2^-18 S^2 + 2^-12 S) * 2 L < MR_TIGHT_DELTA holds for the triangle; otherwise (slivers, huge triangles clipped by
+// the frame) the full loops run. The chain still starts at the reference's first column (a skipped column costs its
+// two additions, not its test). tests/test_gpu_invariance.py compares tight and full scans bit for bit.
+#define MR_TIGHT_DELTA 0.0625f
 
 __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float4 a, const float4 b, const float4 c, Setup& s)
 {
@@ -172,14 +193,16 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float
 	s.n1y = (a.x - c.x) * i2a;
 	s.n2x = -(b.y - a.y) * i2a;
 	s.n2y = (b.x - a.x) * i2a;
+	const float bx0 = minx, bx1 = maxx, by0 = miny, by1 = maxy; // the box before clamping
 	minx = tclamp(minx, 0.0f, w - 1.0f);
 	maxx = tclamp(maxx, 0.0f, w - 1.0f);
 	miny = tclamp(miny, 0.0f, h - 1.0f);
 	maxy = tclamp(maxy, 0.0f, h - 1.0f);
 	// Pixel loops: x = floor(minx)+0.5, +1 ... while x <= maxx+0.5 (float sum), same in y.
 	// All loop values are exact half-integers, so the last index is floor((max+0.5f) - 0.5f).
-	s.x0 = (int)floorf(minx);
-	s.y0 = (int)floorf(miny);
+	const float fx0 = floorf(minx), fy0 = floorf(miny);
+	s.x0 = (int)fx0;
+	s.y0 = (int)fy0;
 	const float xlim = maxx + 0.5f, ylim = maxy + 0.5f;
 	int x1 = (int)floorf(xlim - 0.5f), y1 = (int)floorf(ylim - 0.5f);
 	if ((float)x1 + 0.5f > xlim) x1--;
@@ -189,6 +212,19 @@ __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float
 	s.x1 = x1;
 	s.y1 = y1;
 	s.flags = 0u;
+	s.skip = 0u;
+	if (fp.tightScan)
+	{
+		const float L = fmaxf(bx1 - bx0, by1 - by0) + 1.0f;
+		const float S = L * L * fabsf(i2a);
+		if ((S * S * 3.814697265625e-6f + S * 2.44140625e-4f) * (2.0f * L) < MR_TIGHT_DELTA) // 2^-18, 2^-12; false for NaN
+		{
+			if (fx0 + 0.5f < bx0 - MR_TIGHT_DELTA) s.skip |= MR_SKIP_L;
+			if ((float)x1 + 0.5f > bx1 + MR_TIGHT_DELTA) s.skip |= MR_SKIP_R;
+			if (fy0 + 0.5f < by0 - MR_TIGHT_DELTA) s.skip |= MR_SKIP_T;
+			if ((float)y1 + 0.5f > by1 + MR_TIGHT_DELTA) s.skip |= MR_SKIP_B;
+		}
+	}
 	return true;
 }
 
@@ -219,27 +255,38 @@ __device__ __forceinline__ void redMin64(unsigned long long* p, unsigned long lo
 #endif
 __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 a, const float4 b, const float4 c, const Setup& s, int id)
 {
-	const int ya = max(s.y0, fp.rowBegin), yb = min(s.y1, fp.rowEnd - 1);
-	const int W = s.x1 - s.x0 + 1;
+	const int skipL = (int)(s.skip & MR_SKIP_L), skipR = (int)((s.skip >> 1) & 1u), skipT = (int)((s.skip >> 2) & 1u), skipB = (int)((s.skip >> 3) & 1u);
+	const int ya = max(s.y0 + skipT, fp.rowBegin), yb = min(s.y1 - skipB, fp.rowEnd - 1);
+	const int W = s.x1 - s.x0 + 1 - skipL - skipR; // columns tested per row
 	const float ptx = (float)s.x0 + 0.5f;
+	// row start (Renderer.cpp:241-242): e = n.x * (x0 - p.x) + n.y * (y - p.y); the first products do not depend on the row
+	const float t1 = s.n1x * (ptx - c.x), t2 = s.n2x * (ptx - a.x);
 	const unsigned long long idp1 = (unsigned long long)(uint32_t)(id + 1);
 	bool any = false;
-	for (int y = ya; y <= yb; y++)
+	if (W > 0)
 	{
-		const float fy = (float)y + 0.5f;
-		float e1 = s.n1x * (ptx - c.x) + s.n1y * (fy - c.y);
-		float e2 = s.n2x * (ptx - a.x) + s.n2y * (fy - a.y);
-		unsigned long long* row = fp.gkeys + (size_t)y * fp.w + s.x0;
-		for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x)
+		float fy = (float)ya + 0.5f;
+		unsigned long long* row = fp.gkeys + (size_t)ya * fp.w + (s.x0 + skipL);
+		for (int y = ya; y <= yb; y++, fy += 1.0f, row += fp.w)
 		{
-			const float k0 = 1.0f - e1 - e2;
-			if (insideTest(e1, e2, k0)) // Renderer.cpp:245
+			float e1 = t1 + s.n1y * (fy - c.y);
+			float e2 = t2 + s.n2y * (fy - a.y);
+			if (skipL) // the chain starts at the reference's first column whether or not that column is tested
 			{
-				const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
-				if (z == z) // a NaN depth never passes `z < pixdepth`
+				e1 += s.n1x;
+				e2 += s.n2x;
+			}
+			for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x)
+			{
+				const float k0 = 1.0f - e1 - e2;
+				if (insideTest(e1, e2, k0)) // Renderer.cpp:245
 				{
-					redMin64(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
-					any = true;
+					const float z = pixelDepth(fp.persp, e1, e2, a.w, b.w, c.w);
+					if (z == z) // a NaN depth never passes `z < pixdepth`
+					{
+						redMin64(row + i, ((unsigned long long)zkey(z) << 32) | idp1);
+						any = true;
+					}
 				}
 			}
 		}

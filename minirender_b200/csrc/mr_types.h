@@ -170,6 +170,7 @@ struct FrameParams
 	float bgPattern[12];    // r g b r g b ...
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
+	int tightScan; // small triangles skip the outermost columns / rows of the reference's loops where those provably cover nothing
 	int stdProj; // standard perspective matrix with the near plane in front of the eye: projectStd() applies
 	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags

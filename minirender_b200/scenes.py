@@ -370,3 +370,48 @@ def fuzz_scene(be, seed, width=384, height=216):
     else:
         proj = frustum(be, width, height, 35.0, 10.0, 7000.0)
     return Setup("fuzz%d" % seed, sc, width, height, proj, view, point_light=bool(seed & 1), light=(40.0, 90.0, 150.0) if seed & 1 else (-0.4, 0.6, 1.0))
+
+
+def tiny_soup_scene(be, seed, width=256, height=160, tris=30000, persp=False):
+    """Tens of thousands of pixel-sized and sub-pixel triangles, many of them slivers (near-collinear corners,
+    aspect ratios up to 1e5), corners on and next to pixel centres and pixel edges: the inputs on which the
+    error bound of the tight scan (mr_kernels.cu, MR_TIGHT_DELTA) decides between skipping and the full loops."""
+    rng = np.random.default_rng(7000 + seed)
+    sc = api.Scene(be, ambient=0.2)
+    # one unit = one pixel under the orthographic projection below
+    centre = rng.uniform([-2, -2], [width + 2, height + 2], (tris, 2))
+    snap = rng.random(tris) < 0.3
+    centre[snap] = np.round(centre[snap] * 2) / 2                       # on pixel centres / edges
+    size = 10.0 ** rng.uniform(-2.5, 0.9, tris)                          # 0.003 .. 8 pixels
+    ang = rng.uniform(0, 2 * np.pi, (tris, 3))
+    rad = rng.uniform(0.2, 1.0, (tris, 3))
+    off = np.stack([np.cos(ang) * rad, np.sin(ang) * rad], -1) * size[:, None, None]
+    sliver = rng.random(tris) < 0.35
+    squash = 10.0 ** rng.uniform(-5, -1, tris)
+    d = rng.uniform(0, 2 * np.pi, tris)
+    dirv = np.stack([np.cos(d), np.sin(d)], -1)
+    nrmv = np.stack([-np.sin(d), np.cos(d)], -1)
+    along = (off * dirv[:, None, :]).sum(-1, keepdims=True)
+    across = (off * nrmv[:, None, :]).sum(-1, keepdims=True)
+    off_s = along * dirv[:, None, :] + across * squash[:, None, None] * nrmv[:, None, :]
+    off = np.where(sliver[:, None, None], off_s, off)
+    xy = centre[:, None, :] + off
+    z = rng.uniform(-900, -100, (tris, 1)) + rng.uniform(-1, 1, (tris, 3))
+    pos = np.empty((tris * 3, 3), f32)
+    pos[:, 0] = (xy[..., 0].reshape(-1) - width / 2).astype(f32)
+    pos[:, 1] = (height / 2 - xy[..., 1].reshape(-1)).astype(f32)
+    pos[:, 2] = z.reshape(-1).astype(f32)
+    if persp:
+        pos[:, 0] *= (-pos[:, 2] / 400.0).astype(f32)                  # undo the perspective divide approximately
+        pos[:, 1] *= (-pos[:, 2] / 400.0).astype(f32)
+    nrm = np.tile(np.array([[0, 0, 1]], f32), (tris * 3, 1))
+    idx = np.arange(tris * 3, dtype=np.int32).reshape(-1, 3)
+    flip = rng.random(tris) < 0.5
+    idx[flip] = idx[flip][:, ::-1]
+    mat = sc.add_material(diffuse=(0.7, 0.6, 0.4), shininess=0.0)
+    sc.add_mesh(pos, nrm, idx, idx, material=mat)
+    if persp:
+        proj = be.projection(api.PROJ_PERSPECTIVE6, -width / 80.0, width / 80.0, -height / 80.0, height / 80.0, 10.0, 2000.0)
+    else:
+        proj = be.projection(api.PROJ_ORTHO6, -width / 2, width / 2, -height / 2, height / 2, 1.0, 2000.0)
+    return Setup("tiny_soup%d" % seed, sc, width, height, proj, be.translate(0, 0, 0), lighting=False)

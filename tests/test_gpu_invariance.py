@@ -1,8 +1,9 @@
 """GPU: shortcuts that must not change a single bit of the result.
 
-Cluster culling (bounding sphere + normal cone per 32 triangles, decided with margins) and the
-standard-perspective vertex path (structural zeros of the projection skipped) only ever drop work the
-reference discards itself / reproduce its roundings. Both have an off switch (mr_set_debug flags 4, 8);
+Cluster culling (bounding sphere + normal cone per 32 triangles, decided with margins), the
+standard-perspective vertex path (structural zeros of the projection skipped) and the tight scan of small
+triangles (outermost columns / rows of the reference's loops skipped where the error bound allows) only ever
+drop work the reference discards itself / reproduce its roundings. Each has an off switch (mr_set_debug flags 4, 8, 16);
 here every randomised scene is rendered with the shortcuts on and off, as a whole and in strips, and
 image, depth and per-pixel winner ids are compared bit for bit. Reference semantics at stake:
 near test src/Renderer.cpp:169-177, off-screen reject :202, area cull :205-210, htransform :13-20."""
@@ -39,9 +40,9 @@ def render_with_flags(be, setup, flags, strips=1):
 @pytest.mark.parametrize("seed", range(24))
 def test_shortcuts_do_not_change_the_frame(be, seed):
     setup = scenes.fuzz_scene(be, seed)
-    img0, dep0, ids0, st0 = render_with_flags(be, setup, 4 | 8)  # everything set up, general htransform
+    img0, dep0, ids0, st0 = render_with_flags(be, setup, 4 | 8 | 16)  # everything set up, general htransform, full scans
     assert (dep0 < 1e10).any(), "fuzz scene %d draws nothing" % seed
-    for flags, strips in ((0, 1), (4, 1), (8, 1), (0, 3)):
+    for flags, strips in ((0, 1), (8 | 16, 1), (4 | 16, 1), (4 | 8, 1), (0, 3)):
         img, dep, ids, st = render_with_flags(be, setup, flags, strips)
         what = "seed %d flags %d strips %d" % (seed, flags, strips)
         assert (bits(dep) == bits(dep0)).all(), what + ": depth differs in %d pixels" % int((bits(dep) != bits(dep0)).sum())
@@ -55,3 +56,15 @@ def test_culling_actually_culls(be):
     _, _, _, on = render_with_flags(be, setup, 0)
     _, _, _, off = render_with_flags(be, setup, 4)
     assert on.records == off.records and on.clusters_visible < 0.8 * off.clusters_visible
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tight_scan_on_tiny_triangles_and_slivers(be, seed):
+    """30 000 pixel-sized / sub-pixel triangles, a third of them slivers: tight scan == the reference's full loops."""
+    setup = scenes.tiny_soup_scene(be, seed, persp=bool(seed & 1))
+    img0, dep0, ids0, st0 = render_with_flags(be, setup, 16)
+    img1, dep1, ids1, st1 = render_with_flags(be, setup, 0)
+    assert (dep0 < 1e10).sum() > 2000, "tiny soup %d draws too little" % seed
+    assert (ids1 == ids0).all(), "winner ids differ in %d pixels" % int((ids1 != ids0).sum())
+    assert (bits(dep1) == bits(dep0)).all() and (bits(img1) == bits(img0)).all()
+    assert st1.records == st0.records and st1.zero_coverage == st0.zero_coverage
