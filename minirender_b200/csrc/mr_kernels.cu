@@ -172,6 +172,10 @@ struct Setup
 // the frame) the full loops run. The chain still starts at the reference's first column (a skipped column costs its
 // two additions, not its test). tests/test_gpu_invariance.py compares tight and full scans bit for bit.
 #define MR_TIGHT_DELTA 0.0625f
+#ifndef MR_RASTER_UNROLL
+#define MR_RASTER_UNROLL 1 // the pixel loop of small triangles is short and branchy: unrolled copies only cost instruction cache
+#endif
+constexpr int kRasterUnroll = MR_RASTER_UNROLL;
 
 __device__ __forceinline__ bool setupTriangle(const FrameParams& fp, const float4 a, const float4 b, const float4 c, Setup& s)
 {
@@ -276,6 +280,7 @@ __device__ __forceinline__ bool rasterSmall(const FrameParams& fp, const float4 
 				e1 += s.n1x;
 				e2 += s.n2x;
 			}
+#pragma unroll kRasterUnroll
 			for (int i = 0; i < W; i++, e1 += s.n1x, e2 += s.n2x)
 			{
 				const float k0 = 1.0f - e1 - e2;
@@ -611,6 +616,79 @@ __device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int 
 	return idx < (long long)nVis ? (int)idx : 0x7fffffff;
 }
 
+// Binning of one warp's larger triangles (`binned` lanes: up to MR_SEG_PER_LANE tiles each, warp-aggregated; more:
+// the whole warp, one triangle at a time) and of the clipper's output triangles. Called by all lanes of the warp.
+__device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, bool binned, int nrecSlow, int sx0, int sx1, int sy0, int sy1, uint2 clip0, uint2 clip1)
+{
+	// ---- binning of the larger triangles: up to MR_SEG_PER_LANE tiles each, warp-aggregated ----
+	if (__any_sync(0xffffffffu, binned))
+	{
+		const int tx0 = sx0 >> MR_TILE_SHIFT, tx1 = sx1 >> MR_TILE_SHIFT;
+		const int ty0 = max(sy0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(sy1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
+		const int nx = tx1 - tx0 + 1;
+		const int ntiles = binned ? nx * (ty1 - ty0 + 1) : 0;
+		const bool big = ntiles > MR_SEG_PER_LANE;
+		const int mine = big ? 0 : ntiles;
+		const int id = 2 * t;
+		const int rounds = __reduce_max_sync(0xffffffffu, mine);
+		// issue the counter atomics of all rounds first, use their results afterwards
+		int tileOf[MR_SEG_PER_LANE], baseOf[MR_SEG_PER_LANE], rankOf[MR_SEG_PER_LANE], leadOf[MR_SEG_PER_LANE];
+#pragma unroll
+		for (int k = 0; k < MR_SEG_PER_LANE; k++)
+		{
+			tileOf[k] = -1; baseOf[k] = 0; rankOf[k] = 0; leadOf[k] = 0;
+			if (k < rounds)
+			{
+				const bool on = k < mine;
+				const int krow = (k >= nx) + (k >= 2 * nx) + (k >= 3 * nx); // k / nx for k < 4
+				const int tile = on ? (ty0 + krow) * fp.tilesX + tx0 + k - krow * nx : -1 - lane;
+				const unsigned peers = __match_any_sync(0xffffffffu, tile);
+				leadOf[k] = __ffs(peers) - 1;
+				rankOf[k] = __popc(peers & ((1u << lane) - 1u));
+				if (on)
+				{
+					tileOf[k] = tile;
+					if (lane == leadOf[k])
+						baseOf[k] = atomicAdd(&fp.tileCount[tile].x, __popc(peers));
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < MR_SEG_PER_LANE; k++)
+			if (k < rounds)
+			{
+				const int slot = __shfl_sync(0xffffffffu, baseOf[k], leadOf[k]) + rankOf[k];
+				if (tileOf[k] >= 0)
+					binStore(fp, tileOf[k], slot, id);
+			}
+		// Triangles spanning more tiles: the warp bins them together, one at a time.
+		unsigned bigLanes = __ballot_sync(0xffffffffu, big);
+		while (bigLanes != 0u)
+		{
+			const int src = __ffs(bigLanes) - 1;
+			bigLanes &= bigLanes - 1u;
+			binCooperative(fp, lane, 2 * (t - lane + src), __shfl_sync(0xffffffffu, sx0, src), __shfl_sync(0xffffffffu, sx1, src),
+			               __shfl_sync(0xffffffffu, sy0, src), __shfl_sync(0xffffffffu, sy1, src));
+		}
+	}
+	// clipper output: binned by the whole warp as well
+	unsigned clipLanes = __ballot_sync(0xffffffffu, nrecSlow != 0);
+	while (clipLanes != 0u)
+	{
+		const int src = __ffs(clipLanes) - 1;
+		clipLanes &= clipLanes - 1u;
+		const int subs = __shfl_sync(0xffffffffu, nrecSlow, src);
+		for (int sub = 0; sub < 2; sub++)
+			if (subs & (1 << sub))
+			{
+				const int id = 2 * (t - lane + src) + sub;
+				const uint32_t xs = __shfl_sync(0xffffffffu, (sub ? clip1.x : clip0.x), src), ys = __shfl_sync(0xffffffffu, (sub ? clip1.y : clip0.y), src);
+				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16);
+			}
+	}
+
+}
+
 // Triangle phase of one cluster for one lane (triangle `lane` of the cluster); see k_geom.
 // acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
 __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEntry& e, const float4* __restrict__ sA, const float4* __restrict__ sB,
@@ -690,72 +768,10 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 		}
 	}
 
-	// ---- binning of the larger triangles: up to MR_SEG_PER_LANE tiles each, warp-aggregated ----
-	if (__any_sync(0xffffffffu, binned))
-	{
-		const int tx0 = s.x0 >> MR_TILE_SHIFT, tx1 = s.x1 >> MR_TILE_SHIFT;
-		const int ty0 = max(s.y0 >> MR_TILE_SHIFT, fp.tileRow0), ty1 = min(s.y1 >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1);
-		const int nx = tx1 - tx0 + 1;
-		const int ntiles = binned ? nx * (ty1 - ty0 + 1) : 0;
-		const bool big = ntiles > MR_SEG_PER_LANE;
-		const int mine = big ? 0 : ntiles;
-		const int id = 2 * t;
-		const int rounds = __reduce_max_sync(0xffffffffu, mine);
-		// issue the counter atomics of all rounds first, use their results afterwards
-		int tileOf[MR_SEG_PER_LANE], baseOf[MR_SEG_PER_LANE], rankOf[MR_SEG_PER_LANE], leadOf[MR_SEG_PER_LANE];
-#pragma unroll
-		for (int k = 0; k < MR_SEG_PER_LANE; k++)
-		{
-			tileOf[k] = -1; baseOf[k] = 0; rankOf[k] = 0; leadOf[k] = 0;
-			if (k < rounds)
-			{
-				const bool on = k < mine;
-				const int krow = (k >= nx) + (k >= 2 * nx) + (k >= 3 * nx); // k / nx for k < 4
-				const int tile = on ? (ty0 + krow) * fp.tilesX + tx0 + k - krow * nx : -1 - lane;
-				const unsigned peers = __match_any_sync(0xffffffffu, tile);
-				leadOf[k] = __ffs(peers) - 1;
-				rankOf[k] = __popc(peers & ((1u << lane) - 1u));
-				if (on)
-				{
-					tileOf[k] = tile;
-					if (lane == leadOf[k])
-						baseOf[k] = atomicAdd(&fp.tileCount[tile].x, __popc(peers));
-				}
-			}
-		}
-#pragma unroll
-		for (int k = 0; k < MR_SEG_PER_LANE; k++)
-			if (k < rounds)
-			{
-				const int slot = __shfl_sync(0xffffffffu, baseOf[k], leadOf[k]) + rankOf[k];
-				if (tileOf[k] >= 0)
-					binStore(fp, tileOf[k], slot, id);
-			}
-		// Triangles spanning more tiles: the warp bins them together, one at a time.
-		unsigned bigLanes = __ballot_sync(0xffffffffu, big);
-		while (bigLanes != 0u)
-		{
-			const int src = __ffs(bigLanes) - 1;
-			bigLanes &= bigLanes - 1u;
-			binCooperative(fp, lane, 2 * (t - lane + src), __shfl_sync(0xffffffffu, s.x0, src), __shfl_sync(0xffffffffu, s.x1, src),
-			               __shfl_sync(0xffffffffu, s.y0, src), __shfl_sync(0xffffffffu, s.y1, src));
-		}
-	}
-	// clipper output: binned by the whole warp as well
-	unsigned clipLanes = __ballot_sync(0xffffffffu, nrecSlow != 0);
-	while (clipLanes != 0u)
-	{
-		const int src = __ffs(clipLanes) - 1;
-		clipLanes &= clipLanes - 1u;
-		const int subs = __shfl_sync(0xffffffffu, nrecSlow, src);
-		for (int sub = 0; sub < 2; sub++)
-			if (subs & (1 << sub))
-			{
-				const int id = 2 * (t - lane + src) + sub;
-				const uint32_t xs = __shfl_sync(0xffffffffu, clipSpans[sub].x, src), ys = __shfl_sync(0xffffffffu, clipSpans[sub].y, src);
-				binCooperative(fp, lane, id, xs & 0xffffu, xs >> 16, ys & 0xffffu, ys >> 16);
-			}
-	}
+	// ---- the larger triangles and the clipper's output go to the tile bins (rare on fine meshes: out of line, so that
+	// the code a warp normally runs stays small) ----
+	if (__any_sync(0xffffffffu, binned || nrecSlow != 0))
+		geomBin(fp, lane, t, binned, nrecSlow, s.x0, s.x1, s.y0, s.y1, clipSpans[0], clipSpans[1]);
 
 	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
 }
