@@ -105,8 +105,8 @@ def check_wide_ops(obj):
     for fn, (st, ld) in counts.items():
         if "k_geom" in fn and st != 5:
             raise RuntimeError("k_geom: expected 5 STG.256 (record pairs), found %d in %s" % (st, fn))
-        if "k_raster" in fn and (st != 3 or ld < 10):
-            raise RuntimeError("k_raster: expected 3 STG.256 / >= 10 LDG.256, found %d / %d in %s" % (st, ld, fn))
+        if "k_raster" in fn and (st != 3 or ld < 7):
+            raise RuntimeError("k_raster: expected 3 STG.256 / >= 7 LDG.256, found %d / %d in %s" % (st, ld, fn))
 
 
 def build_oracle():

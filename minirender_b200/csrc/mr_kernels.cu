@@ -780,6 +780,7 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 // Experiment build only: per-warp time stamps (globaltimer, ns) of k_geom's phases, read back by mr_debug_timeline().
 #define MR_TL_SLOTS 8
 __device__ unsigned long long g_timeline[1024 * MR_GEOM_WARPS * MR_TL_SLOTS];
+__device__ unsigned long long g_rtl[8192 * 4]; // k_raster: per tile CTA start, dependency resolved, end, SM
 __device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MR_TL(slot) do { if (lane == 0 && blockIdx.x < 1024) g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + (slot)] = globalTimer(); } while (0)
 #define MR_TL_ADD(slot, v) do { if (lane == 0 && blockIdx.x < 1024) g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + (slot)] += (v); } while (0)
@@ -1033,6 +1034,9 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 //   depth, perspective correction, texture and Blinn-Phong exactly as Renderer.cpp:253-305;
 //   pixels without a winner get the clear values (Renderer.cpp:113-119) unless fp.keep.
 // ------------------------------------------------------------------------------------------
+#ifndef MR_RASTER_THREADS
+#define MR_RASTER_THREADS 128
+#endif
 #define MR_FQ_CAP 64   // fragment queue entries per warp (power of two)
 #define MR_FQ_SLOTS 64 // triangle slots per warp: 32 lanes per iteration, two iterations in flight
 
@@ -1088,25 +1092,64 @@ __device__ __forceinline__ void pushFragment(const FrameParams& fp, WarpQueue& w
 	}
 }
 
-// pow(base, shininess) in double, as the reference evaluates it. Shininess is almost always a
-// small whole number: then the power is a few double multiplications (relative error below
-// 2^-49, invisible after the result is narrowed to float); anything else takes the library pow.
-__device__ __forceinline__ double powShininess(double base, float shininess)
+// ---- shading (Renderer.cpp:271-305) ----
+// Coverage, depth and the winner of a pixel are bit-exact; its colour has to match the reference's within 1 LSB of the
+// 8-bit image (north star), i.e. within 1/255 - seven orders of magnitude above float rounding. So everything
+// downstream of the (exact) barycentrics uses the fast forms: fused multiply-adds (explicit intrinsics: the file is
+// compiled with --fmad=false for the geometry), MUFU reciprocal / reciprocal square root instead of IEEE division and
+// square root, and the specular power in float (integer exponents by squaring, others through exp2(y log2 x))
+// instead of the reference's double pow(). Texture coordinates keep the reference's unfused expression: they select
+// a texel. MR_EXACT_SHADING=1 restores the reference's operation order and double pow (float RGB bit-identical).
+#ifndef MR_EXACT_SHADING
+#define MR_EXACT_SHADING 0
+#endif
+
+#if MR_EXACT_SHADING
+__device__ __forceinline__ float interp3(float a, float b, float c, float k0, float k1, float k2) { return a * k0 + b * k1 + c * k2; }
+__device__ __forceinline__ float sdot3(V3 a, V3 b) { return dot3(a, b); }
+__device__ __forceinline__ float srlen3(V3 a) { return 1.0f / len3(a); }
+__device__ __forceinline__ float sdiv(float a, float b) { return a / b; }
+// pow(base, shininess) in double, as the reference evaluates it (its unqualified pow() is the double overload).
+__device__ __forceinline__ float powShininess(float base, float shininess)
 {
 	const int n = (int)shininess;
-	if ((float)n == shininess && n >= 1 && n <= 1024 && base >= 0.0 && base <= 2.0)
+	if ((float)n == shininess && n >= 1 && n <= 1024 && base >= 0.0f && base <= 2.0f)
 	{
-		double r = 1.0, b = base;
+		double r = 1.0, b = (double)base;
 		for (int e = n; e != 0; e >>= 1)
 		{
 			if (e & 1)
 				r *= b;
 			b *= b;
 		}
+		return (float)r;
+	}
+	return (float)pow((double)base, (double)shininess);
+}
+#else
+__device__ __forceinline__ float interp3(float a, float b, float c, float k0, float k1, float k2) { return __fmaf_rn(c, k2, __fmaf_rn(b, k1, a * k0)); }
+__device__ __forceinline__ float sdot3(V3 a, V3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float srlen3(V3 a) { return rsqrtf(sdot3(a, a)); }
+__device__ __forceinline__ float sdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float powShininess(float base, float shininess)
+{
+	const int n = (int)shininess;
+	if ((float)n == shininess && n >= 1 && n <= 64)
+	{
+		float r = 1.0f, b = base;
+#pragma unroll
+		for (int bit = 0; bit < 7; bit++) // warp-uniform exponent: a handful of multiplications
+		{
+			if ((n >> bit) & 1)
+				r *= b;
+			if ((n >> bit) > 1)
+				b *= b;
+		}
 		return r;
 	}
-	return pow(base, (double)shininess);
+	return __powf(base, shininess); // exp2(y * log2(x)); base == 0 gives 0
 }
+#endif
 
 // Renderer.cpp:271-305 for one pixel; returns the pixel value (and writes the normals image).
 __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& mat, float k0, float k1, float k2,
@@ -1129,25 +1172,39 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 	}
 	if (fp.lighting)
 	{
-		const V3 position = mk3(c0.px * k0 + c1.px * k1 + c2.px * k2, c0.py * k0 + c1.py * k1 + c2.py * k2,
-		                        c0.pz * k0 + c1.pz * k1 + c2.pz * k2);
+		const V3 position = mk3(interp3(c0.px, c1.px, c2.px, k0, k1, k2), interp3(c0.py, c1.py, c2.py, k0, k1, k2), interp3(c0.pz, c1.pz, c2.pz, k0, k1, k2));
 		const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
-		const V3 lightdir = fp.lightIsPoint ? normalized3(sub3(light, position)) : light;
-		const V3 normal = mk3(c0.nx * k0 + c1.nx * k1 + c2.nx * k2, c0.ny * k0 + c1.ny * k1 + c2.ny * k2,
-		                      c0.nz * k0 + c1.nz * k1 + c2.nz * k2);
-		const float nl = dot3(normal, lightdir);
+		V3 lightdir = light;
+		if (fp.lightIsPoint)
+		{
+			const V3 l = sub3(light, position);
+			lightdir = scale3(l, srlen3(l));
+		}
+		const V3 normal = mk3(interp3(c0.nx, c1.nx, c2.nx, k0, k1, k2), interp3(c0.ny, c1.ny, c2.ny, k0, k1, k2), interp3(c0.nz, c1.nz, c2.nz, k0, k1, k2));
+		const float nl = sdot3(normal, lightdir);
+		const float rnlen = srlen3(normal); // 1 / |normal|
+#if MR_EXACT_SHADING
 		const float nlen = len3(normal);
 		const float d = ((0.0f > nl) ? 0.0f : nl) / nlen + fp.ambient;
 		value = add3(value, scale3(color, d));
+#else
+		const float d = __fmaf_rn((0.0f > nl) ? 0.0f : nl, rnlen, fp.ambient);
+		value = mk3(__fmaf_rn(color.x, d, value.x), __fmaf_rn(color.y, d, value.y), __fmaf_rn(color.z, d, value.z));
+#endif
 		if (mat.shininess != 0.0f)
 		{
-			const V3 viewdir = normalized3(position);
+			const V3 viewdir = scale3(position, srlen3(position));
 			const V3 hv = sub3(lightdir, viewdir);
-			const float hn = dot3(hv, normal);
+			const float hn = sdot3(hv, normal);
+#if MR_EXACT_SHADING
 			const float base = ((hn > 0.0f) ? hn : 0.0f) / (len3(hv) * nlen);
-			// the reference's unqualified pow() is the double overload
-			const float specular = (float)powShininess((double)base, mat.shininess);
+			const float specular = powShininess(base, mat.shininess);
 			value = add3(value, scale3(mk3(mat.specular[0], mat.specular[1], mat.specular[2]), specular));
+#else
+			const float base = ((hn > 0.0f) ? hn : 0.0f) * (srlen3(hv) * rnlen);
+			const float specular = powShininess(base, mat.shininess);
+			value = mk3(__fmaf_rn(mat.specular[0], specular, value.x), __fmaf_rn(mat.specular[1], specular, value.y), __fmaf_rn(mat.specular[2], specular, value.z));
+#endif
 		}
 		if (fp.saveNormals && fp.normals)
 		{
@@ -1302,6 +1359,47 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	}
 	parity ^= 1;
 	__syncwarp();
+}
+
+// Phase 1 of a tile with binned triangles (see k_raster): their coverage and depth into the tile's shared-memory keys.
+// (ptxas 12.9 crashes on this as a __noinline__ function; inlined, it sits between the hot parts of k_raster without being fetched. The
+// issue rate of a kernel falls off once its hot instructions exceed the ~32 KB instruction cache: tools/ubench/icache.cu.)
+__device__ __forceinline__ void rasterBinned(const FrameParams& fp, int tile, int total, unsigned long long ovfTotal, unsigned long long* keys, WarpQueue* queues,
+                                          int tileX0, int tileY0)
+{
+	const int tid = threadIdx.x, lane = tid & 31;
+	WarpQueue& wq = queues[tid >> 5];
+	const int count = min(total, fp.binCap);
+	const int* bin = fp.bins + (size_t)tile * fp.binCap;
+	int qhead = 0, qcount = 0; // warp-uniform
+	int parity = 0;
+	for (int base = (tid >> 5) * 32; base < count; base += MR_RASTER_THREADS)
+	{
+		const int i = base + lane;
+		const bool have = i < count;
+		const int id = have ? __ldg(&bin[i]) : 0;
+		rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
+	}
+	if (total > fp.binCap)
+	{
+		// this tile spilled: its remaining triangles are somewhere in the global overflow list
+		const unsigned long long n = min(ovfTotal, (unsigned long long)fp.ovfCap);
+		for (unsigned long long base = (unsigned long long)(tid >> 5) * 32; base < n; base += MR_RASTER_THREADS)
+		{
+			const unsigned long long i = base + lane;
+			int2 p = make_int2(-1, 0);
+			if (i < n)
+				p = __ldg(&fp.ovfPairs[i]);
+			const bool have = p.x == tile;
+			if (__any_sync(0xffffffffu, have))
+				rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, p.y, tileX0, tileY0);
+		}
+	}
+	if (qcount > 0)
+	{
+		__syncwarp();
+		consumeFragments(fp, wq, keys, qhead, qcount, lane);
+	}
 }
 
 #ifndef MR_PREFIX_SHARE_MIN
@@ -1496,38 +1594,7 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		if (tid == 0)
 			atomicAdd(&fp.ctr->pairTotal[tile & (MR_STAT_SLOTS - 1)], (unsigned long long)total);
 		__syncthreads();
-		WarpQueue& wq = queues[tid >> 5];
-		const int count = min(total, fp.binCap);
-		const int* bin = fp.bins + (size_t)tile * fp.binCap;
-		int qhead = 0, qcount = 0; // warp-uniform
-		int parity = 0;
-		for (int base = (tid >> 5) * 32; base < count; base += NT)
-		{
-			const int i = base + lane;
-			const bool have = i < count;
-			const int id = have ? __ldg(&bin[i]) : 0;
-			rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
-		}
-		if (total > fp.binCap)
-		{
-			// this tile spilled: its remaining triangles are somewhere in the global overflow list
-			const unsigned long long n = min(ovfTotal, (unsigned long long)fp.ovfCap);
-			for (unsigned long long base = (unsigned long long)(tid >> 5) * 32; base < n; base += NT)
-			{
-				const unsigned long long i = base + lane;
-				int2 p = make_int2(-1, 0);
-				if (i < n)
-					p = __ldg(&fp.ovfPairs[i]);
-				const bool have = p.x == tile;
-				if (__any_sync(0xffffffffu, have))
-					rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, p.y, tileX0, tileY0);
-			}
-		}
-		if (qcount > 0)
-		{
-			__syncwarp();
-			consumeFragments(fp, wq, keys, qhead, qcount, lane);
-		}
+		rasterBinned(fp, tile, total, ovfTotal, keys, queues, tileX0, tileY0);
 		__syncthreads();
 #pragma unroll
 		for (int pp = 0; pp < PP; pp++)
@@ -1553,40 +1620,36 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 		return;
 	}
 
-	// ---- phase 2: resolve + shade, 256 / NT pixels per thread ----
-	V3 value[PP];
-	float zout[PP];
-	bool store[PP];
-#pragma unroll
+	// ---- phase 2: resolve + shade, 256 / NT pixels per thread, one after the other through the same code (a second
+	// inlined copy would double the hot instructions); results are staged in shared memory (the fragment queues are
+	// idle now) and written as whole rows ----
+	TileOut* to = reinterpret_cast<TileOut*>(queues);
+#pragma unroll 1
 	for (int pp = 0; pp < PP; pp++)
-		resolvePixel<TM>(fp, key[pp], tilePixel<NT>(tid, pp), tileX0, tileY0, lane, value[pp], zout[pp], store[pp]);
-
-	// ---- tile store ----
+	{
+		V3 value;
+		float zout;
+		bool store;
+		const int pi = tilePixel<NT>(tid, pp);
+		resolvePixel<TM>(fp, (pp == 0) ? key[0] : key[PP - 1], pi, tileX0, tileY0, lane, value, zout, store);
+		if (vec)
+		{
+			const int r = pi >> 4, c = pi & 15;
+			to->px[r][3 * c] = value.x;
+			to->px[r][3 * c + 1] = value.y;
+			to->px[r][3 * c + 2] = value.z;
+			to->px[r][48 + c] = zout;
+		}
+		else if (store)
+		{
+			const size_t pix = (size_t)(tileY0 + (pi >> 4)) * fp.w + tileX0 + (pi & 15);
+			float* img = fp.image + 3 * pix;
+			img[0] = value.x; img[1] = value.y; img[2] = value.z;
+			fp.depth[pix] = zout;
+		}
+	}
 	if (vec)
 	{
-		// stage the tile in shared memory (the fragment queues are idle now) and write full rows
-		TileOut* to = reinterpret_cast<TileOut*>(queues);
-		if (PP == 2)
-		{
-			const int pi = 2 * tid, r = pi >> 4, c = pi & 15; // c even: 24 contiguous, 8-byte aligned bytes of rgb
-			float2* d = reinterpret_cast<float2*>(&to->px[r][3 * c]);
-			d[0] = make_float2(value[0].x, value[0].y);
-			d[1] = make_float2(value[0].z, value[PP - 1].x);
-			d[2] = make_float2(value[PP - 1].y, value[PP - 1].z);
-			*reinterpret_cast<float2*>(&to->px[r][48 + c]) = make_float2(zout[0], zout[PP - 1]);
-		}
-		else
-		{
-#pragma unroll
-			for (int pp = 0; pp < PP; pp++)
-			{
-				const int pi = tilePixel<NT>(tid, pp), r = pi >> 4, c = pi & 15;
-				to->px[r][3 * c] = value[pp].x;
-				to->px[r][3 * c + 1] = value[pp].y;
-				to->px[r][3 * c + 2] = value[pp].z;
-				to->px[r][48 + c] = zout[pp];
-			}
-		}
 		__syncthreads();
 		if (full)
 			storeFullTile128<false>(fp, tileX0, tileY0, tid, to);
@@ -1594,27 +1657,11 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 			for (int pi = tid; pi < MR_TILE_PIXELS; pi += NT)
 				storeTileRows(fp, tileX0, tileY0, pi, to);
 	}
-	else
-	{
-#pragma unroll
-		for (int pp = 0; pp < PP; pp++)
-			if (store[pp])
-			{
-				const int pi = tilePixel<NT>(tid, pp);
-				const size_t pix = (size_t)(tileY0 + (pi >> 4)) * fp.w + tileX0 + (pi & 15);
-				float* img = fp.image + 3 * pix;
-				img[0] = value[pp].x; img[1] = value[pp].y; img[2] = value[pp].z;
-				fp.depth[pix] = zout[pp];
-			}
-	}
 }
 
 // One CTA per tile. (Persistent CTAs measured slower twice: with a global tile counter, -10 %, and
 // with a static round-robin plus next-tile prefetch, 46 vs 44 us on the sphere and 255 vs 189 us on
 // the cloud scene — the hardware CTA scheduler balances 8160 uneven tiles better.)
-#ifndef MR_RASTER_THREADS
-#define MR_RASTER_THREADS 128
-#endif
 #ifndef MR_RASTER_MINB
 #define MR_RASTER_MINB (1024 / MR_RASTER_THREADS)
 #endif
@@ -1623,7 +1670,14 @@ __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(co
 {
 	__shared__ unsigned long long keys[MR_TILE_PIXELS];
 	__shared__ WarpQueue queues[MR_RASTER_THREADS / 32 < 4 ? 4 : MR_RASTER_THREADS / 32]; // also >= sizeof(TileOut)
+#ifdef MR_TIMELINE
+	const int tlTile = (blockIdx.y * gridDim.x + blockIdx.x);
+	if (threadIdx.x == 0 && tlTile < 8192) g_rtl[tlTile * 4 + 0] = globalTimer();
+#endif
 	pdlWait(); // k_geom's keys, bins and records
+#ifdef MR_TIMELINE
+	if (threadIdx.x == 0 && tlTile < 8192) g_rtl[tlTile * 4 + 1] = globalTimer();
+#endif
 	if (blockIdx.x == 0 && blockIdx.y == 0)
 	{
 		// k_geom is done with its work list and this frame's statistics are where they belong:
@@ -1634,6 +1688,15 @@ __global__ void __launch_bounds__(MR_RASTER_THREADS, MR_RASTER_MINB) k_raster(co
 			reinterpret_cast<unsigned long long*>(fp.ctrNext)[i] = 0ull;
 	}
 	rasterTile<MR_RASTER_THREADS, TM>(fp, blockIdx.x, fp.tileRow0 + blockIdx.y, keys, queues);
+#ifdef MR_TIMELINE
+	if (threadIdx.x == 0 && tlTile < 8192)
+	{
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		g_rtl[tlTile * 4 + 2] = globalTimer();
+		g_rtl[tlTile * 4 + 3] = smid;
+	}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1783,6 +1846,11 @@ void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStr
 }
 
 #ifdef MR_TIMELINE
+extern "C" __attribute__((visibility("default"))) int mr_debug_raster_timeline(unsigned long long* out, int nWords)
+{
+	const size_t n = std::min((size_t)nWords, sizeof(g_rtl) / 8);
+	return cudaMemcpyFromSymbol(out, g_rtl, n * 8) == cudaSuccess ? (int)n : -1;
+}
 extern "C" __attribute__((visibility("default"))) int mr_debug_timeline(unsigned long long* out, int nWords)
 {
 	const size_t n = std::min((size_t)nWords, sizeof(g_timeline) / 8);
