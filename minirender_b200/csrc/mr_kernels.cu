@@ -999,6 +999,14 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	}
 
 	MR_TL(4); // warp out of work
+	{
+		// k_raster starts every tile with a read of its counters; a cold L2 (they are reset, not rewritten, where nothing
+		// was drawn) would make that a DRAM round trip per tile: the warps that are done here pull the array into L2
+		const char* tc = reinterpret_cast<const char*>(fp.tileCount);
+		const size_t bytes = sizeof(int2) * (size_t)fp.tilesX * fp.tilesY;
+		for (size_t o = ((size_t)blockIdx.x * MR_GEOM_THREADS + tid) * 128; o < bytes; o += (size_t)gridDim.x * MR_GEOM_THREADS * 128)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(tc + o));
+	}
 	// ---- statistics: one shared-memory atomic per warp, one RED per counter per CTA ----
 	unsigned long long sum = acc;
 #pragma unroll
