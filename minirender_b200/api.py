@@ -48,6 +48,8 @@ _COMMON = {
     "mrx_renderer_clear": (C.c_int, [C.c_void_p]),
     "mrx_renderer_render": (C.c_int, [C.c_void_p]),
     "mrx_renderer_paint_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, F32P]),
+    "mrx_renderer_paint_triangle": (C.c_int, [C.c_void_p, F32P, C.c_int]),
+    "mrx_renderer_set_material": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mrx_renderer_get_image": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mrx_renderer_get_depth": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mrx_renderer_get_normals": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -327,6 +329,14 @@ class Renderer:
     def set_background(self, c): self._c(self.be.lib.mrx_renderer_set_background(self.h_, _fp(_f32(c))), "set_background")
     def clear(self): self._c(self.be.lib.mrx_renderer_clear(self.h_), "clear")
     def render(self): self._c(self.be.lib.mrx_renderer_render(self.h_), "render")
+
+    def paint_triangle(self, verts, world=True):
+        """Renderer::paintTriangle: verts = 3 x (position xyz, normal xyz, uv), in view space."""
+        v = _f32(np.asarray(verts, np.float32).reshape(24))
+        self._c(self.be.lib.mrx_renderer_paint_triangle(self.h_, _fp(v), 1 if world else 0), "paint_triangle")
+
+    def set_material(self, scene, material):
+        self._c(self.be.lib.mrx_renderer_set_material(self.h_, scene.h, material), "set_material")
 
     def paint_mesh(self, scene, node, xf=None):
         self._c(self.be.lib.mrx_renderer_paint_mesh(self.h_, scene.h, node, _fp(_f32(xf))), "paint_mesh")

@@ -136,6 +136,8 @@ struct Renderer::Impl
 	Vec3 lightdir;
 	float znear, ambient;
 	bool haveSnapshot;
+	bool skipNearTest;   // paintTriangle(..., world = false) in progress
+	bool buffersDefined; // the device buffers hold a frame or the clear values (the reference's ctor / setSize run clear())
 
 	// lazily filled host mirrors of the device images
 	Array2<Vec3> image, normals, points;
@@ -144,7 +146,7 @@ struct Renderer::Impl
 	void* pinnedImage; // page-locked (mr_host_register) so that D2H runs at full PCIe rate
 	void* pinnedDepth;
 
-	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), upStamp(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false),
+	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), upStamp(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false), skipNearTest(false), buffersDefined(false),
 	         imageValid(false), depthValid(false), normalsValid(false), pinnedImage(0), pinnedDepth(0)
 	{
 		memset(&sceneDesc, 0, sizeof(sceneDesc));
@@ -220,9 +222,11 @@ void Renderer::ensureContext()
 			fail(0, "mr_create (this library has no CPU rasterizer; a CUDA device is required)", status);
 		s.ctxW = s.ctxH = 0;
 		s.uploaded = false;
+		s.buffersDefined = false;
 	}
 	if (s.ctxW != _w || s.ctxH != _h)
 	{
+		s.buffersDefined = false;
 		int rc = mr_set_size(s.ctx, _w, _h);
 		if (rc)
 			fail(s.ctx, "mr_set_size", rc);
@@ -483,10 +487,14 @@ void Renderer::render()
 	prepare();
 	ensureContext();
 	Impl& s = *_impl;
+	const bool strip = _rowEnd > _rowBegin && (_rowBegin > 0 || _rowEnd < _h);
+	if (strip && !s.buffersDefined)
+		clear(); // a strip only writes its own rows: the others show the cleared buffers
 	syncGeometry(s, _geometryStamp, false);
 	int rc = mr_render(s.ctx, &s.frame);
 	if (rc)
 		fail(s.ctx, "mr_render", rc);
+	s.buffersDefined = true;
 	s.imageValid = s.depthValid = s.normalsValid = false;
 }
 
@@ -514,6 +522,7 @@ void Renderer::clear()
 	int rc = mr_render(s.ctx, &f);
 	if (rc)
 		fail(s.ctx, "mr_render(clear)", rc);
+	s.buffersDefined = true;
 	s.imageValid = s.depthValid = s.normalsValid = false;
 }
 
@@ -523,6 +532,8 @@ void Renderer::paintMesh(TriMesh* mesh, const Matrix4& transform)
 {
 	ensureContext();
 	Impl& s = *_impl;
+	if (!s.buffersDefined)
+		clear(); // painting into a fresh renderer starts from the cleared buffers (reference ctor / setSize)
 	if (!s.haveSnapshot)
 	{
 		s.lightdir = _lightIsPoint ? _view * _light : _light.normalized();
@@ -535,7 +546,9 @@ void Renderer::paintMesh(TriMesh* mesh, const Matrix4& transform)
 	one << Renderable(mesh, transform);
 	describe(s, one, _view, _defmaterial);
 	_material = mesh->material ? mesh->material : _defmaterial; // reference Renderer.cpp:336
-	fillFrameConstants(s.frame, _projection, s.lightdir, _lightIsPoint, s.ambient, s.znear, _lighting, _texturing, _saveNormals,
+	// (paintTriangle(..., world = false) is the reference's entry for its own clipper's output: no near test,
+	// Renderer.cpp:169. A near plane no vertex can be in front of has the same effect on the device.)
+	fillFrameConstants(s.frame, _projection, s.lightdir, _lightIsPoint, s.ambient, s.skipNearTest ? 3.0e38f : s.znear, _lighting, _texturing, _saveNormals,
 	                   _bgcolor, _rowBegin, _rowEnd, 1);
 	syncGeometry(s, _geometryStamp, true);
 	int rc = mr_render(s.ctx, &s.frame);
@@ -548,10 +561,8 @@ void Renderer::paintMesh(TriMesh* mesh, const Matrix4& transform)
 
 void Renderer::paintTriangle(const Vertex& a, const Vertex& b, const Vertex& c, bool world)
 {
-	// Vertices are already in view space (reference Renderer.cpp:163-177). With world == false
-	// the reference skips the near-plane test; that variant only exists for its own clipper, so
-	// here it is accepted only for triangles that are entirely in front of the near plane.
-	(void)world;
+	// Vertices are already in view space (reference Renderer.cpp:163-177): one-triangle mesh under an identity
+	// modelview. With world == false the reference skips the near-plane test (its clipper re-enters that way).
 	TriMesh tri;
 	tri.vertices << a.position << b.position << c.position;
 	tri.normals << a.normal << b.normal << c.normal;
@@ -562,6 +573,7 @@ void Renderer::paintTriangle(const Vertex& a, const Vertex& b, const Vertex& c, 
 	tri.material = _material;
 	const Matrix4 savedView = _view;
 	_view = Matrix4::identity();
+	_impl->skipNearTest = !world;
 	try
 	{
 		paintMesh(&tri, Matrix4::identity());
@@ -569,15 +581,17 @@ void Renderer::paintTriangle(const Vertex& a, const Vertex& b, const Vertex& c, 
 	catch (...)
 	{
 		_view = savedView;
+		_impl->skipNearTest = false;
 		throw;
 	}
+	_impl->skipNearTest = false;
 	_view = savedView;
 }
 
 Array2<Vec3> Renderer::getImage() const
 {
 	Impl& s = *_impl;
-	if (!s.ctx)
+	if (!s.ctx || !s.buffersDefined) // a fresh renderer shows the cleared buffers, like the reference's (ctor / setSize end with clear())
 		const_cast<Renderer*>(this)->clear();
 	if (!s.imageValid)
 	{
@@ -599,7 +613,7 @@ Array2<Vec3> Renderer::getImage() const
 Array2<float> Renderer::getDepth() const
 {
 	Impl& s = *_impl;
-	if (!s.ctx)
+	if (!s.ctx || !s.buffersDefined) // a fresh renderer shows the cleared buffers, like the reference's (ctor / setSize end with clear())
 		const_cast<Renderer*>(this)->clear();
 	if (!s.depthValid)
 	{
@@ -621,7 +635,7 @@ Array2<float> Renderer::getDepth() const
 Array2<Vec3> Renderer::getNormalsImage() const
 {
 	Impl& s = *_impl;
-	if (!s.ctx)
+	if (!s.ctx || !s.buffersDefined) // a fresh renderer shows the cleared buffers, like the reference's (ctor / setSize end with clear())
 		const_cast<Renderer*>(this)->clear();
 	if (!s.normalsValid)
 	{
@@ -655,7 +669,7 @@ Array2<Vec3> Renderer::getRangeImage()
 Array<byte> Renderer::getImageRGB8() const
 {
 	Impl& s = *_impl;
-	if (!s.ctx)
+	if (!s.ctx || !s.buffersDefined) // a fresh renderer shows the cleared buffers, like the reference's (ctor / setSize end with clear())
 		const_cast<Renderer*>(this)->clear();
 	Array<byte> out(_w * _h * 3);
 	int rc = mr_read_rgb8(s.ctx, out.ptr());

@@ -373,6 +373,36 @@ int mrx_renderer_paint_mesh(void* r, void* scene, int node, const float* xf)
 	MRX_CATCH(-1)
 }
 
+int mrx_renderer_paint_triangle(void* r, const float* v, int world)
+{
+	MRX_TRY
+	Vertex c[3];
+	for (int i = 0; i < 3; i++)
+	{
+		const float* p = v + 8 * i;
+		c[i].position = Vec3(p[0], p[1], p[2]);
+		c[i].normal = Vec3(p[3], p[4], p[5]);
+		c[i].uv = Vec2(p[6], p[7]);
+	}
+	((Renderer*)r)->paintTriangle(c[0], c[1], c[2], world != 0);
+	return 0;
+	MRX_CATCH(-1)
+}
+
+int mrx_renderer_set_material(void* r, void* scene, int material)
+{
+	MRX_TRY
+	SceneBox* sb = (SceneBox*)scene;
+	if (material < 0 || material >= (int)sb->materials.size())
+	{
+		g_error = "material index out of range";
+		return -1;
+	}
+	((Renderer*)r)->setMaterial(sb->materials[material]);
+	return 0;
+	MRX_CATCH(-1)
+}
+
 int mrx_renderer_get_image(void* r, float* out)
 {
 	MRX_TRY

@@ -62,6 +62,9 @@ MRX_API int mrx_renderer_set_background(void* r, const float* rgb);
 MRX_API int mrx_renderer_clear(void* r);
 MRX_API int mrx_renderer_render(void* r);
 MRX_API int mrx_renderer_paint_mesh(void* r, void* scene, int node, const float* xf);
+/* Renderer::paintTriangle: three vertices of 8 floats each (position, normal, uv), already in view space */
+MRX_API int mrx_renderer_paint_triangle(void* r, const float* v24, int world);
+MRX_API int mrx_renderer_set_material(void* r, void* scene, int material);
 MRX_API int mrx_renderer_get_image(void* r, float* out /* h*w*3 */);
 MRX_API int mrx_renderer_get_depth(void* r, float* out /* h*w */);
 MRX_API int mrx_renderer_get_normals(void* r, float* out /* h*w*3 */);

@@ -134,12 +134,12 @@ def sphere_view(be, i=0, d=400.0):
     return be.mul(be.translate(0, 0, -d), be.rotate_x(f32(math.radians(-70.0))), be.rotate_z(f32(0.07) * f32(i)))
 
 
-def sphere_scene(be, width=1920, height=1080, lat=501, lon=1000, radius=100.0, frame=0, d=400.0, textured=False):
+def sphere_scene(be, width=1920, height=1080, lat=501, lon=1000, radius=100.0, frame=0, d=400.0, textured=False, tex_size=256):
     sc = api.Scene(be, ambient=0.2)
     mat = -1
     if textured:
         rng = np.random.default_rng(7)
-        tex = rng.random((256, 256, 3)).astype(f32)
+        tex = rng.random((tex_size, tex_size, 3)).astype(f32)
         mat = sc.add_material(texture=tex)
     node = sc.add_sphere(radius, lat, lon, material=mat, with_uv_index=textured)
     return Setup("sphere_%dx%d" % (lat, lon), sc, width, height, frustum(be, width, height), sphere_view(be, frame, d),

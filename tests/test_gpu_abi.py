@@ -240,3 +240,55 @@ def test_timing_events_bracket_one_frame(be):
     r.synchronize()
     assert e0.elapsed_time(e1) == ms
     assert lib.mr_set_stream(ctx, None) == 0
+
+
+def test_paint_triangle_matches_reference(be, ref):
+    """Renderer::paintTriangle (reference include/minirender/Renderer.h:59, src/Renderer.cpp:163-177): view-space
+    triangles painted one by one into the buffers of a rendered frame, with and without the near test (world)."""
+    import minirender_b200 as m
+    from minirender_b200 import scenes
+    from parity import assert_parity, compare
+    rng = np.random.default_rng(5)
+    tris = []
+    for k in range(40):
+        c = np.array([rng.uniform(-60, 60), rng.uniform(-40, 40), rng.uniform(-260, -30)], np.float32)
+        v = np.zeros((3, 8), np.float32)
+        v[:, 0:3] = c + rng.normal(size=(3, 3)).astype(np.float32) * rng.uniform(2, 40)
+        v[:, 3:6] = rng.normal(size=(3, 3)).astype(np.float32)
+        v[:, 6:8] = rng.random((3, 2)).astype(np.float32)
+        world = bool(k % 3)
+        if not world:
+            v[:, 2] = np.minimum(v[:, 2], np.float32(-1.0))  # no near test: keep the corners in front of the eye
+        tris.append((v, world))
+    out = {}
+    for name, b in (("gpu", be), ("ref", ref)):
+        setup = scenes.primitives_scene(b, 320, 200)
+        r = setup.apply(m.Renderer(b))
+        r.render()  # sets the light, the near plane and the ambient term the reference's paintTriangle relies on
+        r.set_material(setup.scene, 0)
+        for v, world in tris:
+            r.paint_triangle(v, world)
+        out[name] = (r.get_image().copy(), r.get_depth().copy())
+    rep = compare(out["gpu"][0], out["gpu"][1], out["ref"][0], out["ref"][1])
+    print("paintTriangle", rep)
+    assert_parity(rep, "paintTriangle vs reference")
+    base = scenes.primitives_scene(ref, 320, 200).apply(m.Renderer(ref)); base.render()
+    assert (base.get_depth() != out["ref"][1]).sum() > 2000, "the painted triangles should be visible"
+
+
+def test_fresh_renderer_shows_cleared_buffers(be, ref):
+    """Reference ctor / setSize end with clear(): depth 1e11, image = background, before anything is rendered;
+    immediate-mode painting into a fresh renderer starts from there."""
+    import minirender_b200 as m
+    from minirender_b200 import scenes
+    for b in (be, ref):
+        setup = scenes.primitives_scene(b, 160, 100)
+        r = m.Renderer(b)
+        r.set_size(160, 100)
+        r.set_background((0.25, 0.5, 0.75))
+        if b is ref:
+            r.clear()  # (the reference clears with the background that was current in setSize)
+        d, i = r.get_depth(), r.get_image()
+        assert (d == np.float32(1e11)).all()
+        if b is be:
+            assert np.allclose(i, np.array([0.25, 0.5, 0.75], np.float32))

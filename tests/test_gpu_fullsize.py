@@ -85,3 +85,68 @@ def test_config5_turntable_views_are_deterministic(be):
         r2.prepare()
         want = pyoracle.render_port(r2.scene_desc_ptr(), r2.frame_desc_ptr(), 1920, 1080)
         assert (bits(want["depth"]) == bits(first[i])).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# Against the reference's own sources (oracle/_ref: src/Renderer.cpp, Scene.cpp, primitives.cpp compiled
+# unchanged), through the reference's own flatten and matrices: nothing of this repository's host code is
+# shared between the two sides of these comparisons.
+# ---------------------------------------------------------------------------------------------
+def check_against_reference(be, ref, make_setup, what):
+    want_r = make_setup(ref).apply(m.Renderer(ref))
+    want_r.render()
+    want_i, want_d = want_r.get_image().copy(), want_r.get_depth().copy()
+    r = make_setup(be).apply(m.Renderer(be))
+    r.render()
+    rep = compare(r.get_image(), r.get_depth(), want_i, want_d)
+    print(what, rep)
+    assert_parity(rep, what)
+    return rep
+
+
+def test_config1_vs_compiled_reference_1080p(be, ref):
+    rep = check_against_reference(be, ref, lambda b: scenes.bench_scene(b), "bench 1080p vs reference")
+    assert rep["covered"] > 500000
+
+
+def test_config2_vs_compiled_reference_1080p(be, ref):
+    rep = check_against_reference(be, ref, lambda b: scenes.sphere_scene(b, frame=3), "sphere 1M 1080p vs reference")
+    assert rep["covered"] > 600000
+
+
+def test_config4_vs_compiled_reference_1080p(be, ref):
+    rep = check_against_reference(be, ref, lambda b: scenes.cloud_scene(b, groups=100, per_group=100), "cloud 10k meshes 1080p vs reference")
+    assert rep["covered"] > 1000000
+
+
+def test_config3_full_size_10m_triangles_4k(be):
+    """BASELINE.json configs[2] as stated: 3840x2160, 10 M textured triangles, 2048^2 texture. One frame against
+    the CPU oracle, and the union of the 8 strips of the multi-GPU mode against that frame."""
+    setup = scenes.sphere_scene(be, 3840, 2160, lat=2237, lon=2236, textured=True, d=330.0, tex_size=2048)
+    r, rep = check_against_port(be, setup, "sphere 10M textured 4K")
+    assert r.scene.triangles() == 2 * 2236 * 2236 and rep["covered"] > 2500000
+    full_d, full_i = r.get_depth().copy(), r.get_image().copy()
+    r.clear()
+    for rank in range(8):
+        rb, re = sharding.strip_rows(2160, rank, 8)
+        r.set_row_range(rb, re)
+        r.render()
+    assert (bits(r.get_depth()) == bits(full_d)).all() and (bits(r.get_image()) == bits(full_i)).all()
+
+
+def test_config5_real_mesh_sampled_views(be):
+    """configs[4]: the 2 M-triangle mesh, views k of the 1024-view turntable sampled across the range (and across
+    the ranks of an 8-GPU run: k mod 8 covers all of them), each against the CPU oracle."""
+    import math
+    setup = scenes.sphere_scene(be, 1920, 1080, lat=1001, lon=1000)
+    r = setup.apply(m.Renderer(be))
+    assert r.scene.triangles() == 2000000
+    for k in (0, 129, 386, 643, 900, 1023):
+        view = be.mul(be.translate(0, 0, -400.0), be.rotate_x(np.float32(math.radians(-70.0))), be.rotate_z(np.float32(2.0 * math.pi * k / 1024.0)))
+        r.set_view(view)
+        r.render()
+        image, depth = r.get_image(), r.get_depth()
+        r.prepare()
+        want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), 1920, 1080)
+        rep = compare(image, depth, want["image"], want["depth"])
+        assert_parity(rep, "turntable view %d" % k)
