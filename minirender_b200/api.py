@@ -48,6 +48,8 @@ _COMMON = {
     "mrx_renderer_clear": (C.c_int, [C.c_void_p]),
     "mrx_renderer_render": (C.c_int, [C.c_void_p]),
     "mrx_renderer_paint_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, F32P]),
+    "mrx_mesh_apply_transform": (C.c_int, [C.c_void_p, C.c_int]),
+    "mrx_mesh_move_vertex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
     "mrx_renderer_paint_triangle": (C.c_int, [C.c_void_p, F32P, C.c_int]),
     "mrx_renderer_set_material": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "mrx_renderer_get_image": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -240,6 +242,13 @@ class Scene:
 
     def set_transform(self, node, xf):
         self.be.check(self.be.lib.mrx_node_set_transform(self.h, node, _fp(_f32(xf))), "mrx_node_set_transform")
+
+    def apply_transform(self, node):
+        """TriMesh::applyTransform(): bakes the node's transform into its vertex / normal arrays, in place."""
+        self.be.check(self.be.lib.mrx_mesh_apply_transform(self.h, node), "mrx_mesh_apply_transform")
+
+    def move_vertex(self, node, i, d):
+        self.be.check(self.be.lib.mrx_mesh_move_vertex(self.h, node, int(i), float(d[0]), float(d[1]), float(d[2])), "mrx_mesh_move_vertex")
 
     def mesh_arrays(self, node):
         counts = np.zeros(6, np.int32)

@@ -1117,7 +1117,7 @@ int mr_render(mr_ctx* c, const mr_frame* f)
 		return setError(c, MR_E_NO_SCENE, "mr_render before mr_upload_scene");
 	if (c->w <= 0)
 		return setError(c, MR_E_INVALID, "mr_render before mr_set_size");
-	if (f->n_renderables < 0 || f->n_materials < 0 || (f->n_renderables > 0 && (!f->renderables || !f->materials)))
+	if (f->n_renderables < 0 || f->n_materials < 0 || (f->n_renderables > 0 && !f->renderables) || (f->n_materials > 0 && !f->materials))
 		return setError(c, MR_E_INVALID, "bad frame descriptor");
 	Bind bind(c->device);
 	rememberFrame(c, f);

@@ -77,12 +77,76 @@ Matrix4 projectionOrtho(float fov, float aspect, float n, float f)
 
 namespace {
 
+// What identifies a mesh's geometry as mirrored in HBM: where its arrays are, how long they are, and a fingerprint of
+// their contents. The reference re-reads every mesh on every render() (Renderer.cpp:341-380), so an edit in place
+// (TriMesh::applyTransform, a deformed vertex array, a mesh freed and another allocated at the same address) shows
+// in its next frame; here it has to be noticed. Hashing tens of megabytes every frame would cost more than the
+// frame, so the fingerprint is taken from samples: arrays up to MR_FP_FULL bytes are hashed whole, longer ones at
+// MR_FP_SAMPLES evenly spaced 16-byte words plus both ends. MINIRENDER_B200_GEOMETRY_CHECK=full hashes everything,
+// =off compares addresses and lengths only; Renderer::invalidateGeometry() forces an upload in any mode.
 struct MeshSig
 {
 	const void* p[6];
 	int n[6];
-	bool operator==(const MeshSig& o) const { return memcmp(this, &o, sizeof(MeshSig)) == 0; }
+	unsigned long long fp;
+	bool operator==(const MeshSig& o) const { return memcmp(p, o.p, sizeof(p)) == 0 && memcmp(n, o.n, sizeof(n)) == 0 && fp == o.fp; }
 };
+
+enum { MR_FP_FULL = 4096, MR_FP_SAMPLES = 61 };
+
+static inline unsigned long long fpMix(unsigned long long h, unsigned long long v)
+{
+	h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+	return h * 0xff51afd7ed558ccdull;
+}
+
+static unsigned long long fingerprint(unsigned long long h, const void* ptr, size_t bytes, int mode)
+{
+	if (!ptr || !bytes || mode == 0)
+		return h;
+	const unsigned char* b = (const unsigned char*)ptr;
+	unsigned long long w;
+	if (mode == 2 || bytes <= MR_FP_FULL)
+	{
+		size_t i = 0;
+		for (; i + 8 <= bytes; i += 8)
+		{
+			memcpy(&w, b + i, 8);
+			h = fpMix(h, w);
+		}
+		for (; i < bytes; i++)
+			h = fpMix(h, b[i]);
+		return h;
+	}
+	for (size_t i = 0; i < 64; i += 8) // both ends
+	{
+		memcpy(&w, b + i, 8);
+		h = fpMix(h, w);
+		memcpy(&w, b + bytes - 64 + i, 8);
+		h = fpMix(h, w);
+	}
+	const size_t step = (bytes - 16) / MR_FP_SAMPLES;
+	for (int k = 1; k < MR_FP_SAMPLES; k++)
+	{
+		const size_t at = (size_t)k * step;
+		memcpy(&w, b + at, 8);
+		h = fpMix(h, w);
+		memcpy(&w, b + at + 8, 8);
+		h = fpMix(h, w);
+	}
+	return h;
+}
+
+static int geometryCheckMode()
+{
+	static int mode = -1;
+	if (mode < 0)
+	{
+		const char* e = getenv("MINIRENDER_B200_GEOMETRY_CHECK");
+		mode = (e && !strcmp(e, "off")) ? 0 : (e && !strcmp(e, "full")) ? 2 : 1;
+	}
+	return mode;
+}
 
 struct TexSig
 {
@@ -454,6 +518,7 @@ const mr_frame* Renderer::frameDesc() const { return &_impl->frame; }
 // Uploads the geometry if what is mirrored in HBM does not match the descriptors.
 static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 {
+	const int mode = geometryCheckMode();
 	std::vector<MeshSig> ms(s.meshes.size());
 	for (size_t i = 0; i < s.meshes.size(); i++)
 	{
@@ -463,6 +528,11 @@ static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 		memset(&ms[i], 0, sizeof(MeshSig));
 		memcpy(ms[i].p, p, sizeof(p));
 		memcpy(ms[i].n, n, sizeof(n));
+		const size_t elem[6] = { 12, 12, 8, 12, 12, 12 };
+		unsigned long long h = 0x243f6a8885a308d3ull;
+		for (int k = 0; k < 6; k++)
+			h = fingerprint(h, p[k], elem[k] * (size_t)n[k], mode);
+		ms[i].fp = h;
 	}
 	std::vector<TexSig> ts(s.textures.size());
 	for (size_t i = 0; i < s.textures.size(); i++)

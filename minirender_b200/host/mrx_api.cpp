@@ -373,6 +373,34 @@ int mrx_renderer_paint_mesh(void* r, void* scene, int node, const float* xf)
 	MRX_CATCH(-1)
 }
 
+int mrx_mesh_apply_transform(void* scene, int node)
+{
+	MRX_TRY
+	TriMesh* m = meshOf((SceneBox*)scene, node);
+	if (!m)
+	{
+		g_error = "node is not a mesh";
+		return -1;
+	}
+	m->applyTransform();
+	return 0;
+	MRX_CATCH(-1)
+}
+
+int mrx_mesh_move_vertex(void* scene, int node, int i, float dx, float dy, float dz)
+{
+	MRX_TRY
+	TriMesh* m = meshOf((SceneBox*)scene, node);
+	if (!m || i < 0 || i >= m->vertices.length())
+	{
+		g_error = "node is not a mesh or vertex index out of range";
+		return -1;
+	}
+	m->vertices[i] = m->vertices[i] + Vec3(dx, dy, dz);
+	return 0;
+	MRX_CATCH(-1)
+}
+
 int mrx_renderer_paint_triangle(void* r, const float* v, int world)
 {
 	MRX_TRY

@@ -61,6 +61,10 @@ MRX_API int mrx_renderer_set_save_normals(void* r, int on);
 MRX_API int mrx_renderer_set_background(void* r, const float* rgb);
 MRX_API int mrx_renderer_clear(void* r);
 MRX_API int mrx_renderer_render(void* r);
+/* In-place edits of a mesh, as reference programs make them between frames: TriMesh::applyTransform(), and
+ * vertex i moved by (dx,dy,dz) in the mesh's own array. */
+MRX_API int mrx_mesh_apply_transform(void* scene, int node);
+MRX_API int mrx_mesh_move_vertex(void* scene, int node, int i, float dx, float dy, float dz);
 MRX_API int mrx_renderer_paint_mesh(void* r, void* scene, int node, const float* xf);
 /* Renderer::paintTriangle: three vertices of 8 floats each (position, normal, uv), already in view space */
 MRX_API int mrx_renderer_paint_triangle(void* r, const float* v24, int world);

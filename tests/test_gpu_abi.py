@@ -292,3 +292,30 @@ def test_fresh_renderer_shows_cleared_buffers(be, ref):
         assert (d == np.float32(1e11)).all()
         if b is be:
             assert np.allclose(i, np.array([0.25, 0.5, 0.75], np.float32))
+
+
+def test_in_place_mesh_edits_are_rendered(be, ref):
+    """The reference reads every mesh again on every render() (src/Renderer.cpp:341-380): TriMesh::applyTransform()
+    and vertices edited in place between frames show in the next frame. The product mirrors geometry in HBM and has
+    to notice such edits (content fingerprint) without being told (invalidateGeometry is an extension)."""
+    import minirender_b200 as m
+    from minirender_b200 import scenes
+    from parity import assert_parity, compare
+    out = {}
+    for name, b in (("gpu", be), ("ref", ref)):
+        setup = scenes.sphere_scene(b, 480, 270, lat=61, lon=120)
+        sc, node = setup.scene, setup.nodes["sphere"]
+        r = setup.apply(m.Renderer(b))
+        frames = []
+        r.render(); frames.append((r.get_image().copy(), r.get_depth().copy()))
+        sc.set_transform(node, b.mul(b.translate(40, 0, 10), b.scale(1.3, 0.7, 1.0)))
+        sc.apply_transform(node)          # vertices / normals rewritten in place, transform back to identity
+        r.render(); frames.append((r.get_image().copy(), r.get_depth().copy()))
+        for i in range(0, 7000, 13):      # a dent: every 13th vertex pushed inwards
+            sc.move_vertex(node, i, (-8.0, 3.0, 5.0))
+        r.render(); frames.append((r.get_image().copy(), r.get_depth().copy()))
+        out[name] = frames
+    for k in range(3):
+        rep = compare(out["gpu"][k][0], out["gpu"][k][1], out["ref"][k][0], out["ref"][k][1])
+        assert_parity(rep, "frame %d after in-place edits" % k)
+    assert (out["ref"][1][1] != out["ref"][0][1]).any() and (out["ref"][2][1] != out["ref"][1][1]).any()
