@@ -137,6 +137,11 @@ class ClockSampler:
                           "reasons over the untimed quarter-second render loop and the timed region"}
 
 
+def config_dict():
+    """The same dictionary in both arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "triangles": 2 * LON * (LAT - 1), "data": "synthetic"}
+
+
 def build_scene(be, frame=0):
     from minirender_b200 import scenes
     return scenes.sphere_scene(be, WIDTH, HEIGHT, LAT, LON, frame=frame)
@@ -195,18 +200,21 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
-    steps = max(1, args.steps)
-    # bound the run: a frame is ~0.1-0.2 s on one core (+ scene build per worker)
-    steps = min(steps, 10)
-    kind, t = cpu_reference_run(steps, min(max(args.warmup, 1), 2), procs)
+    procs = max(1, cores)  # every host thread: one single-threaded reference renderer per core
+    # every step = one frame per worker (~0.1-0.2 s each): --steps / --warmup are honoured up to a bound that keeps the
+    # run within a few minutes; the line reports what actually ran
+    steps = max(1, min(args.steps, 400))
+    warm = max(1, min(args.warmup, 10))
+    kind, t = cpu_reference_run(steps, warm, procs)
     fps = procs * steps / t
     n_tri = 2 * LON * (LAT - 1)
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "impl": "reference",
-            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / steps,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * t / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mtri_per_s": fps * n_tri / 1e6, "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
-            "config": {"workload": WORKLOAD, "note": "one frame per worker process per step, %d processes" % procs},
+            "config": config_dict(),
+            "notes": {"arm": "the reference's own src/Renderer.cpp (oracle/_ref) on the host: one frame per worker process per step, %d "
+                             "single-threaded workers; warm-up frames per worker: %d" % (procs, warm)},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": kind,
                              "sample": "%d frames per worker x %d workers" % (steps, procs)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -374,16 +382,36 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_rgb8_s = time.perf_counter() - t0
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0, warm_ms, e2e_block_s * 1000.0, e2e_rgb8_s * 1000.0], dtype=torch.float64, device="cuda")
+    # (d) what the box can do: every rank copies image-sized device buffers into its page-locked host memory at the same
+    # time, nothing else running. The e2e figures above are bounded by this (PCIe / host memory), not by the kernels.
+    dimg = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32, device="cuda")
+    for i in range(3):
+        host[i & 1].copy_(dimg, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        host[i & 1].copy_(dimg, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_only_s = time.perf_counter() - t0
+    barrier()
+    del dimg
+
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, warm_ms, e2e_block_s * 1000.0, e2e_rgb8_s * 1000.0, d2h_only_s * 1000.0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, warm_ms_max, e2e_block_ms_max, e2e_rgb8_ms_max = (float(x) for x in t)
+    dev_ms_max, e2e_ms_max, warm_ms_max, e2e_block_ms_max, e2e_rgb8_ms_max, d2h_only_ms_max = (float(x) for x in t)
     per_rank = [dev_ms / K]
     if dist is not None:
         mine = torch.tensor([dev_ms / K], dtype=torch.float64, device="cuda")
         everyone = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(everyone, mine)
         per_rank = [float(x[0]) for x in everyone]
+
+    strips = None
+    if world > 1 and not args.no_strips:
+        # BASELINE.json configs[2] in the same run: one 4K frame of 10 M textured triangles, strips sharded over the ranks
+        r.synchronize()
+        strips = measure_strips(args, rank, local_rank, world, dist, min(K, 50), 5)
 
     if rank == 0:
         n_tri = int(st.triangles_in)
@@ -409,9 +437,10 @@ def run_ours(args, rank, local_rank, world):
             "extra_warmup_frames": n_ramp,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "mtri_per_s": fps * n_tri / 1e6, "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
-            "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) before every timed step, outside the timed events",
-                       "multi_gpu": "view batch: rank r renders views r, r+N, ... of a scene replica; no collective on the data path",
-                       "parity": "depth/coverage bit-exact, RGB <= 1 LSB vs the reference (tests/test_gpu_parity.py)"},
+            "config": config_dict(),
+            "notes": {"l2": "flushed (256 MiB write + 256 MiB read) before every timed step, outside the timed events",
+                      "multi_gpu": "view batch: rank r renders views r, r+N, ... of a scene replica; no collective on the data path",
+                      "parity": "depth/coverage/winner ids bit-exact, RGB <= 1 LSB vs the reference (tests/test_gpu_fullsize.py)"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "per step: setView, render(), float RGB image copied to page-locked host memory and read there; two output "
                             "slots, so the copy of frame i overlaps the kernels of frame i+1 (mr_read_image_begin / mr_read_wait)"},
@@ -420,6 +449,11 @@ def run_ours(args, rank, local_rank, world):
             "e2e_rgb8": {"value": world * K / (e2e_rgb8_ms_max / 1000.0), "unit": "frames/s", "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
                          "note": "setView + render() + mr_read_rgb8: the 8-bit image of savePPM (io.cpp:358-361) quantised on the device, "
                                  "blocking D2H of 3 bytes per pixel (not the headline: the reference API returns float RGB)"},
+            "d2h_ceiling": {"value": world * K / (d2h_only_ms_max / 1000.0), "unit": "frames/s",
+                            "gb_per_s": world * K * d2h / (d2h_only_ms_max / 1000.0) / 1e9,
+                            "note": "every rank copying %d-byte float images from its GPU into its own page-locked host memory at the same time, "
+                                    "no rendering: the ceiling of `e2e` on this box (PCIe + host memory); e2e / d2h_ceiling = %.2f"
+                                    % (d2h, (world * K / (e2e_ms_max / 1000.0)) / (world * K / (d2h_only_ms_max / 1000.0)))},
             "warm_l2_pipelined": {"value": world * K / (warm_ms_max / 1000.0), "unit": "frames/s", "ms_per_step": warm_ms_max / K,
                                   "note": "same K steps back to back, no L2 flush (not the headline)"},
             "gpu_launches": int(st.kernels_launched) * K,
@@ -435,6 +469,8 @@ def run_ours(args, rank, local_rank, world):
             "host_loop_wall_s": wall_dev_loop,
             "stats": {"triangles_in": n_tri, "records": int(st.records), "bin_entries": int(st.bin_entries)},
         }
+        if strips is not None:
+            line["strips4k"] = strips
         if world == 1 and not args.no_cpu_baseline:
             import pyoracle
             kind = "reference" if pyoracle.have_ref() else "port"
@@ -454,87 +490,134 @@ def run_ours(args, rank, local_rank, world):
 # strips sharded across the ranks (strong scaling). Not the headline line; run with
 #   --workload strips4k [--gather peer|nccl]
 # ------------------------------------------------------------------------------------------------
-def run_strips(args, rank, local_rank, world):
+def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
+    """One 3840x2160 frame of the 10 M-triangle textured sphere per step, rank r rendering the rows
+    sharding.strip_rows(2160, r, N) straight into rank 0's framebuffer over NVLink (tile stores through peer memory),
+    ranks joined on the device (mr_stream_signal / mr_stream_wait: no collective, no host sync per frame).
+    Returns the dict that goes into the bench line (rank 0) or None."""
     import torch
     import minirender_b200 as m
     from minirender_b200 import cabi, scenes, sharding
 
+    lib = cabi.load()
+    be = m.Backend()
+    W4, H4, LAT4, LON4 = 3840, 2160, 2237, 2236  # createSphere(r, 2237, 2236): 9,999,392 triangles
+    setup = scenes.sphere_scene(be, W4, H4, lat=LAT4, lon=LON4, textured=True, d=330.0, tex_size=2048)
+    r = setup.apply(m.Renderer(be))
+    r.set_device(local_rank)
+    ctx = r.context_ptr()
+    stream = torch.cuda.current_stream()
+    assert lib.mr_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
+    rb, re = sharding.strip_rows(H4, rank, world)
+    r.clear()
+    r.synchronize()
+    close = join = None
+    if world > 1:
+        dist.barrier()
+        close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
+        join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0)
+    r.set_row_range(rb, re)
+    view = lambda i: scenes.sphere_view(be, i, d=330.0)
+    counter = [0]
+
+    def frame(i):
+        k = counter[0]
+        counter[0] += 1
+        r.set_view(view(i))
+        if join:
+            join.begin(k)
+        r.render()
+        if join:
+            join.end(k)
+
+    for i in range(warmup):
+        frame(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(steps):
+        frame(warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    # per-rank device time of its own strip (stage events, L2 not flushed: the working set exceeds it)
+    lib.mr_set_debug(ctx, 0)
+    r.prepare()
+    assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 5) == 0, lib.mr_last_error(ctx)
+    st = cabi.Stats()
+    lib.mr_get_stats(ctx, C.byref(st))
+    mine = torch.tensor([dev_ms, wall * 1000.0, st.ms_kernel[5], st.ms_kernel[1], st.ms_kernel[4]], dtype=torch.float64, device="cuda")
+    everyone = [mine]
+    if dist is not None:
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+    # ---- the assembled frame against the same frame rendered by rank 0 alone ----
+    identical = None
+    last = warmup + steps - 1
+    if rank == 0:
+        img, dep = sharding.device_tensors(lib, ctx, H4, W4, torch.device("cuda", local_rank))
+        got_i, got_d = img.clone(), dep.clone()
+    if dist is not None:
+        dist.barrier()
+    if close:
+        close()
+    if join:
+        join.close()
+    if rank == 0:
+        r.set_row_range(0, H4)
+        r.set_view(view(last))
+        r.render()
+        r.synchronize()
+        img, dep = sharding.device_tensors(lib, ctx, H4, W4, torch.device("cuda", local_rank))
+        identical = bool(torch.equal(img.view(torch.int32), got_i.view(torch.int32)) and torch.equal(dep.view(torch.int32), got_d.view(torch.int32)))
+        # single-GPU time of the whole frame, for the strong-scaling factor
+        lib.mr_set_debug(ctx, 0)
+        r.prepare()
+        assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 5) == 0
+        lib.mr_get_stats(ctx, C.byref(st))
+        whole_ms = float(st.ms_kernel[5])
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        return None
+    per_rank = [[float(x) for x in t] for t in everyone]
+    ms = max(max(p[0], p[1]) for p in per_rank) / steps
+    strips = sharding.all_strips(H4, world)
+    nvlink_bytes = sum((e - b) * W4 * 16 for r_, (b, e) in enumerate(strips) if r_ != 0)
+    return {"metric": "frames_per_sec_4k_10Mtri_strips", "value": 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "scaling": "strong",
+            "workload": "configs[2]: 3840x2160, createSphere(100,2237,2236) = 9,999,392 triangles, 2048x2048 float texture, one strip of "
+                        "whole tile rows per rank (sort-first: every rank culls all clusters, sets up the ones its rows can see)",
+            "gather": "tile stores into rank 0's framebuffer over NVLink (peer memory) + device-side join (stream-ordered flags)" if world > 1 else "none",
+            "nvlink_bytes_per_frame": nvlink_bytes,
+            "ms_per_step_device_rank0": per_rank[0][0] / steps, "ms_per_step_host_wall_max": max(p[1] for p in per_rank) / steps,
+            "strip_device_ms_per_rank": [p[2] for p in per_rank], "strip_geom_ms_per_rank": [p[3] for p in per_rank],
+            "strip_raster_ms_per_rank": [p[4] for p in per_rank],
+            "single_gpu_frame_ms": whole_ms, "speedup_vs_single_gpu_frame": whole_ms / ms,
+            "assembled_frame_identical_to_single_gpu": identical,
+            "mtri_per_s": 9.999392 / ms * 1e3, "mpix_per_s": W4 * H4 / ms / 1e3}
+
+
+def run_strips(args, rank, local_rank, world):
+    import torch
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = cabi.load()
-    be = m.Backend()
-    W4, H4, LAT4 = 3840, 2160, 2237  # createSphere(r, 2237, 2237): 10,003,864 triangles
-    setup = scenes.sphere_scene(be, W4, H4, lat=LAT4, lon=LAT4, textured=True, d=330.0)
-    r = setup.apply(m.Renderer(be))
-    r.set_device(local_rank)
-    ctx = r.context_ptr()
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
-    assert lib.mr_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
-    rb, re = sharding.strip_rows(H4, rank, world)
-    r.clear()
-    r.synchronize()
-    close = None
-    if world > 1 and args.gather == "peer":
-        dist.barrier()
-        close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
-    r.set_row_range(rb, re)
-    img = dep = None
-    if world > 1 and args.gather == "nccl":
-        img, dep = sharding.device_tensors(lib, ctx, H4, W4, torch.device("cuda", local_rank))
-
-    token = torch.zeros(1, device="cuda")
-
-    def frame(i):
-        r.set_view(scenes.sphere_view(be, i, d=330.0))
-        r.render()
-        if world > 1:
-            if args.gather == "nccl":
-                r.synchronize()
-                sharding.gather_strips(img, dep, H4, rank, world, dist, dst=0)
-            else:
-                # every strip has landed in rank 0's framebuffer once all ranks have passed this
-                # stream-ordered all-reduce (enqueued behind the frame's kernels; no host sync)
-                dist.all_reduce(token)
-
-    K, Wm = max(1, args.steps), max(3, args.warmup)
-    for i in range(Wm):
-        frame(i)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K):
-        frame(Wm + i)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = e0.elapsed_time(e1)
-    t = torch.tensor([max(dev_ms, wall * 1000.0)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    st = cabi.Stats()
-    lib.mr_get_stats(ctx, C.byref(st))
+    res = measure_strips(args, rank, local_rank, world, dist, max(1, args.steps), max(3, args.warmup))
     if rank == 0:
-        ms = float(t[0]) / K
-        print(json.dumps({"metric": "frames_per_sec_4k_10Mtri_strips", "value": 1000.0 / ms, "unit": "frames/s", "n_gpus": world,
-                          "steps": K, "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "mtri_per_s": st.triangles_in / ms / 1e3, "mpix_per_s": W4 * H4 / ms / 1e3,
-                          "ms_per_step_device": dev_ms / K, "ms_per_step_host_wall": wall * 1000.0 / K,
-                          "config": {"workload": "configs[2]: 3840x2160, createSphere(100,2237,2237) = 10.0M triangles, 256x256 float texture, "
-                                                 "strips of whole tile rows per rank (sort-first: every rank sets up all triangles)",
-                                     "gather": args.gather if world > 1 else "none", "l2": "working set (> 1 GB) exceeds the L2"},
-                          "stats": {"triangles_in": int(st.triangles_in), "records_rank0": int(st.records)}}), flush=True)
-    if close:
-        close()
+        res.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": res.pop("workload"), "gather": res["gather"], "l2": "working set (> 1 GB) exceeds the L2"}})
+        print(json.dumps(res), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -543,12 +626,12 @@ def run_strips(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the configs[2] strip-sharded frame (extra key strips4k)")
     ap.add_argument("--workload", default="sphere1m", choices=["sphere1m", "strips4k", "turntable2m"])
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -208,6 +208,20 @@ MR_API int mr_ipc_export(mr_ctx* ctx, void* handles128);
 MR_API int mr_ipc_open(mr_ctx* ctx, const void* handles128, void** d_image, void** d_depth);
 MR_API int mr_ipc_close(mr_ctx* ctx, void* d_image, void* d_depth);
 
+/* Joining the ranks of a strip-sharded frame on the device, without a collective and without the host:
+ * mr_sync_words gives a small zeroed device buffer of 32-bit words on this context's GPU (exported to the peers with
+ * mr_ipc_export_ptr / opened with mr_ipc_open_ptr). mr_stream_signal makes the context's stream store `value` into a
+ * word - local or a peer's - once everything enqueued before it (a rank's tile stores into the gathering rank's
+ * framebuffer, say) is visible system-wide; mr_stream_wait makes the stream wait until each of `n` words has reached
+ * `value`. A frame of the strip mode is then: every rank renders its rows into rank 0's framebuffer and signals
+ * arrived[rank] = frame + 1; rank 0 waits for all of them; before the next frame the peers wait for rank 0's go word. */
+MR_API int mr_sync_words(mr_ctx* ctx, int n_words, void** d_words);
+MR_API int mr_ipc_export_ptr(mr_ctx* ctx, const void* d_ptr, void* handle64);
+MR_API int mr_ipc_open_ptr(mr_ctx* ctx, const void* handle64, void** d_ptr);
+MR_API int mr_ipc_close_ptr(mr_ctx* ctx, void* d_ptr);
+MR_API int mr_stream_signal(mr_ctx* ctx, void* d_word, uint32_t value);
+MR_API int mr_stream_wait(mr_ctx* ctx, const void* d_words, int n, uint32_t value);
+
 /* Page-lock caller memory so the mr_read_* copies run at full PCIe rate (optional). */
 MR_API int mr_host_register(void* host, size_t bytes);
 MR_API int mr_host_unregister(void* host);

@@ -90,6 +90,12 @@ PROTOTYPES = {
     "mr_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mr_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mr_sync_words": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "mr_ipc_export_ptr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mr_ipc_open_ptr": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mr_ipc_close_ptr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mr_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mr_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "mr_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mr_host_unregister": (C.c_int, [C.c_void_p]),
     "mr_set_debug": (C.c_int, [C.c_void_p, C.c_int]),

@@ -127,7 +127,7 @@ struct mr_ctx
 	// outputs
 	// outputs: one or two sets of image/depth buffers (mr_set_output_slots); `image`/`depth` below always
 	// denote the set the newest frame went to
-	DevBuf imageSlot[2], depthSlot[2], normals, winner, scratchOut, flushBuf;
+	DevBuf imageSlot[2], depthSlot[2], normals, winner, scratchOut, flushBuf, syncWords;
 	int outSlots, outCur;
 	cudaStream_t copy;          // device->host copies that overlap the next frame (mr_read_image_begin)
 	cudaEvent_t frameDone[2];   // render stream: the frame in slot s is complete
@@ -893,7 +893,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->meshlets, &c->meshletDir, &c->texels, &c->clusters, &c->triBlockCl, &c->visEntries, &c->geomSync, &c->rstat,
 		               &c->rdyn, &c->mats, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf };
+		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf, &c->syncWords };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)
@@ -1390,6 +1390,74 @@ int mr_ipc_close(mr_ctx* c, void* image, void* depth)
 	MR_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (image) MR_CUDA(c, cudaIpcCloseMemHandle(image));
 	if (depth) MR_CUDA(c, cudaIpcCloseMemHandle(depth));
+	return MR_OK;
+}
+
+int mr_sync_words(mr_ctx* c, int n, void** words)
+{
+	if (!c || n <= 0 || n > 1024 || !words)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	if (!c->syncWords.p)
+	{
+		// (its own allocation: exported to other processes as a whole)
+		MR_CUDA(c, c->syncWords.ensure(4096, true));
+		MR_CUDA(c, cudaMemsetAsync(c->syncWords.p, 0, 4096, c->stream));
+		MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	*words = c->syncWords.p;
+	return MR_OK;
+}
+
+int mr_ipc_export_ptr(mr_ctx* c, const void* dptr, void* handle64)
+{
+	if (!c || !dptr || !handle64)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	cudaIpcMemHandle_t h;
+	MR_CUDA(c, cudaIpcGetMemHandle(&h, (void*)dptr));
+	memcpy(handle64, &h, sizeof(h));
+	return MR_OK;
+}
+
+int mr_ipc_open_ptr(mr_ctx* c, const void* handle64, void** dptr)
+{
+	if (!c || !handle64 || !dptr)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	MR_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return MR_OK;
+}
+
+int mr_ipc_close_ptr(mr_ctx* c, void* dptr)
+{
+	if (!c || !dptr)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	MR_CUDA(c, cudaIpcCloseMemHandle(dptr));
+	return MR_OK;
+}
+
+int mr_stream_signal(mr_ctx* c, void* word, uint32_t value)
+{
+	if (!c || !word)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	mrk_launch_signal((unsigned*)word, value, c->stream);
+	MR_CUDA(c, cudaGetLastError());
+	return MR_OK;
+}
+
+int mr_stream_wait(mr_ctx* c, const void* words, int n, uint32_t value)
+{
+	if (!c || !words || n <= 0)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	mrk_launch_wait((const unsigned*)words, n, value, c->stream);
+	MR_CUDA(c, cudaGetLastError());
 	return MR_OK;
 }
 

@@ -1774,6 +1774,25 @@ __global__ void k_flush_read(const float4* __restrict__ src, size_t n, float* si
 		*sink = acc;
 }
 
+// Stream-ordered flags in (peer) device memory: see mr_stream_signal / mr_stream_wait.
+__global__ void k_signal(unsigned* word, unsigned value)
+{
+	__threadfence_system(); // everything this stream did before is visible to the other GPUs first
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(word), "r"(value) : "memory");
+}
+
+__global__ void k_wait(const unsigned* words, int n, unsigned value)
+{
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		unsigned v;
+		do
+		{
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(words + i) : "memory");
+		} while ((int)(v - value) < 0);
+	}
+}
+
 __global__ void k_selftest(const float* in, float* out)
 {
 	// with contraction, a*b+c keeps the exact product; without, the product rounds first
@@ -1882,6 +1901,9 @@ int mrk_selftest_no_fma(cudaStream_t stream)
 		return -1;
 	return (r == 0.0f) ? 0 : 1; // fused would give 2^-24
 }
+
+void mrk_launch_signal(unsigned* word, unsigned value, cudaStream_t stream) { k_signal<<<1, 1, 0, stream>>>(word, value); }
+void mrk_launch_wait(const unsigned* words, int n, unsigned value, cudaStream_t stream) { k_wait<<<1, 32, 0, stream>>>(words, n, value); }
 
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream)
 {

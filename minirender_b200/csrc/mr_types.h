@@ -226,6 +226,8 @@ int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes);
 void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* stageEvents /* 3 or NULL */,
                       cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl);
 int mrk_selftest_no_fma(cudaStream_t stream);
+void mrk_launch_signal(unsigned* word, unsigned value, cudaStream_t stream);
+void mrk_launch_wait(const unsigned* words, int n, unsigned value, cudaStream_t stream);
 void mrk_launch_flush_read(const void* buf, size_t bytes, float* sink, cudaStream_t stream);
 void mrk_launch_range(const float* depth, float* xyz, int w, int h, const float* P16, cudaStream_t stream);
 void mrk_launch_rgb8(const float* image, uint8_t* out, size_t nFloats, cudaStream_t stream);

@@ -96,3 +96,52 @@ def open_peer_target(ctx_lib, ctx, rank, world, dist, dst=0):
         ctx_lib.mr_set_remote_target(ctx, None, None)
         ctx_lib.mr_ipc_close(ctx, pi, pd)
     return close
+
+
+class StripJoin:
+    """Device-side join of a strip-sharded frame (mr_stream_signal / mr_stream_wait): no collective and no host
+    synchronisation on the per-frame path. Rank `dst` owns the words: arrived[r] (written by rank r over NVLink after
+    its rows have landed in dst's framebuffer) and go (written by dst when a frame is complete and may be overwritten).
+
+        join = StripJoin(lib, ctx, rank, world, dist)
+        for i in range(frames):
+            join.begin(i)        # peers: wait until dst has released the framebuffer of frame i - 1
+            renderer.render()    # rows of this rank, stored straight into dst's framebuffer
+            join.end(i)          # signal arrival; dst: wait for every rank, (consume the frame,) release
+    """
+
+    def __init__(self, ctx_lib, ctx, rank, world, dist, dst=0):
+        self.lib, self.ctx, self.rank, self.world, self.dst = ctx_lib, ctx, rank, world, dst
+        self.words = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if rank == dst:
+            assert ctx_lib.mr_sync_words(ctx, world + 1, C.byref(self.words)) == 0
+            assert ctx_lib.mr_ipc_export_ptr(ctx, self.words, handle) == 0
+        payload = [bytes(handle) if rank == dst else None]
+        dist.broadcast_object_list(payload, src=dst)
+        self.opened = False
+        if rank != dst:
+            buf = (C.c_ubyte * 64).from_buffer_copy(payload[0])
+            rc = ctx_lib.mr_ipc_open_ptr(ctx, buf, C.byref(self.words))
+            if rc != 0:
+                raise RuntimeError("mr_ipc_open_ptr failed: %s" % ctx_lib.mr_last_error(ctx).decode())
+            self.opened = True
+
+    def _word(self, i):
+        return C.c_void_p(self.words.value + 4 * i)
+
+    def begin(self, frame):
+        if self.rank != self.dst and frame > 0:
+            assert self.lib.mr_stream_wait(self.ctx, self._word(self.world), 1, frame) == 0
+
+    def end(self, frame):
+        assert self.lib.mr_stream_signal(self.ctx, self._word(self.rank), frame + 1) == 0
+        if self.rank == self.dst:
+            assert self.lib.mr_stream_wait(self.ctx, self._word(0), self.world, frame + 1) == 0
+            # (a consumer of the assembled frame would be enqueued here)
+            assert self.lib.mr_stream_signal(self.ctx, self._word(self.world), frame + 1) == 0
+
+    def close(self):
+        if self.opened:
+            self.lib.mr_ipc_close_ptr(self.ctx, self.words)
+            self.opened = False
