@@ -517,8 +517,12 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
         close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
         join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0)
     r.set_row_range(rb, re)
+    if world > 1 and rank != 0:
+        assert lib.mr_set_sparse_remote_stores(ctx, 1) == 0  # only the tiles this rank draws into cross NVLink
     view = lambda i: scenes.sphere_view(be, i, d=330.0)
     counter = [0]
+    peer_rows = [s_ for k_, s_ in enumerate(sharding.all_strips(H4, world)) if k_ != 0 and s_[1] > s_[0]]
+    total_frames = warmup + steps
 
     def frame(i):
         k = counter[0]
@@ -528,7 +532,9 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
             join.begin(k)
         r.render()
         if join:
-            join.end(k)
+            # rank 0 resets the peers' rows to the clear values before it lets them in again (not after the last frame:
+            # that one is compared with a single-GPU render below)
+            join.end(k, clear_rows=(setup.background, peer_rows) if (rank == 0 and k + 1 < total_frames) else None)
 
     for i in range(warmup):
         frame(i)
@@ -552,7 +558,7 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
     assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 5) == 0, lib.mr_last_error(ctx)
     st = cabi.Stats()
     lib.mr_get_stats(ctx, C.byref(st))
-    mine = torch.tensor([dev_ms, wall * 1000.0, st.ms_kernel[5], st.ms_kernel[1], st.ms_kernel[4]], dtype=torch.float64, device="cuda")
+    mine = torch.tensor([dev_ms, wall * 1000.0, st.ms_kernel[5], st.ms_kernel[1], st.ms_kernel[4], float(st.tiles_stored)], dtype=torch.float64, device="cuda")
     everyone = [mine]
     if dist is not None:
         everyone = [torch.zeros_like(mine) for _ in range(world)]
@@ -589,13 +595,15 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
     per_rank = [[float(x) for x in t] for t in everyone]
     ms = max(max(p[0], p[1]) for p in per_rank) / steps
     strips = sharding.all_strips(H4, world)
-    nvlink_bytes = sum((e - b) * W4 * 16 for r_, (b, e) in enumerate(strips) if r_ != 0)
+    nvlink_bytes = int(sum(p[5] for p in per_rank[1:]) * 256 * 16)  # tiles the peers stored x 256 pixels x (12 + 4) bytes
+    nvlink_bytes_dense = sum((e - b) * W4 * 16 for r_, (b, e) in enumerate(strips) if r_ != 0)
     return {"metric": "frames_per_sec_4k_10Mtri_strips", "value": 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "scaling": "strong",
             "workload": "configs[2]: 3840x2160, createSphere(100,2237,2236) = 9,999,392 triangles, 2048x2048 float texture, one strip of "
                         "whole tile rows per rank (sort-first: every rank culls all clusters, sets up the ones its rows can see)",
-            "gather": "tile stores into rank 0's framebuffer over NVLink (peer memory) + device-side join (stream-ordered flags)" if world > 1 else "none",
-            "nvlink_bytes_per_frame": nvlink_bytes,
+            "gather": "tile stores into rank 0's framebuffer over NVLink (peer memory, touched tiles only: rank 0 clears the rest itself) + device-side "
+                      "join (stream-ordered flags; a peer's geometry runs ahead, its tile kernel waits for rank 0)" if world > 1 else "none",
+            "nvlink_bytes_per_frame": nvlink_bytes, "nvlink_bytes_per_frame_if_every_tile_were_sent": nvlink_bytes_dense,
             "ms_per_step_device_rank0": per_rank[0][0] / steps, "ms_per_step_host_wall_max": max(p[1] for p in per_rank) / steps,
             "strip_device_ms_per_rank": [p[2] for p in per_rank], "strip_geom_ms_per_rank": [p[3] for p in per_rank],
             "strip_raster_ms_per_rank": [p[4] for p in per_rank],

@@ -152,6 +152,7 @@ typedef struct mr_stats
 	int64_t h2d_bytes;         /* host->device bytes the last mr_render copied (per-frame tables) */
 	int64_t clusters;          /* 32-triangle clusters of the frame ... */
 	int64_t clusters_visible;  /* ... and how many of them survived cluster culling */
+	int64_t tiles_stored;      /* 16x16 tiles the tile kernel wrote (with sparse remote stores: the touched ones only) */
 } mr_stats;
 
 MR_API int mr_abi_version(void);
@@ -220,6 +221,14 @@ MR_API int mr_ipc_export_ptr(mr_ctx* ctx, const void* d_ptr, void* handle64);
 MR_API int mr_ipc_open_ptr(mr_ctx* ctx, const void* handle64, void** d_ptr);
 MR_API int mr_ipc_close_ptr(mr_ctx* ctx, void* d_ptr);
 MR_API int mr_stream_signal(mr_ctx* ctx, void* d_word, uint32_t value);
+/* One shot: the next mr_render waits for *d_word >= value between its geometry kernel and its tile kernel, so that a
+ * peer's geometry for frame i + 1 runs while the gathering rank still owns the framebuffer of frame i. */
+MR_API int mr_set_raster_gate(mr_ctx* ctx, const void* d_word, uint32_t value);
+/* With a remote target set: tiles nothing was drawn into are not stored (flag != 0); the owner of the framebuffer
+ * writes the clear values of those rows itself (mr_clear_rows) before it lets the peers in. */
+MR_API int mr_set_sparse_remote_stores(mr_ctx* ctx, int flag);
+/* Clear values (background / 1e11) into rows [row_begin,row_end) of the current output buffers, stream ordered. */
+MR_API int mr_clear_rows(mr_ctx* ctx, const float* background3, int row_begin, int row_end);
 MR_API int mr_stream_wait(mr_ctx* ctx, const void* d_words, int n, uint32_t value);
 
 /* Page-lock caller memory so the mr_read_* copies run at full PCIe rate (optional). */

@@ -59,7 +59,7 @@ class Stats(C.Structure):
                 ("bin_entries", C.c_int64), ("zero_coverage", C.c_int64),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("regrows", C.c_int32),
                 ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8), ("h2d_bytes", C.c_int64),
-                ("clusters", C.c_int64), ("clusters_visible", C.c_int64)]
+                ("clusters", C.c_int64), ("clusters_visible", C.c_int64), ("tiles_stored", C.c_int64)]
 
 
 FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
@@ -95,6 +95,9 @@ PROTOTYPES = {
     "mr_ipc_open_ptr": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mr_ipc_close_ptr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mr_set_raster_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mr_set_sparse_remote_stores": (C.c_int, [C.c_void_p, C.c_int]),
+    "mr_clear_rows": (C.c_int, [C.c_void_p, F32P, C.c_int, C.c_int]),
     "mr_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "mr_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mr_host_unregister": (C.c_int, [C.c_void_p]),

@@ -135,6 +135,9 @@ struct mr_ctx
 	bool copyPending[2];
 	int copyRing[2];            // frame-ring slot of the frame whose image the pending copy of output set s reads
 	void *remoteImage, *remoteDepth;
+	bool sparseRemote;          // mr_set_sparse_remote_stores
+	const unsigned* gateWord;   // mr_set_raster_gate (one shot)
+	unsigned gateValue;
 	int debugFlags;
 	cudaEvent_t timingStart, timingStop; // mr_set_timing_events: recorded around the next frame's launches
 
@@ -146,7 +149,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), noTightScan(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0),
+	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), noTightScan(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0), sparseRemote(false), gateWord(0), gateValue(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -204,18 +207,20 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun = fals
 void absorbCounters(mr_ctx* c, const Counters& k)
 {
 	c->stats.triangles_in = (int64_t)k.trianglesIn;
-	unsigned long long rec = 0, clip = 0, pairs = 0, zero = 0;
+	unsigned long long rec = 0, clip = 0, pairs = 0, zero = 0, stored = 0;
 	for (int i = 0; i < MR_STAT_SLOTS; i++)
 	{
 		rec += k.records[i];
 		clip += k.clippedIn[i];
 		pairs += k.pairTotal[i];
+		stored += k.tilesStored[i];
 		zero += k.zeroCov[i];
 	}
 	c->stats.records = (int64_t)rec;
 	c->stats.clipped_in = (int64_t)clip;
 	c->stats.bin_entries = (int64_t)pairs;
 	c->stats.zero_coverage = (int64_t)zero;
+	c->stats.tiles_stored = (int64_t)stored;
 	c->stats.clusters = (int64_t)k.clusters;
 	c->stats.clusters_visible = (int64_t)k.visible;
 	c->stats.tiles_x = c->tilesX;
@@ -610,7 +615,9 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
 	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
 
-	mrk_launch_frame(fp, c->geomGrid, c->geomSmem, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop, !c->noPdl);
+	fp.sparseStores = (c->sparseRemote && c->remoteImage && !f->keep && !f->save_normals && !(c->debugFlags & 1)) ? 1 : 0;
+	mrk_launch_frame(fp, c->geomGrid, c->geomSmem, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop, !c->noPdl, c->gateWord, c->gateValue);
+	c->gateWord = 0;
 	if (!ev)
 		c->timingStart = c->timingStop = 0;
 	MR_CUDA(c, cudaGetLastError());
@@ -1457,6 +1464,35 @@ int mr_stream_wait(mr_ctx* c, const void* words, int n, uint32_t value)
 		return MR_E_INVALID;
 	Bind bind(c->device);
 	mrk_launch_wait((const unsigned*)words, n, value, c->stream);
+	MR_CUDA(c, cudaGetLastError());
+	return MR_OK;
+}
+
+int mr_set_raster_gate(mr_ctx* c, const void* word, uint32_t value)
+{
+	if (!c)
+		return MR_E_INVALID;
+	c->gateWord = (const unsigned*)word;
+	c->gateValue = value;
+	return MR_OK;
+}
+
+int mr_set_sparse_remote_stores(mr_ctx* c, int flag)
+{
+	if (!c)
+		return MR_E_INVALID;
+	c->sparseRemote = flag != 0;
+	return MR_OK;
+}
+
+int mr_clear_rows(mr_ctx* c, const float* bg, int rb, int re)
+{
+	if (!c || !bg || rb < 0 || re > c->h || re < rb)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	if (!c->imageSlot[c->outCur].p)
+		return setError(c, MR_E_INVALID, "mr_clear_rows before mr_set_size");
+	mrk_launch_clear_rows(c->imageSlot[c->outCur].as<float>(), c->depthSlot[c->outCur].as<float>(), c->w, rb, re, bg[0], bg[1], bg[2], c->stream);
 	MR_CUDA(c, cudaGetLastError());
 	return MR_OK;
 }

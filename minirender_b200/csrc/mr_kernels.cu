@@ -1548,7 +1548,8 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	if (full && tinfo.x == 0 && tinfo.y == 0 && !(fp.saveNormals && fp.normals) && !fp.winner)
 	{
 		// nothing has touched this tile: clear values only (Renderer.cpp:113-119), its keys are not even read
-		storeFullTile128<true>(fp, tileX0, tileY0, tid, 0);
+		if (!fp.sparseStores)
+			storeFullTile128<true>(fp, tileX0, tileY0, tid, 0);
 		return;
 	}
 	// ---- phase 0: the tile's keys out of gkeys, merged with the clear / kept depth; gkeys reset ----
@@ -1617,7 +1618,10 @@ __device__ __forceinline__ void rasterTile(const FrameParams& fp, int tx, int ty
 	// (this barrier also separates the previous tile's staging reads from this tile's staging writes)
 	const bool anyWinTile = __syncthreads_or(anyWin);
 	if (tid == 0 && (tinfo.x | tinfo.y) != 0)
+	{
 		fp.tileCount[tile] = make_int2(0, 0); // every thread has read it: ready for the next frame
+		atomicAdd(&fp.ctr->tilesStored[tile & (MR_STAT_SLOTS - 1)], 1ull);
+	}
 	if (!anyWinTile && vec && !(fp.saveNormals && fp.normals) && !fp.winner)
 	{
 		if (full)
@@ -1774,6 +1778,19 @@ __global__ void k_flush_read(const float4* __restrict__ src, size_t n, float* si
 		*sink = acc;
 }
 
+// Clear values into the pixels [p0, p1) of an image / depth pair (mr_clear_rows).
+__global__ void k_clear_rows(float* image, float* depth, size_t p0, size_t p1, float r, float g, float b)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	for (size_t p = p0 + first; p < p1; p += stride)
+	{
+		image[3 * p] = r;
+		image[3 * p + 1] = g;
+		image[3 * p + 2] = b;
+		depth[p] = 1e11f;
+	}
+}
+
 // Stream-ordered flags in (peer) device memory: see mr_stream_signal / mr_stream_wait.
 __global__ void k_signal(unsigned* word, unsigned value)
 {
@@ -1827,7 +1844,8 @@ int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes)
 	return 0;
 }
 
-void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* ev, cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl)
+void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* ev, cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl,
+                      const unsigned* gateWord, unsigned gateValue)
 {
 	if (bracketStart) cudaEventRecord(bracketStart, stream);
 	if (ev) cudaEventRecord(ev[0], stream);
@@ -1851,6 +1869,12 @@ void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStr
 			cudaLaunchKernelEx(&cfg, k_geom<TM_GLOBAL>, fp);
 	}
 	if (ev) cudaEventRecord(ev[1], stream);
+	if (gateWord)
+	{
+		// strip mode: the tile kernel's stores go to another rank's framebuffer, which must be free first
+		k_wait<<<1, 32, 0, stream>>>(gateWord, 1, gateValue);
+		pdl = false;
+	}
 	if (fp.tileRows > 0)
 	{
 		// k_raster may become resident while k_geom drains (unless stage events sit between)
@@ -1900,6 +1924,12 @@ int mrk_selftest_no_fma(cudaStream_t stream)
 	if (e != cudaSuccess)
 		return -1;
 	return (r == 0.0f) ? 0 : 1; // fused would give 2^-24
+}
+
+void mrk_launch_clear_rows(float* image, float* depth, int w, int rowBegin, int rowEnd, float r, float g, float b, cudaStream_t stream)
+{
+	if (rowEnd > rowBegin)
+		k_clear_rows<<<148 * 4, 256, 0, stream>>>(image, depth, (size_t)rowBegin * w, (size_t)rowEnd * w, r, g, b);
 }
 
 void mrk_launch_signal(unsigned* word, unsigned value, cudaStream_t stream) { k_signal<<<1, 1, 0, stream>>>(word, value); }

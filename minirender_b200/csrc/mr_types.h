@@ -149,6 +149,7 @@ struct Counters
 	unsigned long long clippedIn[MR_STAT_SLOTS]; // input triangles crossing the near plane
 	unsigned long long zeroCov[MR_STAT_SLOTS];   // set-up small triangles that cover no pixel centre (dropped)
 	unsigned long long pairTotal[MR_STAT_SLOTS]; // (tile, triangle) pairs of the frame (summed by the tile kernel)
+	unsigned long long tilesStored[MR_STAT_SLOTS]; // tiles the tile kernel wrote to the framebuffer
 };
 
 #define MR_INLINE_TABLE 32 // renderables / materials that travel inside the kernel parameters
@@ -171,6 +172,7 @@ struct FrameParams
 	int rowBegin, rowEnd;   // pixel rows [rowBegin,rowEnd)
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int tightScan; // small triangles skip the outermost columns / rows of the reference's loops where those provably cover nothing
+	int sparseStores; // tiles nothing was drawn into are not written (the target already holds the clear values)
 	int stdProj; // standard perspective matrix with the near plane in front of the eye: projectStd() applies
 	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags
@@ -224,7 +226,8 @@ struct FrameParams
 // kernel launchers (mr_kernels.cu)
 int mrk_geom_config(int nvCap, int smCount, int* grid, int* smemBytes);
 void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStream_t stream, cudaEvent_t* stageEvents /* 3 or NULL */,
-                      cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl);
+                      cudaEvent_t bracketStart, cudaEvent_t bracketStop, bool pdl, const unsigned* gateWord, unsigned gateValue);
+void mrk_launch_clear_rows(float* image, float* depth, int w, int rowBegin, int rowEnd, float r, float g, float b, cudaStream_t stream);
 int mrk_selftest_no_fma(cudaStream_t stream);
 void mrk_launch_signal(unsigned* word, unsigned value, cudaStream_t stream);
 void mrk_launch_wait(const unsigned* words, int n, unsigned value, cudaStream_t stream);

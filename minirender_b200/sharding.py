@@ -131,14 +131,21 @@ class StripJoin:
         return C.c_void_p(self.words.value + 4 * i)
 
     def begin(self, frame):
+        # a peer's geometry may run ahead; only its tile kernel (which stores into dst's framebuffer) waits for dst
         if self.rank != self.dst and frame > 0:
-            assert self.lib.mr_stream_wait(self.ctx, self._word(self.world), 1, frame) == 0
+            assert self.lib.mr_set_raster_gate(self.ctx, self._word(self.world), frame) == 0
 
-    def end(self, frame):
+    def end(self, frame, clear_rows=None):
+        """clear_rows = (background rgb, [(row_begin, row_end), ...]) on dst: with sparse remote stores the peers only
+        write the tiles they drew into, so dst resets their rows to the clear values before it lets them in again."""
         assert self.lib.mr_stream_signal(self.ctx, self._word(self.rank), frame + 1) == 0
         if self.rank == self.dst:
             assert self.lib.mr_stream_wait(self.ctx, self._word(0), self.world, frame + 1) == 0
             # (a consumer of the assembled frame would be enqueued here)
+            if clear_rows is not None:
+                bg = (C.c_float * 3)(*clear_rows[0])
+                for rb, re in clear_rows[1]:
+                    assert self.lib.mr_clear_rows(self.ctx, bg, rb, re) == 0
             assert self.lib.mr_stream_signal(self.ctx, self._word(self.world), frame + 1) == 0
 
     def close(self):
