@@ -68,6 +68,15 @@ _COMMON = {
     "mrx_mat_inverse": (None, [F32P, F32P]),
     "mrx_projection": (C.c_int, [F32P, C.c_int, F32P]),
     "mrx_projection_cv": (None, [F32P, F32P, C.c_float, C.c_float, C.c_float, C.c_float]),
+    # file formats (include/minirender/io.h)
+    "mrx_save_ppm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "mrx_load_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mrx_scene_load": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "mrx_scene_node_count": (C.c_int, [C.c_void_p]),
+    "mrx_node_info": (C.c_int, [C.c_void_p, C.c_int, I32P, I32P, F32P]),
+    "mrx_mesh_material": (C.c_int, [C.c_void_p, C.c_int, F32P, I32P, I32P]),
+    "mrx_save_stl": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "mrx_save_xyz": (C.c_int, [C.c_void_p, C.c_int, C.c_int, F32P, C.c_char_p]),
 }
 
 _PRODUCT_ONLY = {
@@ -82,14 +91,6 @@ _PRODUCT_ONLY = {
     "mrx_renderer_synchronize": (C.c_int, [C.c_void_p]),
     "mrx_renderer_image_ptr": (C.POINTER(C.c_float), [C.c_void_p]),
     "mrx_renderer_depth_ptr": (C.POINTER(C.c_float), [C.c_void_p]),
-    "mrx_save_ppm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
-    "mrx_load_ppm": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "mrx_scene_load": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
-    "mrx_scene_node_count": (C.c_int, [C.c_void_p]),
-    "mrx_node_info": (C.c_int, [C.c_void_p, C.c_int, I32P, I32P, F32P]),
-    "mrx_mesh_material": (C.c_int, [C.c_void_p, C.c_int, F32P, I32P, I32P]),
-    "mrx_save_stl": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
-    "mrx_save_xyz": (C.c_int, [C.c_void_p, C.c_int, C.c_int, F32P, C.c_char_p]),
     "mrx_triangulate": (C.c_int, [I32P, C.c_int, I32P]),
 }
 

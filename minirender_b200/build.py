@@ -6,6 +6,7 @@
                                               only where /root/reference exists)
 """
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -98,9 +99,9 @@ def check_wide_ops(obj):
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
             counts[fn] = [0, 0]
-        elif fn and "STG.E.ENL2.256" in line:
+        elif fn and re.search(r"STG\.E\.E[NLF]L2\.256", line):
             counts[fn][0] += 1
-        elif fn and "LDG.E.ENL2.256" in line:
+        elif fn and re.search(r"LDG\.E\.E[NLF]L2\.256", line):
             counts[fn][1] += 1
     for fn, (st, ld) in counts.items():
         if "k_geom" in fn and st != 5:

@@ -312,22 +312,54 @@ struct __align__(32) F8
 	float4 a, b;
 };
 
+// L2 eviction priority of the 256-bit accesses (PTX level2::eviction_priority, SASS .ENL2 / .ELL2 / .EFL2):
+// records are written once by k_geom and read back by k_raster within the frame (keep: evict_last),
+// finished tiles are never read again on the device (evict_first).
+enum { L2_NORMAL = 0, L2_LAST = 1, L2_FIRST = 2 };
+#ifndef MR_REC_STORE_HINT
+#define MR_REC_STORE_HINT L2_LAST
+#endif
+#ifndef MR_REC_LOAD_HINT
+#define MR_REC_LOAD_HINT L2_FIRST
+#endif
+#ifndef MR_TILE_STORE_HINT
+#define MR_TILE_STORE_HINT L2_FIRST
+#endif
+
+template <int HINT = MR_REC_LOAD_HINT>
 __device__ __forceinline__ F8 ldPair(const F8* p) // read-only path (records are written by an earlier kernel)
 {
 	F8 r;
-	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
-	             : "l"(p));
+	if (HINT == L2_FIRST)
+		asm volatile("ld.global.nc.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+		             : "l"(p));
+	else if (HINT == L2_LAST)
+		asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+		             : "l"(p));
+	else
+		asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+		             : "l"(p));
 	return r;
 }
 
 // WIDE = false: two 16-byte stores. (ptxas 12.9 assembles st.global.v8 inside the out-of-line near-plane
 // path as a plain 32-bit STG — found through the clipping parity test — so that rare path keeps float4 stores;
 // minirender_b200/build.py counts the wide instructions in the SASS after every compile.)
-template <bool WIDE>
+template <bool WIDE, int HINT = L2_NORMAL>
 __device__ __forceinline__ void stPair(F8* p, const float4 a, const float4 b)
 {
-	if (WIDE)
+	if (WIDE && HINT == L2_LAST)
+		asm volatile("st.global.L2::evict_last.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+		             "f"(b.y), "f"(b.z), "f"(b.w)
+		             : "memory");
+	else if (WIDE && HINT == L2_FIRST)
+		asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+		             "f"(b.y), "f"(b.z), "f"(b.w)
+		             : "memory");
+	else if (WIDE)
 		asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
 		             "f"(b.z), "f"(b.w)
 		             : "memory");
@@ -364,8 +396,8 @@ __device__ __forceinline__ RecRef recRef(const FrameParams& fp, int id)
 template <bool WIDE>
 __device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission)
 {
-	stPair<WIDE>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
-	stPair<WIDE>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
+	stPair<WIDE, MR_REC_STORE_HINT>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
+	stPair<WIDE, MR_REC_STORE_HINT>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
 	       make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
 	                   __uint_as_float(s.flags), __uint_as_float((uint32_t)submission)));
 }
@@ -381,9 +413,9 @@ struct Corner
 template <bool WIDE>
 __device__ __forceinline__ void storeShadeRec(const RecRef d, const float4 B0, const float4 B1, const float4 B2, const float4 C0, const float4 C1, const float4 C2)
 {
-	stPair<WIDE>(d.p + 2 * d.stride, B0, B1);
-	stPair<WIDE>(d.p + 3 * d.stride, B2, C0);
-	stPair<WIDE>(d.p + 4 * d.stride, C1, C2);
+	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 2 * d.stride, B0, B1);
+	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 3 * d.stride, B2, C0);
+	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 4 * d.stride, C1, C2);
 }
 
 // reference clip(), Renderer.cpp:121-129
@@ -890,6 +922,7 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	__syncthreads();
 	const int nVis = gs.nVis;
 	MR_TL(2); // work list complete
+
 #ifdef MR_TIMELINE
 	if (lane == 0 && blockIdx.x < 1024)
 		g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 5] = g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 6] = 0ull;
@@ -1289,7 +1322,7 @@ __device__ __forceinline__ void storeFullTile128(const FrameParams& fp, int tile
 		v0 = *reinterpret_cast<const float4*>(&to->px[row][8 * j]);
 		v1 = *reinterpret_cast<const float4*>(&to->px[row][8 * j + 4]);
 	}
-	stPair<true>(reinterpret_cast<F8*>(dst), v0, v1);
+	stPair<true, MR_TILE_STORE_HINT>(reinterpret_cast<F8*>(dst), v0, v1);
 }
 
 // Phase 1 for one batch of up to 32 binned triangles (a lane each; `have` lanes hold record `id`).

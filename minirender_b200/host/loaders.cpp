@@ -7,7 +7,6 @@
 // Deliberate, documented differences (all on inputs the reference handles by accident):
 //  * one mesh per OBJ material is emitted in order of first use; the reference iterates an asl::Dic
 //    (hash order, unspecified). Only the submission order of exactly coincident surfaces depends on it.
-//  * quotes around an X3D ImageTexture url are stripped before the extension is replaced by .ppm.
 //  * an X3D <Inline> is read by its own reader; the reference re-uses one reader object and thereby
 //    overwrites the document it is still iterating (x3d.cpp:169,176-180).
 #include <minirender/io.h>
@@ -787,11 +786,8 @@ struct X3dReader
 		}
 		if (const XmlNode* tex = appx ? get(appx->child("ImageTexture")) : 0)
 		{
-			std::string url;
-			const std::string raw = tex->attr("url");
-			for (size_t i = 0; i < raw.size(); i++)
-				if (raw[i] != '"')
-					url.push_back(raw[i]);
+			// the url is used as written (x3d.cpp:93-94): a quoted MFString url keeps its quotes and finds no file, like the reference
+			const std::string url = tex->attr("url");
 			const std::string name = noExt(url) + ".ppm"; // textures are looked up as PPM (x3d.cpp:96)
 			mesh->material->textureName = String(name);
 			if (mesh->material->textureName.ok())

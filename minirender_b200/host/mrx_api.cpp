@@ -5,8 +5,8 @@
 #include <minirender/Renderer.h>
 #include <minirender/Scene.h>
 #include <minirender/primitives.h>
-#ifdef MRX_PRODUCT
 #include <minirender/io.h>
+#ifdef MRX_PRODUCT
 #include <minirender_b200.h>
 #endif
 
@@ -577,6 +577,10 @@ int mrx_renderer_synchronize(void* r)
 	MRX_CATCH(-1)
 }
 
+#endif // MRX_PRODUCT
+
+// ---- file formats (the reference's include/minirender/io.h): the same calls on either build ----
+
 int mrx_save_ppm(const float* image, int w, int h, const char* filename)
 {
 	MRX_TRY
@@ -677,6 +681,8 @@ int mrx_save_xyz(const float* points, int w, int h, const float* m16, const char
 	MRX_CATCH(-1)
 }
 
+#ifdef MRX_PRODUCT
+// x3d.cpp's fan triangulation is a file-local function in the reference; the product exposes its own for the tests
 int mrx_triangulate(const int32_t* in, int n, int32_t* out)
 {
 	Array<int> a;

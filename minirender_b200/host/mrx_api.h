@@ -105,7 +105,7 @@ MRX_API const float* mrx_renderer_image_ptr(void* r);
 MRX_API const float* mrx_renderer_depth_ptr(void* r);
 MRX_API int mrx_renderer_synchronize(void* r);
 MRX_API int mrx_save_ppm(const float* image, int w, int h, const char* filename);
-/* mesh files (product only): loadMesh() under `parent`; the loaded subtree's nodes get consecutive ids
+/* mesh files: loadMesh() under `parent`; the loaded subtree's nodes get consecutive ids
  * in pre-order, the first of which is returned */
 MRX_API int mrx_scene_load(void* scene, int parent, const char* filename);
 MRX_API int mrx_scene_node_count(void* scene);

@@ -276,7 +276,7 @@ def load_x3d(path):
                 mat["shininess"] = float(f32(attr(m, "shininess", "0.5")) * f32(8))
             t = get(appx.find("ImageTexture")) if appx is not None else None
             if t is not None:
-                url = attr(t, "url").replace('"', "")
+                url = attr(t, "url")  # as written: quotes are not stripped (x3d.cpp:93-94)
                 name = os.path.splitext(url)[0] + ".ppm"
                 mat["texture_name"] = name
                 p = os.path.join(d, name)

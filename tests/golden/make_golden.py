@@ -103,6 +103,21 @@ def turntable_reference():
     print(out, end="")
 
 
+def loaders_reference():
+    """tests/golden/formats/loaders.npz: what the reference's own src/io.cpp + src/x3d.cpp (compiled unchanged into oracle/_ref)
+    return for the fixed files of tests/loader_cases.py."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import loader_cases as lc
+    want = lc.dump(m.Backend(pyoracle.REF_PATH), tempfile.mkdtemp())
+    os.makedirs(os.path.join(HERE, "formats"), exist_ok=True)
+    path = os.path.join(HERE, "formats", "loaders.npz")
+    np.savez_compressed(path, **want)
+    print("loaders.npz: %d arrays, %.1f KiB" % (len(want), os.path.getsize(path) / 1024.0))
+
+
 if __name__ == "__main__":
-    main()
-    turntable_reference()
+    if "--loaders-only" not in sys.argv:
+        main()
+        turntable_reference()
+    loaders_reference()

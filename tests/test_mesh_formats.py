@@ -244,7 +244,7 @@ def test_x3d_hierarchy_def_use_and_defaults(be, tmp_path):
 
 def test_x3d_inline_and_texture(be, tmp_path):
     write_ppm(tmp_path / "wood.ppm", 8, 8, seed=9)
-    inner = ('<X3D><Scene><Shape><Appearance><ImageTexture url=\'"wood.png"\'/></Appearance>'
+    inner = ('<X3D><Scene><Shape><Appearance><ImageTexture url="wood.png"/></Appearance>'
              '<IndexedFaceSet coordIndex="0 1 2 3 -1" texCoordIndex="0 1 2 3 -1"><Coordinate point="0 0 0 4 0 0 4 4 0 0 4 0"/>'
              '<TextureCoordinate point="0 0 1 0 1 1 0 1"/></IndexedFaceSet></Shape></Scene></X3D>')
     write(tmp_path / "inner.x3d", inner)
