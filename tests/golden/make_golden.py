@@ -116,8 +116,20 @@ def loaders_reference():
     print("loaders.npz: %d arrays, %.1f KiB" % (len(want), os.path.getsize(path) / 1024.0))
 
 
+def samples_reference():
+    """tests/golden/formats/samples.npz: the frames the reference's own sample programs write (oracle/_ref/sample_*_ref)."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_cpp_dropin as t
+    frames = t.run_samples("ref", tempfile.mkdtemp())
+    path = os.path.join(HERE, "formats", "samples.npz")
+    np.savez_compressed(path, **frames)
+    print("samples.npz: %s, %.1f KiB" % (sorted(frames), os.path.getsize(path) / 1024.0))
+
+
 if __name__ == "__main__":
     if "--loaders-only" not in sys.argv:
         main()
         turntable_reference()
     loaders_reference()
+    samples_reference()
