@@ -168,13 +168,18 @@ MR_API int mr_set_size(mr_ctx* ctx, int width, int height);
 MR_API int mr_upload_scene(mr_ctx* ctx, const mr_scene_desc* scene);
 
 MR_API int mr_render(mr_ctx* ctx, const mr_frame* frame);
-/* n frames over the same scene, pipelined over the context's frame slots. After each frame
- * completes its float image/depth stay in slot (i % slots); `sink` (may be NULL) is called in
- * order with device pointers once frame i is complete. */
+/* n frames over the same scene. `sink` (may be NULL) is called once per frame, in order, with device
+ * pointers to the finished frame's float image / depth; they stay valid until the sink returns. With two output sets
+ * (mr_set_output_slots(ctx, 2)) frame i + 1 is already running on the device while the sink sees frame i - no
+ * device-wide synchronisation per frame; with one set every frame is finished and delivered before the next is launched.
+ * A frame that overflowed its spill list is rendered again before it is delivered. Without a sink the frames are
+ * launched back to back and the call returns when the last one is complete. */
 typedef void (*mr_frame_sink)(void* user, int index, const float* d_image, const float* d_depth);
 MR_API int mr_render_batch(mr_ctx* ctx, int n, const mr_frame* frames, mr_frame_sink sink, void* user);
 
 MR_API int mr_synchronize(mr_ctx* ctx);
+/* blocking copy out of a device pointer the library handed out (a sink's d_image / d_depth, mr_device_buffers) */
+MR_API int mr_download(mr_ctx* ctx, void* host, const void* d_src, size_t bytes);
 
 /* Blocking device->host reads of the last frame (full image, row-major, row 0 = top). */
 MR_API int mr_read_image(mr_ctx* ctx, float* host_rgb /* h*w*3 */);

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "mr_render": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_render_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mr_synchronize": (C.c_int, [C.c_void_p]),
+    "mr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "mr_read_image": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_read_depth": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_read_normals": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -321,6 +322,17 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.mr_synchronize(self.ctx), "mr_synchronize")
+
+    def render_batch(self, frames, sink=None):
+        """mr_render_batch over a list of FrameArrays. `sink(index, d_image, d_depth)` gets device pointers (ints)."""
+        arr = (Frame * max(len(frames), 1))(*[f.frame for f in frames])
+        cb = FRAME_SINK((lambda user, i, di, dd: sink(i, di, dd)) if sink else 0)
+        self._check(self.lib.mr_render_batch(self.ctx, len(frames), arr, cb if sink else None, None), "mr_render_batch")
+
+    def download(self, d_ptr, shape):
+        out = np.empty(shape, np.float32)
+        self._check(self.lib.mr_download(self.ctx, out.ctypes.data, d_ptr, out.nbytes), "mr_download")
+        return out
 
     def read_image(self, out=None):
         out = np.empty((self.h, self.w, 3), np.float32) if out is None else out

@@ -1131,23 +1131,80 @@ int mr_render(mr_ctx* c, const mr_frame* f)
 	return launchFrame(c, f, 0);
 }
 
+// Delivers frame `index` of a batch to the sink once it is complete. `slot` / `out` are the frame slot (counters) and
+// the output set it was rendered into. A frame that overflowed its spill list is rendered again first (everything in
+// flight is finished for that: rare, and the capacities have been raised by then).
+static int deliverBatchFrame(mr_ctx* c, const mr_frame* frames, int index, int slot, int out, mr_frame_sink sink, void* user)
+{
+	int rc = retireSlot(c, slot); // waits for the frame's kernels and its counters, not for younger frames
+	if (rc < 0)
+		return rc;
+	if (rc > 0)
+	{
+		rc = finishFrame(c); // (re-renders the newest frame too if that one overflowed as well)
+		if (rc)
+			return rc;
+		const int keepCur = c->outCur;
+		c->outCur = out; // render into the set the frame was in: the younger frame's set stays untouched
+		MR_CUDA(c, cudaMemsetAsync(c->gkeys.p, 0xff, (size_t)c->w * c->h * 8, c->stream));
+		rc = launchFrame(c, &frames[index], 0, true);
+		if (rc == MR_OK)
+			rc = retireSlot(c, c->slotNewest) > 0 ? setError(c, MR_E_OVERFLOW, "batch frame %d kept overflowing its spill list", index) : MR_OK;
+		c->outCur = keepCur;
+		if (rc)
+			return rc;
+		MR_CUDA(c, cudaMemsetAsync(c->gkeys.p, 0xff, (size_t)c->w * c->h * 8, c->stream));
+		MR_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	sink(user, index, c->imageSlot[out].as<float>(), c->depthSlot[out].as<float>());
+	return MR_OK;
+}
+
 int mr_render_batch(mr_ctx* c, int n, const mr_frame* frames, mr_frame_sink sink, void* user)
 {
 	if (!c || n < 0 || (n > 0 && !frames))
 		return MR_E_INVALID;
+	Bind bind(c->device);
+	// With two output sets the kernels of frame i + 1 are in flight while the sink looks at frame i; with one set
+	// every frame is finished and delivered before the next one is launched.
+	int prevSlot = -1, prevOut = -1;
 	for (int i = 0; i < n; i++)
 	{
+		if (sink && prevSlot >= 0 && c->outSlots < 2)
+		{
+			const int rc = deliverBatchFrame(c, frames, i - 1, prevSlot, prevOut, sink, user);
+			if (rc)
+				return rc;
+			prevSlot = -1;
+		}
 		int rc = mr_render(c, &frames[i]);
 		if (rc)
 			return rc;
-		if (sink)
+		const int slot = c->slotNewest, out = c->outCur;
+		if (sink && prevSlot >= 0)
 		{
-			rc = finishFrame(c);
+			rc = deliverBatchFrame(c, frames, i - 1, prevSlot, prevOut, sink, user);
 			if (rc)
 				return rc;
-			sink(user, i, c->imageSlot[c->outCur].as<float>(), c->depthSlot[c->outCur].as<float>());
 		}
+		prevSlot = slot;
+		prevOut = out;
 	}
+	if (sink && prevSlot >= 0)
+	{
+		const int rc = deliverBatchFrame(c, frames, n - 1, prevSlot, prevOut, sink, user);
+		if (rc)
+			return rc;
+	}
+	return sink ? MR_OK : finishFrame(c);
+}
+
+int mr_download(mr_ctx* c, void* host, const void* d_src, size_t bytes)
+{
+	if (!c || !host || !d_src)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	MR_CUDA(c, cudaMemcpy(host, d_src, bytes, cudaMemcpyDeviceToHost));
 	return MR_OK;
 }
 

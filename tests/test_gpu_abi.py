@@ -319,3 +319,48 @@ def test_in_place_mesh_edits_are_rendered(be, ref):
         rep = compare(out["gpu"][k][0], out["gpu"][k][1], out["ref"][k][0], out["ref"][k][1])
         assert_parity(rep, "frame %d after in-place edits" % k)
     assert (out["ref"][1][1] != out["ref"][0][1]).any() and (out["ref"][2][1] != out["ref"][1][1]).any()
+
+
+def _turntable_frames(be, n, **kw):
+    """n views of the small benchmark scene as self-contained mr_frame descriptors (+ the scene descriptor's owner)."""
+    setup = scenes.SMALL_SCENES["bench_small"](be)
+    r = setup.apply(m.Renderer(be))
+    frames = []
+    for i in range(n):
+        r.set_view(be.mul(be.translate(0, 0, -700), be.rotate_x(np.float32(-1.2)), be.rotate_z(np.float32(0.35 * i))))
+        r.prepare()
+        frames.append(cabi.FrameArrays(**dict(cabi.frame_to_dict(r.frame_desc_ptr()), **kw)))
+    return setup, r, frames
+
+
+@pytest.mark.parametrize("slots", [1, 2])
+def test_render_batch_equals_frames_rendered_one_by_one(be, ctx, slots):
+    """mr_render_batch: every frame reaches the sink once, in order, bit-identical to mr_render of the
+    same descriptor - with two output sets the next frame is already in flight while the sink copies this one."""
+    setup, r, frames = _turntable_frames(be, 7)
+    ctx.set_size(setup.width, setup.height)
+    ctx.upload_scene(r.scene_desc_ptr())
+    ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 1), "slots")
+    single = []
+    for f in frames:
+        ctx.render(f.ptr)
+        single.append((ctx.read_image(), ctx.read_depth()))
+    assert (bits(single[0][0]) != bits(single[3][0])).any()
+    ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, slots), "slots")
+    got = {}
+
+    def sink(i, d_image, d_depth):
+        assert i == len(got)
+        got[i] = (ctx.download(d_image, (setup.height, setup.width, 3)), ctx.download(d_depth, (setup.height, setup.width)))
+    try:
+        ctx.render_batch(frames, sink)
+        assert sorted(got) == list(range(7))
+        for i in range(7):
+            assert (bits(got[i][0]) == bits(single[i][0])).all(), i
+            assert (bits(got[i][1]) == bits(single[i][1])).all(), i
+        # without a sink: launched back to back, the last frame is what the context holds afterwards
+        ctx.render_batch(frames[:4])
+        assert (bits(ctx.read_depth()) == bits(single[3][1])).all()
+        assert (bits(ctx.read_image()) == bits(single[3][0])).all()
+    finally:
+        ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 1), "slots")
