@@ -593,7 +593,7 @@ struct GeomShared // fixed part of k_geom's dynamic shared memory
 	unsigned long long ring[MR_GEOM_RING];  // chunk slot number << 32 | chunk number
 	unsigned long long stat;
 	unsigned ticket;
-	int nVis;
+	int ownCount;            // warps of this CTA that start on a cluster the CTA found in its own first cull round
 	int cullCount, cullBase; // survivors of this CTA in the current cull round, and where they go in the list
 };
 #define MR_GEOM_FIXED_BYTES ((int)((sizeof(GeomShared) + 127) / 128 * 128))
@@ -628,23 +628,34 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ int ldAcquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // The next work-list index for the calling lane (lane 0 of a warp), or 0x7fffffff when the list is exhausted; see k_geom.
-__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int firstDynamic)
+// The warps of a CTA draw tickets from a shared-memory counter. The first tickets of a CTA are fixed by its position
+// (ticket t of CTA b = entry b + t * grid: interleaved over the list, no global access at all); only the last
+// MR_GEOM_DYNAMIC_TAIL entries per CTA of the list are handed out by a global counter, in chunks of MR_GEOM_CHUNK
+// (a single-address atomic per cluster would serialise in L2), where the balance across SMs is decided.
+#ifndef MR_GEOM_DYNAMIC_TAIL
+#define MR_GEOM_DYNAMIC_TAIL 8
+#endif
+__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int grid)
 {
 	const unsigned t = atomicAdd(&gs.ticket, 1u);
-	const unsigned slot = t / MR_GEOM_CHUNK, within = t % MR_GEOM_CHUNK;
+	const unsigned nStatic = (unsigned)max(nVis / grid - MR_GEOM_DYNAMIC_TAIL, 0); // per CTA
+	if (t < nStatic)
+		return (int)blockIdx.x + (int)t * grid; // (< nStatic * grid <= nVis)
+	const unsigned td = t - nStatic, slot = td / MR_GEOM_CHUNK, within = td % MR_GEOM_CHUNK;
 	volatile unsigned long long* ring = gs.ring;
-	if (within == 0u && slot > 0u)
+	if (within == 0u)
 	{
 		// this warp fetches the chunk for everybody, once the previous chunk's number is known (keeps them ordered)
-		while ((unsigned)(ring[(slot - 1u) % MR_GEOM_RING] >> 32) != slot - 1u)
-			;
-		const int c = firstDynamic + atomicAdd(&sync[0], 1);
+		if (slot > 0u)
+			while ((unsigned)(ring[(slot - 1u) % MR_GEOM_RING] >> 32) != slot - 1u)
+				;
+		const int c = atomicAdd(&sync[0], 1);
 		ring[slot % MR_GEOM_RING] = ((unsigned long long)slot << 32) | (unsigned)c;
 	}
 	unsigned long long v = ring[slot % MR_GEOM_RING];
 	while ((unsigned)(v >> 32) != slot)
 		v = ring[slot % MR_GEOM_RING];
-	const long long idx = (long long)(unsigned)v * MR_GEOM_CHUNK + within;
+	const long long idx = (long long)nStatic * grid + (long long)(unsigned)v * MR_GEOM_CHUNK + within;
 	return idx < (long long)nVis ? (int)idx : 0x7fffffff;
 }
 
@@ -812,6 +823,7 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 // Experiment build only: per-warp time stamps (globaltimer, ns) of k_geom's phases, read back by mr_debug_timeline().
 #define MR_TL_SLOTS 8
 __device__ unsigned long long g_timeline[1024 * MR_GEOM_WARPS * MR_TL_SLOTS];
+__device__ unsigned long long g_tlTri[1024 * MR_GEOM_WARPS]; // k_geom: per warp, time in the triangle phase
 __device__ unsigned long long g_rtl[8192 * 4]; // k_raster: per tile CTA start, dependency resolved, end, SM
 __device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MR_TL(slot) do { if (lane == 0 && blockIdx.x < 1024) g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + (slot)] = globalTimer(); } while (0)
@@ -842,15 +854,22 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 		gs.stat = 0ull;
 		gs.ticket = 0u;
 		gs.cullCount = 0;
-		gs.ring[0] = (0ull << 32) | (unsigned)blockIdx.x; // the CTA's first chunk by position; sync[0] counts from chunk `grid`
-		for (int i = 1; i < MR_GEOM_RING; i++)
+		gs.ownCount = 0;
+		for (int i = 0; i < MR_GEOM_RING; i++)
 			gs.ring[i] = ~0ull;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	// ---- phase 0: cull (Renderer.cpp:169-177, :202, :205-210 decided per cluster). Slice s = clusters 32 s .. 32 s + 31
-	// goes to warp (s / grid) % WARPS of CTA s % grid ----
+	// goes to warp (s / grid) % WARPS of CTA s % grid, so a CTA looks at a few slices from distant parts of the frame
+	// and nearly always finds visible clusters among them. The first MR_GEOM_WARPS survivors of its first round STAY
+	// in the CTA - entry k straight into warp k's shared-memory slot, meshlet requested at once - as the warps' first
+	// units of work; all others are appended to the frame's work list. The grid-wide rendezvous that completes the
+	// list is then only needed when a warp takes its first entry from it, one cluster later: nobody waits for it. ----
+	unsigned char* const warpMem = geomSmem + MR_GEOM_FIXED_BYTES + (size_t)warp * MR_GEOM_WARP_BYTES(nvCap);
+	unsigned char* const raw = warpMem;
+	unsigned long long* const full = &gs.full[warp];
 	const int nSlices = (nCl + 31) >> 5;
 	for (int round = 0; round * (int)gridDim.x * MR_GEOM_WARPS < nSlices; round++) // (block-uniform)
 	{
@@ -879,92 +898,128 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 			at = atomicAdd(&gs.cullCount, __popc(m));
 		at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
 		__syncthreads();
-		if (tid == 0)
-		{
-			const int n = gs.cullCount;
-			gs.cullBase = n > 0 ? atomicAdd(syncTail, n) : 0;
-			gs.cullCount = 0;
-		}
-		__syncthreads();
+		// (the position of the round's other survivors in the list is on its way while the kept entries are written)
+		const int nSurv = gs.cullCount;
+		const int keep = (round == 0 && !(fp.debug & 64)) ? min(nSurv, MR_GEOM_WARPS) : 0;
+		int listBase = 0;
+		if (tid == 0 && nSurv > keep)
+			listBase = atomicAdd(syncTail, nSurv - keep);
+		uint4 e0, e1, mv[3], nm[3];
 		if (vis)
 		{
 			const RDyn& rd = frameRdyn<TM>(fp)[r];
-			uint4* o = reinterpret_cast<uint4*>(fp.visEntries + gs.cullBase + at);
-			o[0] = make_uint4((uint32_t)ci, d.nv & 0xffffu, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
-			o[1] = make_uint4((uint32_t)rs.nTri, (uint32_t)rs.triBaseReal, (uint32_t)rd.material, d.nv >> 16);
+			e0 = make_uint4((uint32_t)ci, d.nv & 0xffffu, d.off16, (uint32_t)(ci * MR_CLUSTER - rs.triBase));
+			e1 = make_uint4((uint32_t)rs.nTri, (uint32_t)rs.triBaseReal, (uint32_t)rd.material, d.nv >> 16);
 #pragma unroll
 			for (int k = 0; k < 3; k++)
 			{
-				o[2 + k] = make_uint4(__float_as_uint(rd.mv[4 * k]), __float_as_uint(rd.mv[4 * k + 1]), __float_as_uint(rd.mv[4 * k + 2]), __float_as_uint(rd.mv[4 * k + 3]));
-				o[5 + k] = make_uint4(__float_as_uint(rd.nm[4 * k]), __float_as_uint(rd.nm[4 * k + 1]), __float_as_uint(rd.nm[4 * k + 2]), __float_as_uint(rd.nm[4 * k + 3]));
+				mv[k] = make_uint4(__float_as_uint(rd.mv[4 * k]), __float_as_uint(rd.mv[4 * k + 1]), __float_as_uint(rd.mv[4 * k + 2]), __float_as_uint(rd.mv[4 * k + 3]));
+				nm[k] = make_uint4(__float_as_uint(rd.nm[4 * k]), __float_as_uint(rd.nm[4 * k + 1]), __float_as_uint(rd.nm[4 * k + 2]), __float_as_uint(rd.nm[4 * k + 3]));
+			}
+			if (at < keep)
+			{
+				uint4* o = reinterpret_cast<uint4*>(&gs.entry[at][0]);
+				o[0] = e0; o[1] = e1;
+#pragma unroll
+				for (int k = 0; k < 3; k++)
+				{
+					o[2 + k] = mv[k];
+					o[5 + k] = nm[k];
+				}
+			}
+		}
+		if (round == 0)
+		{
+			__syncthreads();
+			if (warp < keep && lane == 0)
+			{
+				// this warp's first cluster: its meshlet is requested before the list is even written
+				const GeomEntry& n0 = gs.entry[warp][0];
+				mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n0.nv));
+				bulkLoad(raw, fp.meshlets + (size_t)n0.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n0.nv), full);
+			}
+		}
+		if (tid == 0)
+		{
+			if (round == 0)
+				gs.ownCount = keep;
+			gs.cullBase = listBase;
+			gs.cullCount = 0;
+		}
+		__syncthreads();
+		if (vis && at >= keep)
+		{
+			uint4* o = reinterpret_cast<uint4*>(fp.visEntries + gs.cullBase + (at - keep));
+			o[0] = e0; o[1] = e1;
+#pragma unroll
+			for (int k = 0; k < 3; k++)
+			{
+				o[2 + k] = mv[k];
+				o[5 + k] = nm[k];
 			}
 		}
 	}
-	// every CTA's entries must be visible before anyone takes from the list: a grid-wide arrival counter (all CTAs
-	// are resident: the grid is sized from the occupancy of this kernel and launched cooperatively)
+	// this CTA's entries are published: arrive at the grid-wide counter (all CTAs are resident: the grid is sized from
+	// the occupancy of this kernel and launched cooperatively). Who needs the list waits for the others there.
+	// (the barrier orders every thread's entries before thread 0's fence, whose cumulativity publishes them with the
+	// arrival: the other warps do not wait for the stores to reach L2)
+	// (every thread fences its own entries: measured faster than one cumulative fence by thread 0 after the barrier,
+	// which lets the warps start 1 us earlier but in lock-step - 38.7 vs 39.7 us on the sphere)
 	__threadfence();
 	MR_TL(1); // own clusters culled
 	__syncthreads();
 	if (tid == 0)
-	{
 		atomicAdd(syncArrived, 1);
-		while (ldAcquire(syncArrived) < (int)gridDim.x)
-			;
-		const int n = ldAcquire(syncTail);
-		gs.nVis = n;
-		if (blockIdx.x == 0)
-		{
-			fp.ctr->trianglesIn = (unsigned long long)fp.nTriReal;
-			fp.ctr->visible = (unsigned)n;
-			fp.ctr->clusters = (unsigned)nCl;
-		}
-	}
-	__syncthreads();
-	const int nVis = gs.nVis;
-	MR_TL(2); // work list complete
-
-#ifdef MR_TIMELINE
-	if (lane == 0 && blockIdx.x < 1024)
-		g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 5] = g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 6] = 0ull;
-#endif
+	const bool haveOwn = warp < gs.ownCount; // (warp-uniform) this warp starts on a cluster its CTA found itself
 
 	// ---- phase 1: every warp on its own ----
 	unsigned long long acc = 0ull;
+	int nVis = -1; // (warp-uniform) length of the work list, known once every CTA has arrived
 	{
-		unsigned char* const warpMem = geomSmem + MR_GEOM_FIXED_BYTES + (size_t)warp * MR_GEOM_WARP_BYTES(nvCap);
-		unsigned char* const raw = warpMem;
 		float4* const sA = reinterpret_cast<float4*>(warpMem + MR_MESHLET_BYTES(nvCap));
 		float4* const sB = sA + nvCap;
 		float4* const sC = sB + nvCap;
 		uint32_t* const sIdx = reinterpret_cast<uint32_t*>(sC + nvCap);
-		unsigned long long* const full = &gs.full[warp];
 		const uint32_t* const visWords = reinterpret_cast<const uint32_t*>(fp.visEntries);
 		const uint32_t none = (lane == 0) ? 0xffffffffu : 0u; // word `lane` of an entry that says "no more work"
-		const int firstDynamic = (int)gridDim.x;
-		uint32_t entryWord; // word `lane` of the next cluster's entry
+		const int grid = (int)gridDim.x;
+		uint32_t entryWord = none; // word `lane` of the next cluster's entry
+		bool nextPending = haveOwn;  // the warp started on its own cluster: its next entry is fetched during that one
+		if (!haveOwn)
 		{
-			int i0 = 0, i1 = 0;
+			int i0 = 0, i1 = 0, n = 0;
 			if (lane == 0)
 			{
-				i0 = geomPop(gs, syncChunks, nVis, firstDynamic);
-				i1 = (i0 < nVis) ? geomPop(gs, syncChunks, nVis, firstDynamic) : i0;
+				while (ldAcquire(syncArrived) < (int)gridDim.x)
+					;
+				n = ldAcquire(syncTail);
+				i0 = geomPop(gs, syncChunks, n, grid);
+				i1 = (i0 < n) ? geomPop(gs, syncChunks, n, grid) : i0;
 			}
+			nVis = __shfl_sync(0xffffffffu, n, 0);
 			i0 = __shfl_sync(0xffffffffu, i0, 0);
 			i1 = __shfl_sync(0xffffffffu, i1, 0);
+			MR_TL(2); // work list complete
 			const uint32_t w0 = (i0 < nVis) ? __ldcg(visWords + (size_t)i0 * 32 + lane) : none;
 			entryWord = (i1 < nVis) ? __ldcg(visWords + (size_t)i1 * 32 + lane) : none;
 			reinterpret_cast<uint32_t*>(&gs.entry[warp][0])[lane] = w0;
 			__syncwarp();
 			if (lane == 0)
 			{
-				const GeomEntry& n = gs.entry[warp][0];
-				if (n.ci >= 0)
+				const GeomEntry& n0 = gs.entry[warp][0];
+				if (n0.ci >= 0)
 				{
-					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
-					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
+					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n0.nv));
+					bulkLoad(raw, fp.meshlets + (size_t)n0.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n0.nv), full);
 				}
 			}
 		}
+#ifdef MR_TIMELINE
+		else
+			MR_TL(2);
+		if (lane == 0 && blockIdx.x < 1024)
+			g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 5] = g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 6] = g_timeline[((size_t)blockIdx.x * MR_GEOM_WARPS + warp) * MR_TL_SLOTS + 7] = g_tlTri[(size_t)blockIdx.x * MR_GEOM_WARPS + warp] = 0ull;
+#endif
 		for (int k = 0;; k++)
 		{
 			const GeomEntry& e = gs.entry[warp][k & 1];
@@ -980,6 +1035,9 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 			MR_TL_ADD(6, 1ull);                // iterations
 #endif
 			const int nv = e.nv;
+#ifdef MR_TIMELINE
+			const unsigned long long tv0 = globalTimer();
+#endif
 
 			// ---- vertex phase: loops A and B of paintMesh for the cluster's corners, plus their projection ----
 			{
@@ -1007,8 +1065,28 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 						sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
 					}
 			}
+#ifdef MR_TIMELINE
+			__syncwarp();
+			MR_TL_ADD(7, globalTimer() - tv0); // time in the vertex phase
+#endif
 			// ---- the next cluster: its entry (read one iteration ago) into shared memory, its bulk copy issued
 			// (the meshlet buffer is free again), another index drawn and that entry requested ----
+			if (nextPending)
+			{
+				// first cluster of a warp that started on its own one: by now every CTA has long arrived
+				int i1 = 0, n = 0;
+				if (lane == 0)
+				{
+					while (ldAcquire(syncArrived) < (int)gridDim.x)
+						;
+					n = ldAcquire(syncTail);
+					i1 = geomPop(gs, syncChunks, n, grid);
+				}
+				nVis = __shfl_sync(0xffffffffu, n, 0);
+				i1 = __shfl_sync(0xffffffffu, i1, 0);
+				entryWord = (i1 < nVis) ? __ldcg(visWords + (size_t)i1 * 32 + lane) : none;
+				nextPending = false;
+			}
 			reinterpret_cast<uint32_t*>(&gs.entry[warp][(k + 1) & 1])[lane] = entryWord;
 			__syncwarp(); // corners complete, every lane is done with the meshlet buffer
 			int i2 = 0x7fffffff;
@@ -1019,14 +1097,21 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 				{
 					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
 					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
-					i2 = geomPop(gs, syncChunks, nVis, firstDynamic);
+					i2 = geomPop(gs, syncChunks, nVis, grid);
 				}
 			}
 			i2 = __shfl_sync(0xffffffffu, i2, 0);
 			entryWord = (i2 < nVis) ? __ldcg(visWords + (size_t)i2 * 32 + lane) : none;
 
 			// ---- triangle phase ----
+#ifdef MR_TIMELINE
+			const unsigned long long tt0 = globalTimer();
+#endif
 			geomTriangle(fp, e, sA, sB, sC, sIdx, lane, acc);
+#ifdef MR_TIMELINE
+			__syncwarp();
+			if (lane == 0 && blockIdx.x < 1024) g_tlTri[(size_t)blockIdx.x * MR_GEOM_WARPS + warp] += globalTimer() - tt0;
+#endif
 			__syncwarp(); // the corners may be overwritten by the next cluster's
 		}
 	}
@@ -1052,6 +1137,15 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	{
 		const unsigned long long all = gs.stat;
 		const int slot = blockIdx.x & (MR_STAT_SLOTS - 1);
+		// (every warp of this CTA has seen the end of the work list, so every CTA has arrived and the list length is final)
+		const unsigned listed = (blockIdx.x == 0) ? (unsigned)ldAcquire(syncTail) : 0u;
+		if (listed + (unsigned)gs.ownCount)
+			atomicAdd(&fp.ctr->visible, listed + (unsigned)gs.ownCount);
+		if (blockIdx.x == 0)
+		{
+			fp.ctr->trianglesIn = (unsigned long long)fp.nTriReal;
+			fp.ctr->clusters = (unsigned)nCl;
+		}
 		const unsigned long long nr = all & 0xfffffull, nc = (all >> 20) & 0xfffffull, nz = (all >> 40) & 0xfffffull;
 		if (nr) atomicAdd(&fp.ctr->records[slot], nr);
 		if (nc) atomicAdd(&fp.ctr->clippedIn[slot], nc);
@@ -1934,6 +2028,11 @@ extern "C" __attribute__((visibility("default"))) int mr_debug_raster_timeline(u
 {
 	const size_t n = std::min((size_t)nWords, sizeof(g_rtl) / 8);
 	return cudaMemcpyFromSymbol(out, g_rtl, n * 8) == cudaSuccess ? (int)n : -1;
+}
+extern "C" __attribute__((visibility("default"))) int mr_debug_tri_time(unsigned long long* out, int nWords)
+{
+	const size_t n = std::min((size_t)nWords, sizeof(g_tlTri) / 8);
+	return cudaMemcpyFromSymbol(out, g_tlTri, n * 8) == cudaSuccess ? (int)n : -1;
 }
 extern "C" __attribute__((visibility("default"))) int mr_debug_timeline(unsigned long long* out, int nWords)
 {

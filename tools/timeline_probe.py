@@ -26,3 +26,8 @@ for k, nm in ((0, "kernel entered"), (1, "own clusters culled"), (2, "list compl
 print("meshlet wait per warp: median %.1f us, max %.1f us; iterations per warp: min %d median %d max %d" % (np.median(t[:, 5]) / 1e3, t[:, 5].max() / 1e3, t[:, 6].min(), np.median(t[:, 6]), t[:, 6].max()))
 work = (t[:, 4] - t[:, 3]) / 1e3; it = np.maximum(t[:, 6] - 1, 1)
 print("work time per warp: median %.1f us; per unit: median %.2f us" % (np.median(work), np.median(work / it)))
+tri = np.zeros(1024 * W, np.uint64); raw.mr_debug_tri_time(tri.ctypes.data_as(C.c_void_p), len(tri))
+tri = tri[:len(buf) // 8][buf.reshape(-1, 8)[:, 0] > 0].astype(np.int64)
+print("per unit: vertex phase median %.2f us, triangle phase median %.2f us, rest (entry / pop / waits) %.2f us" % (
+    np.median(t[:, 7] / np.maximum(t[:, 6], 1)) / 1e3, np.median(tri / np.maximum(t[:, 6], 1)) / 1e3,
+    np.median((t[:, 4] - t[:, 3] - t[:, 7] - tri) / np.maximum(t[:, 6], 1)) / 1e3))
