@@ -426,10 +426,19 @@ def run_ours(args, rank, local_rank, world):
         # index arrays, k_raster writes image + depth
         dom_bytes = {"k_geom": 24 * n_pos + 24 * n_tri, "k_raster": raster_bytes}[dom]
         ach = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes of the dominant kernel from the committed ncu capture - only if that capture was made on the kernel
+        # source this run executes (profiles/ncu_summary.json records the file's hash: tools/make_ncu_summary.py)
+        traffic, traffic_note, frame_traffic = None, "no ncu capture of this kernel source (profiles/ncu_summary.json is missing or older than mr_kernels.cu)", None
         try:
+            import hashlib
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+                summ = json.load(f)
+            with open(os.path.join(ROOT, "minirender_b200", "csrc", "mr_kernels.cu"), "rb") as f:
+                fresh = summ.get("kernels_sha256") == hashlib.sha256(f.read()).hexdigest()
+            if fresh:
+                traffic = summ.get(dom, {}).get("dram_bytes_per_launch")
+                frame_traffic = summ.get("frame", {}).get("dram_bytes_per_frame_no_flush")
+                traffic_note = summ.get(dom, {}).get("source")
         except Exception:
             pass
         line = {
@@ -460,9 +469,10 @@ def run_ours(args, rank, local_rank, world):
             "kernels_per_step": int(st.kernels_launched),
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src},
             "frame_roofline": {"algorithmic_bytes_per_frame": frame_bytes, "achieved": frame_bytes / (dev_ms_max / K * 1e-3) / 1e9,
-                               "unit": "GB/s", "frac": frame_bytes / (dev_ms_max / K * 1e-3) / 1e9 / peak},
+                               "unit": "GB/s", "frac": frame_bytes / (dev_ms_max / K * 1e-3) / 1e9 / peak,
+                               "traffic_no_flush": frame_traffic},
             "ms_per_step_per_rank": per_rank,
             "ms_per_step_rank0": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
             "clocks": clocks,
