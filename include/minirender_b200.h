@@ -153,6 +153,8 @@ typedef struct mr_stats
 	int64_t clusters;          /* 32-triangle clusters of the frame ... */
 	int64_t clusters_visible;  /* ... and how many of them survived cluster culling */
 	int64_t tiles_stored;      /* 16x16 tiles the tile kernel wrote (with sparse remote stores: the touched ones only) */
+	int64_t chk_entries;       /* edge-chain checkpoints written for wide triangles (0: the frame ran without k_chain) */
+	int64_t chk_demand;        /* ... and how many the frame's wide triangles asked for */
 } mr_stats;
 
 MR_API int mr_abi_version(void);
@@ -246,7 +248,10 @@ MR_API int mr_host_unregister(void* host);
  * flags & 4 turns cluster culling off, flags & 8 the standard-perspective vertex path and flags & 16 the tight scan of
  * small triangles (every cluster is set up / every corner goes through the general htransform / every pixel centre of
  * the reference's loops is tested): the image must not change, which is what the tests use them for. (The environment
- * variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ / MR_NO_TIGHT_SCAN do the same for a whole process.) */
+ * variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ / MR_NO_TIGHT_SCAN do the same for a whole process.)
+ * flags & 64: no warp starts on a cluster of its own cull round (every cluster goes through the work list).
+ * flags & 128 / 256: edge-chain checkpoints of wide triangles (k_chain) forced on from the first frame / off (normally a
+ * frame runs k_chain when the frame before it had wide triangles; MR_NO_CHAIN_CHECKPOINTS in the environment = 256). */
 MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 

@@ -59,7 +59,8 @@ class Stats(C.Structure):
                 ("bin_entries", C.c_int64), ("zero_coverage", C.c_int64),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("regrows", C.c_int32),
                 ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8), ("h2d_bytes", C.c_int64),
-                ("clusters", C.c_int64), ("clusters_visible", C.c_int64), ("tiles_stored", C.c_int64)]
+                ("clusters", C.c_int64), ("clusters_visible", C.c_int64), ("tiles_stored", C.c_int64),
+                ("chk_entries", C.c_int64), ("chk_demand", C.c_int64)]
 
 
 FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)

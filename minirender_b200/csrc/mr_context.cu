@@ -117,8 +117,11 @@ struct mr_ctx
 
 	// scratch
 	DevBuf recs, recs1, tileCount, ovfPairs, bins, ctr, gkeys;
+	DevBuf chkPool, chkItems; // edge-chain checkpoints of wide triangles (k_chain): sized from the previous frames' demand
+	size_t chkWantEntries, chkWantItems;
+	bool chkActive;           // the most recently retired frame had wide triangles: the following frames run k_chain
 	bool slotOverflowed; // a frame older than the newest one overflowed its spill list (async readers are told)
-	bool noClusterCull, noPdl, noStdProj, noTightScan; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
+	bool noClusterCull, noPdl, noStdProj, noTightScan, noChain; // MR_NO_CLUSTER_CULL / MR_NO_PDL in the environment when the context was created
 	int binCap;    // entries per tile bin
 	int binCapWanted;
 	size_t ovfCap; // entries in the overflow list
@@ -149,7 +152,7 @@ struct mr_ctx
 	mr_stats stats;
 
 	mr_ctx() : device(0), stream(0), ownStream(false), aux(0), w(0), h(0), tilesX(0), tilesY(0), haveScene(false), sceneSerial(0),
-	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), noTightScan(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0), sparseRemote(false), gateWord(0), gateValue(0),
+	           structureSerial(~0u), geomVertCap(0), geomGrid(0), geomSmem(0), nTriInst(0), slotOverflowed(false), noClusterCull(false), noPdl(false), noStdProj(false), noTightScan(false), noChain(false), chkWantEntries(0), chkWantItems(0), chkActive(false), slotNext(0), slotNewest(-1), binCap(0), binCapWanted(0), ovfCap(0), h2dBytesLastFrame(0), remoteImage(0), sparseRemote(false), gateWord(0), gateValue(0),
 	           remoteDepth(0), debugFlags(0), timingStart(0), timingStop(0), haveFrame(false), outSlots(1), outCur(0), copy(0)
 	{
 		frameDone[0] = frameDone[1] = copyDone[0] = copyDone[1] = 0;
@@ -247,6 +250,17 @@ int retireSlot(mr_ctx* c, int i)
 			want <<= 1;
 		c->binCapWanted = std::max(c->binCapWanted, want);
 	}
+	// wide triangles: their checkpoint demand decides whether the next frames run k_chain and with how much room
+	// (k_chain costs a launch and one serial walk over the widest row, ~4-8 us: it pays in frames dominated by triangles
+	// hundreds of pixels wide - a floor, walls, a backdrop - measured 312 -> 139 us of k_raster on two dozen of them)
+	c->chkActive = k.chkDemand >= (1u << 16);
+	if (k.chkDemand > 0)
+	{
+		c->chkWantEntries = std::max(c->chkWantEntries, (size_t)std::min<unsigned long long>(k.chkDemand + k.chkDemand / 4 + 4096, 0x7ff00000ull));
+		c->chkWantItems = std::max(c->chkWantItems, (size_t)k.chkItemDemand + (size_t)k.chkItemDemand / 4 + 1024);
+	}
+	c->stats.chk_entries = (int64_t)std::min<unsigned long long>(k.chkUsed, c->chkPool.cap / sizeof(float2));
+	c->stats.chk_demand = (int64_t)k.chkDemand;
 	if (!k.overflow)
 		return 0;
 	c->ovfCap = std::max(c->ovfCap, (size_t)k.ovfTotal + (size_t)k.ovfTotal / 4 + 1024);
@@ -392,6 +406,15 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 			return setError(c, MR_E_OVERFLOW, "more than 2^31 spilled (tile, triangle) pairs");
 		MR_CUDA(c, c->bins.ensure(sizeof(int) * (size_t)c->binCap * (size_t)nTiles));
 		MR_CUDA(c, c->ovfPairs.ensure(sizeof(int2) * c->ovfCap));
+	}
+	const bool chkEnable = (c->chkActive || (c->debugFlags & 128)) && !c->noChain && !(c->debugFlags & 256);
+	if (chkEnable)
+	{
+		// at most 1 GiB of checkpoints (a triangle that does not fit walks its chain in the tile kernel, as without them)
+		const size_t entries = std::min<size_t>(std::max<size_t>(c->chkWantEntries, (size_t)1 << 20), ((size_t)1 << 30) / sizeof(float2));
+		const size_t items = std::min<size_t>(std::max<size_t>(c->chkWantItems, (size_t)1 << 16), (size_t)1 << 24);
+		MR_CUDA(c, c->chkPool.ensure(sizeof(float2) * entries));
+		MR_CUDA(c, c->chkItems.ensure(sizeof(int4) * items));
 	}
 	int rc = ensureOutputs(c, f->save_normals != 0, (c->debugFlags & 1) != 0);
 	if (rc)
@@ -615,6 +638,12 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	fp.normals = f->save_normals ? c->normals.as<float>() : 0;
 	fp.winner = (c->debugFlags & 1) ? c->winner.as<int>() : 0;
 
+	fp.chkEnable = chkEnable ? 1 : 0;
+	fp.chkMinTiles = (c->debugFlags & 128) ? 2 : MR_CHK_MIN_TILES; // (forced on for verification: also for narrow triangles)
+	fp.chkPool = c->chkPool.as<float2>();
+	fp.chkItems = c->chkItems.as<int4>();
+	fp.chkCap = (int)std::min<size_t>(c->chkPool.cap / sizeof(float2), 0x7ff00000);
+	fp.chkItemCap = (int)std::min<size_t>(c->chkItems.cap / sizeof(int4), 0x7fffffff);
 	fp.sparseStores = (c->sparseRemote && c->remoteImage && !f->keep && !f->save_normals && !(c->debugFlags & 1)) ? 1 : 0;
 	mrk_launch_frame(fp, c->geomGrid, c->geomSmem, c->stream, ev, ev ? 0 : c->timingStart, ev ? 0 : c->timingStop, !c->noPdl, c->gateWord, c->gateValue);
 	c->gateWord = 0;
@@ -628,7 +657,7 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	slot.pending = true;
 	c->slotNewest = slotIndex;
 	c->slotNext = (slotIndex + 1) % mr_ctx::kSlots;
-	c->stats.kernels_launched = (fp.tileRows > 0) ? 2 : 1;
+	c->stats.kernels_launched = (fp.tileRows > 0) ? (chkEnable ? 3 : 2) : 1;
 	return MR_OK;
 }
 
@@ -850,6 +879,7 @@ mr_ctx* mr_create(int device, int* status)
 		cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device);
 		c->noClusterCull = getenv("MR_NO_CLUSTER_CULL") != 0; // verification switches, read once
 		c->noPdl = getenv("MR_NO_PDL") != 0;
+		c->noChain = getenv("MR_NO_CHAIN_CHECKPOINTS") != 0;
 		c->noStdProj = getenv("MR_NO_STD_PROJ") != 0;
 		c->noTightScan = getenv("MR_NO_TIGHT_SCAN") != 0;
 		bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -900,7 +930,7 @@ void mr_destroy(mr_ctx* c)
 		cudaStreamSynchronize(c->stream);
 	DevBuf* bufs[] = { &c->meshlets, &c->meshletDir, &c->texels, &c->clusters, &c->triBlockCl, &c->visEntries, &c->geomSync, &c->rstat,
 		               &c->rdyn, &c->mats, &c->recs, &c->tileCount,
-		               &c->ovfPairs, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf, &c->syncWords };
+		               &c->ovfPairs, &c->chkPool, &c->chkItems, &c->bins, &c->recs1, &c->gkeys, &c->ctr, &c->imageSlot[0], &c->depthSlot[0], &c->imageSlot[1], &c->depthSlot[1], &c->normals, &c->winner, &c->scratchOut, &c->flushBuf, &c->syncWords };
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		bufs[i]->release();
 	for (int i = 0; i < mr_ctx::kSlots; i++)

@@ -418,6 +418,32 @@ __device__ __forceinline__ void storeShadeRec(const RecRef d, const float4 B0, c
 	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 4 * d.stride, C1, C2);
 }
 
+// Edge-chain checkpoints for a wide binned triangle (record `id`, pixel loops x0..x1, y0..y1): reserves rows x (tile
+// boundaries inside the bbox) pool entries and one k_chain work item per block of 32 rows. Returns what goes into
+// bits 1..31 of the record's flags word (1 + first pool entry), or 0 - not wide enough, no k_chain this frame, or
+// the buffers are full - in which case the tile kernel walks the chain from the triangle's first column as before.
+// What the frame would have needed is counted either way: the host sizes the next frames' buffers from it.
+__device__ __noinline__ uint32_t chkReserve(const FrameParams& fp, int id, int x0, int x1, int y0, int y1)
+{
+	const int ntb = (x1 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT);
+	if (ntb < fp.chkMinTiles || y1 < y0)
+		return 0u;
+	const int rows = y1 - y0 + 1, nblk = (rows + 31) >> 5;
+	const unsigned n = (unsigned)rows * (unsigned)ntb;
+	atomicAdd(&fp.ctr->chkDemand, (unsigned long long)n);
+	atomicAdd(&fp.ctr->chkItemDemand, (unsigned)nblk);
+	if (!fp.chkEnable)
+		return 0u;
+	const unsigned base = atomicAdd(&fp.ctr->chkUsed, n);
+	const bool fits = (unsigned long long)base + n <= (unsigned long long)fp.chkCap && base + n < 0x7fffffffu;
+	const unsigned it = atomicAdd(&fp.ctr->chkItems, (unsigned)nblk);
+	const bool ok = fits && it + (unsigned)nblk <= (unsigned)fp.chkItemCap;
+	for (int b = 0; b < nblk; b++)
+		if (it + (unsigned)b < (unsigned)fp.chkItemCap)
+			fp.chkItems[it + b] = make_int4(ok ? id : -1, (int)base, b, 0); // (a reserved item is always written: k_chain reads them all)
+	return ok ? (base + 1u) << 1 : 0u;
+}
+
 // reference clip(), Renderer.cpp:121-129
 __device__ __forceinline__ Corner clipEdge(float z, const Corner& a, const Corner& b)
 {
@@ -527,13 +553,14 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 			continue;
 		if (min(s.y1 >> MR_TILE_SHIFT, tyHi) < max(s.y0 >> MR_TILE_SHIFT, tyLo))
 			continue;
-		s.flags = MR_REC_CLIPPED;
 		const int id = 2 * t + sub;
+		s.flags = MR_REC_CLIPPED | chkReserve(fp, id, s.x0, s.x1, s.y0, s.y1);
 		const RecRef ref = recRef(fp, id);
 		storeRec<false>(ref, a, b, c, s, material, submission + sub);
 		storeShadeRec<false>(ref, make_float4(o0.px, o0.py, o0.pz, o0.u), make_float4(o1.px, o1.py, o1.pz, o1.u), make_float4(o2.px, o2.py, o2.pz, o2.u),
 		                     make_float4(o0.nx, o0.ny, o0.nz, o0.v), make_float4(o1.nx, o1.ny, o1.nz, o1.v), make_float4(o2.nx, o2.ny, o2.nz, o2.v));
-		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
+		// (a sub-triangle with checkpoints is binned by k_chain: an empty span for the caller's warp)
+		spans[sub] = (s.flags >> 1) ? make_uint2(1u, 1u) : make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
 		nrec |= 1 << sub;
 	}
 	return nrec;
@@ -663,6 +690,18 @@ __device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int 
 // the whole warp, one triangle at a time) and of the clipper's output triangles. Called by all lanes of the warp.
 __device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, bool binned, int nrecSlow, int sx0, int sx1, int sy0, int sy1, uint2 clip0, uint2 clip1)
 {
+	// ---- wide triangles get checkpoints of their edge chains (k_chain): the first pool entry goes into the flags word of
+	// the record this lane has just stored (same thread, same address: ordered behind that store) ----
+	if (binned && (sx1 >> MR_TILE_SHIFT) - (sx0 >> MR_TILE_SHIFT) >= fp.chkMinTiles)
+	{
+		const uint32_t f = chkReserve(fp, 2 * t, sx0, sx1, sy0, sy1);
+		if (f != 0u)
+		{
+			const RecRef ref = recRef(fp, 2 * t);
+			reinterpret_cast<uint32_t*>(ref.p + ref.stride)[6] = f; // pair 1 = (depth terms, material | spans, FLAGS, submission)
+			binned = false; // k_chain bins it as well: one warp per 32 rows instead of this warp for the whole triangle
+		}
+	}
 	// ---- binning of the larger triangles: up to MR_SEG_PER_LANE tiles each, warp-aggregated ----
 	if (__any_sync(0xffffffffu, binned))
 	{
@@ -1154,6 +1193,70 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel 2 (only in frames with wide triangles): edge-chain checkpoints. The reference accumulates a row's edge
+// functions column by column from the triangle's first column (e1 += n1.x, Renderer.cpp:243); a tile far to the right
+// of that column would have to replay the whole prefix for each of its rows - quadratic in the triangle's width over
+// its tiles (the X3D-style cloud scene of configs[3] has triangles 958 pixels wide: 184 of its 243 us went there).
+// Here a warp takes one work item (a wide triangle, a block of 32 rows), a lane walks one row ONCE, with the
+// reference's own additions in the reference's order, and stores (e1, e2) as they stand at every tile boundary; the
+// tile kernel then starts at its own left edge with bit-identical values.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chain(const __grid_constant__ FrameParams fp)
+{
+	pdlLaunchDependents(); // k_raster's CTAs may become resident; they wait for this grid
+	pdlWait();             // k_geom's records, work items and counters
+	const int lane = threadIdx.x & 31;
+	const int nW = (int)(gridDim.x * blockDim.x) >> 5, gw = (int)(blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int n = (int)min(fp.ctr->chkItems, (unsigned)fp.chkItemCap);
+	for (int i = gw; i < n; i += nW)
+	{
+		const int4 it = fp.chkItems[i];
+		if (it.x < 0)
+			continue;
+		const RecRef ref = recRef(fp, it.x);
+		const F8 f01 = ldPair<L2_NORMAL>(ref.p), f23 = ldPair<L2_NORMAL>(ref.p + ref.stride);
+		const uint32_t xspan = __float_as_uint(f23.b.x), yspan = __float_as_uint(f23.b.y);
+		const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
+		const int ntb = (x1 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT);
+		{
+			// binning of this block's tiles (k_geom leaves triangles with checkpoints to this kernel): a tile row belongs
+			// to the block that holds its first row inside the bbox
+			const int ra = y0 + it.z * 32, rb = min(ra + 31, y1);
+			const int tx0 = x0 >> MR_TILE_SHIFT;
+			for (int ty = max(ra >> MR_TILE_SHIFT, fp.tileRow0); ty <= min(rb >> MR_TILE_SHIFT, fp.tileRow0 + fp.tileRows - 1); ty++)
+				if (max(ty << MR_TILE_SHIFT, y0) >= ra)
+					for (int tx = tx0 + lane; tx <= tx0 + ntb; tx += 32)
+					{
+						const int tile = ty * fp.tilesX + tx;
+						binStore(fp, tile, atomicAdd(&fp.tileCount[tile].x, 1), it.x);
+					}
+		}
+		const int row = it.z * 32 + lane, y = y0 + row;
+		if (y > y1 || y < fp.rowBegin || y >= fp.rowEnd)
+			continue;
+		const float n1x = f01.b.x, n1y = f01.b.y, n2x = f01.b.z, n2y = f01.b.w;
+		const float ptx = (float)x0 + 0.5f, fy = (float)y + 0.5f;
+		float e1 = n1x * (ptx - f01.a.z) + n1y * (fy - f01.a.w); // row start, Renderer.cpp:241-242
+		float e2 = n2x * (ptx - f01.a.x) + n2y * (fy - f01.a.y);
+		// entry (boundary tb, row) of a triangle's block is at tb * rows + row: the lanes of this warp (consecutive rows)
+		// write, and the 16 rows of a tile read, consecutive entries
+		const int rows = y1 - y0 + 1;
+		float2* out = fp.chkPool + (size_t)it.y + (size_t)row;
+		int x = x0;
+		for (int tb = 0; tb < ntb; tb++)
+		{
+			const int xe = ((x0 >> MR_TILE_SHIFT) + tb + 1) << MR_TILE_SHIFT; // the next tile boundary
+			for (; x < xe; x++)
+			{
+				e1 += n1x;
+				e2 += n2x;
+			}
+			out[(size_t)tb * rows] = make_float2(e1, e2);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel 3: tile rasterizer + resolve + shader. One CTA per 16x16 tile.
 // Phase 0: the tile's depth keys are fetched from gkeys (the small triangles' fragments have
 //   already been depth-tested there by k_setup) and the entries are reset for the next frame.
@@ -1436,40 +1539,57 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
 	__syncwarp();
 
-	// a quad of lanes scans each triangle of the batch, rows interleaved
+	// a group of lanes scans each triangle of the batch, rows interleaved: quads while the warp holds more than four
+	// triangles, 8 or 16 lanes each for the last few (a tile with a handful of big triangles keeps every lane busy)
 	unsigned large = __ballot_sync(0xffffffffu, have);
 	while (large != 0u)
 	{
-		const int q = lane & 3, quad = lane >> 2;
-		const int src = __fns(large, 0, quad + 1); // lane that owns this quad's triangle, or -1
+		const int left = __popc(large);
+		const int gshift = (left <= 2) ? 4 : (left <= 4) ? 3 : 2, G = 1 << gshift;
+		const int q = lane & (G - 1), quad = lane >> gshift;
+		const int src = __fns(large, 0, quad + 1); // lane that owns this group's triangle, or -1
 		const bool on = src >= 0 && src < 32;
 		const int s = on ? src : 0;
 		const float p0x = __shfl_sync(0xffffffffu, q0.x, s), p0y = __shfl_sync(0xffffffffu, q0.y, s);
 		const float p2x = __shfl_sync(0xffffffffu, q0.z, s), p2y = __shfl_sync(0xffffffffu, q0.w, s);
 		const float n1x = __shfl_sync(0xffffffffu, q1.x, s), n1y = __shfl_sync(0xffffffffu, q1.y, s);
 		const float n2x = __shfl_sync(0xffffffffu, q1.z, s), n2y = __shfl_sync(0xffffffffu, q1.w, s);
+		const int ry0 = __shfl_sync(0xffffffffu, y0, s);
 		const int bx0 = __shfl_sync(0xffffffffu, x0, s), bx1 = min(__shfl_sync(0xffffffffu, x1, s), tileX0 + MR_TILE - 1);
-		const int by0 = max(__shfl_sync(0xffffffffu, y0, s), tileY0), by1 = min(__shfl_sync(0xffffffffu, y1, s), tileY0 + MR_TILE - 1);
+		const int ry1 = __shfl_sync(0xffffffffu, y1, s);
+		const int by0 = max(ry0, tileY0), by1 = min(ry1, tileY0 + MR_TILE - 1);
+		// checkpoints of a wide triangle's chain (k_chain): 1 + its first pool entry, 0 = none
+		const uint32_t chk = __shfl_sync(0xffffffffu, __float_as_uint(q3.z), s) >> 1;
 		const int tslot = parity * 32 + s;
 		const int xs = max(bx0, tileX0);
 		const int ncols = on ? max(bx1 - xs + 1, 0) : 0;
-		const int myRows = on ? max((by1 - by0 - q + 4) >> 2, 0) : 0; // rows by0+q, by0+q+4, ...
+		const int myRows = on ? max((by1 - by0 - q + G) >> gshift, 0) : 0; // rows by0+q, by0+q+G, ...
 		const float ptx = (float)bx0 + 0.5f;
 		const int maxRows = __reduce_max_sync(0xffffffffu, myRows);
 		const int maxCols = __reduce_max_sync(0xffffffffu, ncols);
 		for (int rr = 0; rr < maxRows; rr++)
 		{
 			const bool rowOn = rr < myRows;
-			const int y = by0 + q + 4 * rr;
+			const int y = by0 + q + G * rr;
 			const float fy = (float)y + 0.5f;
 			float e1 = n1x * (ptx - p2x) + n1y * (fy - p2y);
 			float e2 = n2x * (ptx - p0x) + n2y * (fy - p0y);
-			if (rowOn)
-				for (int x = bx0; x < xs; x++) // chain prefix left of the tile
+			if (rowOn && xs > bx0)
+			{
+				if (chk != 0u)
 				{
-					e1 += n1x;
-					e2 += n2x;
+					// the chain as it stands at this tile's left edge, accumulated once by k_chain
+					const float2 cp = __ldg(fp.chkPool + (size_t)(chk - 1u) + (size_t)((tileX0 >> MR_TILE_SHIFT) - (bx0 >> MR_TILE_SHIFT) - 1) * (ry1 - ry0 + 1) + (y - ry0));
+					e1 = cp.x;
+					e2 = cp.y;
 				}
+				else
+					for (int x = bx0; x < xs; x++) // chain prefix left of the tile
+					{
+						e1 += n1x;
+						e2 += n2x;
+					}
+			}
 			const uint32_t rowInfo = (uint32_t)((y - tileY0) * MR_TILE + (xs - tileX0)) | ((uint32_t)tslot << 8);
 			for (int cc = 0; cc < maxCols; cc++, e1 += n1x, e2 += n2x)
 			{
@@ -1478,8 +1598,8 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 				pushFragment(fp, wq, keys, qhead, qcount, lane, inside, e1, e2, rowInfo + (uint32_t)cc);
 			}
 		}
-		// drop the (up to) eight triangles just done
-		for (int k = 0; k < 8 && large != 0u; k++)
+		// drop the triangles just done
+		for (int k = 0; k < (32 >> gshift) && large != 0u; k++)
 			large &= large - 1u;
 	}
 	// Triangle slots of this parity are overwritten two batches from now; fragments still queued
@@ -1508,9 +1628,10 @@ __device__ __forceinline__ void rasterBinned(const FrameParams& fp, int tile, in
 	const int* bin = fp.bins + (size_t)tile * fp.binCap;
 	int qhead = 0, qcount = 0; // warp-uniform
 	int parity = 0;
-	for (int base = (tid >> 5) * 32; base < count; base += MR_RASTER_THREADS)
+	// (the bin's triangles are dealt round-robin to the CTA's warps: a short bin is shared by all of them)
+	for (int base = 0; base < count; base += MR_RASTER_THREADS)
 	{
-		const int i = base + lane;
+		const int i = base + lane * (MR_RASTER_THREADS / 32) + (tid >> 5);
 		const bool have = i < count;
 		const int id = have ? __ldg(&bin[i]) : 0;
 		rasterBatch(fp, wq, keys, qhead, qcount, parity, lane, have, id, tileX0, tileY0);
@@ -1580,6 +1701,17 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	{
 		// (a prefix of a few columns is cheaper walked by every lane than matched and shuffled)
 		int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
+		const uint32_t chk = __float_as_uint(q3.z) >> 1;
+		if (prefix > 0 && chk != 0u)
+		{
+			// a wide triangle with checkpoints (k_chain): the chain as it stands at this tile's left edge
+			const int ry0 = (int)(__float_as_uint(q3.y) & 0xffffu), ry1 = (int)(__float_as_uint(q3.y) >> 16);
+			const float2 cp = __ldg(fp.chkPool + (size_t)(chk - 1u) + (size_t)((tileX0 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT) - 1) * (ry1 - ry0 + 1) + (py - ry0));
+			e1 = cp.x;
+			e2 = cp.y;
+			xcur = tileX0;
+			prefix = 0;
+		}
 		if (prefix <= MR_PREFIX_SHARE_MIN)
 			prefix = 0;
 		if (__any_sync(0xffffffffu, prefix > 0))
@@ -1994,6 +2126,17 @@ void mrk_launch_frame(const FrameParams& fp, int geomGrid, int geomSmem, cudaStr
 			cudaLaunchKernelEx(&cfg, k_geom<TM_INLINE>, fp);
 		else
 			cudaLaunchKernelEx(&cfg, k_geom<TM_GLOBAL>, fp);
+	}
+	if (fp.chkEnable && fp.tileRows > 0)
+	{
+		// frames with wide triangles: the checkpoints of their edge chains, between the two kernels
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.numAttrs = pdl ? 1 : 0;
+		cfg.gridDim = dim3(148 * 4);
+		cfg.blockDim = dim3(128);
+		cfg.dynamicSmemBytes = 0;
+		cudaLaunchKernelEx(&cfg, k_chain, fp);
 	}
 	if (ev) cudaEventRecord(ev[1], stream);
 	if (gateWord)

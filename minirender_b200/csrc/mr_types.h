@@ -102,7 +102,8 @@ struct __align__(16) MatDev
 
 // 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
 #define MR_REC_FIELDS 10 // float4 fields per record: 4 raster (struct Rec) + 6 shading (struct ShadeRec)
-#define MR_REC_CLIPPED 1u // produced by the near-plane clipper
+#define MR_REC_CLIPPED 1u // produced by the near-plane clipper (bits 1..31 of a record's flags word: 1 + its first checkpoint, 0 = none)
+#define MR_CHK_MIN_TILES 16 // triangles spanning at least this many tile-column boundaries get edge-chain checkpoints
 #define MR_KEY_EMPTY 0xffffffffffffffffull // gkeys[] entry no fragment has touched
 struct __align__(16) Rec
 {
@@ -139,7 +140,12 @@ struct Counters
 	unsigned int overflow;          // the overflow list did not fit: the frame must be re-run with more room
 	unsigned int pad0;
 	unsigned int visible, clusters; // k_geom: clusters that survived culling / clusters of the frame
-	unsigned long long pad1[12];
+	// edge-chain checkpoints of wide triangles (see k_chain): pool entries / work items handed out this frame, and what
+	// the frame would have needed (the host sizes the buffers of the following frames from these)
+	unsigned int chkUsed, chkItems;
+	unsigned long long chkDemand;
+	unsigned int chkItemDemand, pad1a;
+	unsigned long long pad1[9];
 	// line 1 (offset 128): written by k_raster
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
 	unsigned int pad2;
@@ -173,6 +179,14 @@ struct FrameParams
 	int persp, lightIsPoint, lighting, texturing, saveNormals, keep;
 	int tightScan; // small triangles skip the outermost columns / rows of the reference's loops where those provably cover nothing
 	int sparseStores; // tiles nothing was drawn into are not written (the target already holds the clear values)
+	// Edge-chain checkpoints (k_chain): for a wide triangle, the accumulated edge functions (e1, e2) of every row at
+	// every 16-column tile boundary of its bbox, so that a tile starts its replay of the reference's chain
+	// (Renderer.cpp:241-243) at its own left edge instead of at the triangle's.
+	float2* chkPool;   // [chkCap] entries; a triangle's block is rows x (tile boundaries inside its bbox), row-major
+	int4* chkItems;    // [chkItemCap] work items of k_chain: (record id, first pool entry, block of 32 rows, -)
+	int chkCap, chkItemCap;
+	int chkEnable;     // this frame runs k_chain: k_geom may hand out checkpoints
+	int chkMinTiles;   // ... to triangles whose bbox spans at least this many tile-column boundaries
 	int stdProj; // standard perspective matrix with the near plane in front of the eye: projectStd() applies
 	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags

@@ -34,6 +34,29 @@ def test_golden_through_c_abi(ctx, name):
         assert np.abs(ctx.read_normals() - want["normals"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["big_triangles", "clip", "ties", "textured"])
+def test_golden_with_edge_chain_checkpoints(name):
+    """The same fixtures with k_chain forced on from the first frame (mr_set_debug 128): wide triangles start their
+    edge chains at each tile's left edge from stored checkpoints; the result must not change by a bit."""
+    scene, frame, want = golden_io.load(name)
+    c = cabi.Context(0)
+    try:
+        c.set_debug(128)
+        c.set_size(want["width"], want["height"])
+        c.upload_scene(scene.ptr)
+        for _ in range(2):
+            c.render(frame.ptr)
+            rep = compare(c.read_image(), c.read_depth(), want["image"], want["depth"])
+            assert_parity(rep, name)
+        st = cabi.Stats()
+        c.lib.mr_get_stats(c.ctx, st)
+        assert st.kernels_launched == 3
+        if name == "big_triangles":
+            assert st.chk_entries == st.chk_demand > 0
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("scene", ["cloud_small", "culling0", "culling2"])
 def test_strips_union_is_byte_identical(be, scene):
     """Strip rendering also narrows the cluster-culling planes to the strip's rows: the union of the

@@ -46,6 +46,57 @@ def test_config4_cloud_10k_meshes_with_clipping(be):
     assert st.clipped_in > 20 and st.triangles_in == r.scene.triangles() > 1000000
 
 
+def test_wide_triangles_edge_chain_checkpoints_leave_the_frame_unchanged(be):
+    """Two dozen triangles hundreds of pixels wide at 1080p. From the second frame on (the first one reports the demand)
+    k_chain bins them, stores their accumulated edge functions at every tile boundary, and the tile kernel starts there
+    instead of replaying the reference's chain from the triangle's first column: every frame must still be the
+    oracle's, and bit for bit the frame rendered without checkpoints."""
+    setup = scenes.big_triangles_scene(be, 1920, 1080, count=24, spread=400.0)
+    r = setup.apply(m.Renderer(be))
+    lib = cabi.load()
+    st = cabi.Stats()
+    r.render()
+    first_i, first_d = r.get_image().copy(), r.get_depth().copy()
+    lib.mr_get_stats(r.context_ptr(), st)
+    assert st.chk_entries == 0 and st.chk_demand > 100000 and st.kernels_launched == 2
+    pairs = st.bin_entries
+    for _ in range(2):
+        r.render()
+        image, depth = r.get_image(), r.get_depth()
+        lib.mr_get_stats(r.context_ptr(), st)
+        assert st.kernels_launched == 3 and st.chk_entries == st.chk_demand > 100000 and st.bin_entries == pairs
+        assert (bits(depth) == bits(first_d)).all() and (bits(image) == bits(first_i)).all()
+    r.prepare()
+    want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), setup.width, setup.height)
+    assert_parity(compare(image, depth, want["image"], want["depth"]), "wide triangles with checkpoints")
+    # strips: checkpoints are per row, a strip uses (and k_chain bins) the rows it owns
+    r.clear()
+    for rank in range(3):
+        rb, re = sharding.strip_rows(setup.height, rank, 3)
+        r.set_row_range(rb, re)
+        r.render()
+    assert (bits(r.get_depth()) == bits(first_d)).all() and (bits(r.get_image()) == bits(first_i)).all()
+
+
+def test_config4_cloud_with_checkpoints_forced_on(be):
+    """configs[3] (near-plane clipping, triangles up to 958 pixels wide) with k_chain forced on for every triangle that
+    crosses two tile boundaries (mr_set_debug 128): clipped sub-triangles take the same path; nothing may change."""
+    setup = scenes.cloud_scene(be, groups=100, per_group=100)
+    lib = cabi.load()
+    r = setup.apply(m.Renderer(be))
+    r.render()
+    plain_i, plain_d = r.get_image().copy(), r.get_depth().copy()
+    r2 = setup.apply(m.Renderer(be))
+    assert lib.mr_set_debug(r2.context_ptr(), 128) == 0
+    for _ in range(2):
+        r2.render()
+        depth, image = r2.get_depth(), r2.get_image()  # (waits for the frame: its counters are in the statistics then)
+        st = cabi.Stats()
+        lib.mr_get_stats(r2.context_ptr(), st)
+        assert st.kernels_launched == 3 and st.chk_entries == st.chk_demand > 100000
+        assert (bits(depth) == bits(plain_d)).all() and (bits(image) == bits(plain_i)).all()
+
+
 def test_config3_4k_textured_strips_property(be):
     """3840x2160, ~2M-triangle textured sphere: the union of 8 strips equals the whole frame, and a
     downsized copy of the same scene matches the oracle (the 4K frame itself is checked through

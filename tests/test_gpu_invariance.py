@@ -42,7 +42,8 @@ def test_shortcuts_do_not_change_the_frame(be, seed):
     setup = scenes.fuzz_scene(be, seed)
     img0, dep0, ids0, st0 = render_with_flags(be, setup, 4 | 8 | 16)  # everything set up, general htransform, full scans
     assert (dep0 < 1e10).any(), "fuzz scene %d draws nothing" % seed
-    for flags, strips in ((0, 1), (8 | 16, 1), (4 | 16, 1), (4 | 8, 1), (0, 3)):
+    # (64: every cluster through the work list; 128: edge-chain checkpoints of wide triangles from the first frame on)
+    for flags, strips in ((0, 1), (8 | 16, 1), (4 | 16, 1), (4 | 8, 1), (0, 3), (64, 1), (128, 1), (128 | 4, 3)):
         img, dep, ids, st = render_with_flags(be, setup, flags, strips)
         what = "seed %d flags %d strips %d" % (seed, flags, strips)
         assert (bits(dep) == bits(dep0)).all(), what + ": depth differs in %d pixels" % int((bits(dep) != bits(dep0)).sum())

@@ -5,7 +5,8 @@ import numpy as np
 import minirender_b200 as m
 from minirender_b200 import scenes, cabi
 be = m.Backend(); lib = cabi.load()
-setup = scenes.sphere_scene(be, frame=8)
+name = sys.argv[1] if len(sys.argv) > 1 else "sphere"
+setup = {"sphere": lambda: scenes.sphere_scene(be, frame=8), "bench": lambda: scenes.bench_scene(be), "cloud": lambda: scenes.cloud_scene(be)}[name]()
 r = setup.apply(m.Renderer(be)); ctx = r.context_ptr()
 for i in range(10): r.render()
 r.synchronize()
@@ -39,3 +40,7 @@ print("CTAs resident before the dependency resolved: %d; started later: %d" % ((
 order = np.argsort(np.maximum(start, dep))
 ts = np.maximum(start, dep)[order]
 print("start times of CTAs (us) at percentiles 10/50/90/100: %.1f %.1f %.1f %.1f" % tuple(np.percentile(ts, [10, 50, 90, 100])))
+slow = np.argsort(-life)[:12]
+st = cabi.Stats(); lib.mr_get_stats(ctx, C.byref(st))
+print("pairs %d; slowest tiles (tx, ty, life us, start us):" % st.bin_entries, [(int(i % 120), int(i // 120), round(float(life[i]), 1), round(float(np.maximum(dep, start)[i]), 1)) for i in slow])
+print("life histogram (us):", np.histogram(life, bins=[0, 1, 2, 4, 8, 16, 32, 64, 128, 256])[0].tolist())
