@@ -518,26 +518,76 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
     ctx = r.context_ptr()
     stream = torch.cuda.current_stream()
     assert lib.mr_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
-    rb, re = sharding.strip_rows(H4, rank, world)
+    view = lambda i: scenes.sphere_view(be, i, d=330.0)
+    strips = sharding.all_strips(H4, world)
+    calibration = None
+    if world > 1 and not getattr(args, "equal_strips", False):
+        # Balanced strips: equal heights give the ranks whose rows cross the middle of the sphere twice the triangles of
+        # the outer ones. A few untimed rounds on each rank's own GPU (device time of its strip, all-gathered; every
+        # rank computes the same new cuts) move the cuts until the strips take about the same time.
+        calibration = []
+        r.set_row_range(*strips[rank])
+        r.set_view(view(0))
+        r.render()  # (uploads the scene)
+        r.synchronize()
+        for _ in range(4):
+            r.set_row_range(*strips[rank])
+            r.set_view(view(0))
+            r.prepare()
+            assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 3) == 0, lib.mr_last_error(ctx)
+            st0 = cabi.Stats()
+            lib.mr_get_stats(ctx, C.byref(st0))
+            t_mine = float(st0.ms_kernel[5])
+            if rank == 0:
+                # the gathering rank also resets the peers' rows of a finished frame to the clear values: part of its loop
+                bg3 = (C.c_float * 3)(*setup.background)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                for k_, (b_, e_) in enumerate(strips):
+                    if k_ != 0 and e_ > b_:
+                        assert lib.mr_clear_rows(ctx, bg3, b_, e_) == 0
+                c1.record(stream)
+                c1.synchronize()
+                t_mine += c0.elapsed_time(c1)
+            mine = torch.tensor([t_mine], dtype=torch.float64, device="cuda")
+            everyone = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            times = [float(x[0]) for x in everyone]
+            calibration.append({"rows": [e - b for b, e in strips], "strip_ms": times})
+            strips = sharding.balanced_strips(H4, strips, times)
+    rb, re = strips[rank]
     r.clear()
     r.synchronize()
     close = join = None
     if world > 1:
+        double = not getattr(args, "single_target", False)
+        if double and rank == 0:
+            # two framebuffers on the gathering rank: the peers store frame i + 1 while it waits for, consumes and clears frame i
+            assert lib.mr_set_output_slots(ctx, 2) == 0
+            bg3 = (C.c_float * 3)(*setup.background)
+            for slot in (0, 1):
+                assert lib.mr_clear_rows_slot(ctx, slot, bg3, 0, H4) == 0
+            r.synchronize()
         dist.barrier()
-        close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
-        join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0)
+        if double:
+            targets, first, close = sharding.open_peer_targets(lib, ctx, rank, world, dist, dst=0)
+            join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0, targets=targets, first=first)
+        else:
+            close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
+            join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0)
     r.set_row_range(rb, re)
     if world > 1 and rank != 0:
         assert lib.mr_set_sparse_remote_stores(ctx, 1) == 0  # only the tiles this rank draws into cross NVLink
-    view = lambda i: scenes.sphere_view(be, i, d=330.0)
     counter = [0]
-    peer_rows = [s_ for k_, s_ in enumerate(sharding.all_strips(H4, world)) if k_ != 0 and s_[1] > s_[0]]
+    peer_rows = [s_ for k_, s_ in enumerate(strips) if k_ != 0 and s_[1] > s_[0]]
     total_frames = warmup + steps
+
+    views = [view(i) for i in range(total_frames)]  # (composing a view through ctypes costs the host 40 us: not per frame)
 
     def frame(i):
         k = counter[0]
         counter[0] += 1
-        r.set_view(view(i))
+        r.set_view(views[i])
         if join:
             join.begin(k)
         r.render()
@@ -604,7 +654,6 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
         return None
     per_rank = [[float(x) for x in t] for t in everyone]
     ms = max(max(p[0], p[1]) for p in per_rank) / steps
-    strips = sharding.all_strips(H4, world)
     nvlink_bytes = int(sum(p[5] for p in per_rank[1:]) * 256 * 16)  # tiles the peers stored x 256 pixels x (12 + 4) bytes
     nvlink_bytes_dense = sum((e - b) * W4 * 16 for r_, (b, e) in enumerate(strips) if r_ != 0)
     return {"metric": "frames_per_sec_4k_10Mtri_strips", "value": 1000.0 / ms, "unit": "frames/s", "n_gpus": world, "steps": steps,
@@ -612,11 +661,14 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
             "workload": "configs[2]: 3840x2160, createSphere(100,2237,2236) = 9,999,392 triangles, 2048x2048 float texture, one strip of "
                         "whole tile rows per rank (sort-first: every rank culls all clusters, sets up the ones its rows can see)",
             "gather": "tile stores into rank 0's framebuffer over NVLink (peer memory, touched tiles only: rank 0 clears the rest itself) + device-side "
-                      "join (stream-ordered flags; a peer's geometry runs ahead, its tile kernel waits for rank 0)" if world > 1 else "none",
+                      "join (stream-ordered flags; rank 0 alternates between two framebuffers, so the peers store frame i + 1 while it waits for, "
+                      "consumes and clears frame i; a peer's tile kernel only waits for the release of frame i - 2)" if world > 1 else "none",
             "nvlink_bytes_per_frame": nvlink_bytes, "nvlink_bytes_per_frame_if_every_tile_were_sent": nvlink_bytes_dense,
             "ms_per_step_device_rank0": per_rank[0][0] / steps, "ms_per_step_host_wall_max": max(p[1] for p in per_rank) / steps,
             "strip_device_ms_per_rank": [p[2] for p in per_rank], "strip_geom_ms_per_rank": [p[3] for p in per_rank],
             "strip_raster_ms_per_rank": [p[4] for p in per_rank],
+            "strip_rows_per_rank": [e - b for b, e in strips],
+            "strip_balancing": calibration if calibration is not None else "equal heights",
             "single_gpu_frame_ms": whole_ms, "speedup_vs_single_gpu_frame": whole_ms / ms,
             "assembled_frame_identical_to_single_gpu": identical,
             "mtri_per_s": 9.999392 / ms * 1e3, "mpix_per_s": W4 * H4 / ms / 1e3}
@@ -649,6 +701,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the configs[2] strip-sharded frame (extra key strips4k)")
+    ap.add_argument("--single-target", action="store_true", help="strips: one framebuffer on the gathering rank instead of two alternating ones")
+    ap.add_argument("--equal-strips", action="store_true", help="strips of equal height instead of heights balanced by measured time")
     ap.add_argument("--workload", default="sphere1m", choices=["sphere1m", "strips4k", "turntable2m"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -214,6 +214,10 @@ MR_API int mr_set_remote_target(mr_ctx* ctx, void* d_peer_image, void* d_peer_de
  * cudaIpcMemHandle_t (128 bytes), open a peer's handles on this context's device, close them. */
 MR_API int mr_ipc_export(mr_ctx* ctx, void* handles128);
 MR_API int mr_ipc_open(mr_ctx* ctx, const void* handles128, void** d_image, void** d_depth);
+/* With two output slots: the handles of slot 0 or 1, and the slot the newest frame was rendered into. A gathering rank
+ * that alternates between two framebuffers lets its peers store frame i + 1 while it still consumes and clears frame i. */
+MR_API int mr_ipc_export_slot(mr_ctx* ctx, int slot, void* handles128);
+MR_API int mr_output_slot(mr_ctx* ctx);
 MR_API int mr_ipc_close(mr_ctx* ctx, void* d_image, void* d_depth);
 
 /* Joining the ranks of a strip-sharded frame on the device, without a collective and without the host:
@@ -236,6 +240,7 @@ MR_API int mr_set_raster_gate(mr_ctx* ctx, const void* d_word, uint32_t value);
 MR_API int mr_set_sparse_remote_stores(mr_ctx* ctx, int flag);
 /* Clear values (background / 1e11) into rows [row_begin,row_end) of the current output buffers, stream ordered. */
 MR_API int mr_clear_rows(mr_ctx* ctx, const float* background3, int row_begin, int row_end);
+MR_API int mr_clear_rows_slot(mr_ctx* ctx, int slot, const float* background3, int row_begin, int row_end);
 MR_API int mr_stream_wait(mr_ctx* ctx, const void* d_words, int n, uint32_t value);
 
 /* Page-lock caller memory so the mr_read_* copies run at full PCIe rate (optional). */

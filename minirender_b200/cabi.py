@@ -90,6 +90,8 @@ PROTOTYPES = {
     "mr_write_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "mr_set_remote_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mr_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mr_ipc_export_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mr_output_slot": (C.c_int, [C.c_void_p]),
     "mr_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mr_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mr_sync_words": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
@@ -100,6 +102,7 @@ PROTOTYPES = {
     "mr_set_raster_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "mr_set_sparse_remote_stores": (C.c_int, [C.c_void_p, C.c_int]),
     "mr_clear_rows": (C.c_int, [C.c_void_p, F32P, C.c_int, C.c_int]),
+    "mr_clear_rows_slot": (C.c_int, [C.c_void_p, C.c_int, F32P, C.c_int, C.c_int]),
     "mr_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "mr_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mr_host_unregister": (C.c_int, [C.c_void_p]),

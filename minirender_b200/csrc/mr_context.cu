@@ -1464,6 +1464,20 @@ int mr_ipc_export(mr_ctx* c, void* handles128)
 	return MR_OK;
 }
 
+int mr_ipc_export_slot(mr_ctx* c, int slot, void* handles128)
+{
+	if (!c || !handles128 || slot < 0 || slot >= c->outSlots || !c->imageSlot[slot].p || !c->depthSlot[slot].p)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	cudaIpcMemHandle_t h[2];
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[0], c->imageSlot[slot].p));
+	MR_CUDA(c, cudaIpcGetMemHandle(&h[1], c->depthSlot[slot].p));
+	memcpy(handles128, h, sizeof(h));
+	return MR_OK;
+}
+
+int mr_output_slot(mr_ctx* c) { return c ? c->outCur : MR_E_INVALID; }
+
 int mr_ipc_open(mr_ctx* c, const void* handles128, void** image, void** depth)
 {
 	if (!c || !handles128 || !image || !depth)
@@ -1580,6 +1594,18 @@ int mr_clear_rows(mr_ctx* c, const float* bg, int rb, int re)
 	if (!c->imageSlot[c->outCur].p)
 		return setError(c, MR_E_INVALID, "mr_clear_rows before mr_set_size");
 	mrk_launch_clear_rows(c->imageSlot[c->outCur].as<float>(), c->depthSlot[c->outCur].as<float>(), c->w, rb, re, bg[0], bg[1], bg[2], c->stream);
+	MR_CUDA(c, cudaGetLastError());
+	return MR_OK;
+}
+
+int mr_clear_rows_slot(mr_ctx* c, int slot, const float* bg, int rb, int re)
+{
+	if (!c || !bg || rb < 0 || re > c->h || re < rb || slot < 0 || slot >= c->outSlots)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	if (!c->imageSlot[slot].p)
+		return setError(c, MR_E_INVALID, "mr_clear_rows_slot before mr_set_size");
+	mrk_launch_clear_rows(c->imageSlot[slot].as<float>(), c->depthSlot[slot].as<float>(), c->w, rb, re, bg[0], bg[1], bg[2], c->stream);
 	MR_CUDA(c, cudaGetLastError());
 	return MR_OK;
 }

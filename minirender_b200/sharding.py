@@ -36,6 +36,36 @@ def all_strips(height, world, tile=TILE):
     return [strip_rows(height, r, world, tile) for r in range(world)]
 
 
+def balanced_strips(height, strips, times, tile=TILE):
+    """Re-cuts `strips` (a list of (begin, end) covering [0, height) in whole tile rows) so that every rank's strip
+    takes about the same time, given the time each rank measured for its current strip: the cost of a tile row is
+    taken as constant within a strip (time / tile rows), and the new cuts split the accumulated cost evenly. Every
+    rank keeps at least one tile row. Pure host logic: every rank calls it with the same (all-gathered) times and
+    gets the same answer; a few rounds converge, also when part of a rank's time does not depend on its rows."""
+    tile_rows = (height + tile - 1) // tile
+    world = len(strips)
+    if world <= 1 or tile_rows < world:
+        return list(strips)
+    cost = [0.0] * tile_rows
+    for (b, e), t in zip(strips, times):
+        n = (e - b + tile - 1) // tile
+        for k in range(n):
+            cost[b // tile + k] = max(float(t), 1e-9) / n
+    total = sum(cost)
+    cuts, acc, row = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while row < tile_rows and acc + cost[row] * 0.5 < target:
+            acc += cost[row]
+            row += 1
+        row = max(row, cuts[-1] + 1)                 # at least one tile row per rank ...
+        row = min(row, tile_rows - (world - r))      # ... for the ranks still to come as well
+        acc = sum(cost[:row])
+        cuts.append(row)
+    cuts.append(tile_rows)
+    return [(min(cuts[r] * tile, height), min(cuts[r + 1] * tile, height)) for r in range(world)]
+
+
 class DeviceArray:
     """Wraps a raw device pointer for torch (``torch.as_tensor(DeviceArray(...), device='cuda')``)."""
 
@@ -98,6 +128,37 @@ def open_peer_target(ctx_lib, ctx, rank, world, dist, dst=0):
     return close
 
 
+def open_peer_targets(ctx_lib, ctx, rank, world, dist, dst=0):
+    """Two-framebuffer form of open_peer_target: rank `dst` (with two output slots) exports both of its framebuffers;
+    returns (targets, first, close): targets[s] = (d_image, d_depth) of dst's slot s as seen from this rank (None on dst),
+    first = the slot dst's next frame will be rendered into (its frames then alternate)."""
+    payload = [None]
+    if rank == dst:
+        hs = []
+        for slot in (0, 1):
+            h = (C.c_ubyte * 128)()
+            assert ctx_lib.mr_ipc_export_slot(ctx, slot, h) == 0, ctx_lib.mr_last_error(ctx)
+            hs.append(bytes(h))
+        payload = [(hs, (ctx_lib.mr_output_slot(ctx) + 1) % 2)]
+    dist.broadcast_object_list(payload, src=dst)
+    hs, first = payload[0]
+    if rank == dst:
+        return None, first, (lambda: None)
+    targets = []
+    for h in hs:
+        buf = (C.c_ubyte * 128).from_buffer_copy(h)
+        pi, pd = C.c_void_p(), C.c_void_p()
+        if ctx_lib.mr_ipc_open(ctx, buf, C.byref(pi), C.byref(pd)) != 0:
+            raise RuntimeError("mr_ipc_open failed: %s" % ctx_lib.mr_last_error(ctx).decode())
+        targets.append((pi, pd))
+
+    def close():
+        ctx_lib.mr_set_remote_target(ctx, None, None)
+        for pi, pd in targets:
+            ctx_lib.mr_ipc_close(ctx, pi, pd)
+    return targets, first, close
+
+
 class StripJoin:
     """Device-side join of a strip-sharded frame (mr_stream_signal / mr_stream_wait): no collective and no host
     synchronisation on the per-frame path. Rank `dst` owns the words: arrived[r] (written by rank r over NVLink after
@@ -110,8 +171,12 @@ class StripJoin:
             join.end(i)          # signal arrival; dst: wait for every rank, (consume the frame,) release
     """
 
-    def __init__(self, ctx_lib, ctx, rank, world, dist, dst=0):
+    def __init__(self, ctx_lib, ctx, rank, world, dist, dst=0, targets=None, first=None):
+        """targets / first (from open_peer_targets): dst alternates between two framebuffers, frame i goes to slot
+        (first + i) % 2. The peers may then store frame i + 1 while dst still waits for, consumes and clears frame i:
+        a peer's tile kernel for frame i only waits until frame i - 2 (the previous user of that buffer) is released."""
         self.lib, self.ctx, self.rank, self.world, self.dst = ctx_lib, ctx, rank, world, dst
+        self.targets, self.first, self.double = targets, first, first is not None
         self.words = C.c_void_p()
         handle = (C.c_ubyte * 64)()
         if rank == dst:
@@ -132,7 +197,14 @@ class StripJoin:
 
     def begin(self, frame):
         # a peer's geometry may run ahead; only its tile kernel (which stores into dst's framebuffer) waits for dst
-        if self.rank != self.dst and frame > 0:
+        if self.rank == self.dst:
+            return
+        if self.double:
+            pi, pd = self.targets[(self.first + frame) % 2]
+            assert self.lib.mr_set_remote_target(self.ctx, pi, pd) == 0
+            if frame > 1:
+                assert self.lib.mr_set_raster_gate(self.ctx, self._word(self.world), frame - 1) == 0
+        elif frame > 0:
             assert self.lib.mr_set_raster_gate(self.ctx, self._word(self.world), frame) == 0
 
     def end(self, frame, clear_rows=None):
@@ -145,7 +217,10 @@ class StripJoin:
             if clear_rows is not None:
                 bg = (C.c_float * 3)(*clear_rows[0])
                 for rb, re in clear_rows[1]:
-                    assert self.lib.mr_clear_rows(self.ctx, bg, rb, re) == 0
+                    if self.double:
+                        assert self.lib.mr_clear_rows_slot(self.ctx, (self.first + frame) % 2, bg, rb, re) == 0
+                    else:
+                        assert self.lib.mr_clear_rows(self.ctx, bg, rb, re) == 0
             assert self.lib.mr_stream_signal(self.ctx, self._word(self.world), frame + 1) == 0
 
     def close(self):

@@ -197,3 +197,26 @@ def test_strip_partition_covers_image_once():
                 rows[b:e] += 1
             assert (rows == 1).all()
     assert sharding.views_for_rank(10, 1, 4) == [1, 5, 9]
+
+
+def test_balanced_strips_partition_and_converge():
+    """sharding.balanced_strips: always a partition of the image into whole tile rows, one strip per rank, and with a
+    time model that has a fixed part plus a density peaked in the middle of the image the slowest strip gets faster."""
+    import math
+    from minirender_b200 import sharding
+    for h, world in ((2160, 8), (1080, 4), (360, 3), (200, 8), (64, 8), (16, 2)):
+        strips = sharding.all_strips(h, world)
+        model = lambda b, e: 40.0 + sum(60.0 * math.exp(-((y - h / 2) / (h / 4.0)) ** 2) / 16 for y in range(b, e, 16))
+        first = max(model(b, e) for b, e in strips)
+        for _ in range(5):
+            strips = sharding.balanced_strips(h, strips, [model(b, e) for b, e in strips])
+            assert strips[0][0] == 0 and strips[-1][1] == h and len(strips) == world
+            assert all(strips[i][1] == strips[i + 1][0] for i in range(world - 1))
+            assert all(b % 16 == 0 for b, e in strips)
+            if (h + 15) // 16 >= world:
+                assert all(e > b for b, e in strips)
+        assert max(model(b, e) for b, e in strips) <= first + 1e-9
+    s8 = sharding.all_strips(2160, 8)
+    t8 = [42, 51, 73, 98, 98, 73, 51, 42]
+    out = sharding.balanced_strips(2160, s8, t8)
+    assert out[3][1] - out[3][0] < 272 < out[0][1] - out[0][0]
