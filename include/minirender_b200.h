@@ -155,6 +155,7 @@ typedef struct mr_stats
 	int64_t tiles_stored;      /* 16x16 tiles the tile kernel wrote (with sparse remote stores: the touched ones only) */
 	int64_t chk_entries;       /* edge-chain checkpoints written for wide triangles (0: the frame ran without k_chain) */
 	int64_t chk_demand;        /* ... and how many the frame's wide triangles asked for */
+	int64_t d2h_bytes;         /* bytes the last mr_read_image_begin / mr_read_image_dirty_begin copied to the host */
 } mr_stats;
 
 MR_API int mr_abi_version(void);
@@ -202,6 +203,14 @@ MR_API int mr_read_rows_async(mr_ctx* ctx, float* host_rgb, float* host_depth, i
 MR_API int mr_set_output_slots(mr_ctx* ctx, int n /* 1 or 2 */);
 MR_API int mr_read_image_begin(mr_ctx* ctx, float* host_rgb /* h*w*3 */, int* ticket);
 MR_API int mr_read_wait(mr_ctx* ctx, int ticket);
+/* The same for a host buffer the application keeps between frames (a turntable writing every image into the same one or
+ * two page-locked buffers): the library remembers which rectangle of `host_rgb` is not background and copies only the
+ * union of that and the rectangle the new frame may have drawn into (known from the frame's counters: k_geom tracks the
+ * tiles of every triangle that emits a fragment or is binned); everything outside already holds the frame's background
+ * on both sides. The buffer ends up bit-identical to a full mr_read_image. The first use of a buffer, a changed size or
+ * background, kept (immediate-mode) or strip frames copy the whole image. Waits for the frame's kernels (its counters)
+ * before it returns; the copy itself is asynchronous like mr_read_image_begin's. mr_stats.d2h_bytes = bytes copied. */
+MR_API int mr_read_image_dirty_begin(mr_ctx* ctx, float* host_rgb /* h*w*3, persistent */, int* ticket);
 
 /* Device pointers of the current output buffers (for interop: NCCL gather, checksums). */
 MR_API int mr_device_buffers(mr_ctx* ctx, void** d_image, void** d_depth, void** d_normals);

@@ -60,7 +60,7 @@ class Stats(C.Structure):
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("regrows", C.c_int32),
                 ("kernels_launched", C.c_int32), ("ms_kernel", C.c_float * 8), ("h2d_bytes", C.c_int64),
                 ("clusters", C.c_int64), ("clusters_visible", C.c_int64), ("tiles_stored", C.c_int64),
-                ("chk_entries", C.c_int64), ("chk_demand", C.c_int64)]
+                ("chk_entries", C.c_int64), ("chk_demand", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 FRAME_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
@@ -111,6 +111,7 @@ PROTOTYPES = {
     "mr_set_output_slots": (C.c_int, [C.c_void_p, C.c_int]),
     "mr_read_image_begin": (C.c_int, [C.c_void_p, F32P, C.POINTER(C.c_int)]),
     "mr_read_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "mr_read_image_dirty_begin": (C.c_int, [C.c_void_p, F32P, C.POINTER(C.c_int)]),
     "mr_read_winner_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "mr_flush_l2": (C.c_int, [C.c_void_p]),

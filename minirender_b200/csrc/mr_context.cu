@@ -108,7 +108,10 @@ struct mr_ctx
 		cudaEvent_t kernelsDone; // on the render stream, after the frame's last kernel
 		cudaEvent_t done;        // on the aux stream, after the counters reached the host
 		bool pending;
-		Slot() : hostCtr(0), kernelsDone(0), done(0), pending(false) {}
+		int dirty[4];      // pixel rectangle [x0, x1) x [y0, y1) the frame may have drawn into (from its counters; empty: x1 <= x0)
+		bool wholeFrame;   // the frame wrote every pixel of the image with clear values outside `dirty` (no keep, no row range)
+		float bg[3];
+		Slot() : hostCtr(0), kernelsDone(0), done(0), pending(false), wholeFrame(false) { dirty[0] = dirty[1] = dirty[2] = dirty[3] = 0; bg[0] = bg[1] = bg[2] = 0; }
 	};
 	enum { kSlots = 4 };
 	Slot slots[kSlots];
@@ -137,6 +140,10 @@ struct mr_ctx
 	cudaEvent_t copyDone[2];    // copy stream: the host copy out of slot s is complete
 	bool copyPending[2];
 	int copyRing[2];            // frame-ring slot of the frame whose image the pending copy of output set s reads
+	// host buffers filled by mr_read_image_dirty_begin: what rectangle of each is not background, so that the next
+	// frame copied into it only needs the union of the old and the new rectangle
+	struct HostMirror { const void* ptr; int w, h; float bg[3]; int rect[4]; };
+	std::vector<HostMirror> mirrors;
 	void *remoteImage, *remoteDepth;
 	bool sparseRemote;          // mr_set_sparse_remote_stores
 	const unsigned* gateWord;   // mr_set_raster_gate (one shot)
@@ -241,6 +248,13 @@ int retireSlot(mr_ctx* c, int i)
 	s.pending = false;
 	const Counters k = *s.hostCtr;
 	absorbCounters(c, k);
+	{
+		const int T = MR_TILE;
+		s.dirty[0] = k.dirty[0] ? std::max(0, (c->tilesX - (int)k.dirty[0]) * T) : 0;
+		s.dirty[1] = std::min(c->w, (int)k.dirty[1] * T);
+		s.dirty[2] = k.dirty[2] ? std::max(0, (c->tilesY - (int)k.dirty[2]) * T) : 0;
+		s.dirty[3] = std::min(c->h, (int)k.dirty[3] * T);
+	}
 	// Many spilled entries make the tile kernel scan a long overflow list: give the bins more room
 	// for the following frames (the current frame is still correct).
 	if (k.ovfTotal > 4096 && k.maxTile > (unsigned)c->binCap)
@@ -650,6 +664,8 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	if (!ev)
 		c->timingStart = c->timingStop = 0;
 	MR_CUDA(c, cudaGetLastError());
+	slot.wholeFrame = !f->keep && rb == 0 && re == c->h && !c->remoteImage;
+	memcpy(slot.bg, f->background, sizeof(slot.bg));
 	MR_CUDA(c, cudaEventRecord(slot.kernelsDone, c->stream));
 	MR_CUDA(c, cudaStreamWaitEvent(c->aux, slot.kernelsDone, 0));
 	MR_CUDA(c, cudaMemcpyAsync(slot.hostCtr, fp.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->aux));
@@ -1356,9 +1372,95 @@ int mr_read_image_begin(mr_ctx* c, float* host, int* ticket)
 	MR_CUDA(c, cudaEventRecord(c->frameDone[sl], c->stream));
 	MR_CUDA(c, cudaStreamWaitEvent(c->copy, c->frameDone[sl], 0));
 	MR_CUDA(c, cudaMemcpyAsync(host, c->imageSlot[sl].p, (size_t)c->w * c->h * 12, cudaMemcpyDeviceToHost, c->copy));
+	c->stats.d2h_bytes = (int64_t)c->w * c->h * 12;
+	for (size_t i = 0; i < c->mirrors.size(); i++)
+		if (c->mirrors[i].ptr == host)
+			c->mirrors[i].w = -1; // (its contents are no longer what the dirty-rectangle bookkeeping assumes)
 	MR_CUDA(c, cudaEventRecord(c->copyDone[sl], c->copy));
 	c->copyPending[sl] = true;
 	c->copyRing[sl] = c->slotNewest;
+	if (ticket)
+		*ticket = sl;
+	return MR_OK;
+}
+
+int mr_read_image_dirty_begin(mr_ctx* c, float* host, int* ticket)
+{
+	if (!c || !host)
+		return MR_E_INVALID;
+	Bind bind(c->device);
+	const int sl = c->outCur;
+	if (c->slotNewest < 0)
+		return setError(c, MR_E_INVALID, "mr_read_image_dirty_begin before mr_render");
+	// the frame's dirty rectangle comes with its counters: wait for them (the frame itself is then complete)
+	mr_ctx::Slot& fs = c->slots[c->slotNewest];
+	const int rc = retireSlot(c, c->slotNewest);
+	if (rc < 0)
+		return rc;
+	if (rc > 0)
+		return setError(c, MR_E_OVERFLOW, "the frame overflowed its spill list (capacities raised): render it again");
+	mr_ctx::HostMirror* hm = 0;
+	for (size_t i = 0; i < c->mirrors.size(); i++)
+		if (c->mirrors[i].ptr == host)
+			hm = &c->mirrors[i];
+	int x0 = 0, x1 = c->w, y0 = 0, y1 = c->h;
+	const bool known = hm && fs.wholeFrame && hm->w == c->w && hm->h == c->h && memcmp(hm->bg, fs.bg, sizeof(fs.bg)) == 0;
+	if (known)
+	{
+		// everything outside (old rectangle U new rectangle) is background in the buffer and in the frame
+		const bool oldEmpty = hm->rect[1] <= hm->rect[0] || hm->rect[3] <= hm->rect[2];
+		const bool newEmpty = fs.dirty[1] <= fs.dirty[0] || fs.dirty[3] <= fs.dirty[2];
+		if (oldEmpty && newEmpty)
+			x0 = x1 = y0 = y1 = 0;
+		else if (oldEmpty)
+		{
+			x0 = fs.dirty[0]; x1 = fs.dirty[1]; y0 = fs.dirty[2]; y1 = fs.dirty[3];
+		}
+		else if (newEmpty)
+		{
+			x0 = hm->rect[0]; x1 = hm->rect[1]; y0 = hm->rect[2]; y1 = hm->rect[3];
+		}
+		else
+		{
+			x0 = std::min(hm->rect[0], fs.dirty[0]); x1 = std::max(hm->rect[1], fs.dirty[1]);
+			y0 = std::min(hm->rect[2], fs.dirty[2]); y1 = std::max(hm->rect[3], fs.dirty[3]);
+		}
+	}
+	if (!hm)
+	{
+		if (c->mirrors.size() >= 16)
+			c->mirrors.erase(c->mirrors.begin());
+		c->mirrors.push_back(mr_ctx::HostMirror());
+		hm = &c->mirrors.back();
+		hm->ptr = host;
+	}
+	hm->w = c->w;
+	hm->h = c->h;
+	memcpy(hm->bg, fs.bg, sizeof(fs.bg));
+	if (fs.wholeFrame)
+		memcpy(hm->rect, fs.dirty, sizeof(fs.dirty));
+	else
+	{
+		hm->rect[0] = 0; hm->rect[1] = c->w; hm->rect[2] = 0; hm->rect[3] = c->h; // unknown contents: the next copy is a full one
+		hm->w = -1;
+	}
+	MR_CUDA(c, cudaEventRecord(c->frameDone[sl], c->stream));
+	MR_CUDA(c, cudaStreamWaitEvent(c->copy, c->frameDone[sl], 0));
+	size_t bytes = 0;
+	if (x1 > x0 && y1 > y0)
+	{
+		const size_t pitch = (size_t)c->w * 12, off = (size_t)y0 * pitch + (size_t)x0 * 12;
+		bytes = (size_t)(x1 - x0) * 12 * (size_t)(y1 - y0);
+		if (x0 == 0 && x1 == c->w)
+			MR_CUDA(c, cudaMemcpyAsync((char*)host + off, (const char*)c->imageSlot[sl].p + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+		else
+			MR_CUDA(c, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)c->imageSlot[sl].p + off, pitch, (size_t)(x1 - x0) * 12, (size_t)(y1 - y0),
+			                             cudaMemcpyDeviceToHost, c->copy));
+	}
+	c->stats.d2h_bytes = (int64_t)bytes;
+	MR_CUDA(c, cudaEventRecord(c->copyDone[sl], c->copy));
+	c->copyPending[sl] = true;
+	c->copyRing[sl] = -1; // (already retired)
 	if (ticket)
 		*ticket = sl;
 	return MR_OK;

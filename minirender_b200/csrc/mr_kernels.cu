@@ -534,7 +534,7 @@ __device__ __forceinline__ Corner cornerOf(const float4 B, const float4 C)
 
 // Near-plane path of k_geom (rare): clips the triangle's view-space corners, sets up and stores the
 // records of the one or two output triangles (the caller's warp bins them). Returns a bit per stored
-// sub-triangle. Out of line so that its stack never touches the fast path.
+// sub-triangle (bits 0, 1; bits 2, 3: k_chain bins that one). Out of line so that its stack never touches the fast path.
 __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int material, int submission, const float4* sB, const float4* sC, int i0, int i1, int i2,
                                          uint2* spans)
 {
@@ -559,9 +559,9 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 		storeRec<false>(ref, a, b, c, s, material, submission + sub);
 		storeShadeRec<false>(ref, make_float4(o0.px, o0.py, o0.pz, o0.u), make_float4(o1.px, o1.py, o1.pz, o1.u), make_float4(o2.px, o2.py, o2.pz, o2.u),
 		                     make_float4(o0.nx, o0.ny, o0.nz, o0.v), make_float4(o1.nx, o1.ny, o1.nz, o1.v), make_float4(o2.nx, o2.ny, o2.nz, o2.v));
-		// (a sub-triangle with checkpoints is binned by k_chain: an empty span for the caller's warp)
-		spans[sub] = (s.flags >> 1) ? make_uint2(1u, 1u) : make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
-		nrec |= 1 << sub;
+		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
+		nrec |= (1 << sub) | ((s.flags >> 1) ? (4 << sub) : 0); // bits 2, 3: the sub-triangle has checkpoints and is binned by k_chain
+
 	}
 	return nrec;
 }
@@ -621,6 +621,7 @@ struct GeomShared // fixed part of k_geom's dynamic shared memory
 	unsigned long long stat;
 	unsigned ticket;
 	int ownCount;            // warps of this CTA that start on a cluster the CTA found in its own first cull round
+	__align__(16) unsigned dirty[MR_GEOM_WARPS][4]; // per warp: tiles it may have drawn into (Counters::dirty encoding)
 	int cullCount, cullBase; // survivors of this CTA in the current cull round, and where they go in the list
 };
 #define MR_GEOM_FIXED_BYTES ((int)((sizeof(GeomShared) + 127) / 128 * 128))
@@ -686,10 +687,41 @@ __device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int 
 	return idx < (long long)nVis ? (int)idx : 0x7fffffff;
 }
 
+// Grows the warp's rectangle of tiles that may have been drawn into (lane 0 calls this; `dirty` is the warp's own
+// 16-byte slot in shared memory: a plain read-modify-write, no atomics).
+__device__ __forceinline__ void markDirty(const FrameParams& fp, unsigned* dirty, int tx0, int tx1, int ty0, int ty1)
+{
+	uint4 cur = *reinterpret_cast<uint4*>(dirty);
+	cur.x = max(cur.x, (unsigned)(fp.tilesX - max(tx0, 0)));
+	cur.y = max(cur.y, (unsigned)(min(tx1, fp.tilesX - 1) + 1));
+	cur.z = max(cur.z, (unsigned)(fp.tilesY - max(ty0, 0)));
+	cur.w = max(cur.w, (unsigned)(min(ty1, fp.tilesY - 1) + 1));
+	*reinterpret_cast<uint4*>(dirty) = cur;
+}
+
 // Binning of one warp's larger triangles (`binned` lanes: up to MR_SEG_PER_LANE tiles each, warp-aggregated; more:
 // the whole warp, one triangle at a time) and of the clipper's output triangles. Called by all lanes of the warp.
-__device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, bool binned, int nrecSlow, int sx0, int sx1, int sy0, int sy1, uint2 clip0, uint2 clip1)
+__device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, bool binned, int nrecSlow, int sx0, int sx1, int sy0, int sy1, uint2 clip0, uint2 clip1,
+                                     unsigned* dirty)
 {
+	{
+		// the tiles these triangles may draw into, for the frame's dirty rectangle
+		int x0 = binned ? sx0 : 0x7fff, x1 = binned ? sx1 : -1, y0 = binned ? sy0 : 0x7fff, y1 = binned ? sy1 : -1;
+		if (nrecSlow & 1)
+		{
+			x0 = min(x0, (int)(clip0.x & 0xffffu)); x1 = max(x1, (int)(clip0.x >> 16));
+			y0 = min(y0, (int)(clip0.y & 0xffffu)); y1 = max(y1, (int)(clip0.y >> 16));
+		}
+		if (nrecSlow & 2)
+		{
+			x0 = min(x0, (int)(clip1.x & 0xffffu)); x1 = max(x1, (int)(clip1.x >> 16));
+			y0 = min(y0, (int)(clip1.y & 0xffffu)); y1 = max(y1, (int)(clip1.y >> 16));
+		}
+		x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+		y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+		if (lane == 0 && x1 >= x0)
+			markDirty(fp, dirty, x0 >> MR_TILE_SHIFT, x1 >> MR_TILE_SHIFT, max(y0, fp.rowBegin) >> MR_TILE_SHIFT, min(y1, fp.rowEnd - 1) >> MR_TILE_SHIFT);
+	}
 	// ---- wide triangles get checkpoints of their edge chains (k_chain): the first pool entry goes into the flags word of
 	// the record this lane has just stored (same thread, same address: ordered behind that store) ----
 	if (binned && (sx1 >> MR_TILE_SHIFT) - (sx0 >> MR_TILE_SHIFT) >= fp.chkMinTiles)
@@ -761,7 +793,7 @@ __device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, boo
 		clipLanes &= clipLanes - 1u;
 		const int subs = __shfl_sync(0xffffffffu, nrecSlow, src);
 		for (int sub = 0; sub < 2; sub++)
-			if (subs & (1 << sub))
+			if ((subs & (1 << sub)) && !(subs & (4 << sub)))
 			{
 				const int id = 2 * (t - lane + src) + sub;
 				const uint32_t xs = __shfl_sync(0xffffffffu, (sub ? clip1.x : clip0.x), src), ys = __shfl_sync(0xffffffffu, (sub ? clip1.y : clip0.y), src);
@@ -774,7 +806,7 @@ __device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, boo
 // Triangle phase of one cluster for one lane (triangle `lane` of the cluster); see k_geom.
 // acc = this thread's statistics: records | clipped inputs << 20 | zero-coverage drops << 40.
 __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEntry& e, const float4* __restrict__ sA, const float4* __restrict__ sB,
-                                             const float4* __restrict__ sC, const uint32_t* __restrict__ sIdx, int lane, unsigned long long& acc)
+                                             const float4* __restrict__ sC, const uint32_t* __restrict__ sIdx, int lane, unsigned long long& acc, unsigned* dirty)
 {
 	const int t = e.ci * MR_CLUSTER + lane; // triangle instance (padded numbering): 2t is its record index
 	const int tri = e.triFirst + lane;      // triangle within the mesh
@@ -836,6 +868,8 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 		const int ty1 = __reduce_max_sync(0xffffffffu, emitted ? (yb >> MR_TILE_SHIFT) : -1);
 		if (tx1 >= tx0)
 		{
+			if (lane == 0)
+				markDirty(fp, dirty, tx0, tx1, ty0, ty1);
 			// 8 x 4 tiles per pass; a warp of neighbouring small triangles spans a few tiles: one pass
 			const int tx = tx0 + (lane & 7), ty = ty0 + (lane >> 3);
 			if (tx1 - tx0 < 8 && ty1 - ty0 < 4)
@@ -853,9 +887,9 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 	// ---- the larger triangles and the clipper's output go to the tile bins (rare on fine meshes: out of line, so that
 	// the code a warp normally runs stays small) ----
 	if (__any_sync(0xffffffffu, binned || nrecSlow != 0))
-		geomBin(fp, lane, t, binned, nrecSlow, s.x0, s.x1, s.y0, s.y1, clipSpans[0], clipSpans[1]);
+		geomBin(fp, lane, t, binned, nrecSlow, s.x0, s.x1, s.y0, s.y1, clipSpans[0], clipSpans[1], dirty);
 
-	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
+	acc += (unsigned long long)((valid ? 1 : 0) + __popc(nrecSlow & 3)) | ((unsigned long long)nclip << 20) | ((unsigned long long)nzero << 40);
 }
 
 #ifdef MR_TIMELINE
@@ -894,6 +928,8 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 		gs.ticket = 0u;
 		gs.cullCount = 0;
 		gs.ownCount = 0;
+		for (int i = 0; i < MR_GEOM_WARPS * 4; i++)
+			(&gs.dirty[0][0])[i] = 0u;
 		for (int i = 0; i < MR_GEOM_RING; i++)
 			gs.ring[i] = ~0ull;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1146,7 +1182,7 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 #ifdef MR_TIMELINE
 			const unsigned long long tt0 = globalTimer();
 #endif
-			geomTriangle(fp, e, sA, sB, sC, sIdx, lane, acc);
+			geomTriangle(fp, e, sA, sB, sC, sIdx, lane, acc, gs.dirty[warp]);
 #ifdef MR_TIMELINE
 			__syncwarp();
 			if (lane == 0 && blockIdx.x < 1024) g_tlTri[(size_t)blockIdx.x * MR_GEOM_WARPS + warp] += globalTimer() - tt0;
@@ -1180,6 +1216,15 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 		const unsigned listed = (blockIdx.x == 0) ? (unsigned)ldAcquire(syncTail) : 0u;
 		if (listed + (unsigned)gs.ownCount)
 			atomicAdd(&fp.ctr->visible, listed + (unsigned)gs.ownCount);
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			unsigned v = 0u;
+			for (int w = 0; w < MR_GEOM_WARPS; w++)
+				v = max(v, gs.dirty[w][k]);
+			if (v)
+				atomicMax(&fp.ctr->dirty[k], v);
+		}
 		if (blockIdx.x == 0)
 		{
 			fp.ctr->trianglesIn = (unsigned long long)fp.nTriReal;

@@ -145,7 +145,11 @@ struct Counters
 	unsigned int chkUsed, chkItems;
 	unsigned long long chkDemand;
 	unsigned int chkItemDemand, pad1a;
-	unsigned long long pad1[9];
+	// tiles this frame may have drawn into, as a rectangle, all four as maxima so that 0 = nothing: tilesX - tx0, tx1 + 1,
+	// tilesY - ty0, ty1 + 1 (k_geom: the bboxes of everything that emitted a fragment or was binned). Everything outside
+	// holds the clear values: a host mirror of the image only needs this rectangle (mr_read_image_dirty_begin).
+	unsigned int dirty[4];
+	unsigned long long pad1[7];
 	// line 1 (offset 128): written by k_raster
 	unsigned int maxTile;           // largest per-tile count among tiles that spilled
 	unsigned int pad2;

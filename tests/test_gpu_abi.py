@@ -387,3 +387,35 @@ def test_render_batch_equals_frames_rendered_one_by_one(be, ctx, slots):
         assert (bits(ctx.read_image()) == bits(single[3][0])).all()
     finally:
         ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 1), "slots")
+
+
+def test_dirty_rectangle_reads_leave_the_host_buffer_identical_to_a_full_read(be, ctx):
+    """mr_read_image_dirty_begin: a turntable into two persistent host buffers copies only the rectangle the new frame and
+    the frame the buffer held may have drawn into; each buffer must still be the whole image, bit for bit."""
+    setup, r, frames = _turntable_frames(be, 9)
+    ctx.set_size(setup.width, setup.height)
+    ctx.upload_scene(r.scene_desc_ptr())
+    ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 2), "slots")
+    full = setup.width * setup.height * 12
+    host = [np.full((setup.height, setup.width, 3), -7.0, np.float32) for _ in range(2)]
+    st = cabi.Stats()
+    try:
+        copied = []
+        for i, f in enumerate(frames):
+            if i == 6:  # another background: everything has to be copied again
+                f = cabi.FrameArrays(**dict(cabi.frame_to_dict(f.ptr), background=(0.25, 0.5, 0.75)))
+            ctx.render(f.ptr)
+            tick = C.c_int(0)
+            ctx._check(ctx.lib.mr_read_image_dirty_begin(ctx.ctx, host[i & 1].ctypes.data_as(cabi.F32P), C.byref(tick)), "dirty read")
+            ctx.lib.mr_get_stats(ctx.ctx, st)
+            copied.append(int(st.d2h_bytes))
+            ctx._check(ctx.lib.mr_read_wait(ctx.ctx, tick.value), "wait")
+            want = ctx.read_image()
+            assert (bits(host[i & 1]) == bits(want)).all(), i
+        assert copied[0] == copied[1] == full            # first use of each buffer
+        assert all(0 < c < 0.8 * full for c in copied[2:6]), copied
+        assert copied[6] == full                          # another background than the buffer holds: everything again
+        assert 0 < copied[7] < 0.8 * full                 # (the other buffer still holds a frame with this background)
+        assert copied[8] == full
+    finally:
+        ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 1), "slots")
