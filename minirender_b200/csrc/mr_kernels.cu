@@ -393,29 +393,53 @@ __device__ __forceinline__ RecRef recRef(const FrameParams& fp, int id)
 	return r;
 }
 
-template <bool WIDE>
-__device__ __forceinline__ void storeRec(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission)
-{
-	stPair<WIDE, MR_REC_STORE_HINT>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
-	stPair<WIDE, MR_REC_STORE_HINT>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
-	       make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)),
-	                   __uint_as_float(s.flags), __uint_as_float((uint32_t)submission)));
-}
-
 // One corner in view space: what paintMesh's loops A/B/C hand to paintTriangle (Renderer.cpp:344-380).
 struct Corner
 {
 	float px, py, pz, nx, ny, nz, u, v;
 };
 
-// The shading half of a record: the three corners as k_geom keeps them in shared memory,
-// B = (view x, y, z, u), C = (view normal x, y, z, v): pairs (B0 B1) (B2 C0) (C1 C2).
-template <bool WIDE>
-__device__ __forceinline__ void storeShadeRec(const RecRef d, const float4 B0, const float4 B1, const float4 B2, const float4 C0, const float4 C1, const float4 C2)
+// A record = 10 float4 fields in 5 pairs. With P = (view position, nx) and Q = (ny, nz, u, v) of a corner - the two
+// planes k_geom keeps its transformed corners in, so that record pairs are whole 16- and 8-byte pieces of them:
+//   pair 0  (a.x a.y c.x c.y)        (n1x n1y n2x n2y)             edge origins, scaled edge normals
+//   pair 1  (a.w b.w c.w material)   P0                            depth terms, material
+//   pair 2  P1                       P2
+//   pair 3  (Q0.xy Q1.xy)            (Q2.xy, x0 | x1 << 16, submission)
+//   pair 4  (Q0.zw Q1.zw)            (Q2.zw, y0 | y1 << 16, flags)   ONLY what textured shading, the binned raster and
+//                                                                    the checkpoints need
+// Pair 4 is written (`pair4`) when the frame textures, runs k_chain, or the triangle is binned / clipped, and read only
+// by those consumers: an untextured pixel is resolved with four 32-byte loads, a small untextured triangle stored with four.
+__device__ __forceinline__ void storeRecClipped(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission,
+                                                const Corner& o0, const Corner& o1, const Corner& o2)
 {
-	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 2 * d.stride, B0, B1);
-	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 3 * d.stride, B2, C0);
-	stPair<WIDE, MR_REC_STORE_HINT>(d.p + 4 * d.stride, C1, C2);
+	stPair<false, L2_NORMAL>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
+	stPair<false, L2_NORMAL>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)), make_float4(o0.px, o0.py, o0.pz, o0.nx));
+	stPair<false, L2_NORMAL>(d.p + 2 * d.stride, make_float4(o1.px, o1.py, o1.pz, o1.nx), make_float4(o2.px, o2.py, o2.pz, o2.nx));
+	stPair<false, L2_NORMAL>(d.p + 3 * d.stride, make_float4(o0.ny, o0.nz, o1.ny, o1.nz),
+	                         make_float4(o2.ny, o2.nz, __uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)submission)));
+	stPair<false, L2_NORMAL>(d.p + 4 * d.stride, make_float4(o0.u, o0.v, o1.u, o1.v),
+	                         make_float4(o2.u, o2.v, __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)), __uint_as_float(s.flags)));
+}
+
+// The same for a triangle whose corners lie in k_geom's shared-memory planes sP / sQ: every piece is fetched right before
+// the pair that needs it (the stores are ordered asm statements, so the fetches stay where they are written).
+__device__ __forceinline__ void storeRecCorners(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission,
+                                                const float4* __restrict__ sP, const float4* __restrict__ sQ, int i0, int i1, int i2, bool pair4)
+{
+	stPair<true, MR_REC_STORE_HINT>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
+	stPair<true, MR_REC_STORE_HINT>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)), sP[i0]);
+	stPair<true, MR_REC_STORE_HINT>(d.p + 2 * d.stride, sP[i1], sP[i2]);
+	{
+		const float2 n0 = *reinterpret_cast<const float2*>(&sQ[i0]), n1 = *reinterpret_cast<const float2*>(&sQ[i1]), n2 = *reinterpret_cast<const float2*>(&sQ[i2]);
+		stPair<true, MR_REC_STORE_HINT>(d.p + 3 * d.stride, make_float4(n0.x, n0.y, n1.x, n1.y),
+		                                make_float4(n2.x, n2.y, __uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)submission)));
+	}
+	if (pair4)
+	{
+		const float2 t0 = reinterpret_cast<const float2*>(&sQ[i0])[1], t1 = reinterpret_cast<const float2*>(&sQ[i1])[1], t2 = reinterpret_cast<const float2*>(&sQ[i2])[1];
+		stPair<true, MR_REC_STORE_HINT>(d.p + 4 * d.stride, make_float4(t0.x, t0.y, t1.x, t1.y),
+		                                make_float4(t2.x, t2.y, __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)), __uint_as_float(s.flags)));
+	}
 }
 
 // Edge-chain checkpoints for a wide binned triangle (record `id`, pixel loops x0..x1, y0..y1): reserves rows x (tile
@@ -527,8 +551,8 @@ __device__ __forceinline__ void binCooperative(const FrameParams& fp, int lane, 
 __device__ __forceinline__ Corner cornerOf(const float4 B, const float4 C)
 {
 	Corner c;
-	c.px = B.x; c.py = B.y; c.pz = B.z; c.u = B.w;
-	c.nx = C.x; c.ny = C.y; c.nz = C.z; c.v = C.w;
+	c.px = B.x; c.py = B.y; c.pz = B.z; c.nx = B.w; // k_geom's planes: (position, nx) (ny, nz, u, v)
+	c.ny = C.x; c.nz = C.y; c.u = C.z; c.v = C.w;
 	return c;
 }
 
@@ -556,9 +580,7 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 		const int id = 2 * t + sub;
 		s.flags = MR_REC_CLIPPED | chkReserve(fp, id, s.x0, s.x1, s.y0, s.y1);
 		const RecRef ref = recRef(fp, id);
-		storeRec<false>(ref, a, b, c, s, material, submission + sub);
-		storeShadeRec<false>(ref, make_float4(o0.px, o0.py, o0.pz, o0.u), make_float4(o1.px, o1.py, o1.pz, o1.u), make_float4(o2.px, o2.py, o2.pz, o2.u),
-		                     make_float4(o0.nx, o0.ny, o0.nz, o0.v), make_float4(o1.nx, o1.ny, o1.nz, o1.v), make_float4(o2.nx, o2.ny, o2.nz, o2.v));
+		storeRecClipped(ref, a, b, c, s, material, submission + sub, o0, o1, o2);
 		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
 		nrec |= (1 << sub) | ((s.flags >> 1) ? (4 << sub) : 0); // bits 2, 3: the sub-triangle has checkpoints and is binned by k_chain
 
@@ -730,7 +752,7 @@ __device__ __noinline__ void geomBin(const FrameParams& fp, int lane, int t, boo
 		if (f != 0u)
 		{
 			const RecRef ref = recRef(fp, 2 * t);
-			reinterpret_cast<uint32_t*>(ref.p + ref.stride)[6] = f; // pair 1 = (depth terms, material | spans, FLAGS, submission)
+			reinterpret_cast<uint32_t*>(ref.p + 4 * ref.stride)[7] = f; // pair 4 = (. . . . | . . rows FLAGS)
 			binned = false; // k_chain bins it as well: one warp per 32 rows instead of this warp for the whole triangle
 		}
 	}
@@ -849,8 +871,7 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 			{
 				// The triangle can own pixels: its record = raster half + its three view-space corners as they lie in shared memory
 				const RecRef ref = recRef(fp, 2 * t);
-				storeRec<true>(ref, a, b, c, s, e.material, 2 * (e.subBase + tri));
-				storeShadeRec<true>(ref, sB[i0], sB[i1], sB[i2], sC[i0], sC[i1], sC[i2]);
+				storeRecCorners(ref, a, b, c, s, e.material, 2 * (e.subBase + tri), sB, sC, i0, i1, i2, binned || fp.texturing || fp.chkEnable || (fp.debug & 512));
 			}
 		}
 	}
@@ -1126,8 +1147,8 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 						const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
 						const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
 						sA[v] = projectStd(fp, view);
-						sB[v] = make_float4(view.x, view.y, view.z, q1.z);
-						sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
+						sB[v] = make_float4(view.x, view.y, view.z, nrm.x); // planes as the records want them:
+						sC[v] = make_float4(nrm.y, nrm.z, q1.z, q1.w);      // (position, nx) (ny, nz, u, v)
 					}
 				else
 					for (int v = lane; v < nv; v += 32)
@@ -1136,8 +1157,8 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 						const V3 view = affine(e.mv, q0.x, q0.y, q0.z);
 						const V3 nrm = affine(e.nm, q0.w, q1.x, q1.y);
 						sA[v] = project(fp, view);
-						sB[v] = make_float4(view.x, view.y, view.z, q1.z);
-						sC[v] = make_float4(nrm.x, nrm.y, nrm.z, q1.w);
+						sB[v] = make_float4(view.x, view.y, view.z, nrm.x); // planes as the records want them:
+						sC[v] = make_float4(nrm.y, nrm.z, q1.z, q1.w);      // (position, nx) (ny, nz, u, v)
 					}
 			}
 #ifdef MR_TIMELINE
@@ -1259,8 +1280,8 @@ __global__ void __launch_bounds__(128) k_chain(const __grid_constant__ FramePara
 		if (it.x < 0)
 			continue;
 		const RecRef ref = recRef(fp, it.x);
-		const F8 f01 = ldPair<L2_NORMAL>(ref.p), f23 = ldPair<L2_NORMAL>(ref.p + ref.stride);
-		const uint32_t xspan = __float_as_uint(f23.b.x), yspan = __float_as_uint(f23.b.y);
+		const F8 f01 = ldPair<L2_NORMAL>(ref.p), f67 = ldPair<L2_NORMAL>(ref.p + 3 * ref.stride), f89 = ldPair<L2_NORMAL>(ref.p + 4 * ref.stride);
+		const uint32_t xspan = __float_as_uint(f67.b.z), yspan = __float_as_uint(f89.b.z);
 		const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
 		const int ntb = (x1 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT);
 		{
@@ -1576,8 +1597,10 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	if (have)
 	{
 		const RecRef ref = recRef(fp, id);
-		const F8 f01 = ldPair(ref.p), f23 = ldPair(ref.p + ref.stride);
-		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b;
+		// (binned triangles always carry pair 4: rows and flags)
+		const F8 f01 = ldPair(ref.p), f23 = ldPair(ref.p + ref.stride), f67 = ldPair(ref.p + 3 * ref.stride), f89 = ldPair(ref.p + 4 * ref.stride);
+		q0 = f01.a; q1 = f01.b; q2 = f23.a;
+		q3 = make_float4(f67.b.z, f89.b.z, f89.b.w, 0.0f); // column span, row span, flags
 		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 	}
 	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
@@ -1728,17 +1751,26 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 		const F8* r8 = ref.p;
 		const int st = ref.stride;
 		const F8 f01 = ldPair(r8), f23 = ldPair(r8 + st);
-		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b;
+		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b; // q3 = P0 = (view position, nx) of corner 0
+		{
+			const F8 f67 = ldPair(r8 + 3 * st); // (the column span lives here: always needed)
+			s2 = f67.a; s3 = f67.b;
+		}
 		if (attrs)
 		{
-			const F8 f45 = ldPair(r8 + 2 * st), f67 = ldPair(r8 + 3 * st), f89 = ldPair(r8 + 4 * st);
-			s0 = f45.a; s1 = f45.b; s2 = f67.a; s3 = f67.b; s4 = f89.a; s5 = f89.b;
+			const F8 f45 = ldPair(r8 + 2 * st);
+			s0 = f45.a; s1 = f45.b;
+		}
+		if (fp.texturing || fp.chkEnable) // texture coordinates; rows and checkpoints of wide triangles
+		{
+			const F8 f89 = ldPair(r8 + 4 * st);
+			s4 = f89.a; s5 = f89.b;
 		}
 	}
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a warp covers 2 or 4 rows) that share a
 	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
 	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
-	const int x0 = (int)(__float_as_uint(q3.x) & 0xffffu);
+	const int x0 = (int)(__float_as_uint(s3.z) & 0xffffu);
 	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
 	float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
 	float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
@@ -1746,11 +1778,11 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	{
 		// (a prefix of a few columns is cheaper walked by every lane than matched and shuffled)
 		int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
-		const uint32_t chk = __float_as_uint(q3.z) >> 1;
+		const uint32_t chk = fp.chkEnable ? __float_as_uint(s5.w) >> 1 : 0u;
 		if (prefix > 0 && chk != 0u)
 		{
 			// a wide triangle with checkpoints (k_chain): the chain as it stands at this tile's left edge
-			const int ry0 = (int)(__float_as_uint(q3.y) & 0xffffu), ry1 = (int)(__float_as_uint(q3.y) >> 16);
+			const int ry0 = (int)(__float_as_uint(s5.z) & 0xffffu), ry1 = (int)(__float_as_uint(s5.z) >> 16);
 			const float2 cp = __ldg(fp.chkPool + (size_t)(chk - 1u) + (size_t)((tileX0 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT) - 1) * (ry1 - ry0 + 1) + (py - ry0));
 			e1 = cp.x;
 			e2 = cp.y;
@@ -1803,16 +1835,17 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 		else
 			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
-			fp.winner[pix] = (int)__float_as_uint(q3.w); // the reference's submission index (instance ids are padded per renderable)
+			fp.winner[pix] = (int)__float_as_uint(s3.w); // the reference's submission index (instance ids are padded per renderable)
 		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
 		Corner c0, c1, c2;
-		// record pairs 2-4 = (B0 B1) (B2 C0) (C1 C2), B = (view position, u), C = (view normal, v)
-		c0.px = s0.x; c0.py = s0.y; c0.pz = s0.z; c0.u = s0.w; c0.v = s3.w;
-		c1.px = s1.x; c1.py = s1.y; c1.pz = s1.z; c1.u = s1.w; c1.v = s4.w;
-		c2.px = s2.x; c2.py = s2.y; c2.pz = s2.z; c2.u = s2.w; c2.v = s5.w;
-		c0.nx = s3.x; c0.ny = s3.y; c0.nz = s3.z;
-		c1.nx = s4.x; c1.ny = s4.y; c1.nz = s4.z;
-		c2.nx = s5.x; c2.ny = s5.y; c2.nz = s5.z;
+		// (layout: storeRec)
+		c0.px = q3.x; c0.py = q3.y; c0.pz = q3.z; c0.nx = q3.w;
+		c1.px = s0.x; c1.py = s0.y; c1.pz = s0.z; c1.nx = s0.w;
+		c2.px = s1.x; c2.py = s1.y; c2.pz = s1.z; c2.nx = s1.w;
+		c0.ny = s2.x; c0.nz = s2.y; c1.ny = s2.z; c1.nz = s2.w;
+		c2.ny = s3.x; c2.nz = s3.y;
+		c0.u = s4.x; c0.v = s4.y; c1.u = s4.z; c1.v = s4.w;
+		c2.u = s5.x; c2.v = s5.y;
 		value = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
 	}
 	else if (inImage && !fp.keep)
