@@ -265,7 +265,8 @@ MR_API int mr_host_unregister(void* host);
  * variables MR_NO_CLUSTER_CULL / MR_NO_STD_PROJ / MR_NO_TIGHT_SCAN do the same for a whole process.)
  * flags & 64: no warp starts on a cluster of its own cull round (every cluster goes through the work list).
  * flags & 128 / 256: edge-chain checkpoints of wide triangles (k_chain) forced on from the first frame / off (normally a
- * frame runs k_chain when the frame before it had wide triangles; MR_NO_CHAIN_CHECKPOINTS in the environment = 256). */
+ * frame runs k_chain when the frame before it had wide triangles; MR_NO_CHAIN_CHECKPOINTS in the environment = 256).
+ * flags & 512: every record is written with its fifth pair (texture coordinates, rows, flags) whether or not anyone reads it. */
 MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 
