@@ -266,7 +266,9 @@ MR_API int mr_host_unregister(void* host);
  * flags & 64: no warp starts on a cluster of its own cull round (every cluster goes through the work list).
  * flags & 128 / 256: edge-chain checkpoints of wide triangles (k_chain) forced on from the first frame / off (normally a
  * frame runs k_chain when the frame before it had wide triangles; MR_NO_CHAIN_CHECKPOINTS in the environment = 256).
- * flags & 512: every record is written with its fifth pair (texture coordinates, rows, flags) whether or not anyone reads it. */
+ * flags & 512: every record is written with its fifth pair (texture coordinates, rows, flags) whether or not anyone reads it.
+ * flags & 2048: records keep the corner positions and shading interpolates them like the reference (Renderer.cpp:281) also
+ * under the standard perspective, where a pixel's position is otherwise taken from its own ray and depth. */
 MR_API int mr_set_debug(mr_ctx* ctx, int flags);
 MR_API int mr_read_winner_ids(mr_ctx* ctx, int32_t* host_ids /* h*w */);
 

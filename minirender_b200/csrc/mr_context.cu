@@ -580,6 +580,20 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 		              f->znear < 0.0f && !c->noStdProj && !(c->debugFlags & 8)) ? 1 : 0;
 	}
 	{
+		const float* P = f->projection;
+		const bool form = fp.persp && P[1] == 0.0f && P[3] == 0.0f && P[4] == 0.0f && P[7] == 0.0f && P[12] == 0.0f && P[13] == 0.0f && P[14] == -1.0f &&
+		                  P[0] != 0.0f && P[5] != 0.0f;
+		fp.unproject = (form && MR_UNPROJECT_POSITIONS && !(c->debugFlags & 2048)) ? 1 : 0;
+		if (fp.unproject)
+		{
+			// ndc.x = (j + 0.5) * 2 / w - 1 = (P0 x + P2 z) / -z  =>  x / -z = (ndc.x + P2) / P0; likewise y with ndc.y = 1 - (i + 0.5) * 2 / h
+			fp.unprojX[0] = (float)(2.0 / (double)c->w / (double)P[0]);
+			fp.unprojX[1] = (float)(((double)P[2] - 1.0) / (double)P[0]);
+			fp.unprojY[0] = (float)(-2.0 / (double)c->h / (double)P[5]);
+			fp.unprojY[1] = (float)(((double)P[6] + 1.0) / (double)P[5]);
+		}
+	}
+	{
 		// Cluster culling needs the standard perspective form (w_clip = -z_view, x and y not mirrored
 		const float* P = f->projection;
 		// ... and no translation in clip x / y: the bounds below are planes through the eye)

@@ -400,39 +400,47 @@ struct Corner
 };
 
 // A record = 10 float4 fields in 5 pairs. With P = (view position, nx) and Q = (ny, nz, u, v) of a corner - the two
-// planes k_geom keeps its transformed corners in, so that record pairs are whole 16- and 8-byte pieces of them:
-//   pair 0  (a.x a.y c.x c.y)        (n1x n1y n2x n2y)             edge origins, scaled edge normals
-//   pair 1  (a.w b.w c.w material)   P0                            depth terms, material
-//   pair 2  P1                       P2
-//   pair 3  (Q0.xy Q1.xy)            (Q2.xy, x0 | x1 << 16, submission)
-//   pair 4  (Q0.zw Q1.zw)            (Q2.zw, y0 | y1 << 16, flags)   ONLY what textured shading, the binned raster and
-//                                                                    the checkpoints need
+// planes k_geom keeps its transformed corners in:
+//   pair 0  (a.x a.y c.x c.y)          (n1x n1y n2x n2y)              edge origins, scaled edge normals
+//   pair 1  (a.w b.w c.w material)     (x0 | x1 << 16, nx0 nx1 nx2)   depth terms, material, column span
+//   pair 2  (Q0.xy Q1.xy)              (Q2.xy, submission, pos2.z)    the other normal components
+//   pair 3  (pos0.xyz pos1.x)          (pos1.yz pos2.xy)              corner positions: ONLY when a pixel's position cannot
+//                                                                     be unprojected from its own ray (fp.unproject == 0)
+//   pair 4  (Q0.zw Q1.zw)              (Q2.zw, y0 | y1 << 16, flags)  ONLY what textured shading, the binned raster and
+//                                                                     the checkpoints need
 // Pair 4 is written (`pair4`) when the frame textures, runs k_chain, or the triangle is binned / clipped, and read only
-// by those consumers: an untextured pixel is resolved with four 32-byte loads, a small untextured triangle stored with four.
-__device__ __forceinline__ void storeRecClipped(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission,
-                                                const Corner& o0, const Corner& o1, const Corner& o2)
+// by those consumers: under the standard perspective an untextured pixel is resolved with three 32-byte loads and a
+// small untextured triangle stored with three.
+__device__ __forceinline__ void storeRecClipped(const FrameParams& fp, const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material,
+                                                int submission, const Corner& o0, const Corner& o1, const Corner& o2)
 {
 	stPair<false, L2_NORMAL>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
-	stPair<false, L2_NORMAL>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)), make_float4(o0.px, o0.py, o0.pz, o0.nx));
-	stPair<false, L2_NORMAL>(d.p + 2 * d.stride, make_float4(o1.px, o1.py, o1.pz, o1.nx), make_float4(o2.px, o2.py, o2.pz, o2.nx));
-	stPair<false, L2_NORMAL>(d.p + 3 * d.stride, make_float4(o0.ny, o0.nz, o1.ny, o1.nz),
-	                         make_float4(o2.ny, o2.nz, __uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)submission)));
+	stPair<false, L2_NORMAL>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
+	                         make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), o0.nx, o1.nx, o2.nx));
+	stPair<false, L2_NORMAL>(d.p + 2 * d.stride, make_float4(o0.ny, o0.nz, o1.ny, o1.nz), make_float4(o2.ny, o2.nz, __uint_as_float((uint32_t)submission), o2.pz));
+	if (!fp.unproject)
+		stPair<false, L2_NORMAL>(d.p + 3 * d.stride, make_float4(o0.px, o0.py, o0.pz, o1.px), make_float4(o1.py, o1.pz, o2.px, o2.py));
 	stPair<false, L2_NORMAL>(d.p + 4 * d.stride, make_float4(o0.u, o0.v, o1.u, o1.v),
 	                         make_float4(o2.u, o2.v, __uint_as_float((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)), __uint_as_float(s.flags)));
 }
 
 // The same for a triangle whose corners lie in k_geom's shared-memory planes sP / sQ: every piece is fetched right before
 // the pair that needs it (the stores are ordered asm statements, so the fetches stay where they are written).
-__device__ __forceinline__ void storeRecCorners(const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material, int submission,
-                                                const float4* __restrict__ sP, const float4* __restrict__ sQ, int i0, int i1, int i2, bool pair4)
+__device__ __forceinline__ void storeRecCorners(const FrameParams& fp, const RecRef d, const float4 a, const float4 b, const float4 c, const Setup& s, int material,
+                                                int submission, const float4* __restrict__ sP, const float4* __restrict__ sQ, int i0, int i1, int i2, bool pair4)
 {
 	stPair<true, MR_REC_STORE_HINT>(d.p, make_float4(a.x, a.y, c.x, c.y), make_float4(s.n1x, s.n1y, s.n2x, s.n2y));
-	stPair<true, MR_REC_STORE_HINT>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)), sP[i0]);
-	stPair<true, MR_REC_STORE_HINT>(d.p + 2 * d.stride, sP[i1], sP[i2]);
+	stPair<true, MR_REC_STORE_HINT>(d.p + d.stride, make_float4(a.w, b.w, c.w, __uint_as_float((uint32_t)material)),
+	                                make_float4(__uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), sP[i0].w, sP[i1].w, sP[i2].w));
 	{
 		const float2 n0 = *reinterpret_cast<const float2*>(&sQ[i0]), n1 = *reinterpret_cast<const float2*>(&sQ[i1]), n2 = *reinterpret_cast<const float2*>(&sQ[i2]);
-		stPair<true, MR_REC_STORE_HINT>(d.p + 3 * d.stride, make_float4(n0.x, n0.y, n1.x, n1.y),
-		                                make_float4(n2.x, n2.y, __uint_as_float((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)), __uint_as_float((uint32_t)submission)));
+		stPair<true, MR_REC_STORE_HINT>(d.p + 2 * d.stride, make_float4(n0.x, n0.y, n1.x, n1.y),
+		                                make_float4(n2.x, n2.y, __uint_as_float((uint32_t)submission), sP[i2].z));
+	}
+	if (!fp.unproject)
+	{
+		const float4 p0 = sP[i0], p1 = sP[i1], p2 = sP[i2];
+		stPair<true, MR_REC_STORE_HINT>(d.p + 3 * d.stride, make_float4(p0.x, p0.y, p0.z, p1.x), make_float4(p1.y, p1.z, p2.x, p2.y));
 	}
 	if (pair4)
 	{
@@ -580,7 +588,7 @@ __device__ __noinline__ int setupClipped(const FrameParams& fp, int t, int mater
 		const int id = 2 * t + sub;
 		s.flags = MR_REC_CLIPPED | chkReserve(fp, id, s.x0, s.x1, s.y0, s.y1);
 		const RecRef ref = recRef(fp, id);
-		storeRecClipped(ref, a, b, c, s, material, submission + sub, o0, o1, o2);
+		storeRecClipped(fp, ref, a, b, c, s, material, submission + sub, o0, o1, o2);
 		spans[sub] = make_uint2((uint32_t)s.x0 | ((uint32_t)s.x1 << 16), (uint32_t)s.y0 | ((uint32_t)s.y1 << 16));
 		nrec |= (1 << sub) | ((s.flags >> 1) ? (4 << sub) : 0); // bits 2, 3: the sub-triangle has checkpoints and is binned by k_chain
 
@@ -871,7 +879,7 @@ __device__ __forceinline__ void geomTriangle(const FrameParams& fp, const GeomEn
 			{
 				// The triangle can own pixels: its record = raster half + its three view-space corners as they lie in shared memory
 				const RecRef ref = recRef(fp, 2 * t);
-				storeRecCorners(ref, a, b, c, s, e.material, 2 * (e.subBase + tri), sB, sC, i0, i1, i2, binned || fp.texturing || fp.chkEnable || (fp.debug & 512));
+				storeRecCorners(fp, ref, a, b, c, s, e.material, 2 * (e.subBase + tri), sB, sC, i0, i1, i2, binned || fp.texturing || fp.chkEnable || (fp.debug & 512));
 			}
 		}
 	}
@@ -1280,8 +1288,8 @@ __global__ void __launch_bounds__(128) k_chain(const __grid_constant__ FramePara
 		if (it.x < 0)
 			continue;
 		const RecRef ref = recRef(fp, it.x);
-		const F8 f01 = ldPair<L2_NORMAL>(ref.p), f67 = ldPair<L2_NORMAL>(ref.p + 3 * ref.stride), f89 = ldPair<L2_NORMAL>(ref.p + 4 * ref.stride);
-		const uint32_t xspan = __float_as_uint(f67.b.z), yspan = __float_as_uint(f89.b.z);
+		const F8 f01 = ldPair<L2_NORMAL>(ref.p), f23 = ldPair<L2_NORMAL>(ref.p + ref.stride), f89 = ldPair<L2_NORMAL>(ref.p + 4 * ref.stride);
+		const uint32_t xspan = __float_as_uint(f23.b.x), yspan = __float_as_uint(f89.b.z);
 		const int x0 = xspan & 0xffffu, x1 = xspan >> 16, y0 = yspan & 0xffffu, y1 = yspan >> 16;
 		const int ntb = (x1 >> MR_TILE_SHIFT) - (x0 >> MR_TILE_SHIFT);
 		{
@@ -1404,9 +1412,6 @@ __device__ __forceinline__ void pushFragment(const FrameParams& fp, WarpQueue& w
 // square root, and the specular power in float (integer exponents by squaring, others through exp2(y log2 x))
 // instead of the reference's double pow(). Texture coordinates keep the reference's unfused expression: they select
 // a texel. MR_EXACT_SHADING=1 restores the reference's operation order and double pow (float RGB bit-identical).
-#ifndef MR_EXACT_SHADING
-#define MR_EXACT_SHADING 0
-#endif
 
 #if MR_EXACT_SHADING
 __device__ __forceinline__ float interp3(float a, float b, float c, float k0, float k1, float k2) { return a * k0 + b * k1 + c * k2; }
@@ -1457,7 +1462,7 @@ __device__ __forceinline__ float powShininess(float base, float shininess)
 
 // Renderer.cpp:271-305 for one pixel; returns the pixel value (and writes the normals image).
 __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& mat, float k0, float k1, float k2,
-                                           const Corner& c0, const Corner& c1, const Corner& c2, size_t pix)
+                                           const Corner& c0, const Corner& c1, const Corner& c2, const V3 ray, size_t pix)
 {
 	V3 color = mk3(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2]);
 	V3 value = mk3(mat.emissive[0], mat.emissive[1], mat.emissive[2]);
@@ -1476,7 +1481,8 @@ __device__ __forceinline__ V3 shadePixel(const FrameParams& fp, const MatDev& ma
 	}
 	if (fp.lighting)
 	{
-		const V3 position = mk3(interp3(c0.px, c1.px, c2.px, k0, k1, k2), interp3(c0.py, c1.py, c2.py, k0, k1, k2), interp3(c0.pz, c1.pz, c2.pz, k0, k1, k2));
+		const V3 position = fp.unproject ? ray // (Renderer.cpp:281 up to rounding: the point of the triangle's plane on this pixel's ray)
+		                                 : mk3(interp3(c0.px, c1.px, c2.px, k0, k1, k2), interp3(c0.py, c1.py, c2.py, k0, k1, k2), interp3(c0.pz, c1.pz, c2.pz, k0, k1, k2));
 		const V3 light = mk3(fp.light[0], fp.light[1], fp.light[2]);
 		V3 lightdir = light;
 		if (fp.lightIsPoint)
@@ -1598,9 +1604,9 @@ __device__ __forceinline__ void rasterBatch(const FrameParams& fp, WarpQueue& wq
 	{
 		const RecRef ref = recRef(fp, id);
 		// (binned triangles always carry pair 4: rows and flags)
-		const F8 f01 = ldPair(ref.p), f23 = ldPair(ref.p + ref.stride), f67 = ldPair(ref.p + 3 * ref.stride), f89 = ldPair(ref.p + 4 * ref.stride);
+		const F8 f01 = ldPair(ref.p), f23 = ldPair(ref.p + ref.stride), f89 = ldPair(ref.p + 4 * ref.stride);
 		q0 = f01.a; q1 = f01.b; q2 = f23.a;
-		q3 = make_float4(f67.b.z, f89.b.z, f89.b.w, 0.0f); // column span, row span, flags
+		q3 = make_float4(f23.b.x, f89.b.z, f89.b.w, 0.0f); // column span, row span, flags
 		wq.tri[slot] = make_float4(q2.x, q2.y, q2.z, __uint_as_float((uint32_t)(id + 1)));
 	}
 	const uint32_t xspan = __float_as_uint(q3.x), yspan = __float_as_uint(q3.y);
@@ -1751,15 +1757,16 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 		const F8* r8 = ref.p;
 		const int st = ref.stride;
 		const F8 f01 = ldPair(r8), f23 = ldPair(r8 + st);
-		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b; // q3 = P0 = (view position, nx) of corner 0
+		q0 = f01.a; q1 = f01.b; q2 = f23.a; q3 = f23.b; // q3 = (column span, nx of the three corners)
+		if (attrs || fp.winner)
 		{
-			const F8 f67 = ldPair(r8 + 3 * st); // (the column span lives here: always needed)
-			s2 = f67.a; s3 = f67.b;
-		}
-		if (attrs)
-		{
-			const F8 f45 = ldPair(r8 + 2 * st);
+			const F8 f45 = ldPair(r8 + 2 * st); // the other normal components, submission index
 			s0 = f45.a; s1 = f45.b;
+		}
+		if (fp.lighting && !fp.unproject)
+		{
+			const F8 f67 = ldPair(r8 + 3 * st); // corner positions
+			s2 = f67.a; s3 = f67.b;
 		}
 		if (fp.texturing || fp.chkEnable) // texture coordinates; rows and checkpoints of wide triangles
 		{
@@ -1770,7 +1777,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a warp covers 2 or 4 rows) that share a
 	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
 	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
-	const int x0 = (int)(__float_as_uint(s3.z) & 0xffffu);
+	const int x0 = (int)(__float_as_uint(q3.x) & 0xffffu);
 	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
 	float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
 	float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
@@ -1835,18 +1842,21 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 		else
 			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
-			fp.winner[pix] = (int)__float_as_uint(s3.w); // the reference's submission index (instance ids are padded per renderable)
+			fp.winner[pix] = (int)__float_as_uint(s1.z); // the reference's submission index (instance ids are padded per renderable)
 		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
 		Corner c0, c1, c2;
 		// (layout: storeRec)
-		c0.px = q3.x; c0.py = q3.y; c0.pz = q3.z; c0.nx = q3.w;
-		c1.px = s0.x; c1.py = s0.y; c1.pz = s0.z; c1.nx = s0.w;
-		c2.px = s1.x; c2.py = s1.y; c2.pz = s1.z; c2.nx = s1.w;
-		c0.ny = s2.x; c0.nz = s2.y; c1.ny = s2.z; c1.nz = s2.w;
-		c2.ny = s3.x; c2.nz = s3.y;
+		c0.nx = q3.y; c1.nx = q3.z; c2.nx = q3.w;
+		c0.ny = s0.x; c0.nz = s0.y; c1.ny = s0.z; c1.nz = s0.w;
+		c2.ny = s1.x; c2.nz = s1.y;
+		c0.px = s2.x; c0.py = s2.y; c0.pz = s2.z;
+		c1.px = s2.w; c1.py = s3.x; c1.pz = s3.y;
+		c2.px = s3.z; c2.py = s3.w; c2.pz = s1.w;
 		c0.u = s4.x; c0.v = s4.y; c1.u = s4.z; c1.v = s4.w;
 		c2.u = s5.x; c2.v = s5.y;
-		value = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, pix);
+		// under the standard perspective the pixel's view-space position is its own ray scaled by the depth
+		const V3 ray = mk3(__fmaf_rn(fp.unprojX[0], (float)px + 0.5f, fp.unprojX[1]) * zout, __fmaf_rn(fp.unprojY[0], (float)py + 0.5f, fp.unprojY[1]) * zout, -zout);
+		value = shadePixel(fp, mat, k0, k1, k2, c0, c1, c2, ray, pix);
 	}
 	else if (inImage && !fp.keep)
 	{

@@ -103,6 +103,10 @@ struct __align__(16) MatDev
 // 64-byte raster record: everything coverage + depth need (reference Renderer.cpp:212-224).
 #define MR_REC_FIELDS 10 // float4 fields per record: 4 raster (struct Rec) + 6 shading (struct ShadeRec)
 #define MR_REC_CLIPPED 1u // produced by the near-plane clipper (bits 1..31 of a record's flags word: 1 + its first checkpoint, 0 = none)
+#ifndef MR_EXACT_SHADING
+#define MR_EXACT_SHADING 0 // 1: shading in the reference's operation order, double pow, corner positions interpolated (float RGB bit-identical)
+#endif
+#define MR_UNPROJECT_POSITIONS (!MR_EXACT_SHADING)
 #define MR_CHK_MIN_TILES 16 // triangles spanning at least this many tile-column boundaries get edge-chain checkpoints
 #define MR_KEY_EMPTY 0xffffffffffffffffull // gkeys[] entry no fragment has touched
 struct __align__(16) Rec
@@ -192,6 +196,12 @@ struct FrameParams
 	int chkEnable;     // this frame runs k_chain: k_geom may hand out checkpoints
 	int chkMinTiles;   // ... to triangles whose bbox spans at least this many tile-column boundaries
 	int stdProj; // standard perspective matrix with the near plane in front of the eye: projectStd() applies
+	// Standard perspective form (whatever the near plane): the view-space position of a covered pixel is its own ray
+	// scaled by the depth, position = z * (unprojX.x * (j + 0.5) + unprojX.y, unprojY.x * (i + 0.5) + unprojY.y, -1) -
+	// the point the reference interpolates from the corners (Renderer.cpp:281), up to rounding, which only shading sees.
+	// Records then carry no corner positions (three 32-byte pairs per untextured triangle instead of four).
+	int unproject;
+	float unprojX[2], unprojY[2];
 	int nRenderables, nTriInst;
 	int debug; // mr_set_debug flags
 	int binCap; // entries per tile bin

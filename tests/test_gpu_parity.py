@@ -74,3 +74,24 @@ def test_stats_match_oracle_counters(be):
     assert st.records + st.zero_coverage == want["counters"]["records"]
     # whole clusters behind the near plane or off screen are dropped before the clipper sees them
     assert 0 <= st.clipped_in <= want["counters"]["clipped_in"]
+
+
+@pytest.mark.parametrize("name", ["primitives", "textured", "bench_small", "cloud_small", "clip"])
+def test_unprojected_positions_shade_like_interpolated_corners(be, name):
+    """Under the standard perspective a pixel's view-space position is taken from its own ray and depth instead of being
+    interpolated from corner positions stored in the record (three 32-byte pairs per triangle instead of four).
+    mr_set_debug 2048 keeps the corners: coverage and depth must be bit-identical, the 8-bit image equal within the
+    shading tolerance (the two positions differ by float rounding only)."""
+    lib = cabi.load()
+    out = []
+    for flags in (0, 2048):
+        setup = scenes.SMALL_SCENES[name](be)
+        r = setup.apply(m.Renderer(be))
+        assert lib.mr_set_debug(r.context_ptr(), flags) == 0
+        r.render()
+        out.append((r.get_image().copy(), r.get_depth().copy()))
+    rep = compare(out[0][0], out[0][1], out[1][0], out[1][1])
+    print(name, rep)
+    assert rep["depth_mismatch"] == 0 and rep["coverage_mismatch"] == 0
+    assert rep["rgb_over_1lsb"] == 0, rep
+    assert rep["float_rgb_max_abs"] < 2e-3, rep
