@@ -87,6 +87,10 @@ __device__ __forceinline__ float4 projectStd(const FrameParams& fp, V3 view)
 
 // order-preserving float -> uint map (so that atomicMin on the key is a depth test);
 // -0 is folded onto +0 because the reference's `z < pixdepth` treats them as equal
+__device__ __forceinline__ float unzkey(uint32_t k) // the float a depth key was made of (+0 for either zero)
+{
+	return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
 __device__ __forceinline__ uint32_t zkey(float z)
 {
 	if (z == 0.0f)
@@ -1768,7 +1772,7 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 			const F8 f67 = ldPair(r8 + 3 * st); // corner positions
 			s2 = f67.a; s3 = f67.b;
 		}
-		if (fp.texturing || fp.chkEnable) // texture coordinates; rows and checkpoints of wide triangles
+		if (fp.texturing) // texture coordinates; rows and checkpoints of wide triangles (the chain is only replayed for texel selection)
 		{
 			const F8 f89 = ldPair(r8 + 4 * st);
 			s4 = f89.a; s5 = f89.b;
@@ -1777,11 +1781,17 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 	// Replay of the winner's edge chain. Lanes of the same pixel row (a warp covers 2 or 4 rows) that share a
 	// winner starting left of the tile share the prefix of the chain up to the tile edge: one
 	// lane walks it, the others receive it by shuffle and only add their in-tile columns.
-	const int x0 = (int)(__float_as_uint(q3.x) & 0xffffu);
+	// Only texel selection has to follow the reference's ACCUMULATED edge functions (a texture coordinate a few 1e-7 off can
+	// pick the neighbouring texel); without texturing the barycentrics only weight the shading inputs, so they are
+	// evaluated directly at the pixel centre (the row-start expression of Renderer.cpp:241-242 with x at this pixel),
+	// and the depth - which must be exact - is the winner's own, taken out of the depth key.
+	const bool replay = fp.texturing != 0;
+	const int x0 = replay ? (int)(__float_as_uint(q3.x) & 0xffffu) : px;
 	const float ptx = (float)x0 + 0.5f, fy = (float)py + 0.5f;
 	float e1 = q1.x * (ptx - q0.z) + q1.y * (fy - q0.w);
 	float e2 = q1.z * (ptx - q0.x) + q1.w * (fy - q0.y);
 	int xcur = x0;
+	if (replay)
 	{
 		// (a prefix of a few columns is cheaper walked by every lane than matched and shuffled)
 		int prefix = (id >= 0) ? tileX0 - x0 : 0; // columns left of the tile
@@ -1832,15 +1842,18 @@ __device__ __forceinline__ void resolvePixel(const FrameParams& fp, unsigned lon
 			e2 += q1.z;
 		}
 		float k0 = 1.0f - e1 - e2, k1 = e1, k2 = e2;
+		// the winning fragment's depth as k_geom / phase 1 computed it (Renderer.cpp:255 / :261 on the accumulated edge
+		// functions), bit for bit, from the key; a key cannot tell -0 from +0, so a zero is computed again
+		const float zk = unzkey((uint32_t)(key >> 32));
 		if (fp.persp)
 		{
-			zout = 1.0f / (k0 * q2.x + k1 * q2.y + k2 * q2.z);
+			zout = (zk != 0.0f) ? zk : 1.0f / (k0 * q2.x + k1 * q2.y + k2 * q2.z);
 			k0 *= q2.x * zout;
 			k1 *= q2.y * zout;
 			k2 *= q2.z * zout;
 		}
 		else
-			zout = k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
+			zout = (zk != 0.0f) ? zk : k0 * q2.x + k1 * q2.y + k2 * q2.z + 0.0f * 1.0f;
 		if (fp.winner)
 			fp.winner[pix] = (int)__float_as_uint(s1.z); // the reference's submission index (instance ids are padded per renderable)
 		const MatDev& mat = frameMats<TM>(fp)[__float_as_uint(q2.w)];
