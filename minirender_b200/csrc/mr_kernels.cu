@@ -697,10 +697,10 @@ __device__ __forceinline__ int ldAcquire(const int* p) { int v; asm volatile("ld
 #ifndef MR_GEOM_DYNAMIC_TAIL
 #define MR_GEOM_DYNAMIC_TAIL 8
 #endif
-__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int grid)
+__device__ __forceinline__ int geomStatic(int nVis, int grid) { return max(nVis / grid - MR_GEOM_DYNAMIC_TAIL, 0); } // positional entries per CTA
+__device__ __forceinline__ int geomPop(GeomShared& gs, int* sync, int nVis, int grid, unsigned nStatic /* geomStatic(nVis, grid): a division, once per warp */)
 {
 	const unsigned t = atomicAdd(&gs.ticket, 1u);
-	const unsigned nStatic = (unsigned)max(nVis / grid - MR_GEOM_DYNAMIC_TAIL, 0); // per CTA
 	if (t < nStatic)
 		return (int)blockIdx.x + (int)t * grid; // (< nStatic * grid <= nVis)
 	const unsigned td = t - nStatic, slot = td / MR_GEOM_CHUNK, within = td % MR_GEOM_CHUNK;
@@ -1083,6 +1083,7 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 	// ---- phase 1: every warp on its own ----
 	unsigned long long acc = 0ull;
 	int nVis = -1; // (warp-uniform) length of the work list, known once every CTA has arrived
+	int nStatic = 0; // (lane 0) entries per CTA dealt by position
 	{
 		float4* const sA = reinterpret_cast<float4*>(warpMem + MR_MESHLET_BYTES(nvCap));
 		float4* const sB = sA + nvCap;
@@ -1101,8 +1102,9 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 				while (ldAcquire(syncArrived) < (int)gridDim.x)
 					;
 				n = ldAcquire(syncTail);
-				i0 = geomPop(gs, syncChunks, n, grid);
-				i1 = (i0 < n) ? geomPop(gs, syncChunks, n, grid) : i0;
+				nStatic = geomStatic(n, grid);
+				i0 = geomPop(gs, syncChunks, n, grid, (unsigned)nStatic);
+				i1 = (i0 < n) ? geomPop(gs, syncChunks, n, grid, (unsigned)nStatic) : i0;
 			}
 			nVis = __shfl_sync(0xffffffffu, n, 0);
 			i0 = __shfl_sync(0xffffffffu, i0, 0);
@@ -1188,7 +1190,8 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 					while (ldAcquire(syncArrived) < (int)gridDim.x)
 						;
 					n = ldAcquire(syncTail);
-					i1 = geomPop(gs, syncChunks, n, grid);
+					nStatic = geomStatic(n, grid);
+					i1 = geomPop(gs, syncChunks, n, grid, (unsigned)nStatic);
 				}
 				nVis = __shfl_sync(0xffffffffu, n, 0);
 				i1 = __shfl_sync(0xffffffffu, i1, 0);
@@ -1205,7 +1208,7 @@ __global__ void __launch_bounds__(MR_GEOM_THREADS, MR_GEOM_MINB) k_geom(const __
 				{
 					mbarExpectTx(full, (uint32_t)MR_MESHLET_BYTES(n.nv));
 					bulkLoad(raw, fp.meshlets + (size_t)n.off16 * 16, (uint32_t)MR_MESHLET_BYTES(n.nv), full);
-					i2 = geomPop(gs, syncChunks, nVis, grid);
+					i2 = geomPop(gs, syncChunks, nVis, grid, (unsigned)nStatic);
 				}
 			}
 			i2 = __shfl_sync(0xffffffffu, i2, 0);
