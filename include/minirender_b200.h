@@ -211,6 +211,10 @@ MR_API int mr_read_wait(mr_ctx* ctx, int ticket);
  * background, kept (immediate-mode) or strip frames copy the whole image. Waits for the frame's kernels (its counters)
  * before it returns; the copy itself is asynchronous like mr_read_image_begin's. mr_stats.d2h_bytes = bytes copied. */
 MR_API int mr_read_image_dirty_begin(mr_ctx* ctx, float* host_rgb /* h*w*3, persistent */, int* ticket);
+/* The library assumes that nobody else writes into such a buffer between two calls. After writing into it, or after
+ * freeing it (another allocation may get the same address), make the library forget it (NULL: all buffers): the next
+ * mr_read_image_dirty_begin into it copies the whole image again. */
+MR_API int mr_read_image_dirty_forget(mr_ctx* ctx, const float* host_rgb);
 
 /* Device pointers of the current output buffers (for interop: NCCL gather, checksums). */
 MR_API int mr_device_buffers(mr_ctx* ctx, void** d_image, void** d_depth, void** d_normals);

@@ -112,6 +112,7 @@ PROTOTYPES = {
     "mr_read_image_begin": (C.c_int, [C.c_void_p, F32P, C.POINTER(C.c_int)]),
     "mr_read_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "mr_read_image_dirty_begin": (C.c_int, [C.c_void_p, F32P, C.POINTER(C.c_int)]),
+    "mr_read_image_dirty_forget": (C.c_int, [C.c_void_p, F32P]),
     "mr_read_winner_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mr_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "mr_flush_l2": (C.c_int, [C.c_void_p]),

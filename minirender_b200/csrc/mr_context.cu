@@ -1480,6 +1480,18 @@ int mr_read_image_dirty_begin(mr_ctx* c, float* host, int* ticket)
 	return MR_OK;
 }
 
+int mr_read_image_dirty_forget(mr_ctx* c, const float* host)
+{
+	if (!c)
+		return MR_E_INVALID;
+	for (size_t i = 0; i < c->mirrors.size();)
+		if (!host || c->mirrors[i].ptr == host)
+			c->mirrors.erase(c->mirrors.begin() + i);
+		else
+			i++;
+	return MR_OK;
+}
+
 int mr_read_wait(mr_ctx* c, int ticket)
 {
 	if (!c || ticket < 0 || ticket > 1)

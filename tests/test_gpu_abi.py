@@ -417,5 +417,14 @@ def test_dirty_rectangle_reads_leave_the_host_buffer_identical_to_a_full_read(be
         assert copied[6] == full                          # another background than the buffer holds: everything again
         assert 0 < copied[7] < 0.8 * full                 # (the other buffer still holds a frame with this background)
         assert copied[8] == full
+        # a buffer the application wrote into: forgotten, so the next read copies everything again
+        host[1][:] = 3.0
+        ctx._check(ctx.lib.mr_read_image_dirty_forget(ctx.ctx, host[1].ctypes.data_as(cabi.F32P)), "forget")
+        ctx.render(frames[7].ptr)
+        tick = C.c_int(0)
+        ctx._check(ctx.lib.mr_read_image_dirty_begin(ctx.ctx, host[1].ctypes.data_as(cabi.F32P), C.byref(tick)), "dirty read")
+        ctx.lib.mr_get_stats(ctx.ctx, st)
+        ctx._check(ctx.lib.mr_read_wait(ctx.ctx, tick.value), "wait")
+        assert int(st.d2h_bytes) == full and (bits(host[1]) == bits(ctx.read_image())).all()
     finally:
         ctx._check(ctx.lib.mr_set_output_slots(ctx.ctx, 1), "slots")
