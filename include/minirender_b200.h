@@ -41,7 +41,7 @@ extern "C" {
 #define MR_API
 #endif
 
-#define MR_ABI_VERSION 1
+#define MR_ABI_VERSION 2 /* 2: mr_stats grew (chk_entries, chk_demand, d2h_bytes); mr_download, mr_read_image_dirty_*, mr_ipc_export_slot, mr_clear_rows_slot, mr_output_slot */
 
 enum
 {

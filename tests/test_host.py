@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_no_cpu_fallback():
     lib = cabi.load()
-    assert lib.mr_abi_version() == 1
+    assert lib.mr_abi_version() == 2
     if lib.mr_device_count() == 0:
         st = C.c_int(0)
         assert not lib.mr_create(0, C.byref(st))
