@@ -95,3 +95,29 @@ def test_unprojected_positions_shade_like_interpolated_corners(be, name):
     assert rep["depth_mismatch"] == 0 and rep["coverage_mismatch"] == 0
     assert rep["rgb_over_1lsb"] == 0, rep
     assert rep["float_rgb_max_abs"] < 2e-3, rep
+
+
+@pytest.mark.parametrize("point_light", [False, True])
+def test_unprojected_positions_under_an_off_centre_projection(be, point_light):
+    """projectionPerspective(l, r, b, t, n, f) with an asymmetric window (P[2], P[6] != 0) and a non-square pixel aspect:
+    the ray a pixel's position is unprojected along must carry those terms. Against the oracle, and against the build's
+    own interpolated corner positions (mr_set_debug 2048)."""
+    import dataclasses
+    lib = cabi.load()
+    base = scenes.SMALL_SCENES["primitives"](be)
+    proj = be.projection(m.api.PROJ_PERSPECTIVE6, -3.0, 6.5, -2.0, 4.5, 10.0, 3000.0)
+    setup = dataclasses.replace(base, projection=proj, point_light=point_light, light=(40.0, 60.0, -20.0) if point_light else base.light)
+    out = []
+    for flags in (0, 2048):
+        r = setup.apply(m.Renderer(be))
+        assert lib.mr_set_debug(r.context_ptr(), flags) == 0
+        r.render()
+        out.append((r.get_image().copy(), r.get_depth().copy(), r))
+    assert (out[0][1] < 1e10).sum() > 2000, "the shifted window still shows the scene"
+    rep = compare(out[0][0], out[0][1], out[1][0], out[1][1])
+    print(rep)
+    assert rep["depth_mismatch"] == 0 and rep["rgb_over_1lsb"] == 0 and rep["float_rgb_max_abs"] < 2e-3, rep
+    r = out[0][2]
+    r.prepare()
+    want = pyoracle.render_port(r.scene_desc_ptr(), r.frame_desc_ptr(), setup.width, setup.height)
+    assert_parity(compare(out[0][0], out[0][1], want["image"], want["depth"]), "off-centre projection")
