@@ -31,11 +31,11 @@ NVCC_FLAGS = [
     "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
 ]
 # Host matrix math must round like the oracle's (reference flags: -O3, no -march, no contraction).
-CXX_FLAGS = ["-std=c++11", "-O3", "-ffp-contract=off", "-fPIC", "-DMRX_PRODUCT"]
+CXX_FLAGS = ["-std=c++11", "-O3", "-ffp-contract=off", "-fPIC", "-pthread", "-DMRX_PRODUCT"]
 
 CU_SOURCES = ["csrc/mr_kernels.cu", "csrc/mr_context.cu"]
 CXX_SOURCES = ["host/Scene.cpp", "host/Renderer.cpp", "host/primitives.cpp", "host/io.cpp", "host/loaders.cpp", "host/mrx_api.cpp"]
-HEADERS = ["csrc/mr_types.h", "host/mrx_api.h", "../include/minirender_b200.h",
+HEADERS = ["csrc/mr_types.h", "host/mrx_api.h", "host/HostPool.h", "host/HostInternal.h", "../include/minirender_b200.h",
            "../include/minirender/Scene.h", "../include/minirender/SceneNode.h", "../include/minirender/Vertex.h",
            "../include/minirender/Material.h", "../include/minirender/Renderer.h",
            "../include/minirender/primitives.h", "../include/minirender/io.h"]
@@ -62,13 +62,14 @@ def build_product(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(PKG, h) for h in HEADERS]
+    cu_headers = [os.path.join(PKG, h) for h in HEADERS if "/host/" not in "/" + h and "include/minirender/" not in h]  # the device side sees the C ABI only
     shim = os.path.join(ROOT, "third_party", "asl_shim")
     headers += [os.path.join(shim, "asl", f) for f in os.listdir(os.path.join(shim, "asl"))]
     objs, log = [], []
     for src in CU_SOURCES:
         s = os.path.join(PKG, src)
         o = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
-        if force or _newer(o, [s] + headers):
+        if force or _newer(o, [s] + cu_headers):
             _run([NVCC] + NVCC_FLAGS + EXTRA + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o], log)
             if src.endswith("mr_kernels.cu") and not EXTRA:
                 check_wide_ops(o)
@@ -80,7 +81,7 @@ def build_product(force=False, verbose=False):
             _run([CXX] + CXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", shim, "-c", s, "-o", o], log)
         objs.append(o)
     if force or _newer(LIB, objs):
-        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, log)
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lpthread"], log)
     if verbose:
         sys.stdout.write("".join(log))
     return LIB

@@ -7,7 +7,11 @@
 // C ABI of <minirender_b200.h>. No pixel is ever produced on the host.
 #include <minirender/Renderer.h>
 #include <minirender_b200.h>
+#include "HostPool.h"
+#include "HostInternal.h"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +19,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 using namespace asl;
@@ -92,7 +97,7 @@ struct MeshSig
 	bool operator==(const MeshSig& o) const { return memcmp(p, o.p, sizeof(p)) == 0 && memcmp(n, o.n, sizeof(n)) == 0 && fp == o.fp; }
 };
 
-enum { MR_FP_FULL = 4096, MR_FP_SAMPLES = 61 };
+enum { MR_FP_FULL = 4096, MR_FP_SAMPLES = 61, MR_FP_BUDGET = 1 << 20 };
 
 static inline unsigned long long fpMix(unsigned long long h, unsigned long long v)
 {
@@ -100,13 +105,36 @@ static inline unsigned long long fpMix(unsigned long long h, unsigned long long 
 	return h * 0xff51afd7ed558ccdull;
 }
 
-static unsigned long long fingerprint(unsigned long long h, const void* ptr, size_t bytes, int mode)
+// How much of an array a frame's fingerprint looks at. A scene of a few meshes gets MR_FP_FULL / MR_FP_SAMPLES; a scene
+// of thousands shares MR_FP_BUDGET bytes per frame between its meshes (hashing every small array of a 10 000-mesh
+// scene whole was measured at 27 ms per frame, twenty times the rest of render()'s host time).
+struct FpPlan
+{
+	size_t full; // arrays up to this many bytes are hashed whole
+	int samples; // longer ones: this many evenly spaced 16-byte words plus `edge` bytes at both ends
+	size_t edge;
+};
+
+static FpPlan fingerprintPlan(size_t nMeshes)
+{
+	FpPlan p = { MR_FP_FULL, MR_FP_SAMPLES, 64 };
+	const size_t perMesh = MR_FP_BUDGET / (nMeshes ? nMeshes : 1); // bytes per mesh (4 to 6 arrays)
+	if (perMesh < 6 * (size_t)MR_FP_FULL)
+	{
+		p.full = std::max<size_t>(64, std::min<size_t>(MR_FP_FULL, perMesh / 6 / 16 * 16));
+		p.samples = (int)std::max<size_t>(2, std::min<size_t>(MR_FP_SAMPLES, perMesh / 6 / 32));
+		p.edge = 16;
+	}
+	return p;
+}
+
+static unsigned long long fingerprint(unsigned long long h, const void* ptr, size_t bytes, int mode, const FpPlan& plan)
 {
 	if (!ptr || !bytes || mode == 0)
 		return h;
 	const unsigned char* b = (const unsigned char*)ptr;
 	unsigned long long w;
-	if (mode == 2 || bytes <= MR_FP_FULL)
+	if (mode == 2 || bytes <= plan.full || bytes < 2 * plan.edge + 32)
 	{
 		size_t i = 0;
 		for (; i + 8 <= bytes; i += 8)
@@ -118,15 +146,15 @@ static unsigned long long fingerprint(unsigned long long h, const void* ptr, siz
 			h = fpMix(h, b[i]);
 		return h;
 	}
-	for (size_t i = 0; i < 64; i += 8) // both ends
+	for (size_t i = 0; i < plan.edge; i += 8) // both ends
 	{
 		memcpy(&w, b + i, 8);
 		h = fpMix(h, w);
-		memcpy(&w, b + bytes - 64 + i, 8);
+		memcpy(&w, b + bytes - plan.edge + i, 8);
 		h = fpMix(h, w);
 	}
-	const size_t step = (bytes - 16) / MR_FP_SAMPLES;
-	for (int k = 1; k < MR_FP_SAMPLES; k++)
+	const size_t step = (bytes - 16) / (size_t)plan.samples;
+	for (int k = 1; k < plan.samples; k++)
 	{
 		const size_t at = (size_t)k * step;
 		memcpy(&w, b + at, 8);
@@ -162,6 +190,24 @@ void copy3x4(float* dst, const Matrix4& m)
 			dst[4 * i + j] = m(i, j);
 }
 
+// Frames with at least this many renderables deal their host work to the pool (HostPool.h), in pieces of MR_POOL_CHUNK
+enum { MR_POOL_MIN_ENTRIES = 1024, MR_POOL_CHUNK = 256 };
+
+// One piece of a flatten dealt to the pool: a sub-tree (node, parent's world transform), or a mesh that the
+// expansion of its parent already placed (emit = true: xform is its own world transform, children are separate items).
+struct FlatItem
+{
+	SceneNode* node;
+	Matrix4 xform;
+	bool emit;
+};
+
+struct MatTex
+{
+	const void* p;
+	int rows, cols;
+};
+
 }
 
 struct Renderer::Impl
@@ -190,10 +236,18 @@ struct Renderer::Impl
 	std::vector<const TriMesh*> cacheUniqMesh;
 	std::vector<const Material*> cacheUniqMat;
 
+	// Many-mesh scenes (HostPool.h): sub-trees flattened side by side, and each material's texture as first noted
+	std::vector<FlatItem> flatItems;
+	std::vector<std::vector<Renderable> > flatOut;
+	std::vector<int> flatOffset;
+	std::vector<MatTex> matTex;
+	std::vector<MeshSig> sigScratch;
+	int lastCount; // renderables of the previous frame: decides whether the next one is worth dealing to the pool
+
 	// what is currently mirrored in HBM
 	std::vector<MeshSig> upMeshes;
 	std::vector<TexSig> upTextures;
-	unsigned upStamp;
+	unsigned upStamp, upEpoch;
 	bool uploaded;
 
 	// frame constants snapshotted by render() (reference members _lightdir/_znear/_ambient)
@@ -210,7 +264,7 @@ struct Renderer::Impl
 	void* pinnedImage; // page-locked (mr_host_register) so that D2H runs at full PCIe rate
 	void* pinnedDepth;
 
-	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), upStamp(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false), skipNearTest(false), buffersDefined(false),
+	Impl() : ctx(0), device(0), ctxW(0), ctxH(0), lastCount(0), upStamp(0), upEpoch(0), uploaded(false), znear(0), ambient(0.1f), haveSnapshot(false), skipNearTest(false), buffersDefined(false),
 	         imageValid(false), depthValid(false), normalsValid(false), pinnedImage(0), pinnedDepth(0)
 	{
 		memset(&sceneDesc, 0, sizeof(sceneDesc));
@@ -326,12 +380,12 @@ void Renderer::setScene(Shared<Scene> scene)
 }
 
 // Geometry descriptor of one mesh: borrows the mesh's own arrays (asl::Vec3 / Vec2 are packed floats).
-static mr_mesh_desc meshDescriptor(const TriMesh* mesh)
+// false: the mesh cannot be drawn (TriMesh::normalsI shorter than TriMesh::indices).
+static bool meshDescriptor(const TriMesh* mesh, mr_mesh_desc& d)
 {
-	if (mesh->normalsI.length() < mesh->indices.length())
-		throw std::runtime_error("minirender_b200: TriMesh::normalsI shorter than TriMesh::indices");
-	mr_mesh_desc d;
 	memset(&d, 0, sizeof(d));
+	if (mesh->normalsI.length() < mesh->indices.length())
+		return false;
 	d.positions = (const float*)mesh->vertices.ptr();
 	d.n_positions = mesh->vertices.length();
 	d.normals = (const float*)mesh->normals.ptr();
@@ -346,53 +400,25 @@ static mr_mesh_desc meshDescriptor(const TriMesh* mesh)
 		d.n_texcoords = mesh->texcoords.length();
 		d.idx_uv = mesh->texcoordsI.ptr();
 	}
-	return d;
+	return true;
 }
 
-// Material descriptor; its texture (if any) is appended to `textures` unless the same texel array is there already.
-static mr_material materialDescriptor(const Material* mat, std::vector<mr_texture_desc>& textures, std::map<const void*, int>& texIndex)
+// Material descriptor without its texture index; what texture it has (if any) is noted in `tex`.
+static void materialDescriptor(const Material* mat, mr_material& m, MatTex& tex)
 {
-	mr_material m;
 	memset(&m, 0, sizeof(m));
 	m.diffuse[0] = mat->diffuse.x; m.diffuse[1] = mat->diffuse.y; m.diffuse[2] = mat->diffuse.z;
 	m.specular[0] = mat->specular.x; m.specular[1] = mat->specular.y; m.specular[2] = mat->specular.z;
 	m.emissive[0] = mat->emissive.x; m.emissive[1] = mat->emissive.y; m.emissive[2] = mat->emissive.z;
 	m.shininess = mat->shininess;
 	m.texture = -1;
+	tex.p = 0;
+	tex.rows = tex.cols = 0;
 	if (mat->texture.rows() > 0 && mat->texture.cols() > 0)
 	{
-		const void* key = mat->texture.data().ptr();
-		std::map<const void*, int>::iterator xi = texIndex.find(key);
-		if (xi == texIndex.end())
-		{
-			mr_texture_desc t;
-			t.texels = (const float*)mat->texture.data().ptr();
-			t.rows = mat->texture.rows();
-			t.cols = mat->texture.cols();
-			m.texture = (int)textures.size();
-			texIndex[key] = m.texture;
-			textures.push_back(t);
-		}
-		else
-			m.texture = xi->second;
-	}
-	return m;
-}
-
-// Per-renderable matrices of entries [i0, i1): the reference's own expressions, one entry at a time.
-// (Spreading the entries of a 10 000-mesh scene over 2-8 host threads was measured: slower than one thread,
-// 1.3-1.6 ms against 1.2 ms: thread start-up costs more than 10 000 x 120 ns of matrix arithmetic.)
-static void describeEntries(Renderer::Impl* s, const Array<Renderable>* list, const Matrix4* view, int i0, int i1)
-{
-	for (int i = i0; i < i1; i++)
-	{
-		mr_renderable& r = s->rlist[(size_t)i];
-		const Matrix4 modelview = *view * (*list)[i].transform;    // reference Renderer.cpp:337
-		const Matrix4 normalmat = modelview.inverse().t();         // reference Renderer.cpp:338
-		copy3x4(r.modelview, modelview);
-		copy3x4(r.normalmat, normalmat);
-		r.mesh = s->cacheMeshId[(size_t)i];
-		r.material = s->cacheMatId[(size_t)i];
+		tex.p = mat->texture.data().ptr();
+		tex.rows = mat->texture.rows();
+		tex.cols = mat->texture.cols();
 	}
 }
 
@@ -400,19 +426,51 @@ static void describeEntries(Renderer::Impl* s, const Array<Renderable>* list, co
 // Everything is re-read from the scene objects on every call (users mutate meshes, materials and
 // transforms between frames); only the *structure* (which entry uses which mesh / material, and the index
 // each distinct one got) is remembered from the previous call, so that a frame of 10 000 renderables does
-// not pay 20 000 map look-ups (5.0 ms -> 1.3 ms on the cloud scene of configs[3]).
+// not pay 20 000 map look-ups (5.0 ms -> 1.3 ms on the cloud scene of configs[3]). Entries, meshes and materials
+// are independent of each other: frames with >= MR_POOL_MIN_ENTRIES renderables deal them to the host pool
+// (1.65 -> 0.4 ms for the same scene on 8 threads; the arithmetic per entry is the same code on any thread).
 static void describe(Renderer::Impl& s, const Array<Renderable>& list, const Matrix4& view, Material* defmat)
 {
 	const int n = list.length();
-	bool same = (int)s.cacheMeshOf.size() == n;
-	for (int i = 0; same && i < n; i++)
+	hostpool::Pool* const pool = n >= MR_POOL_MIN_ENTRIES ? hostpool::Pool::get() : 0;
+	const Renderable* const entries = n ? &list[0] : 0;
+
+	// ---- per entry: does it use the mesh / material it used last time; modelview and normal matrix ----
+	const bool sized = (int)s.cacheMeshOf.size() == n && (int)s.cacheMatOf.size() == n && (int)s.cacheMeshId.size() == n && (int)s.cacheMatId.size() == n;
+	std::atomic<int> differs(sized ? 0 : 1);
+	s.rlist.resize((size_t)n);
+	struct Entries
 	{
-		TriMesh* mesh = list[i].mesh;
-		const Material* mat = mesh->material ? (Material*)mesh->material : defmat;
-		same = mesh == s.cacheMeshOf[i] && mat == s.cacheMatOf[i];
-	}
-	if (!same)
+		Renderer::Impl& s; const Renderable* list; const Matrix4& view; Material* defmat; int n; bool sized; std::atomic<int>& differs;
+		void operator()(int c) const
+		{
+			const int i0 = c * MR_POOL_CHUNK, i1 = std::min(n, i0 + MR_POOL_CHUNK);
+			bool same = sized;
+			for (int i = i0; i < i1; i++)
+			{
+				const TriMesh* mesh = list[i].mesh;
+				mr_renderable& r = s.rlist[(size_t)i];
+				const Matrix4 modelview = view * list[i].transform;    // reference Renderer.cpp:337
+				const Matrix4 normalmat = modelview.inverse().t();     // reference Renderer.cpp:338
+				copy3x4(r.modelview, modelview);
+				copy3x4(r.normalmat, normalmat);
+				if (sized)
+				{
+					const Material* mat = mesh->material ? (Material*)mesh->material : defmat;
+					same = same && mesh == s.cacheMeshOf[(size_t)i] && mat == s.cacheMatOf[(size_t)i];
+					r.mesh = s.cacheMeshId[(size_t)i];
+					r.material = s.cacheMatId[(size_t)i];
+				}
+			}
+			if (!same)
+				differs.store(1, std::memory_order_relaxed);
+		}
+	} perEntry = { s, entries, view, defmat, n, sized, differs };
+	hostpool::parallelFor(pool, (n + MR_POOL_CHUNK - 1) / MR_POOL_CHUNK, perEntry);
+
+	if (differs.load())
 	{
+		// the structure changed (or this is the first frame): number the distinct meshes and materials again
 		std::map<const TriMesh*, int> meshIndex;
 		std::map<const Material*, int> matIndex;
 		s.cacheMeshOf.resize(n); s.cacheMatOf.resize(n); s.cacheMeshId.resize(n); s.cacheMatId.resize(n);
@@ -435,33 +493,60 @@ static void describe(Renderer::Impl& s, const Array<Renderable>& list, const Mat
 			}
 			s.cacheMeshOf[i] = mesh; s.cacheMatOf[i] = mat;
 			s.cacheMeshId[i] = mi->second; s.cacheMatId[i] = ti->second;
+			s.rlist[(size_t)i].mesh = mi->second;
+			s.rlist[(size_t)i].material = ti->second;
 		}
 	}
 
-	std::map<const void*, int> texIndex;
-	s.meshes.clear();
-	s.textures.clear();
-	s.materials.clear();
-	s.meshes.reserve(s.cacheUniqMesh.size());
-	s.materials.reserve(s.cacheUniqMat.size());
-	try
+	// ---- per distinct mesh / material: descriptors ----
+	const int nMesh = (int)s.cacheUniqMesh.size(), nMat = (int)s.cacheUniqMat.size();
+	s.meshes.resize((size_t)nMesh);
+	s.materials.resize((size_t)nMat);
+	s.matTex.resize((size_t)nMat);
+	std::atomic<int> rejected(0);
+	struct Descriptors
 	{
-		for (size_t k = 0; k < s.cacheUniqMesh.size(); k++)
-			s.meshes.push_back(meshDescriptor(s.cacheUniqMesh[k]));
-	}
-	catch (...)
+		Renderer::Impl& s; int nMesh, nMat; std::atomic<int>& rejected;
+		void operator()(int c) const
+		{
+			const int k0 = c * MR_POOL_CHUNK, k1 = k0 + MR_POOL_CHUNK;
+			for (int k = k0; k < std::min(k1, nMesh); k++)
+				if (!meshDescriptor(s.cacheUniqMesh[(size_t)k], s.meshes[(size_t)k]))
+					rejected.store(1, std::memory_order_relaxed);
+			for (int k = k0; k < std::min(k1, nMat); k++)
+				materialDescriptor(s.cacheUniqMat[(size_t)k], s.materials[(size_t)k], s.matTex[(size_t)k]);
+		}
+	} perDistinct = { s, nMesh, nMat, rejected };
+	hostpool::parallelFor(pool, (std::max(nMesh, nMat) + MR_POOL_CHUNK - 1) / MR_POOL_CHUNK, perDistinct);
+	if (rejected.load())
 	{
 		// do not trust the cache after a rejected mesh
 		s.cacheMeshOf.clear(); s.cacheMatOf.clear(); s.cacheMeshId.clear(); s.cacheMatId.clear();
 		s.cacheUniqMesh.clear(); s.cacheUniqMat.clear();
 		s.meshes.clear();
-		throw;
+		throw std::runtime_error("minirender_b200: TriMesh::normalsI shorter than TriMesh::indices");
 	}
-	for (size_t k = 0; k < s.cacheUniqMat.size(); k++)
-		s.materials.push_back(materialDescriptor(s.cacheUniqMat[k], s.textures, texIndex));
+	// textures in first-use order of the materials; the same texel array is listed once
+	std::map<const void*, int> texIndex;
+	s.textures.clear();
+	for (int k = 0; k < nMat; k++)
+	{
+		const MatTex& t = s.matTex[(size_t)k];
+		if (!t.p)
+			continue;
+		std::map<const void*, int>::iterator xi = texIndex.find(t.p);
+		if (xi == texIndex.end())
+		{
+			mr_texture_desc d;
+			d.texels = (const float*)t.p;
+			d.rows = t.rows;
+			d.cols = t.cols;
+			xi = texIndex.insert(std::make_pair(t.p, (int)s.textures.size())).first;
+			s.textures.push_back(d);
+		}
+		s.materials[(size_t)k].texture = xi->second;
+	}
 
-	s.rlist.resize((size_t)n);
-	describeEntries(&s, &list, &view, 0, n);
 	s.sceneDesc.meshes = s.meshes.empty() ? 0 : &s.meshes[0];
 	s.sceneDesc.n_meshes = (int)s.meshes.size();
 	s.sceneDesc.textures = s.textures.empty() ? 0 : &s.textures[0];
@@ -470,6 +555,131 @@ static void describe(Renderer::Impl& s, const Array<Renderable>& list, const Mat
 	s.frame.n_renderables = (int)s.rlist.size();
 	s.frame.materials = s.materials.empty() ? 0 : &s.materials[0];
 	s.frame.n_materials = (int)s.materials.size();
+}
+
+// ---- flatten (reference src/Scene.cpp:13-36) dealt to the host pool ----
+
+// 2: exactly a TriMesh, 1: exactly one of the other node types of the API, 0: a type of the application's.
+static inline int stockKind(const SceneNode* node)
+{
+	const std::type_info& t = typeid(*node);
+	if (t == typeid(TriMesh))
+		return 2;
+	return (t == typeid(SceneNode) || t == typeid(Scene) || t == typeid(Shape)) ? 1 : 0;
+}
+
+// What SceneNode::collectShapes / TriMesh::collectShapes (host/Scene.cpp) do for a sub-tree of stock nodes, without the
+// virtual calls; false as soon as a node of another type turns up (its own collectShapes has to run, on the caller's thread).
+static bool flattenStock(SceneNode* node, const Matrix4& xform, std::vector<Renderable>& out)
+{
+	const int kind = stockKind(node);
+	if (!kind)
+		return false;
+	const Matrix4 world = xform * node->transform;
+	if (kind == 2)
+		out.push_back(Renderable(static_cast<TriMesh*>(node), world));
+	for (int i = 0; i < node->children.length(); i++)
+		if (!flattenStock(node->children[i], world, out))
+			return false;
+	return true;
+}
+
+// The scene's renderables into s.renderables, in the order collectShapes gives them: the top levels of the graph are
+// opened on this thread until there are enough sub-trees, each sub-tree is flattened into its own list by whichever
+// thread takes it, and the lists are put behind each other. false: nothing usable was produced (a node type this
+// library does not know, or too little to share out) and the caller runs collectShapes itself.
+static bool flattenParallel(Renderer::Impl& s, Scene* scene, hostpool::Pool* pool)
+{
+	std::vector<FlatItem>& items = s.flatItems;
+	std::vector<FlatItem> opened;
+	items.clear();
+	FlatItem root = { scene, Matrix4::identity(), false };
+	items.push_back(root);
+	const size_t want = (size_t)pool->width() * 4;
+	for (int level = 0; level < 3 && items.size() < want; level++)
+	{
+		opened.clear();
+		for (size_t k = 0; k < items.size(); k++)
+		{
+			const FlatItem& it = items[k];
+			if (it.emit)
+			{
+				opened.push_back(it);
+				continue;
+			}
+			const int kind = stockKind(it.node);
+			if (!kind)
+				return false;
+			const Matrix4 world = it.xform * it.node->transform;
+			if (kind == 2)
+			{
+				FlatItem e = { it.node, world, true };
+				opened.push_back(e);
+			}
+			for (int i = 0; i < it.node->children.length(); i++)
+			{
+				FlatItem c = { it.node->children[i], world, false };
+				opened.push_back(c);
+			}
+		}
+		items.swap(opened);
+	}
+	const int nItems = (int)items.size();
+	if (nItems < 2)
+		return false;
+	if ((int)s.flatOut.size() < nItems)
+		s.flatOut.resize((size_t)nItems);
+	std::atomic<int> foreign(0);
+	struct Flatten
+	{
+		Renderer::Impl& s; std::atomic<int>& foreign;
+		void operator()(int c) const
+		{
+			const FlatItem& it = s.flatItems[(size_t)c];
+			std::vector<Renderable>& out = s.flatOut[(size_t)c];
+			out.clear();
+			if (it.emit)
+				out.push_back(Renderable(static_cast<TriMesh*>(it.node), it.xform));
+			else if (!foreign.load(std::memory_order_relaxed) && !flattenStock(it.node, it.xform, out))
+				foreign.store(1, std::memory_order_relaxed);
+		}
+	} perItem = { s, foreign };
+	hostpool::parallelFor(pool, nItems, perItem);
+	if (foreign.load())
+		return false;
+
+	s.flatOffset.resize((size_t)nItems + 1);
+	int total = 0;
+	for (int k = 0; k < nItems; k++)
+	{
+		s.flatOffset[(size_t)k] = total;
+		total += (int)s.flatOut[(size_t)k].size();
+	}
+	s.flatOffset[(size_t)nItems] = total;
+	s.renderables.resize(total);
+	if (total == 0)
+		return true;
+	struct Gather
+	{
+		Renderer::Impl& s; Renderable* dst; int total, nItems;
+		void operator()(int c) const
+		{
+			const int i0 = c * MR_POOL_CHUNK, i1 = std::min(total, i0 + MR_POOL_CHUNK);
+			// the item that holds entry i0: the last one that starts at or before it and is not empty
+			int k = (int)(std::upper_bound(s.flatOffset.begin(), s.flatOffset.begin() + nItems, i0) - s.flatOffset.begin()) - 1;
+			for (int i = i0; i < i1; k++)
+			{
+				const std::vector<Renderable>& src = s.flatOut[(size_t)k];
+				const int first = i - s.flatOffset[(size_t)k];
+				const int count = std::min((int)src.size() - first, i1 - i);
+				for (int j = 0; j < count; j++)
+					dst[i + j] = src[(size_t)(first + j)];
+				i += count;
+			}
+		}
+	} gather = { s, &s.renderables[0], total, nItems };
+	hostpool::parallelFor(pool, (total + MR_POOL_CHUNK - 1) / MR_POOL_CHUNK, gather);
+	return true;
 }
 
 static void fillFrameConstants(mr_frame& f, const Matrix4& P, const Vec3& lightdir, bool point, float ambient, float znear,
@@ -496,8 +706,14 @@ void Renderer::prepare()
 	Impl& s = *_impl;
 	if (!_scene)
 		throw std::runtime_error("minirender_b200: Renderer::render() without a scene");
-	s.renderables.clear();
-	_scene->collectShapes(s.renderables, Matrix4::identity());
+	// (a frame as large as the last one was: sub-trees of stock nodes side by side on the host pool, HostPool.h)
+	hostpool::Pool* const pool = s.lastCount >= MR_POOL_MIN_ENTRIES ? hostpool::Pool::get() : 0;
+	if (!pool || !flattenParallel(s, _scene, pool))
+	{
+		s.renderables.clear();
+		_scene->collectShapes(s.renderables, Matrix4::identity());
+	}
+	s.lastCount = s.renderables.length();
 
 	// reference Renderer.cpp:317-326
 	s.lightdir = _lightIsPoint ? _view * _light : _light.normalized();
@@ -519,21 +735,33 @@ const mr_frame* Renderer::frameDesc() const { return &_impl->frame; }
 static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 {
 	const int mode = geometryCheckMode();
-	std::vector<MeshSig> ms(s.meshes.size());
-	for (size_t i = 0; i < s.meshes.size(); i++)
+	const size_t nMeshes = s.meshes.size();
+	const FpPlan plan = fingerprintPlan(nMeshes);
+	std::vector<MeshSig>& ms = s.sigScratch;
+	ms.resize(nMeshes);
+	struct Signatures
 	{
-		const mr_mesh_desc& d = s.meshes[i];
-		const void* p[6] = { d.positions, d.normals, d.texcoords, d.idx_pos, d.idx_nrm, d.idx_uv };
-		const int n[6] = { d.n_positions, d.n_normals, d.n_texcoords, d.n_triangles, d.n_triangles, d.idx_uv ? d.n_triangles : 0 };
-		memset(&ms[i], 0, sizeof(MeshSig));
-		memcpy(ms[i].p, p, sizeof(p));
-		memcpy(ms[i].n, n, sizeof(n));
-		const size_t elem[6] = { 12, 12, 8, 12, 12, 12 };
-		unsigned long long h = 0x243f6a8885a308d3ull;
-		for (int k = 0; k < 6; k++)
-			h = fingerprint(h, p[k], elem[k] * (size_t)n[k], mode);
-		ms[i].fp = h;
-	}
+		Renderer::Impl& s; std::vector<MeshSig>& ms; int mode; const FpPlan& plan;
+		void operator()(int c) const
+		{
+			const size_t i0 = (size_t)c * MR_POOL_CHUNK, i1 = std::min(ms.size(), i0 + MR_POOL_CHUNK);
+			for (size_t i = i0; i < i1; i++)
+			{
+				const mr_mesh_desc& d = s.meshes[i];
+				const void* p[6] = { d.positions, d.normals, d.texcoords, d.idx_pos, d.idx_nrm, d.idx_uv };
+				const int n[6] = { d.n_positions, d.n_normals, d.n_texcoords, d.n_triangles, d.n_triangles, d.idx_uv ? d.n_triangles : 0 };
+				memset(&ms[i], 0, sizeof(MeshSig));
+				memcpy(ms[i].p, p, sizeof(p));
+				memcpy(ms[i].n, n, sizeof(n));
+				const size_t elem[6] = { 12, 12, 8, 12, 12, 12 };
+				unsigned long long h = 0x243f6a8885a308d3ull;
+				for (int k = 0; k < 6; k++)
+					h = fingerprint(h, p[k], elem[k] * (size_t)n[k], mode, plan);
+				ms[i].fp = h;
+			}
+		}
+	} perMesh = { s, ms, mode, plan };
+	hostpool::parallelFor(nMeshes >= (size_t)MR_POOL_MIN_ENTRIES ? hostpool::Pool::get() : 0, (int)((nMeshes + MR_POOL_CHUNK - 1) / MR_POOL_CHUNK), perMesh);
 	std::vector<TexSig> ts(s.textures.size());
 	for (size_t i = 0; i < s.textures.size(); i++)
 	{
@@ -541,7 +769,8 @@ static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 		ts[i].rows = s.textures[i].rows;
 		ts[i].cols = s.textures[i].cols;
 	}
-	if (!force && s.uploaded && stamp == s.upStamp && ms == s.upMeshes && ts == s.upTextures)
+	const unsigned epoch = geometryEpoch().load(std::memory_order_acquire); // bumped by TriMesh::applyTransform()
+	if (!force && s.uploaded && stamp == s.upStamp && epoch == s.upEpoch && ms == s.upMeshes && ts == s.upTextures)
 		return;
 	int rc = mr_upload_scene(s.ctx, &s.sceneDesc);
 	if (rc)
@@ -549,6 +778,7 @@ static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 	s.upMeshes.swap(ms);
 	s.upTextures.swap(ts);
 	s.upStamp = stamp;
+	s.upEpoch = epoch;
 	s.uploaded = true;
 }
 

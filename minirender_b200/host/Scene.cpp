@@ -4,12 +4,19 @@
 // children, a TriMesh emits itself before its own children) is what defines the submission
 // order the rasterizer's depth ties are resolved in.
 #include <minirender/Scene.h>
+#include "HostInternal.h"
 
 using asl::Array;
 using asl::Matrix4;
 using asl::Vec3;
 
 namespace minirender {
+
+std::atomic<unsigned>& geometryEpoch()
+{
+	static std::atomic<unsigned> epoch(0);
+	return epoch;
+}
 
 SceneNode::SceneNode() : visible(true), transform(Matrix4::identity()) {}
 
@@ -59,6 +66,7 @@ void TriMesh::applyTransform()
 	for (int i = 0; i < normals.length(); i++)
 		normals[i] = (nm % normals[i]).normalized();
 	transform = Matrix4::identity();
+	geometryEpoch().fetch_add(1u, std::memory_order_release); // the arrays changed in place (host/Renderer.cpp: syncGeometry)
 }
 
 Material::Material()
