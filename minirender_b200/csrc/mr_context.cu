@@ -4,6 +4,7 @@
 // needs a CUDA device and fails with MR_E_NO_DEVICE / MR_E_CUDA otherwise.
 #include "../../include/minirender_b200.h"
 #include "mr_types.h"
+#include "../host/HostPool.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -348,6 +349,38 @@ int ensureOutputs(mr_ctx* c, bool normals, bool winner)
 	return MR_OK;
 }
 
+// Frames with at least kHostPoolMin renderables deal their per-renderable host loops to the library's host threads
+// (host/HostPool.h) in pieces of kHostChunk.
+enum { kHostPoolMin = 1024, kHostChunk = 256 };
+
+// A renderable's per-frame entry of the device table: matrices, material, and what the cluster cull needs to know
+// about the modelview.
+static void fillDynamic(RDyn& d, const mr_renderable& r)
+{
+	memcpy(d.mv, r.modelview, sizeof(float) * 12);
+	memcpy(d.nm, r.normalmat, sizeof(float) * 12);
+	d.material = r.material;
+	{
+		// Is the modelview a similarity (uniform scale x rotation) with positive determinant? Then a
+		// cluster's normal cone is still a cone in view space and its bounding radius scales by s.
+		const float* m = d.mv;
+		const double c0[3] = { m[0], m[4], m[8] }, c1[3] = { m[1], m[5], m[9] }, c2[3] = { m[2], m[6], m[10] };
+		const double l0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], l1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
+		             l2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+		const double d01 = c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2], d02 = c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2],
+		             d12 = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
+		const double det = c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c0[1] * (c1[0] * c2[2] - c1[2] * c2[0]) + c0[2] * (c1[0] * c2[1] - c1[1] * c2[0]);
+		const double lmax = std::max(l0, std::max(l1, l2)), lmin = std::min(l0, std::min(l1, l2));
+		const double tol = 1e-4 * lmax;
+		const bool similar = lmax > 0 && (lmax - lmin) <= tol && fabs(d01) <= tol && fabs(d02) <= tol && fabs(d12) <= tol && lmax == lmax;
+		d.cullFlags = (similar && det > 0) ? 1 : 0;
+		// the largest stretch of the linear part: s for a similarity, the Frobenius norm otherwise
+		const double stretch = similar ? sqrt(lmax) : sqrt(l0 + l1 + l2);
+		d.radiusScale = (stretch == stretch) ? (float)(stretch * 1.0001) : INFINITY;
+		d.pad = 0;
+	}
+}
+
 int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 {
 	const int nR = f->n_renderables;
@@ -488,30 +521,18 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 	}
 	off = (off + 15) & ~(size_t)15;
 	RDyn* rd = (RDyn*)(sp + off);
-	for (int i = 0; i < nR; i++)
 	{
-		memcpy(rd[i].mv, f->renderables[i].modelview, sizeof(float) * 12);
-		memcpy(rd[i].nm, f->renderables[i].normalmat, sizeof(float) * 12);
-		rd[i].material = f->renderables[i].material;
+		// (independent per renderable: frames with thousands of them share the loop out, host/HostPool.h)
+		struct Dynamic
 		{
-			// Is the modelview a similarity (uniform scale x rotation) with positive determinant? Then a
-			// cluster's normal cone is still a cone in view space and its bounding radius scales by s.
-			const float* m = rd[i].mv;
-			const double c0[3] = { m[0], m[4], m[8] }, c1[3] = { m[1], m[5], m[9] }, c2[3] = { m[2], m[6], m[10] };
-			const double l0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2], l1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2],
-			             l2 = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
-			const double d01 = c0[0] * c1[0] + c0[1] * c1[1] + c0[2] * c1[2], d02 = c0[0] * c2[0] + c0[1] * c2[1] + c0[2] * c2[2],
-			             d12 = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
-			const double det = c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) - c0[1] * (c1[0] * c2[2] - c1[2] * c2[0]) + c0[2] * (c1[0] * c2[1] - c1[1] * c2[0]);
-			const double lmax = std::max(l0, std::max(l1, l2)), lmin = std::min(l0, std::min(l1, l2));
-			const double tol = 1e-4 * lmax;
-			const bool similar = lmax > 0 && (lmax - lmin) <= tol && fabs(d01) <= tol && fabs(d02) <= tol && fabs(d12) <= tol && lmax == lmax;
-			rd[i].cullFlags = (similar && det > 0) ? 1 : 0;
-			// the largest stretch of the linear part: s for a similarity, the Frobenius norm otherwise
-			const double stretch = similar ? sqrt(lmax) : sqrt(l0 + l1 + l2);
-			rd[i].radiusScale = (stretch == stretch) ? (float)(stretch * 1.0001) : INFINITY;
-			rd[i].pad = 0;
-		}
+			RDyn* rd; const mr_renderable* in; int nR;
+			void operator()(int chunk) const
+			{
+				for (int i = chunk * kHostChunk; i < std::min(nR, (chunk + 1) * kHostChunk); i++)
+					fillDynamic(rd[i], in[i]);
+			}
+		} perRenderable = { rd, f->renderables, nR };
+		minirender::hostpool::parallelFor(nR >= kHostPoolMin ? minirender::hostpool::Pool::get() : 0, (nR + kHostChunk - 1) / kHostChunk, perRenderable);
 	}
 	const bool inlineTables = nR <= MR_INLINE_TABLE && f->n_materials <= MR_INLINE_TABLE;
 	if (szDyn && !inlineTables) MR_CUDA(c, cudaMemcpyAsync(c->rdyn.p, rd, szDyn, cudaMemcpyHostToDevice, c->stream));
@@ -694,8 +715,24 @@ int launchFrame(mr_ctx* c, const mr_frame* f, cudaEvent_t* ev, bool rerun)
 int rememberFrame(mr_ctx* c, const mr_frame* f)
 {
 	c->lastFrame = *f;
-	c->lastRenderables.assign(f->renderables, f->renderables + f->n_renderables);
-	c->lastMaterials.assign(f->materials, f->materials + f->n_materials);
+	// (what a re-render after an overflow, mr_profile_frame and the immediate-mode calls go back to; a megabyte per
+	// frame for 10 000 renderables, copied in pieces by the host threads when there are that many)
+	c->lastRenderables.resize((size_t)f->n_renderables);
+	c->lastMaterials.resize((size_t)f->n_materials);
+	struct Copy
+	{
+		mr_ctx* c; const mr_frame* f;
+		void operator()(int chunk) const
+		{
+			const int i0 = chunk * kHostChunk;
+			if (i0 < f->n_renderables)
+				memcpy(&c->lastRenderables[(size_t)i0], f->renderables + i0, sizeof(mr_renderable) * (size_t)std::min((int)kHostChunk, f->n_renderables - i0));
+			if (i0 < f->n_materials)
+				memcpy(&c->lastMaterials[(size_t)i0], f->materials + i0, sizeof(mr_material) * (size_t)std::min((int)kHostChunk, f->n_materials - i0));
+		}
+	} copy = { c, f };
+	const int most = std::max(f->n_renderables, f->n_materials);
+	minirender::hostpool::parallelFor(most >= kHostPoolMin ? minirender::hostpool::Pool::get() : 0, (most + kHostChunk - 1) / kHostChunk, copy);
 	c->lastFrame.renderables = 0;
 	c->lastFrame.materials = 0;
 	c->haveFrame = true;

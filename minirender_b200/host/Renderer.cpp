@@ -165,6 +165,26 @@ static unsigned long long fingerprint(unsigned long long h, const void* ptr, siz
 	return h;
 }
 
+// The lines fingerprint() will read of a long array, requested ahead of time: the arrays of a many-mesh scene are
+// scattered over far more memory than the caches hold, and a frame's fingerprints are a few cache misses per array.
+static inline void fingerprintPrefetch(const void* ptr, size_t bytes, int mode, const FpPlan& plan)
+{
+	if (!ptr || !bytes || mode == 0)
+		return;
+	const unsigned char* b = (const unsigned char*)ptr;
+	if (mode == 2 || bytes <= plan.full || bytes < 2 * plan.edge + 32)
+	{
+		for (size_t i = 0; i < bytes && i < 512; i += 64)
+			__builtin_prefetch(b + i);
+		return;
+	}
+	__builtin_prefetch(b);
+	__builtin_prefetch(b + bytes - plan.edge);
+	const size_t step = (bytes - 16) / (size_t)plan.samples;
+	for (int k = 1; k < plan.samples && k < 16; k++)
+		__builtin_prefetch(b + (size_t)k * step);
+}
+
 static int geometryCheckMode()
 {
 	static int mode = -1;
@@ -739,28 +759,54 @@ static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 	const FpPlan plan = fingerprintPlan(nMeshes);
 	std::vector<MeshSig>& ms = s.sigScratch;
 	ms.resize(nMeshes);
+	const bool comparable = !force && s.uploaded && s.upMeshes.size() == nMeshes;
+	std::atomic<int> changed(comparable ? 0 : 1);
 	struct Signatures
 	{
-		Renderer::Impl& s; std::vector<MeshSig>& ms; int mode; const FpPlan& plan;
+		Renderer::Impl& s; std::vector<MeshSig>& ms; int mode; const FpPlan& plan; bool comparable; std::atomic<int>& changed;
+		static void arrays(const mr_mesh_desc& d, const void* p[6], int n[6])
+		{
+			const void* pp[6] = { d.positions, d.normals, d.texcoords, d.idx_pos, d.idx_nrm, d.idx_uv };
+			const int nn[6] = { d.n_positions, d.n_normals, d.n_texcoords, d.n_triangles, d.n_triangles, d.idx_uv ? d.n_triangles : 0 };
+			memcpy(p, pp, sizeof(pp));
+			memcpy(n, nn, sizeof(nn));
+		}
 		void operator()(int c) const
 		{
+			const size_t elem[6] = { 12, 12, 8, 12, 12, 12 };
+			const size_t ahead = 3; // meshes whose sample lines are on their way while one is hashed
 			const size_t i0 = (size_t)c * MR_POOL_CHUNK, i1 = std::min(ms.size(), i0 + MR_POOL_CHUNK);
+			const void* p[6];
+			int n[6];
+			for (size_t i = i0; i < std::min(i1, i0 + ahead); i++)
+			{
+				arrays(s.meshes[i], p, n);
+				for (int k = 0; k < 6; k++)
+					fingerprintPrefetch(p[k], elem[k] * (size_t)n[k], mode, plan);
+			}
+			bool same = comparable;
 			for (size_t i = i0; i < i1; i++)
 			{
-				const mr_mesh_desc& d = s.meshes[i];
-				const void* p[6] = { d.positions, d.normals, d.texcoords, d.idx_pos, d.idx_nrm, d.idx_uv };
-				const int n[6] = { d.n_positions, d.n_normals, d.n_texcoords, d.n_triangles, d.n_triangles, d.idx_uv ? d.n_triangles : 0 };
+				if (i + ahead < i1)
+				{
+					arrays(s.meshes[i + ahead], p, n);
+					for (int k = 0; k < 6; k++)
+						fingerprintPrefetch(p[k], elem[k] * (size_t)n[k], mode, plan);
+				}
+				arrays(s.meshes[i], p, n);
 				memset(&ms[i], 0, sizeof(MeshSig));
-				memcpy(ms[i].p, p, sizeof(p));
-				memcpy(ms[i].n, n, sizeof(n));
-				const size_t elem[6] = { 12, 12, 8, 12, 12, 12 };
+				memcpy(ms[i].p, p, sizeof(ms[i].p));
+				memcpy(ms[i].n, n, sizeof(ms[i].n));
 				unsigned long long h = 0x243f6a8885a308d3ull;
 				for (int k = 0; k < 6; k++)
 					h = fingerprint(h, p[k], elem[k] * (size_t)n[k], mode, plan);
 				ms[i].fp = h;
+				same = same && ms[i] == s.upMeshes[i];
 			}
+			if (!same)
+				changed.store(1, std::memory_order_relaxed);
 		}
-	} perMesh = { s, ms, mode, plan };
+	} perMesh = { s, ms, mode, plan, comparable, changed };
 	hostpool::parallelFor(nMeshes >= (size_t)MR_POOL_MIN_ENTRIES ? hostpool::Pool::get() : 0, (int)((nMeshes + MR_POOL_CHUNK - 1) / MR_POOL_CHUNK), perMesh);
 	std::vector<TexSig> ts(s.textures.size());
 	for (size_t i = 0; i < s.textures.size(); i++)
@@ -770,7 +816,7 @@ static void syncGeometry(Renderer::Impl& s, unsigned stamp, bool force)
 		ts[i].cols = s.textures[i].cols;
 	}
 	const unsigned epoch = geometryEpoch().load(std::memory_order_acquire); // bumped by TriMesh::applyTransform()
-	if (!force && s.uploaded && stamp == s.upStamp && epoch == s.upEpoch && ms == s.upMeshes && ts == s.upTextures)
+	if (!changed.load() && stamp == s.upStamp && epoch == s.upEpoch && ts == s.upTextures)
 		return;
 	int rc = mr_upload_scene(s.ctx, &s.sceneDesc);
 	if (rc)

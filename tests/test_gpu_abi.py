@@ -344,6 +344,49 @@ def test_in_place_mesh_edits_are_rendered(be, ref):
     assert (out["ref"][1][1] != out["ref"][0][1]).any() and (out["ref"][2][1] != out["ref"][1][1]).any()
 
 
+@pytest.mark.gpu
+def test_many_mesh_scene_through_the_host_pool(be, ref):
+    """1 296 meshes under 36 groups: flatten, matrices, descriptors and geometry fingerprints of such a frame are dealt
+    to the library's host threads (host/HostPool.h) and each mesh gets a smaller share of the per-frame fingerprint
+    budget. Frames must still equal the reference's, also after a node moved, after applyTransform() on a mesh
+    (epoch) and after a mesh was displaced in place by hand (every vertex: any sample sees it)."""
+    import minirender_b200 as m
+    from minirender_b200 import scenes
+    from parity import assert_parity, compare
+    out = {}
+    for name, b in (("gpu", be), ("ref", ref)):
+        rng = np.random.default_rng(5)
+        sc = m.Scene(b, ambient=0.15)
+        ids = []
+        for g in range(36):
+            grp = sc.add_group(xf=b.mul(b.translate(float(g % 6) * 30 - 75, float(g // 6) * 30 - 75, 0), b.rotate_z(0.1 * g)))
+            for k in range(36):
+                mat = sc.add_material(diffuse=rng.random(3).astype(np.float32), shininess=float(rng.uniform(2, 20)))
+                ids.append(sc.add_sphere(float(rng.uniform(1.5, 2.6)), 6, 8, parent=grp, material=mat,
+                                         xf=b.mul(b.translate(float(k % 6) * 4.5 - 11, float(k // 6) * 4.5 - 11, float(rng.uniform(-3, 3))),
+                                                  b.scale(1.0, float(rng.uniform(0.7, 1.3)), 1.0))))
+        setup = scenes.Setup("many", sc, 480, 300, scenes.frustum(b, 480, 300, near=5.0, far=2000.0), b.translate(0, 0, -330))
+        r = setup.apply(m.Renderer(b))
+        frames = []
+        def shot():
+            r.render(); frames.append((r.get_image().copy(), r.get_depth().copy()))
+        shot(); shot()
+        sc.set_transform(ids[700], b.mul(b.translate(3, -2, 6), b.scale(2.0, 2.0, 2.0)))
+        shot()
+        sc.apply_transform(ids[700])
+        sc.set_transform(ids[700], b.translate(-6, 0, 0))
+        shot()
+        for i in range(sc.mesh_arrays(ids[40])["positions"].shape[0]):
+            sc.move_vertex(ids[40], i, (1.5, 2.5, 4.0))
+        shot()
+        out[name] = frames
+    for k in range(5):
+        rep = compare(out["gpu"][k][0], out["gpu"][k][1], out["ref"][k][0], out["ref"][k][1])
+        assert_parity(rep, "many-mesh frame %d" % k)
+    assert all((out["ref"][k][1] != out["ref"][k - 1][1]).any() for k in (2, 3, 4))
+    assert (out["ref"][3][1] < 1e10).sum() > 20000
+
+
 def _turntable_frames(be, n, **kw):
     """n views of the small benchmark scene as self-contained mr_frame descriptors (+ the scene descriptor's owner)."""
     setup = scenes.SMALL_SCENES["bench_small"](be)
