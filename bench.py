@@ -607,9 +607,61 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
         else:
             close = sharding.open_peer_target(lib, ctx, rank, world, dist, dst=0)
             join = sharding.StripJoin(lib, ctx, rank, world, dist, dst=0)
-    r.set_row_range(rb, re)
     if world > 1 and rank != 0:
         assert lib.mr_set_sparse_remote_stores(ctx, 1) == 0  # only the tiles this rank draws into cross NVLink
+    if world > 1 and calibration is not None and not getattr(args, "local_calibration", False):
+        # Second stage of the balancing, with the stores where they go in the timed loop: a peer's tile kernel is slower
+        # when its tiles cross NVLink (and the more so the more tiles it touches), which the rounds above cannot see.
+        # All ranks render their strips at the same time (the peers share rank 0's NVLink ingress), unsynchronised and
+        # untimed; the cuts move again. Rank 0 then resets its framebuffers and tells the peers which one comes first.
+        for _ in range(3):
+            r.set_row_range(*strips[rank])
+            r.set_view(view(0))
+            if rank != 0:
+                if double:
+                    assert lib.mr_set_remote_target(ctx, *targets[join.first % 2]) == 0
+                assert lib.mr_set_raster_gate(ctx, None, 0) == 0
+            r.prepare()
+            torch.cuda.synchronize()
+            dist.barrier()
+            # (nine timed frames per round: with seven peers storing into one GPU a strip's time varies by +-15 % from frame to frame)
+            assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 9) == 0, lib.mr_last_error(ctx)
+            st0 = cabi.Stats()
+            lib.mr_get_stats(ctx, C.byref(st0))
+            t_mine = float(st0.ms_kernel[5])
+            if rank == 0:
+                bg3 = (C.c_float * 3)(*setup.background)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                for k_, (b_, e_) in enumerate(strips):
+                    if k_ != 0 and e_ > b_:
+                        assert lib.mr_clear_rows(ctx, bg3, b_, e_) == 0
+                c1.record(stream)
+                c1.synchronize()
+                t_mine += c0.elapsed_time(c1)
+            mine = torch.tensor([t_mine], dtype=torch.float64, device="cuda")
+            everyone = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            times = [float(x[0]) for x in everyone]
+            calibration.append({"rows": [e - b for b, e in strips], "strip_ms": times, "stores": "into rank 0 over NVLink"})
+            strips = sharding.balanced_strips(H4, strips, times)
+        torch.cuda.synchronize()
+        dist.barrier()
+        first = [None]
+        if rank == 0:
+            bg3 = (C.c_float * 3)(*setup.background)
+            if double:
+                for slot in (0, 1):
+                    assert lib.mr_clear_rows_slot(ctx, slot, bg3, 0, H4) == 0
+                first = [(lib.mr_output_slot(ctx) + 1) % 2]
+            else:
+                assert lib.mr_clear_rows(ctx, bg3, 0, H4) == 0
+            r.synchronize()
+        dist.broadcast_object_list(first, src=0)
+        if double:
+            join.first = first[0]
+        rb, re = strips[rank]
+    r.set_row_range(rb, re)
     counter = [0]
     peer_rows = [s_ for k_, s_ in enumerate(strips) if k_ != 0 and s_[1] > s_[0]]
     total_frames = warmup + steps
@@ -639,6 +691,7 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
     for i in range(steps):
         frame(warmup + i)
     e1.record(stream)
+    enqueue = time.perf_counter() - t0  # host time spent issuing the frames (a rank whose queue never fills is host-bound)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if dist is not None:
@@ -650,7 +703,8 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
     assert lib.mr_profile_frame(ctx, r.frame_desc_ptr(), 5) == 0, lib.mr_last_error(ctx)
     st = cabi.Stats()
     lib.mr_get_stats(ctx, C.byref(st))
-    mine = torch.tensor([dev_ms, wall * 1000.0, st.ms_kernel[5], st.ms_kernel[1], st.ms_kernel[4], float(st.tiles_stored)], dtype=torch.float64, device="cuda")
+    mine = torch.tensor([dev_ms, wall * 1000.0, st.ms_kernel[5], st.ms_kernel[1], st.ms_kernel[4], float(st.tiles_stored), enqueue * 1000.0 / steps],
+                        dtype=torch.float64, device="cuda")
     everyone = [mine]
     if dist is not None:
         everyone = [torch.zeros_like(mine) for _ in range(world)]
@@ -699,6 +753,7 @@ def measure_strips(args, rank, local_rank, world, dist, steps, warmup):
             "ms_per_step_device_rank0": per_rank[0][0] / steps, "ms_per_step_host_wall_max": max(p[1] for p in per_rank) / steps,
             "strip_device_ms_per_rank": [p[2] for p in per_rank], "strip_geom_ms_per_rank": [p[3] for p in per_rank],
             "strip_raster_ms_per_rank": [p[4] for p in per_rank],
+            "host_enqueue_ms_per_frame_per_rank": [p[6] for p in per_rank],
             "strip_rows_per_rank": [e - b for b, e in strips],
             "strip_balancing": calibration if calibration is not None else "equal heights",
             "single_gpu_frame_ms": whole_ms, "speedup_vs_single_gpu_frame": whole_ms / ms,
@@ -735,6 +790,7 @@ def main():
     ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the configs[2] strip-sharded frame (extra key strips4k)")
     ap.add_argument("--single-target", action="store_true", help="strips: one framebuffer on the gathering rank instead of two alternating ones")
     ap.add_argument("--equal-strips", action="store_true", help="strips of equal height instead of heights balanced by measured time")
+    ap.add_argument("--local-calibration", action="store_true", help="balance the strips with local stores only (without the second stage that measures them with the stores going to rank 0)")
     ap.add_argument("--workload", default="sphere1m", choices=["sphere1m", "strips4k", "turntable2m"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

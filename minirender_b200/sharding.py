@@ -36,6 +36,18 @@ def all_strips(height, world, tile=TILE):
     return [strip_rows(height, r, world, tile) for r in range(world)]
 
 
+def merge_row_ranges(ranges):
+    """Adjacent or overlapping (begin, end) row ranges joined: the peers of a gathering rank usually own one contiguous
+    block of rows, which is then one clear instead of one per peer."""
+    out = []
+    for b, e in sorted((b, e) for b, e in ranges if e > b):
+        if out and b <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], e))
+        else:
+            out.append((b, e))
+    return out
+
+
 def balanced_strips(height, strips, times, tile=TILE):
     """Re-cuts `strips` (a list of (begin, end) covering [0, height) in whole tile rows) so that every rank's strip
     takes about the same time, given the time each rank measured for its current strip: the cost of a tile row is
@@ -210,18 +222,25 @@ class StripJoin:
     def end(self, frame, clear_rows=None):
         """clear_rows = (background rgb, [(row_begin, row_end), ...]) on dst: with sparse remote stores the peers only
         write the tiles they drew into, so dst resets their rows to the clear values before it lets them in again."""
-        assert self.lib.mr_stream_signal(self.ctx, self._word(self.rank), frame + 1) == 0
-        if self.rank == self.dst:
-            assert self.lib.mr_stream_wait(self.ctx, self._word(0), self.world, frame + 1) == 0
-            # (a consumer of the assembled frame would be enqueued here)
-            if clear_rows is not None:
-                bg = (C.c_float * 3)(*clear_rows[0])
-                for rb, re in clear_rows[1]:
-                    if self.double:
-                        assert self.lib.mr_clear_rows_slot(self.ctx, (self.first + frame) % 2, bg, rb, re) == 0
-                    else:
-                        assert self.lib.mr_clear_rows(self.ctx, bg, rb, re) == 0
-            assert self.lib.mr_stream_signal(self.ctx, self._word(self.world), frame + 1) == 0
+        if self.rank != self.dst:
+            assert self.lib.mr_stream_signal(self.ctx, self._word(self.rank), frame + 1) == 0
+            return
+        # dst's own rows are ordered by its stream: it waits for the others' words only (the words before and behind
+        # its own) and clears the peers' rows in as few launches as they form blocks: the gathering rank enqueues
+        # the most per frame, and its host time per frame is part of the frame rate at eight ranks
+        if self.dst > 0:
+            assert self.lib.mr_stream_wait(self.ctx, self._word(0), self.dst, frame + 1) == 0
+        if self.dst + 1 < self.world:
+            assert self.lib.mr_stream_wait(self.ctx, self._word(self.dst + 1), self.world - self.dst - 1, frame + 1) == 0
+        # (a consumer of the assembled frame would be enqueued here)
+        if clear_rows is not None:
+            bg = (C.c_float * 3)(*clear_rows[0])
+            for rb, re in merge_row_ranges(clear_rows[1]):
+                if self.double:
+                    assert self.lib.mr_clear_rows_slot(self.ctx, (self.first + frame) % 2, bg, rb, re) == 0
+                else:
+                    assert self.lib.mr_clear_rows(self.ctx, bg, rb, re) == 0
+        assert self.lib.mr_stream_signal(self.ctx, self._word(self.world), frame + 1) == 0
 
     def close(self):
         if self.opened:
