@@ -197,6 +197,13 @@ def test_strip_partition_covers_image_once():
                 rows[b:e] += 1
             assert (rows == 1).all()
     assert sharding.views_for_rank(10, 1, 4) == [1, 5, 9]
+    # the rows a gathering rank clears for its peers: adjacent strips are one block, empty ones vanish
+    assert sharding.merge_row_ranges([(272, 544), (544, 816), (816, 816), (1088, 2160), (816, 1088)]) == [(272, 2160)]
+    assert sharding.merge_row_ranges([(0, 16), (32, 48)]) == [(0, 16), (32, 48)]
+    assert sharding.merge_row_ranges([]) == []
+    for world in (2, 3, 8):
+        strips = sharding.all_strips(2160, world)
+        assert sharding.merge_row_ranges(strips[1:]) == [(strips[0][1], 2160)]
 
 
 def test_balanced_strips_partition_and_converge():
