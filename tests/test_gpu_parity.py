@@ -63,6 +63,34 @@ def test_small_scene_vs_reference(be, ref, name):
     assert_parity(rep, name + " vs reference")
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_scene_vs_reference(be, ref, seed):
+    """scenes.fuzz_scene (random similarity / non-uniform / mirrored / sheared transforms, objects around the camera and
+    across the near plane, symmetric / off-centre perspective and orthographic projections, both kinds of light):
+    the CUDA path with every shortcut on against the reference's own code rendering its own flatten of the same
+    scene. tests/test_gpu_invariance.py shows the shortcuts do not change the GPU's frame; this shows the frame is right."""
+    sg = scenes.fuzz_scene(be, seed)
+    got = render_gpu(be, sg)
+    sr = scenes.fuzz_scene(ref, seed)
+    rr = sr.apply(m.Renderer(ref))
+    rr.render()
+    rep = compare(got["image"], got["depth"], rr.get_image(), rr.get_depth())
+    print("fuzz", seed, rep)
+    assert (rr.get_depth() < 1e10).any()
+    assert_parity(rep, "fuzz scene %d vs reference" % seed)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_tiny_triangles_vs_reference(be, ref, seed):
+    """30 000 pixel-sized / sub-pixel triangles and slivers (scenes.tiny_soup_scene) against the reference's own code."""
+    sg = scenes.tiny_soup_scene(be, seed, persp=bool(seed & 1))
+    got = render_gpu(be, sg)
+    sr = scenes.tiny_soup_scene(ref, seed, persp=bool(seed & 1))
+    rr = sr.apply(m.Renderer(ref))
+    rr.render()
+    assert_parity(compare(got["image"], got["depth"], rr.get_image(), rr.get_depth()), "tiny soup %d vs reference" % seed)
+
+
 def test_stats_match_oracle_counters(be):
     setup = scenes.SMALL_SCENES["cloud_small"](be)
     got = render_gpu(be, setup)

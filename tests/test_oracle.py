@@ -40,6 +40,33 @@ def test_port_matches_compiled_reference(be, ref, name):
         assert (bits(got["normals"]) == bits(rr.get_normals())).all()
 
 
+def _port_vs_reference(be, ref, make):
+    sr = make(ref)
+    rr = sr.apply(m.Renderer(ref))
+    rr.render()
+    sp = make(be)
+    rp = sp.apply(m.Renderer(be))
+    rp.prepare()
+    got = pyoracle.render_port(rp.scene_desc_ptr(), rp.frame_desc_ptr(), sp.width, sp.height, normals=sp.save_normals)
+    assert (rr.get_depth() < 1e10).any(), "%s draws nothing" % sp.name
+    assert (bits(got["depth"]) == bits(rr.get_depth())).all(), sp.name
+    assert (bits(got["image"]) == bits(rr.get_image())).all(), sp.name
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_port_matches_compiled_reference_on_fuzz_scenes(be, ref, seed):
+    """Randomised transforms (similarity, non-uniform, mirrored, sheared), objects enclosing the camera or crossing the
+    near plane and the screen edges, symmetric / off-centre perspective and orthographic projections, directional and
+    point lights (minirender_b200/scenes.py:fuzz_scene): the C restatement against the reference's own code, bit for bit."""
+    _port_vs_reference(be, ref, lambda b: scenes.fuzz_scene(b, seed))
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_port_matches_compiled_reference_on_tiny_triangles(be, ref, seed):
+    """30 000 pixel-sized and sub-pixel triangles, a third of them slivers, corners on pixel centres and edges."""
+    _port_vs_reference(be, ref, lambda b: scenes.tiny_soup_scene(b, seed, persp=bool(seed & 1)))
+
+
 def test_port_strip_union_equals_full_frame(be):
     """Rows are independent: rendering [0,h) in strips and stacking them is the full frame."""
     from minirender_b200 import sharding
