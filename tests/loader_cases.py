@@ -198,3 +198,249 @@ def same(got, want):
         if a.shape != b.shape or a.dtype != b.dtype or a.tobytes() != b.tobytes():
             bad.append(k)
     return bad
+
+
+# ---- randomised files (tests/test_loader_parity.py: product build vs reference build on the same bytes) ----
+
+def _num(rng, v):
+    """One number as text, in one of the spellings mesh files use."""
+    k = rng.randint(0, 5)
+    if k == 0:
+        return "%g" % v
+    if k == 1:
+        return "%.4f" % v
+    if k == 2:
+        return "%.7e" % v
+    if k == 3:
+        return "%d" % int(round(v))
+    return repr(float(np.float32(v)))
+
+
+def random_obj(rng, d, stem):
+    """A well-formed OBJ (+ MTL, sometimes with a PPM texture): shared vertex / normal / texcoord pools, polygons of 3-6
+    corners, faces spread over several materials that are switched back and forth, comments and blank lines."""
+    nv, has_n, has_t = rng.randint(3, 40), rng.rand() < 0.6, rng.rand() < 0.5
+    nn, nt = rng.randint(1, 12), rng.randint(1, 12)
+    mats = ["m%d" % i for i in range(rng.randint(0, 4))]
+    lines = ["# random case " + stem]
+    if mats:
+        lines.append("mtllib %s.mtl" % stem)
+        mtl = []
+        for i, name in enumerate(mats):
+            mtl.append("newmtl " + name)
+            if rng.rand() < 0.8: mtl.append("Kd " + " ".join(_num(rng, x) for x in rng.rand(3)))
+            if rng.rand() < 0.5: mtl.append("Ks " + " ".join(_num(rng, x) for x in rng.rand(3)))
+            if rng.rand() < 0.3: mtl.append("Ke " + " ".join(_num(rng, x) for x in rng.rand(3) * 0.1))
+            if rng.rand() < 0.7: mtl.append("Ns " + _num(rng, rng.choice([0.0, 5.0, 33.5, 200.0])))
+            if rng.rand() < 0.3: mtl.append("d " + _num(rng, rng.rand()))
+            if rng.rand() < 0.3:
+                mtl.append("map_Kd %s_%d.ppm" % (stem, i))
+                write_ppm(os.path.join(d, "%s_%d.ppm" % (stem, i)), rng.randint(1, 6), rng.randint(1, 6), seed=rng.randint(0, 1000), comment=rng.rand() < 0.5)
+            if rng.rand() < 0.3: mtl.append("")
+        write(os.path.join(d, stem + ".mtl"), "\n".join(mtl) + "\n")
+    for _ in range(nv):
+        lines.append("v " + " ".join(_num(rng, x) for x in rng.uniform(-50, 50, 3)))
+    if has_n:
+        for _ in range(nn):
+            lines.append("vn " + " ".join(_num(rng, x) for x in rng.uniform(-1, 1, 3)))
+    if has_t:
+        for _ in range(nt):
+            lines.append("vt " + " ".join(_num(rng, x) for x in rng.uniform(-0.5, 1.5, 2)))
+    for _ in range(rng.randint(1, 30)):
+        if mats and rng.rand() < 0.3:
+            lines.append("usemtl " + (rng.choice(mats) if rng.rand() < 0.9 else "undefined_material"))
+        if rng.rand() < 0.1:
+            lines.append(rng.choice(["", "# a comment", "g group%d" % rng.randint(0, 9), "s 1"]))
+        corners = []
+        for _ in range(rng.randint(3, 7)):
+            v = rng.randint(1, nv + 1)
+            if has_n and has_t: corners.append("%d/%d/%d" % (v, rng.randint(1, nt + 1), rng.randint(1, nn + 1)))
+            elif has_n: corners.append("%d//%d" % (v, rng.randint(1, nn + 1)))
+            elif has_t: corners.append("%d/%d" % (v, rng.randint(1, nt + 1)))
+            else: corners.append("%d" % v)
+        lines.append("f " + (" " if rng.rand() < 0.8 else "  ").join(corners))
+    write(os.path.join(d, stem + ".obj"), "\n".join(lines) + ("\n" if rng.rand() < 0.8 else ""))
+    return stem + ".obj"
+
+
+def random_stl(rng, d, stem):
+    n = rng.randint(1, 25)
+    if rng.rand() < 0.5:
+        facets = rng.uniform(-100, 100, (n, 12)).astype(np.float32)
+        with open(os.path.join(d, stem + ".stl"), "wb") as f:
+            f.write((b"binary " + stem.encode()).ljust(80, b" ") + struct.pack("<i", n))
+            for r in facets:
+                f.write(r.tobytes() + struct.pack("<H", rng.randint(0, 65536)))
+    else:
+        out = ["solid " + stem]
+        for _ in range(n):
+            out.append(" facet normal " + " ".join(_num(rng, x) for x in rng.uniform(-1, 1, 3)))
+            out.append("  outer loop")
+            for _ in range(3):
+                out.append("   vertex " + " ".join(_num(rng, x) for x in rng.uniform(-100, 100, 3)))
+            out.append("  endloop")
+            out.append(" endfacet")
+        out.append("endsolid " + stem)
+        write(os.path.join(d, stem + ".stl"), "\n".join(out) + "\n")
+    return stem + ".stl"
+
+
+def canonical_child_order(dump_of_file):
+    """loadOBJ returns one mesh per material in the iteration order of an asl::Dic (io.cpp:196, :304): a hash map in real
+    ASL, a sorted map in the stand-in the reference is compiled against here, first use in the product - the order is
+    not something the reference defines. For a comparison the children behind the root are put into one order:
+    by material values, then index arrays."""
+    groups = {}
+    for key, v in dump_of_file.items():
+        stem, k, field = key.split("/")
+        groups.setdefault(int(k), {})[field] = v
+    stem = next(iter(dump_of_file)).split("/")[0]
+    rest = sorted((k for k in groups if k > 0),
+                  key=lambda k: tuple(np.asarray(groups[k].get(f, np.zeros(0))).tobytes() for f in ("material", "idx_pos", "idx_nrm", "idx_uv")))
+    out = {}
+    for new, k in enumerate([0] + rest if 0 in groups else rest):
+        for field, v in groups[k].items():
+            out["%s/%d/%s" % (stem, new, field)] = v
+    return out
+
+
+def dump_files(be, d, names, canonical=False):
+    """What loadMesh() returns for each of `names` in directory d, as {name: array} (the per-file part of dump())."""
+    d, out = str(d), {}
+    if canonical:
+        for name in names:
+            one = dump_files(be, d, [name])
+            key = name.replace(".", "_")
+            out[key + "/nodes"] = one.pop(key + "/nodes")
+            out.update(canonical_child_order(one) if name.endswith(".obj") else one)
+        return out
+    for name in names:
+        sc = m.Scene(be)
+        ids = sc.load(os.path.join(d, name))
+        key = name.replace(".", "_")
+        out[key + "/nodes"] = np.array(len(ids), np.int32)
+        for k, i in enumerate(ids):
+            inf = sc.node_info(i)
+            out["%s/%d/kind" % (key, k)] = np.array([int(inf["is_mesh"]), inf["children"]], np.int32)
+            out["%s/%d/transform" % (key, k)] = inf["transform"].astype(np.float32)
+            if inf["is_mesh"]:
+                for a, v in sc.mesh_arrays(i).items():
+                    out["%s/%d/%s" % (key, k, a)] = v
+                try:
+                    mat = sc.mesh_material(i)
+                except RuntimeError:
+                    out["%s/%d/material" % (key, k)] = np.zeros(0, np.float32)
+                    continue
+                out["%s/%d/material" % (key, k)] = np.concatenate([mat["diffuse"], mat["specular"], mat["emissive"],
+                                                                    [mat["shininess"], mat["opacity"]]]).astype(np.float32)
+                out["%s/%d/texture_shape" % (key, k)] = np.array(mat["texture_shape"], np.int32)
+    return out
+
+
+def random_x3d(rng, d, stem):
+    """A well-formed X3D scene: nested Transform / Group nodes with random subsets of translation / rotation / scale,
+    Shapes with IndexedFaceSet (polygons of 3-5 corners, optional normalIndex / texCoordIndex) or IndexedTriangleSet,
+    Appearance / Material / Coordinate shared through DEF / USE, commas or blanks between numbers, nodes the loader
+    ignores, comments, sometimes a PPM texture."""
+    defs = {"Appearance": [], "Material": [], "Coordinate": []}
+    counter = [0]
+
+    def nums(vals, per):
+        vals = [_num(rng, v) for v in vals]
+        sep = ", " if rng.rand() < 0.3 else " "
+        return sep.join(" ".join(vals[i:i + per]) for i in range(0, len(vals), per))
+
+    def coordinate():
+        if defs["Coordinate"] and rng.rand() < 0.25:
+            name, n = defs["Coordinate"][rng.randint(len(defs["Coordinate"]))]
+            return '<Coordinate USE="%s"/>' % name, n
+        n = rng.randint(3, 13)
+        tag = '<Coordinate'
+        if rng.rand() < 0.4:
+            counter[0] += 1
+            name = "C%d" % counter[0]
+            defs["Coordinate"].append((name, n))
+            tag += ' DEF="%s"' % name
+        return tag + ' point="%s"/>' % nums(rng.uniform(-20, 20, 3 * n), 3), n
+
+    def material():
+        if defs["Material"] and rng.rand() < 0.3:
+            return '<Material USE="%s"/>' % defs["Material"][rng.randint(len(defs["Material"]))]
+        tag = "<Material"
+        if rng.rand() < 0.4:
+            counter[0] += 1
+            defs["Material"].append("M%d" % counter[0])
+            tag += ' DEF="M%d"' % counter[0]
+        if rng.rand() < 0.8: tag += ' diffuseColor="%s"' % nums(rng.rand(3), 3)
+        if rng.rand() < 0.5: tag += ' specularColor="%s"' % nums(rng.rand(3), 3)
+        if rng.rand() < 0.3: tag += ' emissiveColor="%s"' % nums(rng.rand(3) * 0.2, 3)
+        if rng.rand() < 0.6: tag += ' shininess="%s"' % _num(rng, rng.rand())
+        return tag + "/>"
+
+    def appearance():
+        if defs["Appearance"] and rng.rand() < 0.3:
+            return '<Appearance USE="%s"/>' % defs["Appearance"][rng.randint(len(defs["Appearance"]))]
+        tag = "<Appearance"
+        if rng.rand() < 0.4:
+            counter[0] += 1
+            defs["Appearance"].append("A%d" % counter[0])
+            tag += ' DEF="A%d"' % counter[0]
+        inner = material() if rng.rand() < 0.8 else ""
+        if rng.rand() < 0.25:
+            counter[0] += 1
+            tex = "%s_t%d" % (stem, counter[0])
+            write_ppm(os.path.join(d, tex + ".ppm"), rng.randint(1, 5), rng.randint(1, 5), seed=rng.randint(0, 1000), comment=rng.rand() < 0.5)
+            inner += '<ImageTexture url="%s.png"/>' % tex
+        return tag + ">" + inner + "</Appearance>"
+
+    def shape():
+        out = ["<Shape>"]
+        if rng.rand() < 0.8:
+            out.append(appearance())
+        coord, n = coordinate()
+        if rng.rand() < 0.7:
+            polys = [[rng.randint(0, n) for _ in range(rng.randint(3, 6))] for _ in range(rng.randint(1, 9))]
+            flat = lambda ps, close_last=True: " ".join(" ".join(str(i) for i in p) + (" -1" if (k + 1 < len(ps) or close_last) else "")
+                                                        for k, p in enumerate(ps))
+            tag = '<IndexedFaceSet coordIndex="%s"' % flat(polys, rng.rand() < 0.8)
+            inner = coord
+            if rng.rand() < 0.5:
+                nn = rng.randint(1, 8)
+                inner += '<Normal vector="%s"/>' % nums(rng.uniform(-1, 1, 3 * nn), 3)
+                if rng.rand() < 0.7:
+                    tag += ' normalIndex="%s"' % flat([[rng.randint(0, nn) for _ in p] for p in polys])
+            if rng.rand() < 0.5:
+                nt = rng.randint(1, 8) if rng.rand() < 0.5 else n
+                inner += '<TextureCoordinate point="%s"/>' % nums(rng.uniform(0, 1, 2 * nt), 2)
+                if rng.rand() < 0.6:
+                    tag += ' texCoordIndex="%s"' % flat([[rng.randint(0, nt) for _ in p] for p in polys])
+            out.append(tag + ">" + inner + "</IndexedFaceSet>")
+        else:
+            idx = [rng.randint(0, n) for _ in range(3 * rng.randint(1, 9))]
+            inner = coord
+            if rng.rand() < 0.4:
+                inner += '<Normal vector="%s"/>' % nums(rng.uniform(-1, 1, 3 * n), 3)
+            if rng.rand() < 0.4:
+                inner += '<TextureCoordinate point="%s"/>' % nums(rng.uniform(0, 1, 2 * n), 2)
+            out.append('<IndexedTriangleSet index="%s">%s</IndexedTriangleSet>' % (" ".join(str(i) for i in idx), inner))
+        out.append("</Shape>")
+        return "".join(out)
+
+    def node(depth):
+        k = rng.rand()
+        if depth >= 3 or k < 0.45:
+            return shape()
+        if k < 0.55:
+            return rng.choice(['<Viewpoint position="0 0 10"/>', "<!-- nothing here -->", '<NavigationInfo type="EXAMINE"/>'])
+        tag = "Transform" if k < 0.85 else "Group"
+        attrs = ""
+        if tag == "Transform":
+            if rng.rand() < 0.7: attrs += ' translation="%s"' % nums(rng.uniform(-10, 10, 3), 3)
+            if rng.rand() < 0.6: attrs += ' rotation="%s"' % nums(list(rng.uniform(-1, 1, 3)) + [rng.uniform(-3, 3)], 4)
+            if rng.rand() < 0.5: attrs += ' scale="%s"' % nums(rng.uniform(0.2, 3, 3), 3)
+        return "<%s%s>%s</%s>" % (tag, attrs, "\n".join(node(depth + 1) for _ in range(rng.randint(0, 4))), tag)
+
+    body = "\n".join(node(0) for _ in range(rng.randint(1, 5)))
+    head = '<?xml version="1.0" encoding="UTF-8"?>\n' if rng.rand() < 0.7 else ""
+    write(os.path.join(d, stem + ".x3d"), head + '<X3D profile="Interchange" version="3.0">\n<Scene>\n' + body + "\n</Scene>\n</X3D>\n")
+    return stem + ".x3d"
