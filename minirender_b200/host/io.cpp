@@ -80,6 +80,9 @@ Array2<Vec3> loadPPM(const String& filename)
 		return image;
 	}
 	image.resize(rows, cols);
+	for (int i = 0; i < rows; i++) // (rows a truncated file does not hold stay black; the reference leaves them unassigned)
+		for (int j = 0; j < cols; j++)
+			image(i, j) = Vec3(0, 0, 0);
 	std::vector<byte> row((size_t)cols * 3);
 	for (int i = 0; i < rows; i++)
 	{

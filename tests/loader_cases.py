@@ -444,3 +444,35 @@ def random_x3d(rng, d, stem):
     head = '<?xml version="1.0" encoding="UTF-8"?>\n' if rng.rand() < 0.7 else ""
     write(os.path.join(d, stem + ".x3d"), head + '<X3D profile="Interchange" version="3.0">\n<Scene>\n' + body + "\n</Scene>\n</X3D>\n")
     return stem + ".x3d"
+
+
+def random_ppm(rng, d, stem):
+    """A binary PPM whose header is spelled one of many ways (comment lines, trailing comments, tabs, several blanks,
+    CR LF, everything on fewer lines), sometimes another magic number, a missing field or truncated pixel data.
+    Returns (file name, number of pixel rows that are complete in the file)."""
+    rows, cols = rng.randint(1, 9), rng.randint(1, 9)
+    px = rng.randint(0, 256, (rows, cols, 3)).astype(np.uint8)
+    magic = b"P6" if rng.rand() < 0.9 else rng.choice([b"P5", b"P3", b"p6", b"P66"])
+    eol = b"\r\n" if rng.rand() < 0.15 else b"\n"
+    blank = lambda: rng.choice([b" ", b"  ", b"\t"])
+    comment = lambda: b"# " + rng.choice([b"made by a test", b"4 4", b"P6", b""]) + eol
+    k = rng.randint(0, 6)
+    size = b"%d" % cols + blank() + b"%d" % rows
+    if k == 0:
+        head = magic + eol + size + eol + b"255" + eol
+    elif k == 1:
+        head = magic + eol + comment() + size + eol + (comment() if rng.rand() < 0.5 else b"") + b"255" + eol
+    elif k == 2:
+        head = magic + blank() + b"# trailing" + eol + size + blank() + b"# trailing too" + eol + b"255" + eol
+    elif k == 3:
+        head = magic + eol + b"%d" % cols + eol + b"%d" % rows + blank() + b"255" + eol          # three newlines, other grouping
+    elif k == 4:
+        head = magic + eol + size + eol + eol                                                     # no maximum value
+    else:
+        head = magic + eol + blank() + size + blank() + eol + b"255" + blank() + eol
+    data = px.tobytes()
+    if rng.rand() < 0.15:
+        data = data[:rng.randint(0, len(data))]                                                   # truncated
+    with open(os.path.join(d, stem + ".ppm"), "wb") as f:
+        f.write(head + data)
+    return stem + ".ppm", len(data) // (3 * cols)  # (rows present in full: the others are never read)
