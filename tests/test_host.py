@@ -83,6 +83,36 @@ def test_primitives_identical_to_reference(be, ref, kind, args):
         assert (out[0][k].view(np.uint8) == out[1][k].view(np.uint8)).all(), k
 
 
+def test_random_primitives_and_projections_identical_to_reference(be, ref):
+    """The generators that define the benchmark meshes (src/primitives.cpp) and the projection builders
+    (src/Renderer.cpp:40-83) over 120 random parameter sets, product build against the reference's own, bit for bit."""
+    rng = np.random.RandomState(31)
+    for _ in range(60):
+        kind = [api.PRIM_CUBE, api.PRIM_SPHERE, api.PRIM_CYLINDER][rng.randint(3)]
+        a = float(np.float32(rng.uniform(0.01, 500)))
+        b = float(np.float32(rng.uniform(0.01, 500)))
+        n1, n2, caps = int(rng.randint(2, 40)), int(rng.randint(1, 40)), bool(rng.randint(2))
+        out = []
+        for bk in (be, ref):
+            sc = api.Scene(bk)
+            out.append(sc.mesh_arrays(sc.add_primitive(kind, a, b, n1, max(n2, 3) if kind == api.PRIM_SPHERE else n2, caps)))
+        for k in out[0]:
+            assert out[0][k].shape == out[1][k].shape and out[0][k].tobytes() == out[1][k].tobytes(), (kind, a, b, n1, n2, caps, k)
+    for _ in range(60):
+        l, r = sorted(rng.uniform(-50, 50, 2)); bt, t = sorted(rng.uniform(-50, 50, 2)); n = rng.uniform(0.01, 50); f = n + rng.uniform(0.1, 9000)
+        fov, aspect = rng.uniform(0.05, 3.0), rng.uniform(0.3, 3.0)
+        for kind, args in ((api.PROJ_ORTHO6, (l, r, bt, t, n, f)), (api.PROJ_PERSPECTIVE6, (l, r, bt, t, n, f)), (api.PROJ_FRUSTUM, (fov, aspect, n, f)),
+                           (api.PROJ_FRUSTUM_H, (fov, aspect, n, f)), (api.PROJ_ORTHO4, (fov * 100, aspect, n, f))):
+            args = [float(np.float32(x)) for x in args]
+            assert be.projection(kind, *args).tobytes() == ref.projection(kind, *args).tobytes(), (kind, args)
+        K = np.eye(4, dtype=np.float32)
+        K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1] = rng.uniform(200, 2000), rng.uniform(200, 2000), rng.uniform(100, 900), rng.uniform(100, 900), rng.uniform(-2, 2)
+        w, h = float(rng.randint(64, 4000)), float(rng.randint(64, 4000))
+        assert be.projection_cv(K, w, h, float(np.float32(n)), float(np.float32(f))).tobytes() == ref.projection_cv(K, w, h, float(np.float32(n)), float(np.float32(f))).tobytes()
+        xa = be.mul(be.translate(*rng.uniform(-9, 9, 3).astype(np.float32)), be.rotate_vec(*rng.uniform(-3, 3, 3).astype(np.float32)), be.scale(*rng.uniform(0.1, 4, 3).astype(np.float32)))
+        assert be.inverse(xa).tobytes() == ref.inverse(xa).tobytes()
+
+
 def test_projection_builders_and_matrices_identical_to_reference(be, ref):
     for kind, args in [(api.PROJ_ORTHO6, (-40, 40, -30, 30, 50, 120)), (api.PROJ_PERSPECTIVE6, (-1, 2, -1.5, 1, 0.5, 90)),
                        (api.PROJ_FRUSTUM, (0.61, 1.7777, 10, 7000)), (api.PROJ_FRUSTUM_H, (0.9, 1.3, 1, 100)),
