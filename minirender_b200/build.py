@@ -62,7 +62,8 @@ def build_product(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(PKG, h) for h in HEADERS]
-    cu_headers = [os.path.join(PKG, h) for h in HEADERS if "/host/" not in "/" + h and "include/minirender/" not in h]  # the device side sees the C ABI only
+    # (the .cu files see the C ABI and, for mr_context.cu's host loops, the host thread pool - not the C++ API)
+    cu_headers = [os.path.join(PKG, h) for h in HEADERS if ("/host/" not in "/" + h or h.endswith("HostPool.h")) and "include/minirender/" not in h]
     shim = os.path.join(ROOT, "third_party", "asl_shim")
     headers += [os.path.join(shim, "asl", f) for f in os.listdir(os.path.join(shim, "asl"))]
     objs, log = [], []

@@ -9,6 +9,7 @@
 // Only library code runs on the workers (never an application's virtual overrides). The pool is created on first
 // use by a frame with enough entries, re-created in a forked child, and joined when the library is unloaded.
 // MINIRENDER_B200_HOST_THREADS=1 turns it off, =N fixes the width (default: min(8, hardware threads)).
+// Jobs must not throw and must not start jobs themselves (one job at a time: callers take turns).
 #ifndef MINIRENDER_B200_HOST_POOL_H
 #define MINIRENDER_B200_HOST_POOL_H
 
@@ -16,6 +17,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 #include <pthread.h>
