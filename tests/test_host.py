@@ -134,6 +134,20 @@ def test_scene_bbox_and_triangle_count_match_reference(be, ref):
             assert (x.view(np.uint32) == y.view(np.uint32)).all()
 
 
+def test_bbox_triangles_and_saved_stl_of_random_scenes_match_reference(be, ref, tmp_path):
+    """Scene::getBbox (src/Scene.cpp:22-47) and saveSTL (src/io.cpp:152-185) on the randomised fuzz scenes: nested
+    transforms incl. shear and mirroring, thousands of triangles; bounding boxes bit for bit, STL files byte for byte."""
+    for seed in range(8):
+        sa, sb = scenes.fuzz_scene(be, seed), scenes.fuzz_scene(ref, seed)
+        assert sa.scene.triangles() == sb.scene.triangles() > 0
+        for x, y in zip(sa.scene.bbox(), sb.scene.bbox()):
+            assert x.tobytes() == y.tobytes(), seed
+        pa, pb = str(tmp_path / ("a%d.stl" % seed)), str(tmp_path / ("b%d.stl" % seed))
+        sa.scene.save_stl(0, pa)
+        sb.scene.save_stl(0, pb)
+        assert open(pa, "rb").read() == open(pb, "rb").read() and os.path.getsize(pa) > 84, seed
+
+
 def test_prepare_flattens_in_submission_order(be):
     setup = scenes.ties_scene(be)
     r = setup.apply(m.Renderer(be))
