@@ -8,7 +8,7 @@
 //
 // Only library code runs on the workers (never an application's virtual overrides). The pool is created on first
 // use by a frame with enough entries, re-created in a forked child, and joined when the library is unloaded.
-// MINIRENDER_B200_HOST_THREADS=1 turns it off, =N fixes the width (default: min(8, hardware threads)).
+// MINIRENDER_B200_HOST_THREADS=1 turns it off, =N fixes the width (default: min(8, hardware threads / 2)).
 // Jobs must not throw and must not start jobs themselves (one job at a time: callers take turns).
 #ifndef MINIRENDER_B200_HOST_POOL_H
 #define MINIRENDER_B200_HOST_POOL_H
@@ -41,7 +41,9 @@ public:
 			p = holder.pool.load(std::memory_order_acquire);
 			if (!p)
 			{
-				int width = (int)std::thread::hardware_concurrency();
+				// half of what the machine reports, at most 8: hardware threads are often two per core, and on a
+				// host whose processors are shared with others a worker that loses its processor holds a frame up
+				int width = (int)std::thread::hardware_concurrency() / 2;
 				if (width > 8)
 					width = 8;
 				const char* e = getenv("MINIRENDER_B200_HOST_THREADS");
