@@ -44,6 +44,23 @@ def algorithmic_bytes(n_pos, n_nrm, n_uv, n_tri, index_arrays, w, h):
     return 12 * n_pos + 12 * n_nrm + 8 * n_uv + 12 * n_tri * index_arrays + 16 * w * h
 
 
+def issue_roofline(summary, sm_mhz, n_sm, ms_per_step):
+    """The frame against the SMs' instruction issue rate - the roof that binds this pipeline (its kernels use 10-25 % of
+    the DRAM bandwidth and half of their issue slots): warp instructions the two kernels execute per frame (ncu
+    `smsp__inst_executed.sum` of the committed capture, same kernel source) / (SMs x 4 schedulers x SM clock). None
+    if the capture does not carry the counts."""
+    try:
+        n = sum(float(summary[k]["warp_instructions"]) for k in ("k_geom", "k_raster"))
+        per_s = float(n_sm) * 4.0 * float(sm_mhz) * 1e6
+        t_min = n / per_s
+        return {"bound": "issue slots", "warp_instructions_per_frame": n, "peak": per_s, "unit": "warp instructions/s",
+                "achieved": n / (ms_per_step * 1e-3), "frac": t_min / (ms_per_step * 1e-3), "t_min_us": t_min * 1e6,
+                "note": "time the frame's executed warp instructions need at one instruction per scheduler per cycle; the HBM time of "
+                        "the frame's algorithmic bytes (roofline / frame_roofline) is about half of it"}
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -456,6 +473,7 @@ def run_ours(args, rank, local_rank, world):
         # dram__bytes of the dominant kernel from the committed ncu capture - only if that capture was made on the kernel
         # source this run executes (profiles/ncu_summary.json records the file's hash: tools/make_ncu_summary.py)
         traffic, traffic_note, frame_traffic = None, "no ncu capture of this kernel source (profiles/ncu_summary.json is missing or older than mr_kernels.cu)", None
+        fresh_summary = None
         try:
             import hashlib
             with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
@@ -463,6 +481,7 @@ def run_ours(args, rank, local_rank, world):
             with open(os.path.join(ROOT, "minirender_b200", "csrc", "mr_kernels.cu"), "rb") as f:
                 fresh = summ.get("kernels_sha256") == hashlib.sha256(f.read()).hexdigest()
             if fresh:
+                fresh_summary = summ
                 traffic = summ.get(dom, {}).get("dram_bytes_per_launch")
                 frame_traffic = summ.get("frame", {}).get("dram_bytes_per_frame_no_flush")
                 traffic_note = summ.get(dom, {}).get("source")
@@ -513,6 +532,13 @@ def run_ours(args, rank, local_rank, world):
         }
         if strips is not None:
             line["strips4k"] = strips
+        try:
+            import torch
+            issue = issue_roofline(fresh_summary, clocks.get("sm_mhz"), torch.cuda.get_device_properties(local_rank).multi_processor_count, dev_ms_max / K) if fresh_summary else None
+            if issue:
+                line["issue_roofline"] = issue
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             import pyoracle
             kind = "reference" if pyoracle.have_ref() else "port"

@@ -271,3 +271,18 @@ def test_balanced_strips_partition_and_converge():
     t8 = [42, 51, 73, 98, 98, 73, 51, 42]
     out = sharding.balanced_strips(2160, s8, t8)
     assert out[3][1] - out[3][0] < 272 < out[0][1] - out[0][0]
+
+
+def test_bench_issue_roofline_from_the_committed_capture():
+    """bench.py's `issue_roofline` key: warp instructions per frame from profiles/ncu_summary.json over SMs x 4 schedulers x
+    clock; absent (None) when the capture carries no counts."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    summary = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    got = bench.issue_roofline(summary, 1965.0, 148, 0.0545)
+    n = summary["k_geom"]["warp_instructions"] + summary["k_raster"]["warp_instructions"]
+    assert got["warp_instructions_per_frame"] == n and abs(got["t_min_us"] - n / (148 * 4 * 1965.0)) < 1e-9
+    assert 0.2 < got["frac"] < 1.0 and abs(got["frac"] - got["t_min_us"] / 54.5) < 1e-9
+    assert bench.issue_roofline({"k_geom": {}}, 1965.0, 148, 0.05) is None

@@ -8,6 +8,7 @@ full = json.load(open(sys.argv[1]))
 out = {"kernels_sha256": hashlib.sha256(open(os.path.join(ROOT, "minirender_b200", "csrc", "mr_kernels.cu"), "rb").read()).hexdigest()}
 for k, v in full["kernels"].items():
     out[k] = {"dram_bytes_per_launch": v.get("dram_bytes_per_launch"), "duration_us": v["duration"]["value"],
+              "warp_instructions": v.get("warp_instructions", {}).get("value"), "issue_slots_busy_pct": v.get("issue_slots_busy_pct", {}).get("value"),
               "source": "%s (ncu --set full, caches flushed before the kernel)" % os.path.relpath(sys.argv[1], ROOT)}
 if len(sys.argv) > 2:
     acc = {}
